@@ -1,0 +1,134 @@
+/*
+ * tiny_llm_b200.h - C ABI of the B200 (sm_100a) backend for tiny-llm's Qwen3
+ * W4A16 inference hot path.
+ *
+ * This is the drop-in boundary: one launcher per native primitive of the
+ * reference's extension (declared in
+ * /root/reference/src/extensions_ref/src/tiny_llm_ext.h:10-141 and exported to
+ * Python by /root/reference/src/extensions_ref/bindings.cpp:14-46).  Where the
+ * reference builds a lazy `mx::array` whose `eval_gpu` encodes a Metal
+ * dispatch, a launcher here enqueues sm_100a kernels on the caller's CUDA
+ * stream.  Conventions:
+ *
+ *   - plain device pointers and sizes; no torch / MLX types;
+ *   - the caller owns every buffer (outputs and workspaces included); a
+ *     launcher never allocates, frees or synchronises, so it is legal inside
+ *     CUDA-graph capture;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default);
+ *   - return 0 on success, a negative TL_E* code otherwise; the message is
+ *     available from tl_last_error() (thread-local); nothing throws across
+ *     the boundary;
+ *   - `dtype` is one of TL_F32 / TL_F16 / TL_BF16 and names the activation /
+ *     storage type; all accumulation is fp32.
+ *
+ * Naming quirk kept from the reference (quantized_matmul.cpp:125-127):
+ * in quantized_matmul `a` is [M, N] with N the REDUCTION length, `b` is
+ * [K, N/8] packed words with K the number of OUTPUT features, out is [M, K].
+ */
+#ifndef TINY_LLM_B200_H
+#define TINY_LLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { TL_F32 = 0, TL_F16 = 1, TL_BF16 = 2 };
+
+enum {
+    TL_OK = 0,
+    TL_EINVAL = -1,      /* bad argument (shape, alignment, unsupported combination) */
+    TL_EDTYPE = -2,      /* dtype not supported by this primitive */
+    TL_EWORKSPACE = -3,  /* workspace missing or too small */
+    TL_ECUDA = -4,       /* CUDA runtime / driver error at launch */
+    TL_ENODEVICE = -5    /* no sm_100 device */
+};
+
+/* Library identity / diagnostics. */
+int tl_abi_version(void);
+const char *tl_last_error(void);
+/* Fills SM count and compute capability of the current device. */
+int tl_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* Number of kernels this library has launched since load (bench bookkeeping). */
+long long tl_launch_count(void);
+
+/* ---- W4A16 (4-bit, group 128) projections -------------------------------
+ * Replaces quantized_matmul (tiny_llm_ext.h:12-21, quantized_matmul.cpp:14-80,
+ * eval_gpu :111-240).  scales/biases [K, N/128] (f16|bf16), a [M, N],
+ * b [K, N/8] u32, out [M, K].  Kernel selection:
+ *   use_simdgroup && M <= TL_MATVEC_MAX_ROWS : weight-streaming tensor-core
+ *       matvec, weights kept fp32-exact (reference: M <= 8 matvec);
+ *   use_simdgroup                            : tiled GEMM, weights rounded to
+ *       the activation dtype before the MMA (reference: simdgroup tile);
+ *   !use_simdgroup                           : scalar control kernel.
+ * use_split_k only requests a split of the reduction; when the policy keeps
+ * split == 1 the very same kernel runs (bit-identical results,
+ * tests_refsol/test_week_2_day_7.py:80-109).  workspace is needed only when
+ * tl_quantized_matmul_workspace() reports a non-zero size. */
+#define TL_MATVEC_MAX_ROWS 32
+size_t tl_quantized_matmul_workspace(int M, int N, int K, int dtype, int use_simdgroup, int use_split_k);
+int tl_quantized_matmul(const void *scales, const void *biases, const void *a, const void *b, void *out, int M,
+                        int N, int K, int dtype, int use_simdgroup, int use_split_k, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* Replaces quantized_embedding (tiny_llm_ext.h:40-41, quantized_matmul.cpp:82-101,
+ * :242-273).  indices int32/uint32 [tokens] (bit pattern), weight [vocab, dim/8] u32,
+ * scales/biases [vocab, dim/128], out [tokens, dim]. */
+int tl_quantized_embedding(const void *indices, const void *scales, const void *biases, const void *weight,
+                           void *out, int tokens, int vocab, int dim, int dtype, void *stream);
+
+/* ---- fused model kernels (week2_kernels.cpp:36-84, :104-211) ------------- */
+/* x [rows, dim], weight [dim], out [rows, dim]:  x * rsqrt(mean(x^2)+eps) * w */
+int tl_rms_norm(const void *x, const void *weight, void *out, int rows, int dim, float eps, int dtype,
+                void *stream);
+/* x,out [B, L, H, D]; offsets int32 [B]; rotates the first `dims` of D. */
+int tl_rope(const void *x, const int32_t *offsets, void *out, int B, int L, int H, int D, int dims, float base,
+            int traditional, int dtype, void *stream);
+/* out = gate / (1 + exp(-gate)) * up, `size` elements. */
+int tl_swiglu(const void *gate, const void *up, void *out, long long size, int dtype, void *stream);
+/* Dense-KV GQA attention: q,out [q_rows, L, D] with q_rows = B*Hq; k,v [B*Hkv, S, D];
+ * mask fp32 [q_rows, L, S] when has_mask (ignored otherwise).  D <= 256. */
+int tl_decode_attention(const void *q, const void *k, const void *v, const float *mask, void *out, int q_rows,
+                        int L, int S, int D, int num_heads, int num_kv_heads, float scale, int is_causal,
+                        int has_mask, int dtype, void *stream);
+
+/* ---- paged KV (paged_attention.cpp:14-31, :38-70, :77-122, :129-225) ------ */
+/* In-place: pages[page_id, :, start:start+length, :] = values[0]; pages [P,H,page,D],
+ * values [1,H,length,D]. */
+int tl_paged_cache_update(void *pages, const void *values, int num_pages, int heads, int page_size, int head_dim,
+                          int length, int page_id, int start, int dtype, void *stream);
+/* q,out [B*Hq, L, D]; pages [P, Hkv, page, D]; block_table int32 [B, max_pages]
+ * (-1 padded); context_lens int32 [B] (post-append).  D <= 128; the tensor-core
+ * prefill branch (L > 8, bf16) requires D == 128.  Rows that see no key are
+ * written as zeros.  Workspace holds split-KV partials for the decode branch. */
+size_t tl_paged_attention_workspace(int rows, int L, int D, int num_kv_heads, int num_heads, int dtype);
+int tl_paged_attention(const void *q, const void *key_pages, const void *value_pages, const int32_t *block_table,
+                       const int32_t *context_lens, void *out, int rows, int L, int D, int num_pages,
+                       int page_size, int max_pages, float scale, int is_causal, int num_kv_heads, int num_heads,
+                       int dtype, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- B200 extensions behind the same per-op semantics ---------------------
+ * Device-driven K/V append for a decode batch (the batched form of
+ * paged_kv_cache.py:196-234 called once per request, kv_cache.py:191-199):
+ * row b writes keys[b]/values[b] ([B, Hkv, 1, D]) to the slot of token
+ * context_lens[b]-1, resolved through block_table; rows with context 0 are
+ * skipped.  Page ids and slots come from device memory, so the call is
+ * CUDA-graph replayable. */
+int tl_paged_cache_append_decode(void *key_pages, void *value_pages, const void *keys, const void *values,
+                                 const int32_t *block_table, const int32_t *context_lens, int batch,
+                                 int num_pages, int heads, int page_size, int head_dim, int max_pages, int dtype,
+                                 void *stream);
+/* out = a + b (residual adds of qwen3_week3.py:204-206), `size` elements. */
+int tl_add(const void *a, const void *b, void *out, long long size, int dtype, void *stream);
+/* Greedy sampler of batch.py:8-13: out_tokens[r] = argmax(logits[r, :]) (the
+ * log-softmax shift is argmax-invariant).  logits [rows, vocab], out int32 [rows]. */
+int tl_argmax(const void *logits, int32_t *out_tokens, int rows, int vocab, int dtype, void *workspace,
+              size_t workspace_bytes, void *stream);
+size_t tl_argmax_workspace(int rows, int vocab);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINY_LLM_B200_H */

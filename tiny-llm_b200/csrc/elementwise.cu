@@ -1,0 +1,493 @@
+// Memory-bound model kernels: RMSNorm, RoPE, SwiGLU, residual add, W4 embedding
+// gather, paged KV writes, greedy argmax.  All are HBM/L2-bound byte movers:
+// 128-bit coalesced accesses when alignment allows, fp32 math, one rounding.
+//
+// Arithmetic follows the reference Metal kernels (paths relative to
+// /root/reference/src/extensions_ref/src): week2_kernels.metal:6-117,
+// quantized_matmul.metal:58-89, paged_attention.metal:82-106.
+#include <float.h>
+#include <limits.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tl {
+
+template <typename T>
+struct Vec {
+    static constexpr int N = 16 / sizeof(T);  // elements per 128-bit access
+};
+
+template <typename T>
+__device__ __forceinline__ void load16(const T *p, float (&v)[Vec<T>::N]) {
+    uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    if constexpr (sizeof(T) == 4) {
+        v[0] = __uint_as_float(raw.x), v[1] = __uint_as_float(raw.y);
+        v[2] = __uint_as_float(raw.z), v[3] = __uint_as_float(raw.w);
+    } else {
+        float2 a = unpack2<T>(raw.x), b = unpack2<T>(raw.y), c = unpack2<T>(raw.z), d = unpack2<T>(raw.w);
+        v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y, v[4] = c.x, v[5] = c.y, v[6] = d.x, v[7] = d.y;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store16(T *p, const float (&v)[Vec<T>::N]) {
+    uint4 raw;
+    if constexpr (sizeof(T) == 4) {
+        raw.x = __float_as_uint(v[0]), raw.y = __float_as_uint(v[1]);
+        raw.z = __float_as_uint(v[2]), raw.w = __float_as_uint(v[3]);
+    } else {
+        raw.x = pack2<T>(v[0], v[1]), raw.y = pack2<T>(v[2], v[3]);
+        raw.z = pack2<T>(v[4], v[5]), raw.w = pack2<T>(v[6], v[7]);
+    }
+    *reinterpret_cast<uint4 *>(p) = raw;
+}
+
+// ---------------------------------------------------------------- RMSNorm --
+// TPR threads cooperate on one row (32: one warp per row for per-head norms of
+// width 128; 256: one CTA per row for hidden-size rows).
+template <typename T, int TPR, bool VEC>
+__global__ void __launch_bounds__(256) rms_norm_kernel(const T *__restrict__ x, const T *__restrict__ w,
+                                                        T *__restrict__ out, int rows, int dim, float eps) {
+    constexpr int ROWS = 256 / TPR;
+    constexpr int EPV = Vec<T>::N;
+    const int sub = threadIdx.x / TPR;
+    const int lane = threadIdx.x % TPR;
+    const int row = blockIdx.x * ROWS + sub;
+    const bool live = row < rows;
+    const T *xr = x + static_cast<size_t>(live ? row : 0) * dim;
+    T *outr = out + static_cast<size_t>(live ? row : 0) * dim;
+
+    float ss = 0.f;
+    if (live) {
+        if constexpr (VEC) {
+            for (int i = lane * EPV; i < dim; i += TPR * EPV) {
+                float v[EPV];
+                load16<T>(xr + i, v);
+#pragma unroll
+                for (int j = 0; j < EPV; ++j) ss += v[j] * v[j];
+            }
+        } else {
+            for (int i = lane; i < dim; i += TPR) {
+                float v = to_f(xr[i]);
+                ss += v * v;
+            }
+        }
+    }
+    ss = warp_sum(ss);
+    if constexpr (TPR > 32) {
+        __shared__ float part[TPR / 32];
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        float t = (threadIdx.x & 31) < TPR / 32 ? part[threadIdx.x & 31] : 0.f;
+        ss = warp_sum(t);
+    }
+    if (!live) return;
+    const float inv = rsqrtf(ss / static_cast<float>(dim) + eps);
+    if constexpr (VEC) {
+        for (int i = lane * EPV; i < dim; i += TPR * EPV) {
+            float v[EPV], g[EPV];
+            load16<T>(xr + i, v);
+            load16<T>(w + i, g);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) v[j] = v[j] * inv * g[j];
+            store16<T>(outr + i, v);
+        }
+    } else {
+        for (int i = lane; i < dim; i += TPR) outr[i] = from_f<T>(to_f(xr[i]) * inv * to_f(w[i]));
+    }
+}
+
+template <typename T>
+static int rms_norm_t(const void *x, const void *w, void *out, int rows, int dim, float eps, cudaStream_t st) {
+    constexpr int EPV = Vec<T>::N;
+    const bool vec = dim % EPV == 0 && aligned16(x) && aligned16(w) && aligned16(out);
+    const T *xp = static_cast<const T *>(x);
+    const T *wp = static_cast<const T *>(w);
+    T *op = static_cast<T *>(out);
+    if (dim <= 512) {
+        dim3 grid(ceil_div(rows, 8));
+        if (vec)
+            rms_norm_kernel<T, 32, true><<<grid, 256, 0, st>>>(xp, wp, op, rows, dim, eps);
+        else
+            rms_norm_kernel<T, 32, false><<<grid, 256, 0, st>>>(xp, wp, op, rows, dim, eps);
+    } else {
+        dim3 grid(rows);
+        if (vec)
+            rms_norm_kernel<T, 256, true><<<grid, 256, 0, st>>>(xp, wp, op, rows, dim, eps);
+        else
+            rms_norm_kernel<T, 256, false><<<grid, 256, 0, st>>>(xp, wp, op, rows, dim, eps);
+    }
+    TL_LAUNCH_CHECK("rms_norm");
+    return TL_OK;
+}
+
+int launch_rms_norm(const void *x, const void *w, void *out, int rows, int dim, float eps, int dtype,
+                    cudaStream_t st) {
+    if (rows == 0) return TL_OK;
+    switch (dtype) {
+        case TL_F32: return rms_norm_t<float>(x, w, out, rows, dim, eps, st);
+        case TL_F16: return rms_norm_t<__half>(x, w, out, rows, dim, eps, st);
+        case TL_BF16: return rms_norm_t<__nv_bfloat16>(x, w, out, rows, dim, eps, st);
+    }
+    return fail(TL_EDTYPE, "rms_norm: expected float32, float16, or bfloat16");
+}
+
+// ------------------------------------------------------------------- RoPE --
+// One thread per (b, l, h, item): item < dims/2 rotates one pair, the remaining
+// items copy the un-rotated tail [dims, D).  Consecutive threads touch
+// consecutive elements, so each warp access is one contiguous segment.
+template <typename T>
+__global__ void rope_kernel(const T *__restrict__ x, const int32_t *__restrict__ offsets, T *__restrict__ out, int B,
+                            int L, int H, int D, int dims, float base, int traditional) {
+    const int half_dim = dims / 2;
+    const int items = half_dim + (D - dims);
+    const long long total = static_cast<long long>(B) * L * H * items;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int item = static_cast<int>(idx % items);
+    const int h = static_cast<int>((idx / items) % H);
+    const int l = static_cast<int>((idx / (static_cast<long long>(items) * H)) % L);
+    const int b = static_cast<int>(idx / (static_cast<long long>(items) * H * L));
+    const size_t head_base = ((static_cast<size_t>(b) * L + l) * H + h) * D;
+    if (item >= half_dim) {
+        const int d = dims + item - half_dim;
+        out[head_base + d] = x[head_base + d];
+        return;
+    }
+    const float power = -static_cast<float>(item) / static_cast<float>(half_dim);
+    const float inv_freq = sizeof(T) == 4 ? powf(base, power) : exp2f(power * log2f(base));
+    const float angle = static_cast<float>(offsets[b] + l) * inv_freq;
+    float s, c;
+    sincosf(angle, &s, &c);
+    const size_t re_i = traditional ? head_base + 2 * item : head_base + item;
+    const size_t im_i = traditional ? re_i + 1 : re_i + half_dim;
+    const float re = to_f(x[re_i]);
+    const float im = to_f(x[im_i]);
+    out[re_i] = from_f<T>(re * c - im * s);
+    out[im_i] = from_f<T>(im * c + re * s);
+}
+
+template <typename T>
+static int rope_t(const void *x, const int32_t *off, void *out, int B, int L, int H, int D, int dims, float base,
+                  int traditional, cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * L * H * (dims / 2 + D - dims);
+    if (total == 0) return TL_OK;
+    const int threads = 256;
+    const long long blocks = ceil_div_ll(total, threads);
+    if (blocks > INT_MAX) return fail(TL_EINVAL, "rope: tensor too large");
+    rope_kernel<T><<<static_cast<unsigned>(blocks), threads, 0, st>>>(static_cast<const T *>(x), off,
+                                                                       static_cast<T *>(out), B, L, H, D, dims, base,
+                                                                       traditional);
+    TL_LAUNCH_CHECK("rope");
+    return TL_OK;
+}
+
+int launch_rope(const void *x, const int32_t *off, void *out, int B, int L, int H, int D, int dims, float base,
+                int traditional, int dtype, cudaStream_t st) {
+    switch (dtype) {
+        case TL_F32: return rope_t<float>(x, off, out, B, L, H, D, dims, base, traditional, st);
+        case TL_F16: return rope_t<__half>(x, off, out, B, L, H, D, dims, base, traditional, st);
+        case TL_BF16: return rope_t<__nv_bfloat16>(x, off, out, B, L, H, D, dims, base, traditional, st);
+    }
+    return fail(TL_EDTYPE, "rope: expected float32, float16, or bfloat16");
+}
+
+// ------------------------------------------------------ SwiGLU / residual --
+enum class Ew { SWIGLU, ADD };
+
+template <typename T, Ew OP, bool VEC>
+__global__ void binary_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out, long long n) {
+    constexpr int EPV = Vec<T>::N;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    auto f = [](float p, float q) -> float {
+        if constexpr (OP == Ew::SWIGLU)
+            return (p / (1.0f + expf(-p))) * q;  // week2_kernels.metal:115-116
+        else
+            return p + q;
+    };
+    if constexpr (VEC) {
+        const long long nv = n / EPV;
+        for (; i < nv; i += stride) {
+            float p[EPV], q[EPV];
+            load16<T>(a + i * EPV, p);
+            load16<T>(b + i * EPV, q);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) p[j] = f(p[j], q[j]);
+            store16<T>(out + i * EPV, p);
+        }
+    } else {
+        for (; i < n; i += stride) out[i] = from_f<T>(f(to_f(a[i]), to_f(b[i])));
+    }
+}
+
+template <typename T, Ew OP>
+static int binary_t(const void *a, const void *b, void *out, long long n, cudaStream_t st, const char *name) {
+    if (n == 0) return TL_OK;
+    constexpr int EPV = Vec<T>::N;
+    const bool vec = n % EPV == 0 && aligned16(a) && aligned16(b) && aligned16(out);
+    const long long work = vec ? n / EPV : n;
+    const int threads = 256;
+    const long long want = ceil_div_ll(work, threads);
+    const unsigned blocks = static_cast<unsigned>(want < 148LL * 16 ? want : 148LL * 16);
+    if (vec)
+        binary_kernel<T, OP, true><<<blocks, threads, 0, st>>>(static_cast<const T *>(a), static_cast<const T *>(b),
+                                                                static_cast<T *>(out), n);
+    else
+        binary_kernel<T, OP, false><<<blocks, threads, 0, st>>>(static_cast<const T *>(a), static_cast<const T *>(b),
+                                                                 static_cast<T *>(out), n);
+    TL_LAUNCH_CHECK(name);
+    return TL_OK;
+}
+
+int launch_swiglu(const void *gate, const void *up, void *out, long long n, int dtype, cudaStream_t st) {
+    switch (dtype) {
+        case TL_F32: return binary_t<float, Ew::SWIGLU>(gate, up, out, n, st, "swiglu");
+        case TL_F16: return binary_t<__half, Ew::SWIGLU>(gate, up, out, n, st, "swiglu");
+        case TL_BF16: return binary_t<__nv_bfloat16, Ew::SWIGLU>(gate, up, out, n, st, "swiglu");
+    }
+    return fail(TL_EDTYPE, "swiglu: expected float32, float16, or bfloat16");
+}
+
+int launch_add(const void *a, const void *b, void *out, long long n, int dtype, cudaStream_t st) {
+    switch (dtype) {
+        case TL_F32: return binary_t<float, Ew::ADD>(a, b, out, n, st, "add");
+        case TL_F16: return binary_t<__half, Ew::ADD>(a, b, out, n, st, "add");
+        case TL_BF16: return binary_t<__nv_bfloat16, Ew::ADD>(a, b, out, n, st, "add");
+    }
+    return fail(TL_EDTYPE, "add: expected float32, float16, or bfloat16");
+}
+
+// ------------------------------------------------------ W4 embedding rows --
+// One thread per packed word: 8 codes -> 8 outputs (one 128-bit store).
+// value = float(code) * scale + bias, rounded once (quantized_matmul.metal:83-88).
+template <typename T>
+__global__ void quantized_embedding_kernel(const int32_t *__restrict__ indices, const T *__restrict__ scales,
+                                           const T *__restrict__ biases, const uint32_t *__restrict__ weight,
+                                           T *__restrict__ out, int tokens, int vocab, int dim, bool vec_store) {
+    const int words = dim / 8;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<long long>(tokens) * words) return;
+    const int token = static_cast<int>(idx / words);
+    const int wcol = static_cast<int>(idx % words);
+    const int row = indices[token];
+    float v[8];
+    if (row < 0 || row >= vocab) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    } else {
+        const uint32_t packed = weight[static_cast<size_t>(row) * words + wcol];
+        const size_t g = static_cast<size_t>(row) * (dim / 128) + wcol / 16;
+        const float s = to_f(scales[g]);
+        const float b = to_f(biases[g]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = static_cast<float>((packed >> (4 * j)) & 0xFu) * s + b;
+    }
+    T *dst = out + static_cast<size_t>(token) * dim + wcol * 8;
+    if (vec_store) {
+        uint4 raw;
+        raw.x = pack2<T>(v[0], v[1]), raw.y = pack2<T>(v[2], v[3]);
+        raw.z = pack2<T>(v[4], v[5]), raw.w = pack2<T>(v[6], v[7]);
+        *reinterpret_cast<uint4 *>(dst) = raw;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = from_f<T>(v[j]);
+    }
+}
+
+template <typename T>
+static int embedding_t(const void *indices, const void *scales, const void *biases, const void *weight, void *out,
+                       int tokens, int vocab, int dim, cudaStream_t st) {
+    const long long total = static_cast<long long>(tokens) * (dim / 8);
+    if (total == 0) return TL_OK;
+    const int threads = 256;
+    quantized_embedding_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, threads)), threads, 0, st>>>(
+        static_cast<const int32_t *>(indices), static_cast<const T *>(scales), static_cast<const T *>(biases),
+        static_cast<const uint32_t *>(weight), static_cast<T *>(out), tokens, vocab, dim, aligned16(out));
+    TL_LAUNCH_CHECK("quantized_embedding");
+    return TL_OK;
+}
+
+int launch_quantized_embedding(const void *indices, const void *scales, const void *biases, const void *weight,
+                               void *out, int tokens, int vocab, int dim, int dtype, cudaStream_t st) {
+    switch (dtype) {
+        case TL_F16: return embedding_t<__half>(indices, scales, biases, weight, out, tokens, vocab, dim, st);
+        case TL_BF16: return embedding_t<__nv_bfloat16>(indices, scales, biases, weight, out, tokens, vocab, dim, st);
+    }
+    return fail(TL_EDTYPE, "quantized_embedding: scales and biases must have the same 16-bit dtype");
+}
+
+// ------------------------------------------------------ paged KV writes ----
+// pages [P, H, page, D]; values [1, H, length, D]  (paged_attention.metal:82-106)
+template <typename V>
+__global__ void paged_cache_update_kernel(const V *__restrict__ values, V *__restrict__ pages, int heads, int length,
+                                          int dvec, int page_size, int page_id, int start) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(heads) * length * dvec;
+    if (idx >= total) return;
+    const int d = static_cast<int>(idx % dvec);
+    const int t = static_cast<int>((idx / dvec) % length);
+    const int h = static_cast<int>(idx / (static_cast<long long>(dvec) * length));
+    const size_t dst = ((static_cast<size_t>(page_id) * heads + h) * page_size + start + t) * dvec + d;
+    pages[dst] = values[idx];
+}
+
+int launch_paged_cache_update(void *pages, const void *values, int heads, int page_size, int head_dim, int length,
+                              int page_id, int start, int dtype, cudaStream_t st) {
+    const int esize = dtype == TL_F32 ? 4 : 2;
+    const long long elems = static_cast<long long>(heads) * length * head_dim;
+    if (elems == 0) return TL_OK;
+    const int threads = 256;
+    const bool vec = (head_dim * esize) % 16 == 0 && aligned16(pages) && aligned16(values);
+    if (vec) {
+        const int dvec = head_dim * esize / 16;
+        const long long total = static_cast<long long>(heads) * length * dvec;
+        paged_cache_update_kernel<uint4><<<static_cast<unsigned>(ceil_div_ll(total, threads)), threads, 0, st>>>(
+            static_cast<const uint4 *>(values), static_cast<uint4 *>(pages), heads, length, dvec, page_size, page_id,
+            start);
+    } else if (esize == 4) {
+        paged_cache_update_kernel<uint32_t><<<static_cast<unsigned>(ceil_div_ll(elems, threads)), threads, 0, st>>>(
+            static_cast<const uint32_t *>(values), static_cast<uint32_t *>(pages), heads, length, head_dim, page_size,
+            page_id, start);
+    } else {
+        paged_cache_update_kernel<uint16_t><<<static_cast<unsigned>(ceil_div_ll(elems, threads)), threads, 0, st>>>(
+            static_cast<const uint16_t *>(values), static_cast<uint16_t *>(pages), heads, length, head_dim, page_size,
+            page_id, start);
+    }
+    TL_LAUNCH_CHECK("paged_cache_update");
+    return TL_OK;
+}
+
+// Decode-batch append: row b owns token ctx[b]-1; page id and slot are read
+// from device memory (graph-replayable).  keys/values [B, H, 1, D].
+template <typename V>
+__global__ void paged_cache_append_decode_kernel(V *__restrict__ key_pages, V *__restrict__ value_pages,
+                                                 const V *__restrict__ keys, const V *__restrict__ values,
+                                                 const int32_t *__restrict__ block_table,
+                                                 const int32_t *__restrict__ context_lens, int batch, int num_pages,
+                                                 int heads, int page_size, int dvec, int max_pages) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(batch) * heads * dvec;
+    if (idx >= total) return;
+    const int d = static_cast<int>(idx % dvec);
+    const int h = static_cast<int>((idx / dvec) % heads);
+    const int b = static_cast<int>(idx / (static_cast<long long>(dvec) * heads));
+    const int ctx = context_lens[b];
+    if (ctx <= 0) return;
+    const int tok = ctx - 1;
+    const int lp = tok / page_size;
+    if (lp >= max_pages) return;
+    const int pid = block_table[static_cast<size_t>(b) * max_pages + lp];
+    if (pid < 0 || pid >= num_pages) return;
+    const size_t dst = ((static_cast<size_t>(pid) * heads + h) * page_size + (tok - lp * page_size)) * dvec + d;
+    key_pages[dst] = keys[idx];
+    value_pages[dst] = values[idx];
+}
+
+int launch_paged_cache_append_decode(void *key_pages, void *value_pages, const void *keys, const void *values,
+                                     const int32_t *block_table, const int32_t *context_lens, int batch,
+                                     int num_pages, int heads, int page_size, int head_dim, int max_pages, int dtype,
+                                     cudaStream_t st) {
+    const int esize = dtype == TL_F32 ? 4 : 2;
+    const long long elems = static_cast<long long>(batch) * heads * head_dim;
+    if (elems == 0) return TL_OK;
+    const int threads = 256;
+    const bool vec = (head_dim * esize) % 16 == 0 && aligned16(key_pages) && aligned16(value_pages) &&
+                     aligned16(keys) && aligned16(values);
+#define TL_APPEND(V, DV)                                                                                         \
+    paged_cache_append_decode_kernel<V>                                                                          \
+        <<<static_cast<unsigned>(ceil_div_ll(static_cast<long long>(batch) * heads * (DV), threads)), threads, 0, \
+           st>>>(static_cast<V *>(key_pages), static_cast<V *>(value_pages), static_cast<const V *>(keys),      \
+                 static_cast<const V *>(values), block_table, context_lens, batch, num_pages, heads, page_size,  \
+                 (DV), max_pages)
+    if (vec) {
+        TL_APPEND(uint4, head_dim * esize / 16);
+    } else if (esize == 4) {
+        TL_APPEND(uint32_t, head_dim);
+    } else {
+        TL_APPEND(uint16_t, head_dim);
+    }
+#undef TL_APPEND
+    TL_LAUNCH_CHECK("paged_cache_append_decode");
+    return TL_OK;
+}
+
+// ---------------------------------------------------------- greedy argmax --
+struct Best {
+    float v;
+    int i;
+};
+__device__ __forceinline__ Best better(Best a, Best b) {
+    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;  // first maximum wins
+}
+__device__ __forceinline__ Best block_best(Best mine) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best other{__shfl_xor_sync(0xffffffffu, mine.v, o), __shfl_xor_sync(0xffffffffu, mine.i, o)};
+        mine = better(mine, other);
+    }
+    if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = mine.v, si[threadIdx.x >> 5] = mine.i;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) / 32;
+    Best r{(threadIdx.x & 31) < nw ? sv[threadIdx.x & 31] : -INFINITY, (threadIdx.x & 31) < nw ? si[threadIdx.x & 31] : INT_MAX};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best other{__shfl_xor_sync(0xffffffffu, r.v, o), __shfl_xor_sync(0xffffffffu, r.i, o)};
+        r = better(r, other);
+    }
+    return r;
+}
+
+template <typename T>
+__global__ void argmax_partial_kernel(const T *__restrict__ logits, float *__restrict__ pv, int *__restrict__ pi,
+                                      int vocab, int chunk) {
+    const int row = blockIdx.y;
+    const int begin = blockIdx.x * chunk;
+    const int end = min(vocab, begin + chunk);
+    const T *src = logits + static_cast<size_t>(row) * vocab;
+    Best mine{-INFINITY, INT_MAX};
+    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) mine = better(mine, Best{to_f(src[i]), i});
+    mine = block_best(mine);
+    if (threadIdx.x == 0) pv[row * gridDim.x + blockIdx.x] = mine.v, pi[row * gridDim.x + blockIdx.x] = mine.i;
+}
+
+__global__ void argmax_final_kernel(const float *__restrict__ pv, const int *__restrict__ pi, int32_t *__restrict__ out,
+                                    int parts) {
+    const int row = blockIdx.x;
+    Best mine{-INFINITY, INT_MAX};
+    for (int i = threadIdx.x; i < parts; i += blockDim.x) mine = better(mine, Best{pv[row * parts + i], pi[row * parts + i]});
+    mine = block_best(mine);
+    if (threadIdx.x == 0) out[row] = mine.i == INT_MAX ? 0 : mine.i;
+}
+
+static int argmax_parts(int vocab) { return vocab <= 4096 ? 1 : (ceil_div(vocab, 4096) < 64 ? ceil_div(vocab, 4096) : 64); }
+
+size_t argmax_workspace(int rows, int vocab) { return static_cast<size_t>(rows) * argmax_parts(vocab) * 8; }
+
+int launch_argmax(const void *logits, int32_t *out, int rows, int vocab, int dtype, void *ws, size_t ws_bytes,
+                  cudaStream_t st) {
+    if (rows == 0) return TL_OK;
+    const int parts = argmax_parts(vocab);
+    if (ws == nullptr || ws_bytes < argmax_workspace(rows, vocab)) return fail(TL_EWORKSPACE, "argmax: workspace too small");
+    float *pv = static_cast<float *>(ws);
+    int *pi = reinterpret_cast<int *>(pv + static_cast<size_t>(rows) * parts);
+    const int chunk = ceil_div(vocab, parts);
+    dim3 grid(parts, rows);
+    switch (dtype) {
+        case TL_F32: argmax_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(logits), pv, pi, vocab, chunk); break;
+        case TL_F16: argmax_partial_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half *>(logits), pv, pi, vocab, chunk); break;
+        case TL_BF16:
+            argmax_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(logits), pv, pi, vocab, chunk);
+            break;
+        default: return fail(TL_EDTYPE, "argmax: expected float32, float16, or bfloat16");
+    }
+    TL_LAUNCH_CHECK("argmax_partial");
+    argmax_final_kernel<<<rows, 64, 0, st>>>(pv, pi, out, parts);
+    TL_LAUNCH_CHECK("argmax_final");
+    return TL_OK;
+}
+
+}  // namespace tl

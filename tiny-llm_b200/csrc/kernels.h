@@ -1,0 +1,58 @@
+// Internal launcher declarations (one translation unit per kernel family);
+// c_abi.cu validates arguments and forwards here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace tl {
+
+// elementwise.cu
+int launch_rms_norm(const void *x, const void *w, void *out, int rows, int dim, float eps, int dtype, cudaStream_t st);
+int launch_rope(const void *x, const int32_t *off, void *out, int B, int L, int H, int D, int dims, float base,
+                int traditional, int dtype, cudaStream_t st);
+int launch_swiglu(const void *gate, const void *up, void *out, long long n, int dtype, cudaStream_t st);
+int launch_add(const void *a, const void *b, void *out, long long n, int dtype, cudaStream_t st);
+int launch_quantized_embedding(const void *indices, const void *scales, const void *biases, const void *weight,
+                               void *out, int tokens, int vocab, int dim, int dtype, cudaStream_t st);
+int launch_paged_cache_update(void *pages, const void *values, int heads, int page_size, int head_dim, int length,
+                              int page_id, int start, int dtype, cudaStream_t st);
+int launch_paged_cache_append_decode(void *key_pages, void *value_pages, const void *keys, const void *values,
+                                     const int32_t *block_table, const int32_t *context_lens, int batch,
+                                     int num_pages, int heads, int page_size, int head_dim, int max_pages, int dtype,
+                                     cudaStream_t st);
+size_t argmax_workspace(int rows, int vocab);
+int launch_argmax(const void *logits, int32_t *out, int rows, int vocab, int dtype, void *ws, size_t ws_bytes,
+                  cudaStream_t st);
+
+// w4a16_matvec.cu
+// Weight-streaming tensor-core kernel for M <= 32 rows per pass (larger M is
+// processed in 32-row passes), and the scalar control kernel.
+int launch_w4a16_stream(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N,
+                        int K, int dtype, cudaStream_t st);
+int launch_w4a16_vanilla(const void *scales, const void *biases, const void *a, const void *b, void *out, int M,
+                         int N, int K, int dtype, cudaStream_t st);
+
+// w4a16_gemm.cu (tcgen05 prefill GEMM)
+bool w4a16_gemm_supported(int M, int N, int K, int dtype);
+int w4a16_gemm_split(int M, int N, int K, int use_split_k);
+size_t w4a16_gemm_workspace(int M, int N, int K, int dtype, int use_split_k);
+int launch_w4a16_gemm(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N,
+                      int K, int dtype, int use_split_k, void *ws, size_t ws_bytes, cudaStream_t st);
+
+// attention_decode.cu
+int launch_decode_attention(const void *q, const void *k, const void *v, const float *mask, void *out, int q_rows,
+                            int L, int S, int D, int num_heads, int num_kv_heads, float scale, int is_causal,
+                            int has_mask, int dtype, cudaStream_t st);
+size_t paged_decode_workspace(int rows, int L, int D, int num_kv_heads, int num_heads, int dtype);
+int launch_paged_decode(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out,
+                        int rows, int L, int D, int num_pages, int page_size, int max_pages, float scale,
+                        int is_causal, int num_kv_heads, int num_heads, int dtype, void *ws, size_t ws_bytes,
+                        cudaStream_t st);
+
+// attention_prefill.cu
+int launch_paged_prefill(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out,
+                         int rows, int L, int D, int num_pages, int page_size, int max_pages, float scale,
+                         int is_causal, int num_kv_heads, int num_heads, int dtype, cudaStream_t st);
+
+}  // namespace tl

@@ -1,0 +1,445 @@
+"""B200 (sm_100a) replacement for tiny-llm's native extension module.
+
+Same function names, positional order, keyword names and defaults as the
+nanobind module ``tiny_llm_ext_ref._ext``
+(``/root/reference/src/extensions_ref/bindings.cpp:14-46``), but the arrays are
+contiguous CUDA ``torch.Tensor`` s instead of ``mx.array`` s and ``stream`` is
+an optional ``torch.cuda.Stream``.  Every function is a thin ctypes call into
+``libtiny_llm_b200.so`` (C ABI: ``include/tiny_llm_b200.h``); torch only owns
+the device memory and the stream.
+
+There is no CPU path: like the reference primitives' ``eval_cpu``
+(``quantized_matmul.cpp:103-109``) a CPU tensor raises
+``"<op>: the course extension is GPU-only"``, and a missing shared library
+raises at import.  Builder-time shape/dtype checks raise ``RuntimeError`` with
+the reference's messages (``quantized_matmul.cpp:24-72``,
+``week2_kernels.cpp:36-84``, ``paged_attention.cpp:14-31,77-122``).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+import torch
+
+__all__ = [
+    "load_library",
+    "quantized_matmul",
+    "quantized_embedding",
+    "rms_norm",
+    "rope",
+    "swiglu",
+    "decode_attention",
+    "paged_cache_update",
+    "paged_attention",
+    # B200 extensions
+    "paged_cache_append_decode",
+    "add",
+    "argmax",
+    "launch_count",
+    "device_info",
+    "current_library_path",
+]
+
+_HERE = Path(__file__).resolve().parent
+_LIB_NAME = "libtiny_llm_b200.so"
+_lib = None
+_lib_path = None
+
+_VP = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+_LL = ctypes.c_longlong
+_SZ = ctypes.c_size_t
+
+_SIGNATURES = {
+    "tl_abi_version": (_I, []),
+    "tl_last_error": (ctypes.c_char_p, []),
+    "tl_launch_count": (_LL, []),
+    "tl_device_info": (_I, [ctypes.POINTER(_I)] * 3),
+    "tl_quantized_matmul_workspace": (_SZ, [_I] * 6),
+    "tl_quantized_matmul": (_I, [_VP] * 5 + [_I] * 6 + [_VP, _SZ, _VP]),
+    "tl_quantized_embedding": (_I, [_VP] * 5 + [_I] * 4 + [_VP]),
+    "tl_rms_norm": (_I, [_VP] * 3 + [_I, _I, _F, _I, _VP]),
+    "tl_rope": (_I, [_VP] * 3 + [_I] * 5 + [_F, _I, _I, _VP]),
+    "tl_swiglu": (_I, [_VP] * 3 + [_LL, _I, _VP]),
+    "tl_add": (_I, [_VP] * 3 + [_LL, _I, _VP]),
+    "tl_decode_attention": (_I, [_VP] * 5 + [_I] * 6 + [_F, _I, _I, _I, _VP]),
+    "tl_paged_cache_update": (_I, [_VP, _VP] + [_I] * 8 + [_VP]),
+    "tl_paged_cache_append_decode": (_I, [_VP] * 6 + [_I] * 7 + [_VP]),
+    "tl_paged_attention_workspace": (_SZ, [_I] * 6),
+    "tl_paged_attention": (_I, [_VP] * 6 + [_I] * 6 + [_F] + [_I] * 4 + [_VP, _SZ, _VP]),
+    "tl_argmax_workspace": (_SZ, [_I, _I]),
+    "tl_argmax": (_I, [_VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load_library(path: str | os.PathLike | None = None) -> None:
+    """Load ``libtiny_llm_b200.so`` (reference: ``load_library(path)`` registers
+    the metallib, ``utils.cpp:9-14``).  Called once at import with the in-tree
+    library; raises ``ImportError`` when it has not been built."""
+    global _lib, _lib_path
+    candidate = Path(path) if path is not None else _HERE / _LIB_NAME
+    if candidate.is_dir():
+        candidate = candidate / _LIB_NAME
+    if not candidate.exists():
+        raise ImportError(
+            f"{candidate} not found: build it with `python tiny-llm_b200/csrc/build.py` "
+            "(there is no CPU fallback for the B200 backend)"
+        )
+    lib = ctypes.CDLL(str(candidate))
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib, _lib_path = lib, candidate
+
+
+def current_library_path() -> Path:
+    return _lib_path
+
+
+_DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_FLOATS = (torch.float32, torch.float16, torch.bfloat16)
+_HALF = (torch.float16, torch.bfloat16)
+_PACKED = (torch.int32, torch.uint32)
+
+
+def _gpu(op: str, *tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(f"{op}: the course extension is GPU-only")
+
+
+def _contig(op: str, **named: torch.Tensor) -> None:
+    for name, t in named.items():
+        if not t.is_contiguous():
+            raise RuntimeError(f"{op}: {name} must be contiguous")
+
+
+def _stream_ptr(stream, ref: torch.Tensor) -> int:
+    if stream is None:
+        return torch.cuda.current_stream(ref.device).cuda_stream
+    return stream.cuda_stream
+
+
+def _check(code: int) -> None:
+    if code != 0:
+        raise RuntimeError(_lib.tl_last_error().decode() or f"tiny_llm_b200 error {code}")
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor | None:
+    if nbytes == 0:
+        return None
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------
+def quantized_matmul(
+    scales,
+    biases,
+    group_size,
+    bits,
+    a,
+    b,
+    transpose_b=False,
+    use_simdgroup=True,
+    use_split_k=False,
+    stream=None,
+):
+    """``a [M,N] @ dequant(b [K,N/8]).T -> [M,K]`` (bindings.cpp:16-33)."""
+    if scales.dtype not in _HALF:
+        raise RuntimeError("quantized_matmul: scales must be float16 or bfloat16")
+    if scales.dtype != biases.dtype:
+        raise RuntimeError("quantized_matmul: scales and biases must be the same dtype")
+    if b.dtype not in _PACKED:
+        raise RuntimeError("quantized_matmul: b must be uint32")
+    if a.dtype != scales.dtype:
+        raise RuntimeError("quantized_matmul: a must be the same dtype as scales")
+    if a.dim() != 2:
+        raise RuntimeError("quantized_matmul: a must be a 2D array")
+    if b.dim() != 2:
+        raise RuntimeError("quantized_matmul: b must be a 2D array")
+    if bits != 4:
+        raise RuntimeError("quantized_matmul: bits must be 4")
+    if group_size != 128:
+        raise RuntimeError("quantized_matmul: group_size must be 128")
+    if not transpose_b:
+        raise RuntimeError("quantized_matmul: b must be transposed")
+    if scales.shape != biases.shape:
+        raise RuntimeError("quantized_matmul: scales and biases must have the same shape")
+    if b.shape[0] != scales.shape[0]:
+        raise RuntimeError("quantized_matmul: b must have the same number of rows as scales")
+    if a.shape[1] % group_size != 0:
+        raise RuntimeError("quantized_matmul: a columns must be divisible by group_size")
+    if scales.shape[1] != a.shape[1] // group_size:
+        raise RuntimeError("quantized_matmul: scales must have one column per input group")
+    if b.shape[1] != a.shape[1] // 8:
+        raise RuntimeError("quantized_matmul: a must have the same number of columns as b")
+    _gpu("quantized_matmul", scales, biases, a, b)
+    _contig("quantized_matmul", a=a, b=b, scales=scales, biases=biases)
+    M, N = a.shape
+    K = b.shape[0]
+    out = torch.empty((M, K), dtype=a.dtype, device=a.device)
+    code = _DTYPE_CODE[a.dtype]
+    ws_bytes = _lib.tl_quantized_matmul_workspace(M, N, K, code, int(use_simdgroup), int(use_split_k))
+    ws = _workspace(ws_bytes, a.device)
+    _check(
+        _lib.tl_quantized_matmul(
+            scales.data_ptr(), biases.data_ptr(), a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, code,
+            int(use_simdgroup), int(use_split_k), None if ws is None else ws.data_ptr(), ws_bytes,
+            _stream_ptr(stream, a),
+        )
+    )
+    return out
+
+
+def quantized_embedding(indices, scales, biases, weight, group_size, bits, stream=None):
+    """Row gather + dequantise (bindings.cpp:34-35)."""
+    if indices.dtype not in _PACKED or weight.dtype not in _PACKED:
+        raise RuntimeError("quantized_embedding: indices and weight must use 32-bit integers")
+    if scales.dtype != biases.dtype or scales.dtype not in _HALF:
+        raise RuntimeError("quantized_embedding: scales and biases must have the same 16-bit dtype")
+    if group_size != 128 or bits != 4 or scales.shape != biases.shape:
+        raise RuntimeError("quantized_embedding: expected 4-bit weights with group size 128")
+    dim = weight.shape[1] * 8
+    if scales.shape[0] != weight.shape[0] or scales.shape[1] != dim // group_size:
+        raise RuntimeError("quantized_embedding: incompatible parameter shapes")
+    _gpu("quantized_embedding", indices, scales, biases, weight)
+    _contig("quantized_embedding", indices=indices, scales=scales, biases=biases, weight=weight)
+    out = torch.empty((*indices.shape, dim), dtype=scales.dtype, device=scales.device)
+    _check(
+        _lib.tl_quantized_embedding(
+            indices.data_ptr(), scales.data_ptr(), biases.data_ptr(), weight.data_ptr(), out.data_ptr(),
+            indices.numel(), weight.shape[0], dim, _DTYPE_CODE[scales.dtype], _stream_ptr(stream, scales),
+        )
+    )
+    return out
+
+
+def rms_norm(x, weight, eps, stream=None):
+    """bindings.cpp:36; week2_kernels.cpp:36-42."""
+    if x.dtype not in _FLOATS:
+        raise RuntimeError("rms_norm: expected float32, float16, or bfloat16")
+    if x.dtype != weight.dtype or weight.dim() != 1 or x.dim() < 1 or weight.shape[0] != x.shape[-1]:
+        raise RuntimeError("rms_norm: weight must match the input dtype and final dimension")
+    _gpu("rms_norm", x, weight)
+    _contig("rms_norm", x=x, weight=weight)
+    out = torch.empty_like(x)
+    dim = x.shape[-1]
+    rows = x.numel() // dim if dim else 0
+    _check(_lib.tl_rms_norm(x.data_ptr(), weight.data_ptr(), out.data_ptr(), rows, dim, float(eps), _DTYPE_CODE[x.dtype], _stream_ptr(stream, x)))
+    return out
+
+
+def rope(x, offsets, dims, base, traditional=False, stream=None):
+    """bindings.cpp:37-38; week2_kernels.cpp:44-55."""
+    if x.dtype not in _FLOATS:
+        raise RuntimeError("rope: expected float32, float16, or bfloat16")
+    if x.dim() != 4 or offsets.dtype != torch.int32 or offsets.dim() != 1 or offsets.shape[0] != x.shape[0]:
+        raise RuntimeError("rope: expected x=[B,L,H,D] and one int32 offset per batch row")
+    if dims <= 0 or dims > x.shape[3] or dims % 2 != 0:
+        raise RuntimeError("rope: dims must be positive, even, and no larger than the head dimension")
+    _gpu("rope", x, offsets)
+    _contig("rope", x=x, offsets=offsets)
+    out = torch.empty_like(x)
+    B, L, H, D = x.shape
+    _check(
+        _lib.tl_rope(x.data_ptr(), offsets.data_ptr(), out.data_ptr(), B, L, H, D, int(dims), float(base), int(bool(traditional)),
+                     _DTYPE_CODE[x.dtype], _stream_ptr(stream, x))
+    )
+    return out
+
+
+def swiglu(gate, up, stream=None):
+    """bindings.cpp:39; week2_kernels.cpp:57-63."""
+    if gate.dtype not in _FLOATS:
+        raise RuntimeError("swiglu: expected float32, float16, or bfloat16")
+    if gate.dtype != up.dtype or gate.shape != up.shape:
+        raise RuntimeError("swiglu: gate and up must have the same shape and dtype")
+    _gpu("swiglu", gate, up)
+    _contig("swiglu", gate=gate, up=up)
+    out = torch.empty_like(gate)
+    _check(_lib.tl_swiglu(gate.data_ptr(), up.data_ptr(), out.data_ptr(), gate.numel(), _DTYPE_CODE[gate.dtype], _stream_ptr(stream, gate)))
+    return out
+
+
+def decode_attention(query, key, value, mask, scale, is_causal, has_mask, num_heads, num_kv_heads, stream=None):
+    """bindings.cpp:40-41; week2_kernels.cpp:65-84."""
+    if query.dtype not in _FLOATS:
+        raise RuntimeError("decode_attention: expected float32, float16, or bfloat16")
+    if query.dtype != key.dtype or query.dtype != value.dtype or mask.dtype != torch.float32:
+        raise RuntimeError("decode_attention: q, k, and v dtypes must match; mask must be float32")
+    if (
+        query.dim() != 3
+        or key.dim() != 3
+        or value.dim() != 3
+        or query.shape[2] > 256
+        or query.shape[2] != key.shape[2]
+        or query.shape[2] != value.shape[2]
+        or key.shape != value.shape
+        or num_heads % num_kv_heads != 0
+    ):
+        raise RuntimeError("decode_attention: incompatible attention shapes")
+    if has_mask and (
+        mask.dim() != 3 or mask.shape[0] != query.shape[0] or mask.shape[1] != query.shape[1] or mask.shape[2] != key.shape[1]
+    ):
+        raise RuntimeError("decode_attention: mask must have shape [B*Hq,L,S]")
+    _gpu("decode_attention", query, key, value, mask)
+    _contig("decode_attention", query=query, key=key, value=value, mask=mask)
+    out = torch.empty_like(query)
+    rows, L, D = query.shape
+    _check(
+        _lib.tl_decode_attention(
+            query.data_ptr(), key.data_ptr(), value.data_ptr(), mask.data_ptr(), out.data_ptr(), rows, L, key.shape[1], D,
+            int(num_heads), int(num_kv_heads), float(scale), int(bool(is_causal)), int(bool(has_mask)),
+            _DTYPE_CODE[query.dtype], _stream_ptr(stream, query),
+        )
+    )
+    return out
+
+
+def paged_cache_update(pages, values, page_id, start, stream=None):
+    """In-place slice write; returns ``pages`` itself, as the reference output
+    aliases its input buffer (bindings.cpp:43-44; paged_attention.cpp:14-31,46-49)."""
+    if pages.dtype not in (torch.float32, torch.bfloat16) or values.dtype != pages.dtype:
+        raise RuntimeError("paged_cache_update: pages and values must have the same float32 or bfloat16 dtype")
+    if pages.dim() != 4 or values.dim() != 4 or values.shape[0] != 1:
+        raise RuntimeError("paged_cache_update: expected pages [P, H, page_size, D] and values [1, H, length, D]")
+    if values.shape[1] != pages.shape[1] or values.shape[3] != pages.shape[3]:
+        raise RuntimeError("paged_cache_update: values must match the page head count and head dimension")
+    if page_id < 0 or page_id >= pages.shape[0] or start < 0 or start + values.shape[2] > pages.shape[2]:
+        raise RuntimeError("paged_cache_update: destination slice is outside page storage")
+    _gpu("paged_cache_update", pages, values)
+    if not pages.is_contiguous() or not values.is_contiguous():
+        raise RuntimeError("paged_cache_update: pages and values must be contiguous")
+    P, H, page_size, D = pages.shape
+    _check(
+        _lib.tl_paged_cache_update(pages.data_ptr(), values.data_ptr(), P, H, page_size, D, values.shape[2], int(page_id), int(start),
+                                   _DTYPE_CODE[pages.dtype], _stream_ptr(stream, pages))
+    )
+    return pages
+
+
+def paged_attention(
+    query,
+    key_pages,
+    value_pages,
+    block_table,
+    context_lens,
+    scale=1.0,
+    is_causal=False,
+    num_kv_heads=None,
+    num_heads=None,
+    stream=None,
+):
+    """bindings.cpp:45-46; paged_attention.cpp:77-122 (checks), :129-225 (dispatch)."""
+    if query.dtype not in (torch.float32, torch.bfloat16) or key_pages.dtype != query.dtype or value_pages.dtype != query.dtype:
+        raise RuntimeError("paged_attention: q, key_pages, and value_pages must have the same float32 or bfloat16 dtype")
+    if block_table.dtype != torch.int32 or context_lens.dtype != torch.int32:
+        raise RuntimeError("paged_attention: block_table and context_lens must be int32")
+    if query.dim() != 3:
+        raise RuntimeError("paged_attention: q must be 3D [B * H_q, L, D]")
+    if key_pages.dim() != 4 or value_pages.dim() != 4:
+        raise RuntimeError("paged_attention: page tensors must be 4D [P, H_kv, page_size, D]")
+    if block_table.dim() != 2 or context_lens.dim() != 1:
+        raise RuntimeError("paged_attention: block_table must be 2D and context_lens must be 1D")
+    if num_heads % num_kv_heads != 0:
+        raise RuntimeError("paged_attention: num_heads must be divisible by num_kv_heads")
+    if query.shape[0] % num_heads != 0:
+        raise RuntimeError("paged_attention: q.shape[0] must be divisible by num_heads")
+    if key_pages.shape != value_pages.shape:
+        raise RuntimeError("paged_attention: key_pages and value_pages must have the same shape")
+    if key_pages.shape[1] != num_kv_heads:
+        raise RuntimeError("paged_attention: page tensor head count must equal num_kv_heads")
+    if query.shape[2] != key_pages.shape[3]:
+        raise RuntimeError("paged_attention: q and page tensors must have the same head dimension")
+    if block_table.shape[0] != context_lens.shape[0]:
+        raise RuntimeError("paged_attention: block_table and context_lens batch sizes must match")
+    if query.shape[0] // num_heads != block_table.shape[0]:
+        raise RuntimeError("paged_attention: q batch size must match block_table batch size")
+    _gpu("paged_attention", query, key_pages, value_pages, block_table, context_lens)
+    if not all(t.is_contiguous() for t in (query, key_pages, value_pages, block_table, context_lens)):
+        raise RuntimeError("paged_attention: all inputs must be contiguous")
+    rows, L, D = query.shape
+    P, _, page_size, _ = key_pages.shape
+    out = torch.empty_like(query)
+    code = _DTYPE_CODE[query.dtype]
+    ws_bytes = _lib.tl_paged_attention_workspace(rows, L, D, int(num_kv_heads), int(num_heads), code)
+    ws = _workspace(ws_bytes, query.device)
+    _check(
+        _lib.tl_paged_attention(
+            query.data_ptr(), key_pages.data_ptr(), value_pages.data_ptr(), block_table.data_ptr(), context_lens.data_ptr(),
+            out.data_ptr(), rows, L, D, P, page_size, block_table.shape[1], float(scale), int(bool(is_causal)),
+            int(num_kv_heads), int(num_heads), code, None if ws is None else ws.data_ptr(), ws_bytes,
+            _stream_ptr(stream, query),
+        )
+    )
+    return out
+
+
+# ---- B200 extensions (not in the reference module) -------------------------
+def paged_cache_append_decode(key_pages, value_pages, keys, values, block_table, context_lens, stream=None):
+    """Batched, device-driven form of the per-request K/V append
+    (kv_cache.py:191-199 -> paged_kv_cache.py:196-234): row ``b`` of
+    ``keys/values [B,H,1,D]`` lands at token ``context_lens[b]-1``."""
+    if key_pages.shape != value_pages.shape or keys.shape != values.shape or keys.dim() != 4 or keys.shape[2] != 1:
+        raise RuntimeError("paged_cache_append_decode: expected keys/values [B, H, 1, D]")
+    if key_pages.dtype != keys.dtype or value_pages.dtype != values.dtype or key_pages.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("paged_cache_append_decode: dtype mismatch")
+    if block_table.dtype != torch.int32 or context_lens.dtype != torch.int32:
+        raise RuntimeError("paged_cache_append_decode: block_table and context_lens must be int32")
+    _gpu("paged_cache_append_decode", key_pages, value_pages, keys, values, block_table, context_lens)
+    _contig("paged_cache_append_decode", key_pages=key_pages, value_pages=value_pages, keys=keys, values=values,
+            block_table=block_table, context_lens=context_lens)
+    P, H, page_size, D = key_pages.shape
+    B = keys.shape[0]
+    _check(
+        _lib.tl_paged_cache_append_decode(
+            key_pages.data_ptr(), value_pages.data_ptr(), keys.data_ptr(), values.data_ptr(), block_table.data_ptr(),
+            context_lens.data_ptr(), B, P, H, page_size, D, block_table.shape[1], _DTYPE_CODE[keys.dtype],
+            _stream_ptr(stream, keys),
+        )
+    )
+
+
+def add(a, b, stream=None):
+    if a.dtype not in _FLOATS or a.dtype != b.dtype or a.shape != b.shape:
+        raise RuntimeError("add: operands must have the same shape and float dtype")
+    _gpu("add", a, b)
+    _contig("add", a=a, b=b)
+    out = torch.empty_like(a)
+    _check(_lib.tl_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _DTYPE_CODE[a.dtype], _stream_ptr(stream, a)))
+    return out
+
+
+def argmax(logits, stream=None):
+    """Greedy token per row of ``logits [rows, vocab]`` -> int32 ``[rows]``."""
+    if logits.dtype not in _FLOATS or logits.dim() != 2:
+        raise RuntimeError("argmax: expected 2D float logits")
+    _gpu("argmax", logits)
+    _contig("argmax", logits=logits)
+    rows, vocab = logits.shape
+    out = torch.empty((rows,), dtype=torch.int32, device=logits.device)
+    ws_bytes = _lib.tl_argmax_workspace(rows, vocab)
+    ws = _workspace(ws_bytes, logits.device)
+    _check(_lib.tl_argmax(logits.data_ptr(), out.data_ptr(), rows, vocab, _DTYPE_CODE[logits.dtype],
+                          None if ws is None else ws.data_ptr(), ws_bytes, _stream_ptr(stream, logits)))
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.tl_launch_count())
+
+
+def device_info() -> tuple[int, int, int]:
+    sms, major, minor = _I(), _I(), _I()
+    _check(_lib.tl_device_info(ctypes.byref(sms), ctypes.byref(major), ctypes.byref(minor)))
+    return sms.value, major.value, minor.value
+
+
+load_library()
