@@ -83,17 +83,39 @@ def _norm_weight(dim: int, gen: torch.Generator) -> SimpleNamespace:
     return SimpleNamespace(weight=(1.0 + 0.1 * torch.randn(dim, generator=gen)).to(torch.bfloat16))
 
 
-def synthetic_qwen3(name_or_dims="qwen3-4b", seed: int = 0, device="cpu", realistic: bool = False, **overrides) -> SimpleNamespace:
+def _empty_norm(dim: int, device) -> SimpleNamespace:
+    return SimpleNamespace(weight=torch.empty((dim,), dtype=torch.bfloat16, device=device))
+
+
+def _empty_layer(out_dim: int, in_dim: int, device) -> SimpleNamespace:
+    return SimpleNamespace(
+        weight=torch.empty((out_dim, in_dim // 8), dtype=torch.int32, device=device).view(torch.uint32),
+        scales=torch.empty((out_dim, in_dim // GROUP_SIZE), dtype=torch.bfloat16, device=device),
+        biases=torch.empty((out_dim, in_dim // GROUP_SIZE), dtype=torch.bfloat16, device=device),
+        group_size=GROUP_SIZE,
+        bits=BITS,
+    )
+
+
+def synthetic_qwen3(name_or_dims="qwen3-4b", seed: int = 0, device="cpu", realistic: bool = False, empty: bool = False,
+                    **overrides) -> SimpleNamespace:
     """Random Qwen3-shaped model.  ``realistic=True`` quantises Gaussian dense
     weights with ``quantize_w4`` (slow, for small models); the default draws
-    codes/scales directly, which is what the 4B-sized benchmarks use."""
+    codes/scales directly, which is what the 4B-sized benchmarks use.
+    ``empty=True`` only allocates (uninitialised, directly on ``device``): the
+    receive side of the data-parallel weight broadcast."""
     args = make_args(name_or_dims, **overrides)
     gen = torch.Generator().manual_seed(seed)
 
     def layer(out_dim: int, in_dim: int) -> SimpleNamespace:
+        if empty:
+            return _empty_layer(out_dim, in_dim, device)
         if realistic:
             return _quantized_layer(out_dim, in_dim, gen, std=in_dim**-0.5)
         return _random_layer(out_dim, in_dim, gen)
+
+    def norm(dim: int) -> SimpleNamespace:
+        return _empty_norm(dim, device) if empty else _norm_weight(dim, gen)
 
     q_width = args.num_attention_heads * args.head_dim
     kv_width = args.num_key_value_heads * args.head_dim
@@ -106,25 +128,25 @@ def synthetic_qwen3(name_or_dims="qwen3-4b", seed: int = 0, device="cpu", realis
                     k_proj=layer(kv_width, args.hidden_size),
                     v_proj=layer(kv_width, args.hidden_size),
                     o_proj=layer(args.hidden_size, q_width),
-                    q_norm=_norm_weight(args.head_dim, gen),
-                    k_norm=_norm_weight(args.head_dim, gen),
+                    q_norm=norm(args.head_dim),
+                    k_norm=norm(args.head_dim),
                 ),
                 mlp=SimpleNamespace(
                     gate_proj=layer(args.intermediate_size, args.hidden_size),
                     up_proj=layer(args.intermediate_size, args.hidden_size),
                     down_proj=layer(args.hidden_size, args.intermediate_size),
                 ),
-                input_layernorm=_norm_weight(args.hidden_size, gen),
-                post_attention_layernorm=_norm_weight(args.hidden_size, gen),
+                input_layernorm=norm(args.hidden_size),
+                post_attention_layernorm=norm(args.hidden_size),
             )
         )
     model = SimpleNamespace(
         args=args,
-        model=SimpleNamespace(embed_tokens=layer(args.vocab_size, args.hidden_size), layers=layers, norm=_norm_weight(args.hidden_size, gen)),
+        model=SimpleNamespace(embed_tokens=layer(args.vocab_size, args.hidden_size), layers=layers, norm=norm(args.hidden_size)),
     )
     if not args.tie_word_embeddings:
         model.lm_head = layer(args.vocab_size, args.hidden_size)
-    return to_device(model, device)
+    return model if empty else to_device(model, device)
 
 
 def to_device(node, device):
