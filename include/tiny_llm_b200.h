@@ -127,6 +127,41 @@ int tl_add(const void *a, const void *b, void *out, long long size, int dtype, v
 int tl_argmax(const void *logits, int32_t *out_tokens, int rows, int vocab, int dtype, void *workspace,
               size_t workspace_bytes, void *stream);
 size_t tl_argmax_workspace(int rows, int vocab);
+/* Fused W4A16 projection for the decode hot loop: the weight-streaming kernel of
+ * tl_quantized_matmul with the neighbouring element-wise operator folded in.
+ * Rounding points are those of the unfused call sequence, so results are
+ * bit-identical to it.
+ *   prologue TL_PRO_NONE    : a = p0 [M, N]
+ *            TL_PRO_RMSNORM : a = rms_norm(p0 [M, N], p1 [N], eps)      (then projected)
+ *            TL_PRO_SWIGLU  : a = swiglu(p0 = gate [M, N], p1 = up [M, N])
+ *   epilogue TL_EPI_NONE    : out = result
+ *            TL_EPI_RESIDUAL: out = residual [M, K] + result
+ * lda is the row stride (elements) of p0 (and of p1 for SWIGLU), so gate/up may
+ * be the two halves of one [M, 2N] buffer. */
+enum { TL_PRO_NONE = 0, TL_PRO_RMSNORM = 1, TL_PRO_SWIGLU = 2 };
+enum { TL_EPI_NONE = 0, TL_EPI_RESIDUAL = 1 };
+int tl_quantized_matmul_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0,
+                              const void *p1, const void *residual, int M, int N, int K, int lda, int prologue,
+                              int epilogue, float eps, int dtype, void *stream);
+/* Decode step, L == 1: per-head q/k RMSNorm + RoPE + K/V append in one launch.
+ * qkv [B, (Hq + 2*Hkv) * D] (q heads | k heads | v heads); q_out [B, Hq, D];
+ * K/V rows land in the page slot of token context_lens[b]-1 (rows with context
+ * 0 are skipped).  Non-traditional RoPE over the full head dimension. */
+int tl_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, const void *k_norm_weight,
+                                  const int32_t *offsets, const int32_t *block_table, const int32_t *context_lens,
+                                  void *q_out, void *key_pages, void *value_pages, int batch, int num_heads,
+                                  int num_kv_heads, int head_dim, float base, float eps, int num_pages, int page_size,
+                                  int max_pages, int dtype, void *stream);
+/* Programmatic dependent launch for the streaming kernels (0 = off, default). */
+int tl_set_pdl(int enabled);
+/* Device-side bookkeeping between two decode steps of a CUDA-graph loop (the
+ * per-request `req.decode_done(token)` + `offset += 1` of batch.py:241-247 done
+ * without a host round trip): for every ACTIVE row (context_lens > 0)
+ *   tokens[b] = next_tokens[b]; offsets[b] += 1; context_lens[b] += 1;
+ * and the sampled row is logged at out_log[*step_counter * batch + b]
+ * (idle rows log -1); *step_counter is then incremented. */
+int tl_decode_advance(int32_t *tokens, const int32_t *next_tokens, int32_t *offsets, int32_t *context_lens,
+                      int32_t *out_log, int32_t *step_counter, int batch, int log_capacity, void *stream);
 
 #ifdef __cplusplus
 }

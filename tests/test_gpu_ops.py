@@ -177,8 +177,11 @@ def test_rope_matches_oracle(dev, case, dtype):
     off = torch.tensor(case["offsets"], dtype=torch.int32)
     want = oracle.rope(x, off, case["dims"], 1000000.0, case.get("traditional", False))
     got = ext.rope(x.to(dev), off.to(dev), case["dims"], 1000000.0, case.get("traditional", False))
-    # stated tolerance of the reference for this op: 2e-2 (test_week_2_day_4.py:51); we hold 1 ulp + angle noise
-    assert_close(got, want, rtol=2 * ULP[dtype] if dtype != F32 else 2e-4, atol=4e-3 if dtype != F32 else 2e-3)
+    # stated tolerance of the reference for this op: 2e-2 (test_week_2_day_4.py:51).  We hold 1 ulp plus
+    # the fp32 angle noise of the reference arithmetic itself, position * 2^-23 rad (0.004 at 32K).
+    far = max(case["offsets"]) + case["shape"][1]
+    noise = 4.0 * far * 2.0**-23
+    assert_close(got, want, rtol=2 * ULP[dtype] if dtype != F32 else 2e-4, atol=(4e-3 if dtype != F32 else 1e-5) + noise)
 
 
 @pytest.mark.parametrize("n", [16, 9728, 3 * 9728, 1001])

@@ -228,4 +228,50 @@ int tl_argmax(const void *logits, int32_t *out_tokens, int rows, int vocab, int 
     return launch_argmax(logits, out_tokens, rows, vocab, dtype, workspace, workspace_bytes, as_stream(stream));
 }
 
+int tl_quantized_matmul_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0,
+                              const void *p1, const void *residual, int M, int N, int K, int lda, int prologue,
+                              int epilogue, float eps, int dtype, void *stream) {
+    if (dtype != TL_F16 && dtype != TL_BF16) return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
+    if (M < 0 || N <= 0 || K < 0 || lda < N) return fail(TL_EINVAL, "quantized_matmul_fused: bad shape");
+    if (N % 128 != 0) return fail(TL_EINVAL, "quantized_matmul: N must be divisible by group_size");
+    if (prologue < TL_PRO_NONE || prologue > TL_PRO_SWIGLU || epilogue < TL_EPI_NONE || epilogue > TL_EPI_RESIDUAL)
+        return fail(TL_EINVAL, "quantized_matmul_fused: unknown prologue/epilogue");
+    if (M == 0 || K == 0) return TL_OK;
+    if (!scales || !biases || !b || !out || !p0 || (prologue != TL_PRO_NONE && !p1) || (epilogue == TL_EPI_RESIDUAL && !residual))
+        return fail(TL_EINVAL, "quantized_matmul_fused: null pointer");
+    return launch_w4a16_fused(scales, biases, b, out, p0, p1, residual, M, N, K, lda, prologue, epilogue, eps, dtype,
+                              as_stream(stream));
+}
+
+int tl_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, const void *k_norm_weight,
+                                  const int32_t *offsets, const int32_t *block_table, const int32_t *context_lens,
+                                  void *q_out, void *key_pages, void *value_pages, int batch, int num_heads,
+                                  int num_kv_heads, int head_dim, float base, float eps, int num_pages, int page_size,
+                                  int max_pages, int dtype, void *stream) {
+    if (dtype != TL_F32 && dtype != TL_BF16) return fail(TL_EDTYPE, "decode_qk_norm_rope_append: bfloat16 or float32 required");
+    if (batch < 0 || num_heads <= 0 || num_kv_heads <= 0 || head_dim <= 0 || head_dim % 2 != 0 || head_dim > 512 ||
+        num_pages <= 0 || page_size <= 0 || max_pages <= 0)
+        return fail(TL_EINVAL, "decode_qk_norm_rope_append: bad shape");
+    if (batch == 0) return TL_OK;
+    if (!qkv || !q_norm_weight || !k_norm_weight || !offsets || !block_table || !context_lens || !q_out || !key_pages || !value_pages)
+        return fail(TL_EINVAL, "decode_qk_norm_rope_append: null pointer");
+    return launch_decode_qk_norm_rope_append(qkv, q_norm_weight, k_norm_weight, offsets, block_table, context_lens, q_out,
+                                             key_pages, value_pages, batch, num_heads, num_kv_heads, head_dim, base, eps,
+                                             num_pages, page_size, max_pages, dtype, as_stream(stream));
+}
+
+int tl_set_pdl(int enabled) {
+    set_use_pdl(enabled != 0);
+    return TL_OK;
+}
+
+int tl_decode_advance(int32_t *tokens, const int32_t *next_tokens, int32_t *offsets, int32_t *context_lens,
+                      int32_t *out_log, int32_t *step_counter, int batch, int log_capacity, void *stream) {
+    if (batch <= 0 || log_capacity < 0) return fail(TL_EINVAL, "decode_advance: bad shape");
+    if (!tokens || !next_tokens || !offsets || !context_lens || !out_log || !step_counter)
+        return fail(TL_EINVAL, "decode_advance: null pointer");
+    return launch_decode_advance(tokens, next_tokens, offsets, context_lens, out_log, step_counter, batch, log_capacity,
+                                 as_stream(stream));
+}
+
 }  // extern "C"

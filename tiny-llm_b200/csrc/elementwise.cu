@@ -155,9 +155,11 @@ __global__ void rope_kernel(const T *__restrict__ x, const int32_t *__restrict__
         out[head_base + d] = x[head_base + d];
         return;
     }
-    const float power = -static_cast<float>(item) / static_cast<float>(half_dim);
-    const float inv_freq = sizeof(T) == 4 ? powf(base, power) : exp2f(power * log2f(base));
-    const float angle = static_cast<float>(offsets[b] + l) * inv_freq;
+    // angle = position * base^(-pair/half) (week2_kernels.metal:86-92).  The frequency is
+    // formed in double so that long contexts (position ~32K) do not inherit the ~1e-7
+    // relative error of an fp32 exp2/pow; the product and sincosf stay fp32.
+    const double inv_freq = exp2(-static_cast<double>(item) / static_cast<double>(half_dim) * log2(static_cast<double>(base)));
+    const float angle = static_cast<float>(static_cast<double>(offsets[b] + l) * inv_freq);
     float s, c;
     sincosf(angle, &s, &c);
     const size_t re_i = traditional ? head_base + 2 * item : head_base + item;
@@ -487,6 +489,126 @@ int launch_argmax(const void *logits, int32_t *out, int rows, int vocab, int dty
     TL_LAUNCH_CHECK("argmax_partial");
     argmax_final_kernel<<<rows, 64, 0, st>>>(pv, pi, out, parts);
     TL_LAUNCH_CHECK("argmax_final");
+    return TL_OK;
+}
+
+// -------------------------------------- fused q/k norm + RoPE + KV append ----
+// Decode step (L == 1).  qkv [B, (Hq + 2*Hkv) * D] holds the q heads, then the k
+// heads, then the v heads of each request.  One CTA per (head, request), D/2
+// threads, thread i owns the non-traditional RoPE pair (i, i + D/2):
+//   q/k heads: n = T(x * rsqrt(mean(x^2)+eps) * w)   -- rounded, as rms_norm stores it
+//              y = T(rope(n))                        -- as rope stores it
+//   q -> q_out [B, Hq, D];  k, v -> page slot of token context_lens[b]-1.
+// Same arithmetic and rounding points as rms_norm -> rope -> paged_cache_update
+// (qwen3_week3.py:69-96), in one launch instead of six.
+template <typename T>
+__global__ void decode_qk_norm_rope_append_kernel(const T *__restrict__ qkv, const T *__restrict__ qw,
+                                                  const T *__restrict__ kw, const int32_t *__restrict__ offsets,
+                                                  const int32_t *__restrict__ bt, const int32_t *__restrict__ cl,
+                                                  T *__restrict__ q_out, T *__restrict__ kp, T *__restrict__ vp, int Hq,
+                                                  int Hkv, int D, float base, float eps, int num_pages, int page_size,
+                                                  int max_pages) {
+    __shared__ float warp_part[8];
+    const int head = blockIdx.x;  // 0..Hq-1 q | Hq..Hq+Hkv-1 k | rest v
+    const int b = blockIdx.y;
+    const int half = D / 2;
+    const int i = threadIdx.x;
+    const T *src = qkv + (static_cast<size_t>(b) * (Hq + 2 * Hkv) + head) * D;
+    const bool is_q = head < Hq;
+    const bool is_k = !is_q && head < Hq + Hkv;
+    const int kvh = is_q ? 0 : (is_k ? head - Hq : head - Hq - Hkv);
+
+    float re = 0.f, im = 0.f;
+    if (i < half) re = to_f(src[i]), im = to_f(src[i + half]);
+    T out_re, out_im;
+    if (is_q || is_k) {
+        float ss = warp_sum(re * re + im * im);
+        if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        const int nw = (blockDim.x + 31) / 32;
+        float tot = (threadIdx.x & 31) < nw ? warp_part[threadIdx.x & 31] : 0.f;
+        tot = warp_sum(tot);
+        const float inv = rsqrtf(tot / static_cast<float>(D) + eps);
+        const T *w = is_q ? qw : kw;
+        float nre = 0.f, nim = 0.f;
+        if (i < half) {
+            nre = to_f(from_f<T>(re * inv * to_f(w[i])));
+            nim = to_f(from_f<T>(im * inv * to_f(w[i + half])));
+        }
+        const double inv_freq = exp2(-static_cast<double>(i) / static_cast<double>(half) * log2(static_cast<double>(base)));
+        const float angle = static_cast<float>(static_cast<double>(offsets[b]) * inv_freq);
+        float s, c;
+        sincosf(angle, &s, &c);
+        out_re = from_f<T>(nre * c - nim * s);
+        out_im = from_f<T>(nim * c + nre * s);
+    } else {
+        out_re = from_f<T>(re);
+        out_im = from_f<T>(im);
+    }
+    if (i >= half) return;
+    if (is_q) {
+        T *dst = q_out + (static_cast<size_t>(b) * Hq + head) * D;
+        dst[i] = out_re, dst[i + half] = out_im;
+        return;
+    }
+    const int ctx = cl[b];
+    if (ctx <= 0) return;
+    const int tok = ctx - 1;
+    const int lp = tok / page_size;
+    if (lp >= max_pages) return;
+    const int pid = bt[static_cast<size_t>(b) * max_pages + lp];
+    if (pid < 0 || pid >= num_pages) return;
+    T *dst = (is_k ? kp : vp) + ((static_cast<size_t>(pid) * Hkv + kvh) * page_size + (tok - lp * page_size)) * D;
+    dst[i] = out_re, dst[i + half] = out_im;
+}
+
+int launch_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_w, const void *k_norm_w, const int32_t *offsets,
+                                      const int32_t *block_table, const int32_t *context_lens, void *q_out, void *key_pages,
+                                      void *value_pages, int batch, int Hq, int Hkv, int D, float base, float eps,
+                                      int num_pages, int page_size, int max_pages, int dtype, cudaStream_t st) {
+    if (batch == 0) return TL_OK;
+    const int threads = ((D / 2 + 31) / 32) * 32;
+    dim3 grid(Hq + 2 * Hkv, batch);
+#define TL_QKN(T)                                                                                                      \
+    decode_qk_norm_rope_append_kernel<T><<<grid, threads, 0, st>>>(                                                    \
+        static_cast<const T *>(qkv), static_cast<const T *>(q_norm_w), static_cast<const T *>(k_norm_w), offsets,     \
+        block_table, context_lens, static_cast<T *>(q_out), static_cast<T *>(key_pages), static_cast<T *>(value_pages), \
+        Hq, Hkv, D, base, eps, num_pages, page_size, max_pages)
+    if (dtype == TL_BF16)
+        TL_QKN(__nv_bfloat16);
+    else if (dtype == TL_F32)
+        TL_QKN(float);
+    else
+        return fail(TL_EDTYPE, "decode_qk_norm_rope_append: bfloat16 or float32 required");
+#undef TL_QKN
+    TL_LAUNCH_CHECK("decode_qk_norm_rope_append");
+    return TL_OK;
+}
+
+// ------------------------------------------------ decode-loop bookkeeping --
+__global__ void decode_advance_kernel(int32_t *tokens, const int32_t *next_tokens, int32_t *offsets,
+                                      int32_t *context_lens, int32_t *out_log, int32_t *step_counter, int batch,
+                                      int log_capacity) {
+    const int step = *step_counter;
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+        const bool active = context_lens[b] > 0;
+        const int32_t tok = next_tokens[b];
+        if (active) {
+            tokens[b] = tok;
+            offsets[b] += 1;
+            context_lens[b] += 1;
+        }
+        if (step < log_capacity) out_log[static_cast<size_t>(step) * batch + b] = active ? tok : -1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *step_counter = step + 1;
+}
+
+int launch_decode_advance(int32_t *tokens, const int32_t *next_tokens, int32_t *offsets, int32_t *context_lens,
+                          int32_t *out_log, int32_t *step_counter, int batch, int log_capacity, cudaStream_t st) {
+    decode_advance_kernel<<<1, 128, 0, st>>>(tokens, next_tokens, offsets, context_lens, out_log, step_counter, batch,
+                                             log_capacity);
+    TL_LAUNCH_CHECK("decode_advance");
     return TL_OK;
 }
 

@@ -25,11 +25,26 @@ size_t argmax_workspace(int rows, int vocab);
 int launch_argmax(const void *logits, int32_t *out, int rows, int vocab, int dtype, void *ws, size_t ws_bytes,
                   cudaStream_t st);
 
+int launch_decode_advance(int32_t *tokens, const int32_t *next_tokens, int32_t *offsets, int32_t *context_lens,
+                          int32_t *out_log, int32_t *step_counter, int batch, int log_capacity, cudaStream_t st);
+
+int launch_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_w, const void *k_norm_w, const int32_t *offsets,
+                                      const int32_t *block_table, const int32_t *context_lens, void *q_out, void *key_pages,
+                                      void *value_pages, int batch, int Hq, int Hkv, int D, float base, float eps,
+                                      int num_pages, int page_size, int max_pages, int dtype, cudaStream_t st);
+
 // w4a16_matvec.cu
 // Weight-streaming tensor-core kernel for M <= 32 rows per pass (larger M is
 // processed in 32-row passes), and the scalar control kernel.
 int launch_w4a16_stream(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N,
                         int K, int dtype, cudaStream_t st);
+// TMA-bulk streaming kernel with optional fused prologue (0 none: p0 = a; 1 rms_norm: p0 = x, p1 = norm weight;
+// 2 swiglu: p0 = gate, p1 = up; lda = row stride of p0/p1 in elements) and epilogue (0 none; 1 out = residual + result).
+int launch_w4a16_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *p1,
+                       const void *residual, int M, int N, int K, int lda, int prologue, int epilogue, float eps, int dtype,
+                       cudaStream_t st);
+void set_use_pdl(bool on);
+bool use_pdl();
 int launch_w4a16_vanilla(const void *scales, const void *biases, const void *a, const void *b, void *out, int M,
                          int N, int K, int dtype, cudaStream_t st);
 

@@ -24,6 +24,8 @@
 // The k-slot <-> n mapping of the MMA is a free permutation (the reduction is
 // commutative), chosen so that a lane's A fragment comes from ITS OWN 128-bit
 // weight load and the matching B fragment is one 128-bit shared-memory load.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -292,12 +294,424 @@ static int stream_t(const void *scales, const void *biases, const void *a, const
     return stream_launch<T, 1>(scales, biases, a, b, out, M, N, K, rpp, teams, st);
 }
 
+int launch_w4a16_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *p1,
+                       const void *residual, int M, int N, int K, int lda, int prologue, int epilogue, float eps, int dtype,
+                       cudaStream_t st);
+
+static bool stream_v1_forced() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("TL_STREAM_V1");
+        cached = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return cached == 1;
+}
+
 int launch_w4a16_stream(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N,
                         int K, int dtype, cudaStream_t st) {
     if (M == 0 || K == 0) return TL_OK;
+    if (!stream_v1_forced())
+        return launch_w4a16_fused(scales, biases, b, out, a, nullptr, nullptr, M, N, K, N, 0, 0, 0.f, dtype, st);
     switch (dtype) {
         case TL_F16: return stream_t<__half>(scales, biases, a, b, out, M, N, K, st);
         case TL_BF16: return stream_t<__nv_bfloat16>(scales, biases, a, b, out, M, N, K, st);
+    }
+    return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
+}
+
+// ---------------------------------------------------------------------------
+// v2: TMA-bulk fed streaming kernel.
+//
+// v1 keeps only ~2 KB of weight bytes in flight per warp (register prefetch),
+// far short of the ~40 KB per SM that 6.5 TB/s at ~800 ns latency needs.  Here a
+// dedicated producer warp streams the packed weights of consecutive 16-row
+// tiles into a shared-memory ring with cp.async.bulk (one 256 B row segment per
+// lane, completion counted on an mbarrier), so a CTA has STAGES x 4 KB in flight
+// at no register cost; eight consumer warps run the same mma-fed arithmetic as
+// v1 out of shared memory.  Weights never depend on the previous kernel, so the
+// producer starts before griddepcontrol.wait (programmatic dependent launch):
+// the ring fills while the previous kernel drains.
+//
+// Optional fusions that keep every rounding point of the unfused call sequence
+// (so results are bit-identical to rms_norm -> matvec, swiglu -> matvec,
+// matvec -> add):
+//   prologue RMSNORM : a = T(x * rsqrt(mean(x^2)+eps) * w)   (week2_kernels.metal:41-47)
+//   prologue SWIGLU  : a = T(g / (1 + exp(-g)) * u)          (week2_kernels.metal:115-116)
+//   epilogue RESIDUAL: out = T(float(res) + float(T(acc)))   (qwen3_week3.py:204-206)
+constexpr int SK_CONSUMERS = 8;                       // consumer warps
+constexpr int SK_THREADS = (SK_CONSUMERS + 1) * 32;   // + 1 producer warp
+constexpr int SK_CG = 4;                              // 128-column groups per ring stage
+constexpr int SK_ROW_BYTES = SK_CG * 64;              // packed bytes of one row in a stage
+constexpr int SK_ROW_STRIDE = SK_ROW_BYTES + 64;      // +64 B: rows g / g+1 hit different bank halves
+constexpr int SK_STAGE_BYTES = 16 * SK_ROW_STRIDE;
+
+enum { PRO_NONE = 0, PRO_RMSNORM = 1, PRO_SWIGLU = 2 };
+enum { EPI_NONE = 0, EPI_RESIDUAL = 1 };
+
+struct StreamArgs {
+    const void *scales, *biases;
+    const uint32_t *b;
+    void *out;
+    const void *p0, *p1, *residual;
+    int M, N, K, lda;
+    int prologue, epilogue;
+    float eps;
+    int rows_per_pass, stages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();  // a lost arrival must not hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void consumer_barrier() {
+    asm volatile("bar.sync 1, %0;" ::"r"(SK_CONSUMERS * 32) : "memory");
+}
+
+template <typename T, int MT>
+__global__ void __launch_bounds__(SK_THREADS) w4a16_stream2_kernel(const StreamArgs args) {
+    extern __shared__ __align__(128) unsigned char smem2_raw[];
+    unsigned char *smem_raw = smem2_raw;
+    const int N = args.N, K = args.K;
+    const int pass = blockIdx.y;
+    const int Mp = min(args.rows_per_pass, args.M - pass * args.rows_per_pass);
+    const int words = N / 8;
+    const int G = N / 128;
+    const int S = args.stages;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // shared layout: ring | barriers | act | asum | row stats | red[2]
+    unsigned char *ring = smem_raw;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + static_cast<size_t>(S) * SK_STAGE_BYTES);
+    uint4 *act = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(bars) + ((2 * S * 8 + 15) & ~15));
+    float *asum = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(act) + static_cast<size_t>(words) * Mp * 16);
+    float *rowstat = asum + ((G * Mp + 3) & ~3);
+    float *red = rowstat + 32;
+    const uint32_t ring_s = smem_u32(ring);
+    const uint32_t full_s = smem_u32(bars);
+    const uint32_t empty_s = full_s + 8 * S;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(full_s + 8 * i, 1);
+            mbar_init(empty_s + 8 * i, SK_CONSUMERS / 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    griddep_launch();
+
+    const int tiles = (K + 15) / 16;
+    const int tile_begin = static_cast<int>(static_cast<long long>(tiles) * blockIdx.x / gridDim.x);
+    const int tile_end = static_cast<int>(static_cast<long long>(tiles) * (blockIdx.x + 1) / gridDim.x);
+    const int cpt = (G + SK_CG - 1) / SK_CG;  // ring stages per tile
+
+    if (warp == SK_CONSUMERS) {
+        // ------------------------------ producer: weights only, no dependency on the previous kernel
+        const unsigned char *bbytes = reinterpret_cast<const unsigned char *>(args.b);
+        int it = 0;
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            const int row = min(tile * 16 + (lane & 15), K - 1);
+            const unsigned char *src_row = bbytes + static_cast<size_t>(row) * (N / 2);
+            for (int c = 0; c < cpt; ++c, ++it) {
+                const int s = it % S;
+                const uint32_t phase = (it / S) & 1;
+                const int groups = min(SK_CG, G - c * SK_CG);
+                mbar_wait(empty_s + 8 * s, phase ^ 1);
+                if (lane == 0) mbar_expect_tx(full_s + 8 * s, 16u * groups * 64u);
+                __syncwarp();
+                if (lane < 16)
+                    bulk_g2s(ring_s + s * SK_STAGE_BYTES + lane * SK_ROW_STRIDE, src_row + static_cast<size_t>(c) * SK_ROW_BYTES,
+                             groups * 64u, full_s + 8 * s);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------- consumers ----------------------------------
+    griddep_wait();  // activations (and the residual) come from the previous kernel
+    const int ctid = threadIdx.x;  // 0 .. 255
+    const T *p0 = static_cast<const T *>(args.p0) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda;
+    const T *p1 = args.prologue == PRO_SWIGLU
+                      ? static_cast<const T *>(args.p1) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda
+                      : static_cast<const T *>(args.p1);
+    if (args.prologue == PRO_RMSNORM) {
+        if (ctid < 32) rowstat[ctid] = 0.f;
+        consumer_barrier();
+        const int total = Mp * words;
+        for (int base = (ctid & ~31); base < total; base += SK_CONSUMERS * 32) {
+            const int idx = base + lane;
+            float part = 0.f;
+            int m = 0;
+            if (idx < total) {
+                m = idx / words;
+                const int c = idx - m * words;
+                const uint4 raw = *reinterpret_cast<const uint4 *>(p0 + static_cast<size_t>(m) * args.lda + c * 8);
+                const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
+                part = f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
+            }
+            // a warp's 32 chunks belong to at most two rows (words % 16 == 0): reduce per half-warp
+            part += __shfl_xor_sync(0xffffffffu, part, 8);
+            part += __shfl_xor_sync(0xffffffffu, part, 4);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[m], part);
+        }
+        consumer_barrier();
+    }
+    {
+        const int total = Mp * words;
+        for (int base = (ctid & ~31); base < total; base += SK_CONSUMERS * 32) {
+            const int idx = base + lane;
+            float part = 0.f;
+            int m = 0, c = 0;
+            if (idx < total) {
+                m = idx / words;
+                c = idx - m * words;
+                uint4 raw = *reinterpret_cast<const uint4 *>(p0 + static_cast<size_t>(m) * args.lda + c * 8);
+                if (args.prologue != PRO_NONE) {
+                    const uint4 aux = *reinterpret_cast<const uint4 *>(
+                        args.prologue == PRO_SWIGLU ? p1 + static_cast<size_t>(m) * args.lda + c * 8 : p1 + c * 8);
+                    const uint32_t xin[4] = {raw.x, raw.y, raw.z, raw.w};
+                    const uint32_t yin[4] = {aux.x, aux.y, aux.z, aux.w};
+                    uint32_t o[4];
+                    const float inv = args.prologue == PRO_RMSNORM ? rsqrtf(rowstat[m] / static_cast<float>(N) + args.eps) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 xv = unpack2<T>(xin[i]), yv = unpack2<T>(yin[i]);
+                        float r0, r1;
+                        if (args.prologue == PRO_RMSNORM) {
+                            r0 = xv.x * inv * yv.x;
+                            r1 = xv.y * inv * yv.y;
+                        } else {
+                            r0 = (xv.x / (1.0f + expf(-xv.x))) * yv.x;
+                            r1 = (xv.y / (1.0f + expf(-xv.y))) * yv.y;
+                        }
+                        o[i] = pack2<T>(r0, r1);
+                    }
+                    raw = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                uint4 p;
+                p.x = __byte_perm(raw.x, raw.z, 0x5410);
+                p.y = __byte_perm(raw.x, raw.z, 0x7632);
+                p.z = __byte_perm(raw.y, raw.w, 0x5410);
+                p.w = __byte_perm(raw.y, raw.w, 0x7632);
+                const int pos = (c & ~15) | ((c & 3) << 2) | ((c >> 2) & 3);
+                act[static_cast<size_t>(pos) * Mp + m] = p;
+                const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
+                part = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 8);
+            part += __shfl_xor_sync(0xffffffffu, part, 4);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            if (idx < total && (c & 15) == 0) asum[(c >> 4) * Mp + m] = part;
+        }
+    }
+    consumer_barrier();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int gi = warp & (SK_CG - 1);  // group of the stage this warp owns
+    const int par = warp >> 2;          // stages with (it & 1) == par are this warp's
+    const T *scales = static_cast<const T *>(args.scales);
+    const T *biases = static_cast<const T *>(args.biases);
+    T *out = static_cast<T *>(args.out) + static_cast<size_t>(pass) * args.rows_per_pass * K;
+    const T *res = args.epilogue == EPI_RESIDUAL ? static_cast<const T *>(args.residual) + static_cast<size_t>(pass) * args.rows_per_pass * K
+                                                 : nullptr;
+
+    int it = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int row0 = min(tile * 16 + g, K - 1);
+        const int row1 = min(tile * 16 + g + 8, K - 1);
+        float acc[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+        for (int c = 0; c < cpt; ++c, ++it) {
+            if ((it & 1) != par) continue;
+            const int s = it % S;
+            const uint32_t phase = (it / S) & 1;
+            const int u = c * SK_CG + gi;
+            float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
+            if (u < G) {
+                s0 = to_f(scales[static_cast<size_t>(row0) * G + u]);
+                s1 = to_f(scales[static_cast<size_t>(row1) * G + u]);
+                c0 = to_f(biases[static_cast<size_t>(row0) * G + u]) - Mma<T>::OFFSET * s0;
+                c1 = to_f(biases[static_cast<size_t>(row1) * G + u]) - Mma<T>::OFFSET * s1;
+            }
+            mbar_wait(full_s + 8 * s, phase);
+            if (u < G) {
+                const unsigned char *stage = ring + s * SK_STAGE_BYTES + gi * 64 + t * 16;
+                const uint4 w0 = *reinterpret_cast<const uint4 *>(stage + g * SK_ROW_STRIDE);
+                const uint4 w1 = *reinterpret_cast<const uint4 *>(stage + (g + 8) * SK_ROW_STRIDE);
+                float d[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.f;
+                const uint32_t x0[4] = {w0.x, w0.y, w0.z, w0.w};
+                const uint32_t x1[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    constexpr uint32_t MASK = 0x000F000Fu;
+                    const uint32_t a0 = (x0[j] & MASK) | Mma<T>::MAGIC;
+                    const uint32_t a1 = ((x0[j] >> 4) & MASK) | Mma<T>::MAGIC;
+                    const uint32_t a2 = ((x0[j] >> 8) & MASK) | Mma<T>::MAGIC;
+                    const uint32_t a3 = ((x0[j] >> 12) & MASK) | Mma<T>::MAGIC;
+                    const uint32_t b0 = (x1[j] & MASK) | Mma<T>::MAGIC;
+                    const uint32_t b1 = ((x1[j] >> 4) & MASK) | Mma<T>::MAGIC;
+                    const uint32_t b2 = ((x1[j] >> 8) & MASK) | Mma<T>::MAGIC;
+                    const uint32_t b3 = ((x1[j] >> 12) & MASK) | Mma<T>::MAGIC;
+                    const int chunk = 16 * u + 4 * j + t;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const int col = mt * 8 + g;
+                        uint4 bf = make_uint4(0u, 0u, 0u, 0u);
+                        if (col < Mp) bf = act[static_cast<size_t>(chunk) * Mp + col];
+                        Mma<T>::mma(d[mt], a0, b0, a1, b1, bf.x, bf.y);
+                        Mma<T>::mma(d[mt], a2, b2, a3, b3, bf.z, bf.w);
+                    }
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int m0 = mt * 8 + 2 * t;
+                    const float as0 = m0 < Mp ? asum[u * Mp + m0] : 0.f;
+                    const float as1 = m0 + 1 < Mp ? asum[u * Mp + m0 + 1] : 0.f;
+                    acc[mt][0] += s0 * d[mt][0] + c0 * as0;
+                    acc[mt][1] += s0 * d[mt][1] + c0 * as1;
+                    acc[mt][2] += s1 * d[mt][2] + c1 * as0;
+                    acc[mt][3] += s1 * d[mt][3] + c1 * as1;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_s + 8 * s);
+        }
+        // ---- cross-warp reduction of the tile (double-buffered scratch, one barrier per tile)
+        float *buf = red + static_cast<size_t>(tile & 1) * SK_CONSUMERS * 16 * 8 * MT;
+        float *wred = buf + static_cast<size_t>(warp) * 16 * 8 * MT;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            wred[g * 8 * MT + mt * 8 + 2 * t] = acc[mt][0];
+            wred[g * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][1];
+            wred[(g + 8) * 8 * MT + mt * 8 + 2 * t] = acc[mt][2];
+            wred[(g + 8) * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][3];
+        }
+        consumer_barrier();
+        for (int o = ctid; o < 16 * 8 * MT; o += SK_CONSUMERS * 32) {
+            const int m = o >> 4, r = o & 15;  // consecutive threads -> consecutive output features
+            const int k = tile * 16 + r;
+            if (m < Mp && k < K) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < SK_CONSUMERS; ++w) v += buf[(w * 16 + r) * 8 * MT + m];
+                T vb = from_f<T>(v);
+                if (res != nullptr) vb = from_f<T>(to_f(res[static_cast<size_t>(m) * K + k]) + to_f(vb));
+                out[static_cast<size_t>(m) * K + k] = vb;
+            }
+        }
+    }
+}
+
+static bool g_use_pdl = false;
+void set_use_pdl(bool on) { g_use_pdl = on; }
+bool use_pdl() { return g_use_pdl; }
+
+static size_t stream2_smem_bytes(int N, int Mp, int MT, int stages) {
+    size_t bytes = static_cast<size_t>(stages) * SK_STAGE_BYTES;
+    bytes += (2 * stages * 8 + 15) & ~15;
+    bytes += static_cast<size_t>(N / 8) * Mp * 16;
+    bytes += static_cast<size_t>(((N / 128) * Mp + 3) & ~3) * 4;
+    bytes += 32 * 4;
+    bytes += 2ull * SK_CONSUMERS * 16 * 8 * MT * 4;
+    return bytes;
+}
+
+template <typename T, int MT>
+static int stream2_launch(StreamArgs args, cudaStream_t st) {
+    const int Mp = args.rows_per_pass < args.M ? args.rows_per_pass : args.M;
+    const size_t fixed = stream2_smem_bytes(args.N, Mp, MT, 0);
+    // ring depth: as deep as fits next to a second resident CTA, within [4, 16] stages
+    const size_t per_cta_budget = fixed > 100 * 1024 ? 220 * 1024 : 110 * 1024;
+    int stages = static_cast<int>((per_cta_budget - fixed) / SK_STAGE_BYTES);
+    stages = stages > 16 ? 16 : stages;
+    if (stages < 2) return fail(TL_EINVAL, "quantized_matmul: activations do not fit in shared memory (N=%d, rows=%d)", args.N, Mp);
+    args.stages = stages;
+    const size_t smem = stream2_smem_bytes(args.N, Mp, MT, stages);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(w4a16_stream2_kernel<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int tiles = ceil_div(args.K, 16);
+    const int ctas_per_sm = smem > 110 * 1024 ? 1 : 2;
+    const int cap = sm_count() * ctas_per_sm;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles < cap ? tiles : cap, ceil_div(args.M, args.rows_per_pass));
+    cfg.blockDim = dim3(SK_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream2_kernel<T, MT>, args);
+    if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream2: launch failed: %s", cudaGetErrorString(e));
+    TL_LAUNCH_CHECK("w4a16_stream2");
+    return TL_OK;
+}
+
+template <typename T>
+static int stream2_t(StreamArgs args, cudaStream_t st) {
+    if (!aligned16(args.p0) || !aligned16(args.b) || (args.p1 && !aligned16(args.p1)) || (args.lda % 8) != 0)
+        return fail(TL_EINVAL, "quantized_matmul: operands must be 16-byte aligned");
+    const size_t budget = 150 * 1024;
+    int rpp = 8;
+    if (args.M > 16 && static_cast<size_t>(args.N) * 32 * 2 <= budget)
+        rpp = 32;
+    else if (args.M > 8 && static_cast<size_t>(args.N) * 16 * 2 <= budget)
+        rpp = 16;
+    args.rows_per_pass = rpp;
+    if (rpp == 32) return stream2_launch<T, 4>(args, st);
+    if (rpp == 16) return stream2_launch<T, 2>(args, st);
+    return stream2_launch<T, 1>(args, st);
+}
+
+int launch_w4a16_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *p1,
+                       const void *residual, int M, int N, int K, int lda, int prologue, int epilogue, float eps, int dtype,
+                       cudaStream_t st) {
+    if (M == 0 || K == 0) return TL_OK;
+    StreamArgs args{};
+    args.scales = scales, args.biases = biases, args.b = static_cast<const uint32_t *>(b), args.out = out;
+    args.p0 = p0, args.p1 = p1, args.residual = residual;
+    args.M = M, args.N = N, args.K = K, args.lda = lda;
+    args.prologue = prologue, args.epilogue = epilogue, args.eps = eps;
+    switch (dtype) {
+        case TL_F16: return stream2_t<__half>(args, st);
+        case TL_BF16: return stream2_t<__nv_bfloat16>(args, st);
     }
     return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
 }

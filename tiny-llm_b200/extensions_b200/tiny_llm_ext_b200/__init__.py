@@ -38,6 +38,10 @@ __all__ = [
     "paged_cache_append_decode",
     "add",
     "argmax",
+    "decode_advance",
+    "quantized_matmul_fused",
+    "decode_qk_norm_rope_append",
+    "set_pdl",
     "launch_count",
     "device_info",
     "current_library_path",
@@ -73,6 +77,10 @@ _SIGNATURES = {
     "tl_paged_attention": (_I, [_VP] * 6 + [_I] * 6 + [_F] + [_I] * 4 + [_VP, _SZ, _VP]),
     "tl_argmax_workspace": (_SZ, [_I, _I]),
     "tl_argmax": (_I, [_VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
+    "tl_decode_advance": (_I, [_VP] * 6 + [_I, _I, _VP]),
+    "tl_quantized_matmul_fused": (_I, [_VP] * 7 + [_I] * 6 + [_F, _I, _VP]),
+    "tl_decode_qk_norm_rope_append": (_I, [_VP] * 9 + [_I] * 4 + [_F, _F] + [_I] * 4 + [_VP]),
+    "tl_set_pdl": (_I, [_I]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -430,6 +438,86 @@ def argmax(logits, stream=None):
     _check(_lib.tl_argmax(logits.data_ptr(), out.data_ptr(), rows, vocab, _DTYPE_CODE[logits.dtype],
                           None if ws is None else ws.data_ptr(), ws_bytes, _stream_ptr(stream, logits)))
     return out
+
+
+def decode_advance(tokens, next_tokens, offsets, context_lens, out_log, step_counter, stream=None):
+    """Feed the sampled tokens back and advance positions on the device (one tiny
+    launch between two graph-captured decode steps)."""
+    for t in (tokens, next_tokens, offsets, context_lens, out_log, step_counter):
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise RuntimeError("decode_advance: expected contiguous int32 tensors")
+    _gpu("decode_advance", tokens, next_tokens, offsets, context_lens, out_log, step_counter)
+    batch = tokens.numel()
+    _check(_lib.tl_decode_advance(tokens.data_ptr(), next_tokens.data_ptr(), offsets.data_ptr(), context_lens.data_ptr(),
+                                  out_log.data_ptr(), step_counter.data_ptr(), batch, out_log.numel() // max(batch, 1),
+                                  _stream_ptr(stream, tokens)))
+
+
+PRO_NONE, PRO_RMSNORM, PRO_SWIGLU = 0, 1, 2
+EPI_NONE, EPI_RESIDUAL = 0, 1
+
+
+def quantized_matmul_fused(scales, biases, b, p0, p1=None, residual=None, prologue=PRO_NONE, epilogue=EPI_NONE, eps=0.0,
+                           out=None, stream=None):
+    """Decode projection with the neighbouring element-wise operator folded in
+    (``include/tiny_llm_b200.h``): ``p0`` is ``[M, N]`` (row stride ``p0.stride(0)``),
+    ``b`` ``[K, N/8]``; bit-identical to the unfused operator sequence."""
+    if p0.dim() != 2 or b.dim() != 2 or p0.stride(1) != 1:
+        raise RuntimeError("quantized_matmul_fused: p0 must be 2D with unit inner stride")
+    M, N = p0.shape
+    K = b.shape[0]
+    if b.shape[1] * 8 != N or tuple(scales.shape) != (K, N // 128) or scales.shape != biases.shape:
+        raise RuntimeError("quantized_matmul_fused: incompatible parameter shapes")
+    if scales.dtype not in _HALF or p0.dtype != scales.dtype or biases.dtype != scales.dtype:
+        raise RuntimeError("quantized_matmul: a must be the same dtype as scales")
+    _gpu("quantized_matmul_fused", scales, biases, b, p0)
+    lda = p0.stride(0)
+    if prologue == PRO_SWIGLU and (p1 is None or p1.shape != p0.shape or p1.stride(0) != lda or p1.stride(1) != 1):
+        raise RuntimeError("quantized_matmul_fused: gate and up must share shape and strides")
+    if prologue == PRO_RMSNORM and (p1 is None or tuple(p1.shape) != (N,) or not p1.is_contiguous()):
+        raise RuntimeError("quantized_matmul_fused: norm weight must be [N]")
+    if epilogue == EPI_RESIDUAL and (residual is None or tuple(residual.shape) != (M, K) or not residual.is_contiguous()):
+        raise RuntimeError("quantized_matmul_fused: residual must be contiguous [M, K]")
+    if out is None:
+        out = torch.empty((M, K), dtype=p0.dtype, device=p0.device)
+    _check(
+        _lib.tl_quantized_matmul_fused(
+            scales.data_ptr(), biases.data_ptr(), b.data_ptr(), out.data_ptr(), p0.data_ptr(),
+            None if p1 is None else p1.data_ptr(), None if residual is None else residual.data_ptr(), M, N, K, lda,
+            int(prologue), int(epilogue), float(eps), _DTYPE_CODE[p0.dtype], _stream_ptr(stream, p0),
+        )
+    )
+    return out
+
+
+def decode_qk_norm_rope_append(qkv, q_norm_weight, k_norm_weight, offsets, block_table, context_lens, key_pages, value_pages,
+                               num_heads, num_kv_heads, base, eps, stream=None):
+    """Fused per-head q/k RMSNorm + RoPE + K/V append of one decode step; returns
+    the rotated queries ``[B, Hq, D]``."""
+    B = qkv.shape[0]
+    P, Hkv, page_size, D = key_pages.shape
+    if qkv.dim() != 2 or qkv.shape[1] != (num_heads + 2 * num_kv_heads) * D or Hkv != num_kv_heads:
+        raise RuntimeError("decode_qk_norm_rope_append: qkv must be [B, (Hq + 2*Hkv) * D]")
+    if qkv.dtype != key_pages.dtype or value_pages.dtype != key_pages.dtype or q_norm_weight.dtype != qkv.dtype:
+        raise RuntimeError("decode_qk_norm_rope_append: dtype mismatch")
+    _gpu("decode_qk_norm_rope_append", qkv, q_norm_weight, k_norm_weight, offsets, block_table, context_lens, key_pages, value_pages)
+    _contig("decode_qk_norm_rope_append", qkv=qkv, offsets=offsets, block_table=block_table, context_lens=context_lens,
+            key_pages=key_pages, value_pages=value_pages)
+    q_out = torch.empty((B, num_heads, D), dtype=qkv.dtype, device=qkv.device)
+    _check(
+        _lib.tl_decode_qk_norm_rope_append(
+            qkv.data_ptr(), q_norm_weight.data_ptr(), k_norm_weight.data_ptr(), offsets.data_ptr(), block_table.data_ptr(),
+            context_lens.data_ptr(), q_out.data_ptr(), key_pages.data_ptr(), value_pages.data_ptr(), B, int(num_heads),
+            int(num_kv_heads), D, float(base), float(eps), P, page_size, block_table.shape[1], _DTYPE_CODE[qkv.dtype],
+            _stream_ptr(stream, qkv),
+        )
+    )
+    return q_out
+
+
+def set_pdl(enabled: bool) -> None:
+    """Programmatic dependent launch for the weight-streaming kernels."""
+    _check(_lib.tl_set_pdl(int(bool(enabled))))
 
 
 def launch_count() -> int:

@@ -1,0 +1,306 @@
+"""CUDA-graph decode engine for the Week-3 paged model (B200 host runtime).
+
+The reference issues ~500 operator calls per generated token from a Python loop
+(SURVEY.md section 3.1); at B200 speeds one W4A16 projection lasts about a
+microsecond, so per-call dispatch would leave the GPU idle >90 % of the time.
+The engine keeps the operator semantics and removes the dispatch:
+
+* one decode step (embedding -> 36 blocks -> norm -> tied head -> greedy
+  argmax) for a fixed number of slots ``B`` is captured once into a CUDA graph
+  over static buffers and replayed per step;
+* everything the step needs from the scheduler is DATA, not kernel arguments:
+  token ids, RoPE offsets, post-append context lengths and the per-layer block
+  tables live in one device buffer that is refreshed with a single pinned
+  host->device copy; K/V appends and attention read page ids from it;
+* the integer page bookkeeping stays on the host in the very same
+  ``TinyKvPagedCache`` / ``TinyKvPagedPool`` objects the per-operator path uses
+  (``append_token_slot``), so block tables, page ids and counters are identical;
+* ``decode_on_device`` runs N greedy steps with no host involvement at all
+  (token feedback + position advance by ``tl_decode_advance``, pages allocated
+  ahead) - the device-resident number of bench.py.
+
+Page slabs must not move while a graph is alive: pools are ``reserve()``d up
+front and the engine re-captures if a slab pointer changes.
+"""
+
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from extensions_b200 import tiny_llm_ext_b200 as ext
+
+from .kv_cache import BatchingKvCache
+from .paged_kv_cache import TinyKvPagedCache
+
+
+def _concat_weights(parts):
+    """Stack packed projections along the output dimension (one launch instead of
+    len(parts)): rows of codes, scales and biases are simply concatenated."""
+    first = parts[0]
+    return SimpleNamespace(
+        weight=torch.cat([p.weight.view(torch.int32) if p.weight.dtype == torch.uint32 else p.weight for p in parts], dim=0).contiguous(),
+        scales=torch.cat([p.scales for p in parts], dim=0).contiguous(),
+        biases=torch.cat([p.biases for p in parts], dim=0).contiguous(),
+        group_size=first.group_size,
+        bits=first.bits,
+    )
+
+
+class DecodeEngine:
+    def __init__(self, model, batch_size: int, max_seq_len: int, device, log_capacity: int = 4096, fused: bool = True):
+        self.model = model
+        self.B = batch_size
+        self.device = torch.device(device)
+        self.page_size = model.page_size
+        self.max_pages = (max_seq_len + self.page_size - 1) // self.page_size
+        self.n_layers = model.num_hidden_layers
+        attn = model.layers_inner[0].self_attn
+        self.Hq, self.Hkv, self.D = attn.num_heads, attn.num_kv_heads, attn.head_dim
+        self.V = model.vocab_size
+        self.log_capacity = log_capacity
+
+        B, Ly, MP = self.B, self.n_layers, self.max_pages
+        # one int32 block: tokens | offsets | context_lens | block tables [Ly, B, MP]
+        self._meta_len = 3 * B + Ly * B * MP
+        self.meta_host = torch.empty(self._meta_len, dtype=torch.int32, pin_memory=True)
+        self.meta_np = self.meta_host.numpy()
+        self.meta_np[: 3 * B] = 0
+        self.meta_np[3 * B :] = -1
+        self.meta_dev = torch.zeros(self._meta_len, dtype=torch.int32, device=self.device)
+        self.tokens = self.meta_dev[0:B]
+        self.offsets = self.meta_dev[B : 2 * B]
+        self.context_lens = self.meta_dev[2 * B : 3 * B]
+        self.tables = self.meta_dev[3 * B :].view(Ly, B, MP)
+        self.tables_np = self.meta_np[3 * B :].reshape(Ly, B, MP)
+        self.next_tokens = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self.out_log = torch.full((log_capacity * B,), -1, dtype=torch.int32, device=self.device)
+        self.step_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.logits = None
+        # which (cache object, pages already mirrored) each table row reflects
+        self._row_owner = [[None] * B for _ in range(Ly)]
+        self._row_pages = [[0] * B for _ in range(Ly)]
+        self._graph = None
+        self._graph_loop = None
+        self._slab_ptrs = None
+        self._stream = torch.cuda.Stream(device=self.device)
+        self.graph_replays = 0
+        self.kernels_per_step = 0
+        rope = attn.rope
+        self.fused = bool(fused) and not rope.traditional and rope.dims == self.D and self.D % 2 == 0
+        self._packed = None
+        if self.fused:
+            # q|k|v and gate|up share their input, so they stream as one launch each.
+            self._packed = [
+                SimpleNamespace(
+                    qkv=_concat_weights([b.self_attn.wq, b.self_attn.wk, b.self_attn.wv]),
+                    gate_up=_concat_weights([b.mlp.w_gate, b.mlp.w_up]),
+                )
+                for b in model.layers_inner
+            ]
+
+    # ------------------------------------------------------------------ pools --
+    def reserve_pools(self, pages_per_layer: int | None = None) -> None:
+        pages = pages_per_layer if pages_per_layer is not None else self.B * self.max_pages + 1
+        for pool in self.model.page_pools:
+            pool.reserve(pages, self.Hkv, self.D, dtype=torch.bfloat16, device=self.device)
+
+    def _slabs(self):
+        return tuple((p._key_pages.data_ptr(), p._value_pages.data_ptr(), p.capacity) for p in self.model.page_pools)
+
+    # ------------------------------------------------------------ graph body --
+    def _forward_unfused(self) -> None:
+        """One decode step over the static buffers, operator by operator (the
+        call sequence of qwen3_week3.py:55-121,139-146,196-207,320-338 at L == 1)."""
+        m = self.model
+        B, Hq, Hkv, D = self.B, self.Hq, self.Hkv, self.D
+        emb = m.embedding.weight
+        x = ext.quantized_embedding(self.tokens, emb.scales, emb.biases, emb.weight, emb.group_size, emb.bits)  # [B, H]
+
+        def proj(h, w):
+            return ext.quantized_matmul(w.scales, w.biases, w.group_size, w.bits, h, w.weight, True)
+
+        for i, block in enumerate(m.layers_inner):
+            at = block.self_attn
+            pool = m.page_pools[i]
+            h = ext.rms_norm(x, block.input_layernorm._weight_as(x.dtype, x.device), block.input_layernorm.eps)
+            q = proj(h, at.wq).view(B, 1, Hq, D)
+            k = proj(h, at.wk).view(B, 1, Hkv, D)
+            v = proj(h, at.wv).view(B, Hkv, 1, D)
+            q = ext.rms_norm(q, at.q_norm._weight_as(x.dtype, x.device), at.q_norm.eps)
+            k = ext.rms_norm(k, at.k_norm._weight_as(x.dtype, x.device), at.k_norm.eps)
+            q = ext.rope(q, self.offsets, at.rope.dims, at.rope.base, at.rope.traditional)
+            k = ext.rope(k, self.offsets, at.rope.dims, at.rope.base, at.rope.traditional)
+            ext.paged_cache_append_decode(pool._key_pages, pool._value_pages, k.view(B, Hkv, 1, D), v, self.tables[i], self.context_lens)
+            y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i], self.context_lens,
+                                    at.scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
+            x = ext.add(x, proj(y.view(B, Hq * D), at.wo))
+            h = ext.rms_norm(x, block.post_attention_layernorm._weight_as(x.dtype, x.device), block.post_attention_layernorm.eps)
+            mlp = block.mlp
+            x = ext.add(x, proj(ext.swiglu(proj(h, mlp.w_gate), proj(h, mlp.w_up)), mlp.w_down))
+        x = ext.rms_norm(x, m.norm._weight_as(x.dtype, x.device), m.norm.eps)
+        head = m.w_lm_head if m.w_lm_head is not None else m.embedding.weight
+        logits = proj(x, head)
+        self.next_tokens.copy_(ext.argmax(logits))
+        if self.logits is None:
+            self.logits = torch.empty_like(logits)
+        self.logits.copy_(logits)
+
+    def _forward_fused(self) -> None:
+        """Same step in ~7 launches per layer: norm / SwiGLU / residual folded into
+        the streaming projections, q/k norm + RoPE + K/V append in one kernel.
+        Every rounding point of the operator-by-operator sequence is kept."""
+        m = self.model
+        B, Hq, Hkv, D = self.B, self.Hq, self.Hkv, self.D
+        inter = m.layers_inner[0].mlp.hidden_dim
+        emb = m.embedding.weight
+        x = ext.quantized_embedding(self.tokens, emb.scales, emb.biases, emb.weight, emb.group_size, emb.bits)
+        for i, block in enumerate(m.layers_inner):
+            at, pk, pool = block.self_attn, self._packed[i], m.page_pools[i]
+            ln1, ln2 = block.input_layernorm, block.post_attention_layernorm
+            qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, x, ln1._weight_as(x.dtype, x.device),
+                                             prologue=ext.PRO_RMSNORM, eps=ln1.eps)
+            q = ext.decode_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
+                                               self.offsets, self.tables[i], self.context_lens, pool._key_pages, pool._value_pages,
+                                               Hq, Hkv, at.rope.base, at.q_norm.eps)
+            y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i], self.context_lens,
+                                    at.scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
+            x = ext.quantized_matmul_fused(at.wo.scales, at.wo.biases, at.wo.weight, y.view(B, Hq * D), residual=x, epilogue=ext.EPI_RESIDUAL)
+            gu = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, x, ln2._weight_as(x.dtype, x.device),
+                                            prologue=ext.PRO_RMSNORM, eps=ln2.eps)
+            wd = block.mlp.w_down
+            x = ext.quantized_matmul_fused(wd.scales, wd.biases, wd.weight, gu[:, :inter], gu[:, inter:], residual=x,
+                                           prologue=ext.PRO_SWIGLU, epilogue=ext.EPI_RESIDUAL)
+        head = m.w_lm_head if m.w_lm_head is not None else m.embedding.weight
+        logits = ext.quantized_matmul_fused(head.scales, head.biases, head.weight, x, m.norm._weight_as(x.dtype, x.device),
+                                            prologue=ext.PRO_RMSNORM, eps=m.norm.eps)
+        self.next_tokens.copy_(ext.argmax(logits))
+        if self.logits is None:
+            self.logits = torch.empty_like(logits)
+        self.logits.copy_(logits)
+
+    def _capture(self) -> None:
+        self._slab_ptrs = self._slabs()
+        forward = self._forward_fused if self.fused else self._forward_unfused
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_stream(torch.cuda.current_stream(self.device))
+            for _ in range(2):  # warm-up: lazy kernel attribute setup must not happen under capture
+                forward()
+            self._stream.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph, stream=self._stream):
+                forward()
+            self._graph_loop = torch.cuda.CUDAGraph()
+            launched = ext.launch_count()
+            with torch.cuda.graph(self._graph_loop, stream=self._stream, pool=self._graph.pool()):
+                forward()
+                ext.decode_advance(self.tokens, self.next_tokens, self.offsets, self.context_lens, self.out_log, self.step_counter)
+            # kernels of libtiny_llm_b200.so recorded into one self-advancing step
+            self.kernels_per_step = ext.launch_count() - launched
+        torch.cuda.current_stream(self.device).wait_stream(self._stream)
+
+    def _ensure_graph(self) -> None:
+        if self._graph is None or self._slab_ptrs != self._slabs():
+            self._capture()
+
+    # ------------------------------------------------------- host bookkeeping --
+    def _slot_caches(self, caches, layer: int):
+        """The per-slot request caches of one layer: a BatchingKvCache table, or a
+        single request's cache list (B == 1)."""
+        entry = caches[layer]
+        if isinstance(entry, BatchingKvCache):
+            return entry.kv_caches
+        return [entry]
+
+    def _mirror_row(self, layer: int, b: int, cache) -> None:
+        """Bring table row (layer, b) in line with ``cache.page_ids``."""
+        if cache is None:
+            if self._row_owner[layer][b] is not None:
+                self.tables_np[layer, b, :] = -1
+                self._row_owner[layer][b] = None
+                self._row_pages[layer][b] = 0
+            return
+        n = len(cache.page_ids)
+        if n > self.max_pages:
+            raise ValueError("request exceeds the engine's max_seq_len")
+        if self._row_owner[layer][b] is cache and self._row_pages[layer][b] == n:
+            return
+        if self._row_owner[layer][b] is cache and self._row_pages[layer][b] == n - 1:
+            self.tables_np[layer, b, n - 1] = cache.page_ids[-1]
+        else:
+            self.tables_np[layer, b, :n] = cache.page_ids
+            self.tables_np[layer, b, n:] = -1
+        self._row_owner[layer][b] = cache
+        self._row_pages[layer][b] = n
+
+    def _advance_host(self, caches, steps: int = 1) -> list[int]:
+        """Append ``steps`` token slots to every active request cache of every
+        layer (host integers only) and mirror the tables.  Returns the context
+        length each slot will have after the FIRST of those steps."""
+        first_ctx = [0] * self.B
+        for layer in range(self.n_layers):
+            slots = self._slot_caches(caches, layer)
+            for b, cache in enumerate(slots):
+                if cache is not None:
+                    if not isinstance(cache, TinyKvPagedCache):
+                        raise ValueError("the decode engine needs paged request caches")
+                    before = cache.offset
+                    for _ in range(steps):
+                        cache.append_token_slot()
+                    if layer == 0:
+                        first_ctx[b] = before + 1
+                self._mirror_row(layer, b, cache)
+        return first_ctx
+
+    def _upload(self) -> None:
+        self.meta_dev.copy_(self.meta_host, non_blocking=True)
+
+    # ------------------------------------------------------------------ steps --
+    def step(self, tokens, offsets, caches):
+        """One decode step.  ``tokens``: B ids (list or tensor), ``offsets``: B
+        RoPE positions; returns (logits [B, 1, V] static buffer, next_tokens [B])."""
+        self._ensure_graph()
+        B = self.B
+        ctx = self._advance_host(caches, 1)
+        if isinstance(tokens, torch.Tensor):
+            tok_host = None
+        else:
+            tok_host = tokens
+            self.meta_np[0:B] = tok_host
+        self.meta_np[B : 2 * B] = offsets
+        self.meta_np[2 * B : 3 * B] = ctx
+        cur = torch.cuda.current_stream(self.device)
+        self._stream.wait_stream(cur)
+        with torch.cuda.stream(self._stream):
+            self._upload()
+            if tok_host is None:
+                self.tokens.copy_(tokens.reshape(-1).to(torch.int32), non_blocking=True)
+            self._graph.replay()
+        cur.wait_stream(self._stream)
+        self.graph_replays += 1
+        return self.logits.view(B, 1, self.V), self.next_tokens
+
+    def decode_on_device(self, tokens, offsets, caches, steps: int) -> torch.Tensor:
+        """``steps`` greedy decode steps with no host round trip: pages for all
+        steps are allocated ahead, then the self-advancing graph is replayed
+        back to back.  Returns the sampled tokens ``[steps, B]`` (device)."""
+        if steps > self.log_capacity:
+            raise ValueError("steps exceed the engine's token log capacity")
+        self._ensure_graph()
+        B = self.B
+        ctx = self._advance_host(caches, steps)
+        self.meta_np[0:B] = tokens
+        self.meta_np[B : 2 * B] = offsets
+        self.meta_np[2 * B : 3 * B] = ctx
+        cur = torch.cuda.current_stream(self.device)
+        self._stream.wait_stream(cur)
+        with torch.cuda.stream(self._stream):
+            self._upload()
+            self.step_counter.zero_()
+            for _ in range(steps):
+                self._graph_loop.replay()
+        cur.wait_stream(self._stream)
+        self.graph_replays += steps
+        return self.out_log[: steps * B].view(steps, B)

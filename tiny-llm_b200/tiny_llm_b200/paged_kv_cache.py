@@ -321,6 +321,26 @@ class TinyKvPagedCache(TinyKvCache):
             self._restore_state(mine)
             raise
 
+    def append_token_slot(self) -> tuple[int, int]:
+        """Host bookkeeping of a ONE-token append whose bytes are written by a
+        device-driven kernel (decode engine): same page/offset evolution as
+        ``_append_chunk`` with S == 1, minus the device write and the snapshot
+        (nothing can fail once the page is allocated).  Returns (page id, slot).
+        The pool slab must already cover the page (``pool.reserve``)."""
+        if self.page_ids and self.page_lens[-1] < self.page_size:
+            slot = self.page_lens[-1]
+            self.page_lens[-1] += 1
+            page_id = self.page_ids[-1]
+        else:
+            if not self.pool.free_page_ids and self.pool.num_pages >= self.pool.capacity:
+                raise RuntimeError("page pool slab exhausted: reserve() more pages before decoding")
+            page_id = self.pool.allocate_page()
+            self.page_ids.append(page_id)
+            self.page_lens.append(1)
+            slot = 0
+        self.offset += 1
+        return page_id, slot
+
     def validate_append(self, key: torch.Tensor, value: torch.Tensor) -> None:
         self.pool.validate_page_chunk(key, value)
 

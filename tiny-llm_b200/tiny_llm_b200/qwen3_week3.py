@@ -229,12 +229,87 @@ class Qwen3ModelWeek3:
         self.norm = FastRMSNorm(args.hidden_size, weight=mlx_model.model.norm.weight, eps=args.rms_norm_eps)
         self.w_lm_head = None if args.tie_word_embeddings else packed(mlx_model.lm_head)
         self.mlx_model = mlx_model
+        # B200 runtime: decode steps (L == 1) of CUDA-resident paged requests are replayed
+        # from a captured CUDA graph instead of ~500 per-operator dispatches (engine.py).
+        # None = automatic (on for CUDA inputs), False = always operator by operator.
+        self.use_decode_graph: bool | None = None
+        self.decode_graph_max_seq_len = 8192
+        self._decode_engines: dict = {}
+        self._paged = enable_paged_attention
 
     def create_kv_cache(self) -> list[TinyKvCache]:
         """One logical cache per layer, all sharing that layer's pool."""
         return [TinyKvPagedCache(pool=pool) for pool in self.page_pools]
 
+    # ---- CUDA-graph decode path ------------------------------------------------
+    def decode_engine(self, batch_size: int, max_seq_len: int | None = None, device=None):
+        """The (cached) graph engine for ``batch_size`` decode slots."""
+        from .engine import DecodeEngine
+
+        limit = max_seq_len or self.decode_graph_max_seq_len
+        key = (batch_size, limit)
+        if key not in self._decode_engines:
+            dev = device if device is not None else self.embedding.weight.scales.device
+            engine = DecodeEngine(self, batch_size, limit, dev)
+            engine.reserve_pools((batch_size + 1) * engine.max_pages + 1)
+            self._decode_engines[key] = engine
+        return self._decode_engines[key]
+
+    def _graph_decode_applies(self, inputs, cache) -> bool:
+        if self.use_decode_graph is False or not self._paged or inputs.dim() != 2 or inputs.shape[1] != 1 or not inputs.is_cuda:
+            return False
+        from .kv_cache import BatchingKvCache
+
+        B = inputs.shape[0]
+        for entry, pool in zip(cache, self.page_pools):
+            if isinstance(entry, BatchingKvCache):
+                slots = entry.kv_caches
+                if entry.max_active_requests != B:
+                    return False
+            elif type(entry) is TinyKvPagedCache and B == 1:
+                slots = [entry]
+            else:
+                return False
+            for slot in slots:
+                if slot is None:
+                    continue
+                if type(slot) is not TinyKvPagedCache or slot.pool is not pool or slot.offset + 1 > self.decode_graph_max_seq_len:
+                    return False
+                if pool._key_pages is not None and pool._key_pages.dtype != torch.bfloat16:
+                    return False
+        return True
+
+    def _graph_decode(self, inputs, offset, cache, logits_to_keep):
+        from .kv_cache import BatchingKvCache
+
+        if logits_to_keep is not None and logits_to_keep <= 0:
+            raise ValueError("logits_to_keep must be positive")
+        B = inputs.shape[0]
+        if isinstance(offset, int):
+            offsets = [offset] * B
+        elif isinstance(offset, torch.Tensor):
+            offsets = offset.reshape(-1).tolist()
+            offsets = offsets * B if len(offsets) == 1 else offsets
+        else:
+            offsets = list(offset)
+        for entry in cache:
+            if isinstance(entry, BatchingKvCache):
+                if not any(slot is not None for slot in entry.kv_caches):
+                    raise ValueError("Cannot build paged metadata without active requests")
+                if entry.max_seq_len is not None and any(s is not None and s.offset + 1 > entry.max_seq_len for s in entry.kv_caches):
+                    raise ValueError("Paged batch append exceeds max_seq_len")
+        engine = self.decode_engine(B)
+        logits, _ = engine.step(inputs, offsets, cache)
+        attn = self.layers_inner[0].self_attn
+        for entry in cache:
+            if isinstance(entry, BatchingKvCache):
+                entry.HD = (attn.num_kv_heads, attn.head_dim)
+                entry.last_batch_bytes = 0
+        return logits.clone()
+
     def __call__(self, inputs, offset, cache: list[TinyKvCache], logits_to_keep: int | None = None):
+        if self._graph_decode_applies(inputs, cache):
+            return self._graph_decode(inputs, offset, cache, logits_to_keep)
         h = self.embedding(inputs)
         for block, layer_cache in zip(self.layers_inner, cache):
             h = block(h, offset, layer_cache, mask="causal")
