@@ -225,6 +225,8 @@ constexpr int GQA_WARPS = 4;
 constexpr int GQA_THREADS = GQA_WARPS * 32;
 constexpr int GQA_STEP = GQA_WARPS * 4;  // tokens per CTA iteration (4 per warp, 8 lanes each)
 constexpr int GQA_MAX_SPLITS = 32;
+constexpr int GQA_RING = 6;          // cp.async steps in flight per lane (64 B each)
+constexpr int GQA_PAGE_CACHE = 264;  // page ids of one split kept in shared memory
 
 // Rows of one KV head are ordered r = head_in_group * L + l.
 template <int RG>
@@ -276,23 +278,62 @@ __global__ void __launch_bounds__(GQA_THREADS) paged_gqa_kernel(
 
     const int begin = split * tokens_per_split;
     const int end = min(vis_max, begin + tokens_per_split);
-    for (int base = begin + warp * 4; base < end; base += GQA_STEP) {
-        const int tok = base + j;
-        bool valid = tok < end;
-        int pid = -1, lp = 0;
-        if (valid) {
-            lp = tok / page_size;
-            pid = bt[static_cast<size_t>(batch) * max_pages + lp];
-            valid = pid >= 0 && pid < num_pages;
+
+    // Page ids of this split, resolved once (no dependent global load inside the token loop).
+    __shared__ int s_pages[GQA_PAGE_CACHE];
+    const int first_page = begin / page_size;
+    {
+        const int last_page = end > begin ? (end - 1) / page_size : first_page - 1;
+        for (int i = threadIdx.x; i <= last_page - first_page && i < GQA_PAGE_CACHE; i += GQA_THREADS)
+            s_pages[i] = bt[static_cast<size_t>(batch) * max_pages + first_page + i];
+    }
+    __syncthreads();
+    auto page_of = [&](int lp) -> int {
+        const int i = lp - first_page;
+        return i < GQA_PAGE_CACHE ? s_pages[i] : bt[static_cast<size_t>(batch) * max_pages + lp];
+    };
+
+    // Each lane owns 32 B of K and 32 B of V of one token per step; those bytes travel through a
+    // PRIVATE shared-memory ring filled by cp.async, GQA_RING steps deep (8-12 KiB in flight per
+    // warp), so the HBM latency is paid once per split instead of once per 4 tokens.
+    extern __shared__ __align__(16) unsigned char s_ring[];  // GQA_THREADS * GQA_RING * 64 bytes (dynamic)
+    unsigned char *my_ring = s_ring + static_cast<size_t>(threadIdx.x) * GQA_RING * 64;
+    const uint32_t my_ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(my_ring));
+    const int steps = end > begin + warp * 4 ? (end - begin - warp * 4 + GQA_STEP - 1) / GQA_STEP : 0;
+    auto token_src = [&](int step, size_t &off) -> bool {
+        const int tok = begin + warp * 4 + step * GQA_STEP + j;
+        if (step >= steps || tok >= end) return false;
+        const int lp = tok / page_size;
+        const int pid = page_of(lp);
+        if (pid < 0 || pid >= num_pages) return false;
+        off = ((static_cast<size_t>(pid) * num_kv_heads + kv_head) * page_size + (tok - lp * page_size)) * GQA_D + c * 16;
+        return true;
+    };
+    auto issue = [&](int step) {
+        size_t off;
+        if (token_src(step, off)) {
+            const uint32_t dst = my_ring_s + (step % GQA_RING) * 64;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(kp + off) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(kp + off + 8) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(vp + off) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 48), "l"(vp + off + 8) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int i = 0; i < GQA_RING - 1; ++i) issue(i);
+
+    for (int step = 0; step < steps; ++step) {
+        const int tok = begin + warp * 4 + step * GQA_STEP + j;
+        size_t unused;
+        const bool valid = token_src(step, unused);
+        asm volatile("cp.async.wait_group %0;" ::"n"(GQA_RING - 2) : "memory");
         uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
-        if (valid) {
-            const size_t off = ((static_cast<size_t>(pid) * num_kv_heads + kv_head) * page_size + (tok - lp * page_size)) * GQA_D + c * 16;
-            k0 = ldg_stream(kp + off);
-            k1 = ldg_stream(kp + off + 8);
-            v0 = ldg_stream(vp + off);
-            v1 = ldg_stream(vp + off + 8);
+        if (valid) {  // a lane reads back only the bytes it copied itself: no cross-lane sync needed
+            const uint4 *slot = reinterpret_cast<const uint4 *>(my_ring + (step % GQA_RING) * 64);
+            k0 = slot[0], k1 = slot[1], v0 = slot[2], v1 = slot[3];
         }
+        issue(step + GQA_RING - 1);
         float kf[16];
         {
             const uint32_t raw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
@@ -351,7 +392,10 @@ __global__ void __launch_bounds__(GQA_THREADS) paged_gqa_kernel(
             m[r] = nm;
         }
     }
-    __shared__ float s_acc[GQA_WARPS][RG][GQA_D];
+    // the ring is drained: reuse its memory for the cross-warp merge
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float(*s_acc)[RG][GQA_D] = reinterpret_cast<float(*)[RG][GQA_D]>(s_ring);
     __shared__ float s_m[GQA_WARPS][RG], s_l[GQA_WARPS][RG];
     if (j == 0) {
 #pragma unroll
@@ -425,7 +469,7 @@ int launch_paged_gqa(const void *q, const void *kp, const void *vp, const int32_
     if (allow_split) {
         const long long target = 4LL * sm_count();
         long long want = ceil_div_ll(target, base_ctas);
-        const long long most = ceil_div_ll(bound, 64);  // at least 64 tokens per split
+        const long long most = bound / 512 > 0 ? bound / 512 : 1;  // at least 512 tokens per split: a short context is one CTA per KV head
         if (want > most) want = most;
         if (want > GQA_MAX_SPLITS) want = GQA_MAX_SPLITS;
         if (want < 1) want = 1;
@@ -450,8 +494,17 @@ int launch_paged_gqa(const void *q, const void *kp, const void *vp, const int32_
     auto kpp = static_cast<const __nv_bfloat16 *>(kp);
     auto vpp = static_cast<const __nv_bfloat16 *>(vp);
     auto op = static_cast<__nv_bfloat16 *>(out);
+    constexpr size_t ring_bytes = static_cast<size_t>(GQA_THREADS) * GQA_RING * 64;
+    static_assert(ring_bytes >= sizeof(float) * GQA_WARPS * 4 * GQA_D, "merge scratch aliases the ring");
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(paged_gqa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ring_bytes));
+        cudaFuncSetAttribute(paged_gqa_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ring_bytes));
+        cudaFuncSetAttribute(paged_gqa_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ring_bytes));
+        configured = true;
+    }
 #define TL_GQA(RGV)                                                                                                   \
-    paged_gqa_kernel<RGV><<<grid, GQA_THREADS, 0, st>>>(qp, kpp, vpp, bt, cl, op, ws_o, ws_m, ws_l, L, num_pages,     \
+    paged_gqa_kernel<RGV><<<grid, GQA_THREADS, ring_bytes, st>>>(qp, kpp, vpp, bt, cl, op, ws_o, ws_m, ws_l, L, num_pages,     \
                                                        page_size, max_pages, scale, is_causal, num_kv_heads,         \
                                                        num_heads, row_groups, splits, tps)
     if (RG == 4)

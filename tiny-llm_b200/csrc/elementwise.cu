@@ -445,12 +445,29 @@ __device__ __forceinline__ Best block_best(Best mine) {
 
 template <typename T>
 __global__ void argmax_partial_kernel(const T *__restrict__ logits, float *__restrict__ pv, int *__restrict__ pi,
-                                      int vocab, int chunk) {
+                                      int vocab, int chunk, int vec) {
     const int row = blockIdx.y;
     const int begin = blockIdx.x * chunk;
     const int end = min(vocab, begin + chunk);
     const T *src = logits + static_cast<size_t>(row) * vocab;
     Best mine{-INFINITY, INT_MAX};
+    if constexpr (sizeof(T) == 2) {
+        if (vec) {  // chunk, vocab and the row pitch are multiples of 8 elements: 128-bit loads
+            for (int i = begin + threadIdx.x * 8; i < end; i += blockDim.x * 8) {
+                const uint4 raw = *reinterpret_cast<const uint4 *>(src + i);
+                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack2<T>(w[j]);
+                    mine = better(mine, Best{f.x, i + 2 * j});
+                    mine = better(mine, Best{f.y, i + 2 * j + 1});
+                }
+            }
+            mine = block_best(mine);
+            if (threadIdx.x == 0) pv[row * gridDim.x + blockIdx.x] = mine.v, pi[row * gridDim.x + blockIdx.x] = mine.i;
+            return;
+        }
+    }
     for (int i = begin + threadIdx.x; i < end; i += blockDim.x) mine = better(mine, Best{to_f(src[i]), i});
     mine = block_best(mine);
     if (threadIdx.x == 0) pv[row * gridDim.x + blockIdx.x] = mine.v, pi[row * gridDim.x + blockIdx.x] = mine.i;
@@ -476,13 +493,14 @@ int launch_argmax(const void *logits, int32_t *out, int rows, int vocab, int dty
     if (ws == nullptr || ws_bytes < argmax_workspace(rows, vocab)) return fail(TL_EWORKSPACE, "argmax: workspace too small");
     float *pv = static_cast<float *>(ws);
     int *pi = reinterpret_cast<int *>(pv + static_cast<size_t>(rows) * parts);
-    const int chunk = ceil_div(vocab, parts);
+    const int chunk = ceil_div(ceil_div(vocab, parts), 8) * 8;
+    const int vec = (vocab % 8 == 0 && aligned16(logits)) ? 1 : 0;
     dim3 grid(parts, rows);
     switch (dtype) {
-        case TL_F32: argmax_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(logits), pv, pi, vocab, chunk); break;
-        case TL_F16: argmax_partial_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half *>(logits), pv, pi, vocab, chunk); break;
+        case TL_F32: argmax_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(logits), pv, pi, vocab, chunk, vec); break;
+        case TL_F16: argmax_partial_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half *>(logits), pv, pi, vocab, chunk, vec); break;
         case TL_BF16:
-            argmax_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(logits), pv, pi, vocab, chunk);
+            argmax_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(logits), pv, pi, vocab, chunk, vec);
             break;
         default: return fail(TL_EDTYPE, "argmax: expected float32, float16, or bfloat16");
     }

@@ -320,30 +320,32 @@ int launch_w4a16_stream(const void *scales, const void *biases, const void *a, c
 }
 
 // ---------------------------------------------------------------------------
-// v2: TMA-bulk fed streaming kernel.
+// v3: per-warp cp.async rings.
 //
-// v1 keeps only ~2 KB of weight bytes in flight per warp (register prefetch),
-// far short of the ~40 KB per SM that 6.5 TB/s at ~800 ns latency needs.  Here a
-// dedicated producer warp streams the packed weights of consecutive 16-row
-// tiles into a shared-memory ring with cp.async.bulk (one 256 B row segment per
-// lane, completion counted on an mbarrier), so a CTA has STAGES x 4 KB in flight
-// at no register cost; eight consumer warps run the same mma-fed arithmetic as
-// v1 out of shared memory.  Weights never depend on the previous kernel, so the
-// producer starts before griddepcontrol.wait (programmatic dependent launch):
-// the ring fills while the previous kernel drains.
+// Measured on B200 (profiles/r01_kbench_*): v1 (register prefetch, 2 KB in flight
+// per warp) reached 31 % of HBM peak on the tied head; v2 (one producer warp issuing
+// 256-byte cp.async.bulk rows into a CTA ring) was slower still - small bulk copies
+// are issue-limited.  v3 gives every warp a PRIVATE ring of RING 1-KiB slots (one
+// 16-row x 128-column weight group each) filled with 16-byte cp.async: 8 KiB in
+// flight per warp, 128+ KiB per SM, no mbarriers and no cross-warp traffic on the
+// load path.  A tile's reduction dimension is split over a team of TW warps
+// (TW = 1..8, chosen so that small projections still put >= 16 warps on every SM);
+// only that team synchronises (named barrier) to combine its partial sums.
+//
+// Weights never depend on the previous kernel: each warp fills its ring BEFORE
+// griddepcontrol.wait, so with programmatic dependent launch the HBM stream of
+// kernel n+1 starts while kernel n drains.
 //
 // Optional fusions that keep every rounding point of the unfused call sequence
-// (so results are bit-identical to rms_norm -> matvec, swiglu -> matvec,
-// matvec -> add):
+// (so results match rms_norm -> matvec, swiglu -> matvec, matvec -> add):
 //   prologue RMSNORM : a = T(x * rsqrt(mean(x^2)+eps) * w)   (week2_kernels.metal:41-47)
 //   prologue SWIGLU  : a = T(g / (1 + exp(-g)) * u)          (week2_kernels.metal:115-116)
 //   epilogue RESIDUAL: out = T(float(res) + float(T(acc)))   (qwen3_week3.py:204-206)
-constexpr int SK_CONSUMERS = 8;                       // consumer warps
-constexpr int SK_THREADS = (SK_CONSUMERS + 1) * 32;   // + 1 producer warp
-constexpr int SK_CG = 4;                              // 128-column groups per ring stage
-constexpr int SK_ROW_BYTES = SK_CG * 64;              // packed bytes of one row in a stage
-constexpr int SK_ROW_STRIDE = SK_ROW_BYTES + 64;      // +64 B: rows g / g+1 hit different bank halves
-constexpr int SK_STAGE_BYTES = 16 * SK_ROW_STRIDE;
+constexpr int S3_WARPS = 8;
+constexpr int S3_THREADS = S3_WARPS * 32;
+constexpr int S3_RING = 8;              // slots per warp
+constexpr int S3_CODE_BYTES = 1024;     // 16 rows x 64 B of packed codes
+constexpr int S3_SLOT_BYTES = 1024 + 128;  // + 16 scale words + 16 bias words (4 B each, see issue())
 
 enum { PRO_NONE = 0, PRO_RMSNORM = 1, PRO_SWIGLU = 2 };
 enum { EPI_NONE = 0, EPI_RESIDUAL = 1 };
@@ -356,156 +358,143 @@ struct StreamArgs {
     int M, N, K, lda;
     int prologue, epilogue;
     float eps;
-    int rows_per_pass, stages;
+    int rows_per_pass, team_warps;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    uint32_t spins = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!done && ++spins > (1u << 24)) __trap();  // a lost arrival must not hang the GPU
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void consumer_barrier() {
-    asm volatile("bar.sync 1, %0;" ::"r"(SK_CONSUMERS * 32) : "memory");
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 template <typename T, int MT>
-__global__ void __launch_bounds__(SK_THREADS) w4a16_stream2_kernel(const StreamArgs args) {
-    extern __shared__ __align__(128) unsigned char smem2_raw[];
-    unsigned char *smem_raw = smem2_raw;
+__global__ void __launch_bounds__(S3_THREADS) w4a16_stream3_kernel(const StreamArgs args) {
+    extern __shared__ __align__(128) unsigned char smem3_raw[];
     const int N = args.N, K = args.K;
     const int pass = blockIdx.y;
     const int Mp = min(args.rows_per_pass, args.M - pass * args.rows_per_pass);
     const int words = N / 8;
     const int G = N / 128;
-    const int S = args.stages;
+    const int TW = args.team_warps;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int team = warp / TW;
+    const int wit = warp - team * TW;
+    const int teams = S3_WARPS / TW;
+    const int g = lane >> 2, t = lane & 3;
 
-    // shared layout: ring | barriers | act | asum | row stats | red[2]
-    unsigned char *ring = smem_raw;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + static_cast<size_t>(S) * SK_STAGE_BYTES);
-    uint4 *act = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(bars) + ((2 * S * 8 + 15) & ~15));
+    // shared layout: rings [8 warps][RING][1 KiB] | act | asum | row stats | red
+    unsigned char *ring = smem3_raw + static_cast<size_t>(warp) * S3_RING * S3_SLOT_BYTES;
+    uint4 *act = reinterpret_cast<uint4 *>(smem3_raw + static_cast<size_t>(S3_WARPS) * S3_RING * S3_SLOT_BYTES);
     float *asum = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(act) + static_cast<size_t>(words) * Mp * 16);
     float *rowstat = asum + ((G * Mp + 3) & ~3);
     float *red = rowstat + 32;
     const uint32_t ring_s = smem_u32(ring);
-    const uint32_t full_s = smem_u32(bars);
-    const uint32_t empty_s = full_s + 8 * S;
 
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < S; ++i) {
-            mbar_init(full_s + 8 * i, 1);
-            mbar_init(empty_s + 8 * i, SK_CONSUMERS / 2);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
     griddep_launch();
 
+    // ---- this warp's work list: tiles of its team, groups u = wit, wit+TW, ... of each tile
     const int tiles = (K + 15) / 16;
-    const int tile_begin = static_cast<int>(static_cast<long long>(tiles) * blockIdx.x / gridDim.x);
-    const int tile_end = static_cast<int>(static_cast<long long>(tiles) * (blockIdx.x + 1) / gridDim.x);
-    const int cpt = (G + SK_CG - 1) / SK_CG;  // ring stages per tile
+    const int team_id = blockIdx.x * teams + team;
+    const int team_count = gridDim.x * teams;
+    const int gpw = (G - wit + TW - 1) / TW;  // groups of one tile that belong to this warp
+    const int my_tiles = team_id < tiles ? (tiles - team_id + team_count - 1) / team_count : 0;
+    const int total_items = my_tiles * gpw;
+    const unsigned char *bbytes = reinterpret_cast<const unsigned char *>(args.b);
+    const int crow = lane >> 1;         // row of the tile this lane copies
+    const int chalf = (lane & 1) * 32;  // which 32 bytes of the row's 64
 
-    if (warp == SK_CONSUMERS) {
-        // ------------------------------ producer: weights only, no dependency on the previous kernel
-        const unsigned char *bbytes = reinterpret_cast<const unsigned char *>(args.b);
-        int it = 0;
-        for (int tile = tile_begin; tile < tile_end; ++tile) {
-            const int row = min(tile * 16 + (lane & 15), K - 1);
-            const unsigned char *src_row = bbytes + static_cast<size_t>(row) * (N / 2);
-            for (int c = 0; c < cpt; ++c, ++it) {
-                const int s = it % S;
-                const uint32_t phase = (it / S) & 1;
-                const int groups = min(SK_CG, G - c * SK_CG);
-                mbar_wait(empty_s + 8 * s, phase ^ 1);
-                if (lane == 0) mbar_expect_tx(full_s + 8 * s, 16u * groups * 64u);
-                __syncwarp();
-                if (lane < 16)
-                    bulk_g2s(ring_s + s * SK_STAGE_BYTES + lane * SK_ROW_STRIDE, src_row + static_cast<size_t>(c) * SK_ROW_BYTES,
-                             groups * 64u, full_s + 8 * s);
+    // Scales/biases ride in the same ring: a 2-byte value cannot be cp.async'ed on its own, so the
+    // aligned 4-byte word that contains it is copied and the consumer picks the half by parity.
+    const unsigned char *sbytes = reinterpret_cast<const unsigned char *>(args.scales);
+    const unsigned char *cbytes = reinterpret_cast<const unsigned char *>(args.biases);
+    const long long sb_elems = static_cast<long long>(K) * G;
+    auto issue = [&](int item) {  // item -> (tile, group); one commit group per item, always
+        if (item < total_items) {
+            const int tile = team_id + (item / gpw) * team_count;
+            const int u = wit + (item % gpw) * TW;
+            const int row = min(tile * 16 + crow, K - 1);
+            const unsigned char *src = bbytes + static_cast<size_t>(row) * (N / 2) + u * 64 + chalf;
+            const uint32_t slot = ring_s + (item % S3_RING) * S3_SLOT_BYTES;
+            const uint32_t dst = slot + crow * 64 + chalf;
+            cp_async16(dst, src);
+            cp_async16(dst + 16, src + 16);
+            const int prow = min(tile * 16 + (lane & 15), K - 1);
+            const long long e = static_cast<long long>(prow) * G + u;
+            const unsigned char *table = lane < 16 ? sbytes : cbytes;
+            const uint32_t pdst = slot + S3_CODE_BYTES + lane * 4;
+            if ((e | 1) < sb_elems) {
+                cp_async4(pdst, table + ((e >> 1) << 2));
+            } else {  // last element of an odd-sized table: its pair would cross the end, copy synchronously
+                const uint16_t v = *reinterpret_cast<const uint16_t *>(table + e * 2);
+                *reinterpret_cast<uint32_t *>(ring + (item % S3_RING) * S3_SLOT_BYTES + S3_CODE_BYTES + lane * 4) =
+                    (e & 1) ? (static_cast<uint32_t>(v) << 16) : static_cast<uint32_t>(v);
             }
         }
-        return;
-    }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < S3_RING - 1; ++i) issue(i);  // fill the ring before touching activations
 
-    // ---------------------------------- consumers ----------------------------------
     griddep_wait();  // activations (and the residual) come from the previous kernel
-    const int ctid = threadIdx.x;  // 0 .. 255
     const T *p0 = static_cast<const T *>(args.p0) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda;
     const T *p1 = args.prologue == PRO_SWIGLU
                       ? static_cast<const T *>(args.p1) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda
                       : static_cast<const T *>(args.p1);
-    if (args.prologue == PRO_RMSNORM) {
-        if (ctid < 32) rowstat[ctid] = 0.f;
-        consumer_barrier();
-        const int total = Mp * words;
-        for (int base = (ctid & ~31); base < total; base += SK_CONSUMERS * 32) {
-            const int idx = base + lane;
-            float part = 0.f;
-            int m = 0;
-            if (idx < total) {
-                m = idx / words;
-                const int c = idx - m * words;
-                const uint4 raw = *reinterpret_cast<const uint4 *>(p0 + static_cast<size_t>(m) * args.lda + c * 8);
-                const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
-                part = f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
-            }
-            // a warp's 32 chunks belong to at most two rows (words % 16 == 0): reduce per half-warp
-            part += __shfl_xor_sync(0xffffffffu, part, 8);
-            part += __shfl_xor_sync(0xffffffffu, part, 4);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[m], part);
-        }
-        consumer_barrier();
-    }
+    // ---- stage activations: each 8-element chunk is loaded ONCE (kept in registers across the
+    // row-statistics barrier when the tile is small enough), transformed by the prologue, rounded
+    // to T, permuted into MMA-fragment order and written to shared memory with its group sum.
     {
+        constexpr int CACHE = 4;
         const int total = Mp * words;
-        for (int base = (ctid & ~31); base < total; base += SK_CONSUMERS * 32) {
-            const int idx = base + lane;
+        const bool cached = total <= CACHE * S3_THREADS;
+        const bool rms = args.prologue == PRO_RMSNORM;
+        uint4 held[CACHE];
+        auto chunk_src = [&](int idx, int &m, int &c) -> const T * {
+            m = idx / words;
+            c = idx - m * words;
+            return p0 + static_cast<size_t>(m) * args.lda + c * 8;
+        };
+        auto half_warp_sum = [](float v) {
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            return v;
+        };
+        auto square_sum = [](const uint4 &raw) {
+            const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
+            return f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
+        };
+        auto emit = [&](int idx, uint4 raw) {  // idx may be >= total (lane padding): contributes nothing
             float part = 0.f;
             int m = 0, c = 0;
             if (idx < total) {
-                m = idx / words;
-                c = idx - m * words;
-                uint4 raw = *reinterpret_cast<const uint4 *>(p0 + static_cast<size_t>(m) * args.lda + c * 8);
+                const T *src = chunk_src(idx, m, c);
                 if (args.prologue != PRO_NONE) {
                     const uint4 aux = *reinterpret_cast<const uint4 *>(
-                        args.prologue == PRO_SWIGLU ? p1 + static_cast<size_t>(m) * args.lda + c * 8 : p1 + c * 8);
+                        args.prologue == PRO_SWIGLU ? p1 + (src - p0) : p1 + c * 8);
                     const uint32_t xin[4] = {raw.x, raw.y, raw.z, raw.w};
                     const uint32_t yin[4] = {aux.x, aux.y, aux.z, aux.w};
                     uint32_t o[4];
-                    const float inv = args.prologue == PRO_RMSNORM ? rsqrtf(rowstat[m] / static_cast<float>(N) + args.eps) : 0.f;
+                    const float inv = rms ? rsqrtf(rowstat[m] / static_cast<float>(N) + args.eps) : 0.f;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float2 xv = unpack2<T>(xin[i]), yv = unpack2<T>(yin[i]);
                         float r0, r1;
-                        if (args.prologue == PRO_RMSNORM) {
+                        if (rms) {
                             r0 = xv.x * inv * yv.x;
                             r1 = xv.y * inv * yv.y;
                         } else {
@@ -521,96 +510,144 @@ __global__ void __launch_bounds__(SK_THREADS) w4a16_stream2_kernel(const StreamA
                 p.y = __byte_perm(raw.x, raw.z, 0x7632);
                 p.z = __byte_perm(raw.y, raw.w, 0x5410);
                 p.w = __byte_perm(raw.y, raw.w, 0x7632);
+                // 4x4 transpose of the chunk order inside a group: the four lanes of an MMA group
+                // then read 64 contiguous bytes per sub-step (no bank conflicts).
                 const int pos = (c & ~15) | ((c & 3) << 2) | ((c >> 2) & 3);
                 act[static_cast<size_t>(pos) * Mp + m] = p;
                 const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
                 part = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
             }
-            part += __shfl_xor_sync(0xffffffffu, part, 8);
-            part += __shfl_xor_sync(0xffffffffu, part, 4);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part = half_warp_sum(part);  // 16 consecutive chunks (one group) live in 16 consecutive lanes
             if (idx < total && (c & 15) == 0) asum[(c >> 4) * Mp + m] = part;
+        };
+        const int base0 = threadIdx.x & ~31;
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < CACHE; ++j) {
+                const int idx = base0 + j * S3_THREADS + lane;
+                held[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (idx < total) {
+                    int m, c;
+                    held[j] = *reinterpret_cast<const uint4 *>(chunk_src(idx, m, c));
+                }
+            }
+        }
+        if (rms) {
+            if (threadIdx.x < 32) rowstat[threadIdx.x] = 0.f;
+            __syncthreads();
+            // a warp's 32 chunks belong to at most two rows (words % 16 == 0): reduce per half-warp
+            if (cached) {
+#pragma unroll
+                for (int j = 0; j < CACHE; ++j) {
+                    const int idx = base0 + j * S3_THREADS + lane;
+                    if (base0 + j * S3_THREADS < total) {
+                        const float part = half_warp_sum(idx < total ? square_sum(held[j]) : 0.f);
+                        if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
+                    }
+                }
+            } else {
+                for (int base = base0; base < total; base += S3_THREADS) {
+                    const int idx = base + lane;
+                    float part = 0.f;
+                    if (idx < total) {
+                        int m, c;
+                        part = square_sum(*reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
+                    }
+                    part = half_warp_sum(part);
+                    if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
+                }
+            }
+            __syncthreads();
+        }
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < CACHE; ++j)
+                if (base0 + j * S3_THREADS < total) emit(base0 + j * S3_THREADS + lane, held[j]);
+        } else {
+            for (int base = base0; base < total; base += S3_THREADS) {
+                const int idx = base + lane;
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if (idx < total) {
+                    int m, c;
+                    raw = *reinterpret_cast<const uint4 *>(chunk_src(idx, m, c));
+                }
+                emit(idx, raw);
+            }
         }
     }
-    consumer_barrier();
+    __syncthreads();
 
-    const int g = lane >> 2, t = lane & 3;
-    const int gi = warp & (SK_CG - 1);  // group of the stage this warp owns
-    const int par = warp >> 2;          // stages with (it & 1) == par are this warp's
-    const T *scales = static_cast<const T *>(args.scales);
-    const T *biases = static_cast<const T *>(args.biases);
     T *out = static_cast<T *>(args.out) + static_cast<size_t>(pass) * args.rows_per_pass * K;
     const T *res = args.epilogue == EPI_RESIDUAL ? static_cast<const T *>(args.residual) + static_cast<size_t>(pass) * args.rows_per_pass * K
                                                  : nullptr;
+    float *team_red = red + static_cast<size_t>(team) * TW * 16 * 8 * MT;
+    const int team_threads = TW * 32;
+    const int ttid = threadIdx.x - team * team_threads;
 
-    int it = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    int item = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+        const int tile = team_id + ti * team_count;
         const int row0 = min(tile * 16 + g, K - 1);
         const int row1 = min(tile * 16 + g + 8, K - 1);
         float acc[MT][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
-        for (int c = 0; c < cpt; ++c, ++it) {
-            if ((it & 1) != par) continue;
-            const int s = it % S;
-            const uint32_t phase = (it / S) & 1;
-            const int u = c * SK_CG + gi;
-            float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
-            if (u < G) {
-                s0 = to_f(scales[static_cast<size_t>(row0) * G + u]);
-                s1 = to_f(scales[static_cast<size_t>(row1) * G + u]);
-                c0 = to_f(biases[static_cast<size_t>(row0) * G + u]) - Mma<T>::OFFSET * s0;
-                c1 = to_f(biases[static_cast<size_t>(row1) * G + u]) - Mma<T>::OFFSET * s1;
-            }
-            mbar_wait(full_s + 8 * s, phase);
-            if (u < G) {
-                const unsigned char *stage = ring + s * SK_STAGE_BYTES + gi * 64 + t * 16;
-                const uint4 w0 = *reinterpret_cast<const uint4 *>(stage + g * SK_ROW_STRIDE);
-                const uint4 w1 = *reinterpret_cast<const uint4 *>(stage + (g + 8) * SK_ROW_STRIDE);
-                float d[MT][4];
+        for (int u = wit; u < G; u += TW, ++item) {
+            cp_async_wait<S3_RING - 2>();  // the oldest outstanding group (this item) has landed
+            __syncwarp();
+            const unsigned char *slot0 = ring + (item % S3_RING) * S3_SLOT_BYTES;
+            const unsigned char *slot = slot0 + t * 16;
+            const uint4 w0 = *reinterpret_cast<const uint4 *>(slot + g * 64);
+            const uint4 w1 = *reinterpret_cast<const uint4 *>(slot + (g + 8) * 64);
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(slot0 + S3_CODE_BYTES);
+            const int par0 = static_cast<int>((static_cast<long long>(row0) * G + u) & 1);
+            const int par1 = static_cast<int>((static_cast<long long>(row1) * G + u) & 1);
+            const float2 sp0 = unpack2<T>(sw[g]), sp1 = unpack2<T>(sw[g + 8]);
+            const float2 cp0 = unpack2<T>(sw[16 + g]), cp1 = unpack2<T>(sw[16 + g + 8]);
+            const float s0 = par0 ? sp0.y : sp0.x, s1 = par1 ? sp1.y : sp1.x;
+            const float c0 = (par0 ? cp0.y : cp0.x) - Mma<T>::OFFSET * s0;
+            const float c1 = (par1 ? cp1.y : cp1.x) - Mma<T>::OFFSET * s1;
+            __syncwarp();                   // every lane has read the slot the next issue may overwrite ...
+            issue(item + S3_RING - 1);      // ... which is slot (item - 1) % RING, consumed one iteration ago
+            float d[MT][4];
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.f;
-                const uint32_t x0[4] = {w0.x, w0.y, w0.z, w0.w};
-                const uint32_t x1[4] = {w1.x, w1.y, w1.z, w1.w};
+            for (int mt = 0; mt < MT; ++mt) d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.f;
+            const uint32_t x0[4] = {w0.x, w0.y, w0.z, w0.w};
+            const uint32_t x1[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    constexpr uint32_t MASK = 0x000F000Fu;
-                    const uint32_t a0 = (x0[j] & MASK) | Mma<T>::MAGIC;
-                    const uint32_t a1 = ((x0[j] >> 4) & MASK) | Mma<T>::MAGIC;
-                    const uint32_t a2 = ((x0[j] >> 8) & MASK) | Mma<T>::MAGIC;
-                    const uint32_t a3 = ((x0[j] >> 12) & MASK) | Mma<T>::MAGIC;
-                    const uint32_t b0 = (x1[j] & MASK) | Mma<T>::MAGIC;
-                    const uint32_t b1 = ((x1[j] >> 4) & MASK) | Mma<T>::MAGIC;
-                    const uint32_t b2 = ((x1[j] >> 8) & MASK) | Mma<T>::MAGIC;
-                    const uint32_t b3 = ((x1[j] >> 12) & MASK) | Mma<T>::MAGIC;
-                    const int chunk = 16 * u + 4 * j + t;
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const int col = mt * 8 + g;
-                        uint4 bf = make_uint4(0u, 0u, 0u, 0u);
-                        if (col < Mp) bf = act[static_cast<size_t>(chunk) * Mp + col];
-                        Mma<T>::mma(d[mt], a0, b0, a1, b1, bf.x, bf.y);
-                        Mma<T>::mma(d[mt], a2, b2, a3, b3, bf.z, bf.w);
-                    }
-                }
+            for (int j = 0; j < 4; ++j) {
+                constexpr uint32_t MASK = 0x000F000Fu;
+                const uint32_t a0 = (x0[j] & MASK) | Mma<T>::MAGIC;
+                const uint32_t a1 = ((x0[j] >> 4) & MASK) | Mma<T>::MAGIC;
+                const uint32_t a2 = ((x0[j] >> 8) & MASK) | Mma<T>::MAGIC;
+                const uint32_t a3 = ((x0[j] >> 12) & MASK) | Mma<T>::MAGIC;
+                const uint32_t b0 = (x1[j] & MASK) | Mma<T>::MAGIC;
+                const uint32_t b1 = ((x1[j] >> 4) & MASK) | Mma<T>::MAGIC;
+                const uint32_t b2 = ((x1[j] >> 8) & MASK) | Mma<T>::MAGIC;
+                const uint32_t b3 = ((x1[j] >> 12) & MASK) | Mma<T>::MAGIC;
+                const int chunk = 16 * u + 4 * j + t;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    const int m0 = mt * 8 + 2 * t;
-                    const float as0 = m0 < Mp ? asum[u * Mp + m0] : 0.f;
-                    const float as1 = m0 + 1 < Mp ? asum[u * Mp + m0 + 1] : 0.f;
-                    acc[mt][0] += s0 * d[mt][0] + c0 * as0;
-                    acc[mt][1] += s0 * d[mt][1] + c0 * as1;
-                    acc[mt][2] += s1 * d[mt][2] + c1 * as0;
-                    acc[mt][3] += s1 * d[mt][3] + c1 * as1;
+                    const int col = mt * 8 + g;
+                    uint4 bf = make_uint4(0u, 0u, 0u, 0u);
+                    if (col < Mp) bf = act[static_cast<size_t>(chunk) * Mp + col];
+                    Mma<T>::mma(d[mt], a0, b0, a1, b1, bf.x, bf.y);
+                    Mma<T>::mma(d[mt], a2, b2, a3, b3, bf.z, bf.w);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_s + 8 * s);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int m0 = mt * 8 + 2 * t;
+                const float as0 = m0 < Mp ? asum[u * Mp + m0] : 0.f;
+                const float as1 = m0 + 1 < Mp ? asum[u * Mp + m0 + 1] : 0.f;
+                acc[mt][0] += s0 * d[mt][0] + c0 * as0;
+                acc[mt][1] += s0 * d[mt][1] + c0 * as1;
+                acc[mt][2] += s1 * d[mt][2] + c1 * as0;
+                acc[mt][3] += s1 * d[mt][3] + c1 * as1;
+            }
         }
-        // ---- cross-warp reduction of the tile (double-buffered scratch, one barrier per tile)
-        float *buf = red + static_cast<size_t>(tile & 1) * SK_CONSUMERS * 16 * 8 * MT;
-        float *wred = buf + static_cast<size_t>(warp) * 16 * 8 * MT;
+        // ---- combine the team's partial sums and store 16 x (8*MT) outputs
+        float *wred = team_red + static_cast<size_t>(wit) * 16 * 8 * MT;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             wred[g * 8 * MT + mt * 8 + 2 * t] = acc[mt][0];
@@ -618,59 +655,69 @@ __global__ void __launch_bounds__(SK_THREADS) w4a16_stream2_kernel(const StreamA
             wred[(g + 8) * 8 * MT + mt * 8 + 2 * t] = acc[mt][2];
             wred[(g + 8) * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][3];
         }
-        consumer_barrier();
-        for (int o = ctid; o < 16 * 8 * MT; o += SK_CONSUMERS * 32) {
+        if (TW == 1)
+            __syncwarp();
+        else
+            named_barrier(1 + team, team_threads);
+        for (int o = ttid; o < 16 * 8 * MT; o += team_threads) {
             const int m = o >> 4, r = o & 15;  // consecutive threads -> consecutive output features
             const int k = tile * 16 + r;
             if (m < Mp && k < K) {
                 float v = 0.f;
-#pragma unroll
-                for (int w = 0; w < SK_CONSUMERS; ++w) v += buf[(w * 16 + r) * 8 * MT + m];
+                for (int w = 0; w < TW; ++w) v += team_red[(w * 16 + r) * 8 * MT + m];
                 T vb = from_f<T>(v);
                 if (res != nullptr) vb = from_f<T>(to_f(res[static_cast<size_t>(m) * K + k]) + to_f(vb));
                 out[static_cast<size_t>(m) * K + k] = vb;
             }
         }
+        if (TW == 1)
+            __syncwarp();
+        else
+            named_barrier(1 + team, team_threads);
     }
+    cp_async_wait<0>();
 }
 
 static bool g_use_pdl = false;
 void set_use_pdl(bool on) { g_use_pdl = on; }
 bool use_pdl() { return g_use_pdl; }
 
-static size_t stream2_smem_bytes(int N, int Mp, int MT, int stages) {
-    size_t bytes = static_cast<size_t>(stages) * SK_STAGE_BYTES;
-    bytes += (2 * stages * 8 + 15) & ~15;
+static size_t stream3_smem_bytes(int N, int Mp, int MT) {
+    size_t bytes = static_cast<size_t>(S3_WARPS) * S3_RING * S3_SLOT_BYTES;
     bytes += static_cast<size_t>(N / 8) * Mp * 16;
     bytes += static_cast<size_t>(((N / 128) * Mp + 3) & ~3) * 4;
     bytes += 32 * 4;
-    bytes += 2ull * SK_CONSUMERS * 16 * 8 * MT * 4;
+    bytes += static_cast<size_t>(S3_WARPS) * 16 * 8 * MT * 4;
     return bytes;
 }
 
 template <typename T, int MT>
-static int stream2_launch(StreamArgs args, cudaStream_t st) {
+static int stream3_launch(StreamArgs args, cudaStream_t st) {
     const int Mp = args.rows_per_pass < args.M ? args.rows_per_pass : args.M;
-    const size_t fixed = stream2_smem_bytes(args.N, Mp, MT, 0);
-    // ring depth: as deep as fits next to a second resident CTA, within [4, 16] stages
-    const size_t per_cta_budget = fixed > 100 * 1024 ? 220 * 1024 : 110 * 1024;
-    int stages = static_cast<int>((per_cta_budget - fixed) / SK_STAGE_BYTES);
-    stages = stages > 16 ? 16 : stages;
-    if (stages < 2) return fail(TL_EINVAL, "quantized_matmul: activations do not fit in shared memory (N=%d, rows=%d)", args.N, Mp);
-    args.stages = stages;
-    const size_t smem = stream2_smem_bytes(args.N, Mp, MT, stages);
+    const size_t smem = stream3_smem_bytes(args.N, Mp, MT);
+    if (smem > 224 * 1024)
+        return fail(TL_EINVAL, "quantized_matmul: activations do not fit in shared memory (N=%d, rows=%d)", args.N, Mp);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(w4a16_stream2_kernel<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(w4a16_stream3_kernel<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
         configured = true;
     }
     const int tiles = ceil_div(args.K, 16);
-    const int ctas_per_sm = smem > 110 * 1024 ? 1 : 2;
-    const int cap = sm_count() * ctas_per_sm;
+    const int G = args.N / 128;
+    const int sms = sm_count();
+    // team width: split a tile's reduction over TW warps until the launch offers ~16 warps per SM
+    int tw = 1;
+    while (tw < S3_WARPS && tiles * tw < sms * 16 && tw * 2 <= G) tw *= 2;
+    args.team_warps = tw;
+    const int teams_per_cta = S3_WARPS / tw;
+    int ctas_per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
+    ctas_per_sm = ctas_per_sm > 3 ? 3 : (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+    const int want = ceil_div(tiles, teams_per_cta);
+    const int cap = sms * ctas_per_sm;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(tiles < cap ? tiles : cap, ceil_div(args.M, args.rows_per_pass));
-    cfg.blockDim = dim3(SK_THREADS);
+    cfg.gridDim = dim3(want < cap ? want : cap, ceil_div(args.M, args.rows_per_pass));
+    cfg.blockDim = dim3(S3_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -678,14 +725,14 @@ static int stream2_launch(StreamArgs args, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream2_kernel<T, MT>, args);
-    if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream2: launch failed: %s", cudaGetErrorString(e));
-    TL_LAUNCH_CHECK("w4a16_stream2");
+    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream3_kernel<T, MT>, args);
+    if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream3: launch failed: %s", cudaGetErrorString(e));
+    TL_LAUNCH_CHECK("w4a16_stream3");
     return TL_OK;
 }
 
 template <typename T>
-static int stream2_t(StreamArgs args, cudaStream_t st) {
+static int stream3_t(StreamArgs args, cudaStream_t st) {
     if (!aligned16(args.p0) || !aligned16(args.b) || (args.p1 && !aligned16(args.p1)) || (args.lda % 8) != 0)
         return fail(TL_EINVAL, "quantized_matmul: operands must be 16-byte aligned");
     const size_t budget = 150 * 1024;
@@ -695,9 +742,9 @@ static int stream2_t(StreamArgs args, cudaStream_t st) {
     else if (args.M > 8 && static_cast<size_t>(args.N) * 16 * 2 <= budget)
         rpp = 16;
     args.rows_per_pass = rpp;
-    if (rpp == 32) return stream2_launch<T, 4>(args, st);
-    if (rpp == 16) return stream2_launch<T, 2>(args, st);
-    return stream2_launch<T, 1>(args, st);
+    if (rpp == 32) return stream3_launch<T, 4>(args, st);
+    if (rpp == 16) return stream3_launch<T, 2>(args, st);
+    return stream3_launch<T, 1>(args, st);
 }
 
 int launch_w4a16_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *p1,
@@ -710,8 +757,8 @@ int launch_w4a16_fused(const void *scales, const void *biases, const void *b, vo
     args.M = M, args.N = N, args.K = K, args.lda = lda;
     args.prologue = prologue, args.epilogue = epilogue, args.eps = eps;
     switch (dtype) {
-        case TL_F16: return stream2_t<__half>(args, st);
-        case TL_BF16: return stream2_t<__nv_bfloat16>(args, st);
+        case TL_F16: return stream3_t<__half>(args, st);
+        case TL_BF16: return stream3_t<__nv_bfloat16>(args, st);
     }
     return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
 }

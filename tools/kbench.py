@@ -111,6 +111,10 @@ def main():
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "kbench.json"))
     ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
+    import os
+
+    if os.environ.get("TL_PDL", "0") == "1":
+        ext.set_pdl(True)
     peak = peak_gbs()
     report = {"hbm_peak_gbs": peak, "gpu": torch.cuda.get_device_name(0), "matvec": [], "attention": [], "small_ops_us": {}}
     shapes = [("q", 2560, 4096), ("kv", 2560, 1024), ("o", 4096, 2560), ("gate_up", 2560, 9728), ("down", 9728, 2560), ("lm_head", 2560, 151936)]
