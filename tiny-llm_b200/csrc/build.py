@@ -28,6 +28,7 @@ SOURCES = [
     "w4a16_matvec.cu",
     "w4a16_gemm.cu",
     "attention_decode.cu",
+    "decode_megakernel.cu",
 ]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

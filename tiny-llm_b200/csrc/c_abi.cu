@@ -260,6 +260,13 @@ int tl_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, co
                                              num_pages, page_size, max_pages, dtype, as_stream(stream));
 }
 
+int tl_decode_step_grid(void) { return mk_grid_size(); }
+
+int tl_decode_step(const tl_decode_args *args, void *stream) {
+    if (args == nullptr || args->layers == nullptr) return fail(TL_EINVAL, "decode_step: null arguments");
+    return launch_decode_megakernel(*args, as_stream(stream));
+}
+
 int tl_set_pdl(int enabled) {
     set_use_pdl(enabled != 0);
     return TL_OK;

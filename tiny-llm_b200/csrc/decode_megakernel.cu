@@ -1,0 +1,792 @@
+// Whole-step persistent decode kernel for the Week-3 Qwen3 model (bf16, W4A16,
+// paged KV), batch M <= 8, one query token per request.
+//
+// Why: at B200 speeds the projections of one decode step last 0.2-2 us each at
+// HBM rate, but a kernel boundary costs ~5 us (launch + two dependent memory
+// round trips before the first byte is used).  Measured (profiles/r01_*): 221
+// fused kernels per token => 2.5 ms/token although the HBM traffic is worth
+// 0.33 ms.  This kernel runs the ENTIRE step as one cooperative launch:
+//
+//   embed | per layer: [rmsnorm+qkv] [qk-norm+rope+append+attention] ([merge])
+//           [o_proj+residual] [rmsnorm+gate|up] [swiglu+down+residual]
+//         | [rmsnorm+head (+argmax partials)] [argmax + advance]
+//
+// with a grid-wide barrier between phases (every phase consumes a full
+// activation vector produced by all CTAs of the previous one).  The point of
+// the design is what happens ACROSS the barriers: every warp owns a private
+// cp.async ring (RING x 1 KiB weight groups + their scales) whose fill cursor
+// walks the concatenated work list of ALL streaming phases, independent of the
+// consume cursor.  While a warp waits at a barrier or re-stages activations,
+// its ring already holds the first groups of the next projection, so HBM keeps
+// streaming through the synchronisation bubbles.
+//
+// Work split of a projection [K rows x N]: CTA c owns rows [K*c/C, K*(c+1)/C)
+// (all CTAs stream the same number of bytes), in 16-row chunks x N/128 groups;
+// the (chunk, group) items are dealt to the CTA's warps as contiguous ranges.
+// A warp accumulates a chunk in registers (mma.sync on exact (128+q) codes, as
+// in w4a16_matvec.cu) and parks its partial sum in shared-memory entry
+// (chunk + warp); entries of a chunk are summed in warp order: deterministic.
+//
+// Arithmetic and rounding points are those of the operator sequence
+// (rms_norm -> quantized_matmul -> ... , see engine.py::_forward_unfused).
+#include <algorithm>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tl {
+
+constexpr int MK_WARPS = 16;
+constexpr int MK_THREADS = MK_WARPS * 32;
+constexpr int MK_CODE = 1024;              // 16 rows x 64 B packed codes
+constexpr int MK_SLOT = MK_CODE + 128;     // + 16 scale words + 16 bias words
+constexpr int MK_MAXB = 8;
+constexpr float MK_LOG2E = 1.44269504089f;
+constexpr float MK_NEG = -1e30f;
+
+typedef __nv_bfloat16 bf16;
+
+// The argument block is the C-ABI struct of include/tiny_llm_b200.h (plain pointers and sizes).
+typedef tl_decode_layer MkLayer;
+typedef tl_decode_args MkArgs;
+
+// ------------------------------------------------------------- primitives --
+__device__ __forceinline__ uint32_t mk_smem(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mk_cp16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mk_cp4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mk_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void mk_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void mk_mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 mk_ldcg16(const void *p) { return __ldcg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ float mk_bf(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float mk_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// Grid-wide barrier: monotonically increasing arrival counter, self-cleaned at kernel exit.
+__device__ __forceinline__ void mk_grid_sync(unsigned *counter, unsigned &epoch) {
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = epoch * gridDim.x;
+        unsigned spins = 0;
+        while (true) {
+            unsigned seen;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            if (seen >= target) break;
+            if (++spins > (1u << 22)) __trap();  // ~seconds: a lost CTA must not hang the GPU
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------- streaming phases --
+struct SPhase {
+    const uint32_t *w;
+    const bf16 *s, *b;
+    int N, K;
+};
+
+__device__ __forceinline__ int mk_num_sphases(const MkArgs &a) { return 4 * a.n_layers + 1; }
+
+__device__ __forceinline__ SPhase mk_sphase(const MkArgs &a, int sp) {
+    SPhase p;
+    if (sp >= 4 * a.n_layers) {
+        p.w = static_cast<const uint32_t *>(a.w_head), p.s = static_cast<const bf16 *>(a.s_head), p.b = static_cast<const bf16 *>(a.b_head), p.N = a.H, p.K = a.V;
+        return p;
+    }
+    const MkLayer &l = a.layers[sp >> 2];
+    switch (sp & 3) {
+        case 0: p.w = static_cast<const uint32_t *>(l.w_qkv), p.s = static_cast<const bf16 *>(l.s_qkv), p.b = static_cast<const bf16 *>(l.b_qkv), p.N = a.H, p.K = (a.Hq + 2 * a.Hkv) * a.D; break;
+        case 1: p.w = static_cast<const uint32_t *>(l.w_o), p.s = static_cast<const bf16 *>(l.s_o), p.b = static_cast<const bf16 *>(l.b_o), p.N = a.Hq * a.D, p.K = a.H; break;
+        case 2: p.w = static_cast<const uint32_t *>(l.w_gu), p.s = static_cast<const bf16 *>(l.s_gu), p.b = static_cast<const bf16 *>(l.b_gu), p.N = a.H, p.K = 2 * a.I; break;
+        default: p.w = static_cast<const uint32_t *>(l.w_down), p.s = static_cast<const bf16 *>(l.s_down), p.b = static_cast<const bf16 *>(l.b_down), p.N = a.I, p.K = a.H; break;
+    }
+    return p;
+}
+
+// Rows of this CTA and the item range of this warp for one streaming phase.
+struct SRange {
+    int r0, r1, G, chunks, begin, end;  // items [begin, end) in chunk-major order
+};
+__device__ __forceinline__ SRange mk_range(const SPhase &p, int warp) {
+    SRange r;
+    r.r0 = static_cast<int>(static_cast<long long>(p.K) * blockIdx.x / gridDim.x);
+    r.r1 = static_cast<int>(static_cast<long long>(p.K) * (blockIdx.x + 1) / gridDim.x);
+    r.G = p.N / 128;
+    r.chunks = (r.r1 - r.r0 + 15) / 16;
+    const int items = r.chunks * r.G;
+    r.begin = static_cast<int>(static_cast<long long>(items) * warp / MK_WARPS);
+    r.end = static_cast<int>(static_cast<long long>(items) * (warp + 1) / MK_WARPS);
+    return r;
+}
+
+// Fill cursor of a warp's ring: walks (streaming phase, item) pairs of the whole step.
+struct Cursor {
+    int sp, i;  // phase and absolute item index inside the phase's CTA item space
+    SPhase p;
+    SRange r;
+};
+__device__ __forceinline__ void mk_cursor_load(const MkArgs &a, Cursor &c, int warp) {
+    while (c.sp < mk_num_sphases(a)) {
+        c.p = mk_sphase(a, c.sp);
+        c.r = mk_range(c.p, warp);
+        if (c.i < c.r.begin) c.i = c.r.begin;
+        if (c.i < c.r.end) return;
+        c.sp += 1;
+        c.i = 0;
+    }
+}
+
+template <int RING>
+struct Ring {
+    unsigned char *base;
+    uint32_t base_s;
+    unsigned issued, consumed;
+};
+
+template <int RING>
+__device__ __forceinline__ void mk_issue(const MkArgs &a, Ring<RING> &ring, Cursor &c, int warp, int lane) {
+    if (c.sp < mk_num_sphases(a)) {
+        const int chunk = c.i / c.r.G;
+        const int u = c.i - chunk * c.r.G;
+        const int row_base = c.r.r0 + chunk * 16;
+        const uint32_t slot = ring.base_s + (ring.issued % RING) * MK_SLOT;
+        const int crow = row_base + (lane >> 1);
+        if (crow < c.r.r1) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(c.p.w) + static_cast<size_t>(crow) * (c.p.N / 2) + u * 64 + (lane & 1) * 32;
+            const uint32_t dst = slot + (lane >> 1) * 64 + (lane & 1) * 32;
+            mk_cp16(dst, src);
+            mk_cp16(dst + 16, src + 16);
+        }
+        const int prow = row_base + (lane & 15);
+        if (prow < c.r.r1) {
+            const long long e = static_cast<long long>(prow) * c.r.G + u;
+            const unsigned char *table = reinterpret_cast<const unsigned char *>(lane < 16 ? c.p.s : c.p.b);
+            const uint32_t pdst = slot + MK_CODE + lane * 4;
+            if ((e | 1) < static_cast<long long>(c.p.K) * c.r.G) {
+                mk_cp4(pdst, table + ((e >> 1) << 2));
+            } else {
+                const uint16_t v = *reinterpret_cast<const uint16_t *>(table + e * 2);
+                *reinterpret_cast<uint32_t *>(ring.base + (ring.issued % RING) * MK_SLOT + MK_CODE + lane * 4) =
+                    (e & 1) ? (static_cast<uint32_t>(v) << 16) : static_cast<uint32_t>(v);
+            }
+        }
+        c.i += 1;
+        if (c.i >= c.r.end) {
+            c.sp += 1;
+            c.i = 0;
+            mk_cursor_load(a, c, warp);
+        }
+    }
+    mk_commit();
+    ring.issued += 1;
+}
+
+// Stage the activation rows of a streaming phase into shared memory in MMA-fragment order.
+// prologue 0: plain; 1: rms_norm(x, w, eps); 2: swiglu(gate, up) with up = in + up_off.
+__device__ void mk_stage(const bf16 *in, int ld, int up_off, int N, int B, int prologue, const bf16 *norm_w, float eps, uint4 *act,
+                         float *asum, float *rowstat) {
+    const int words = N / 8;
+    const int total = B * words;
+    const int lane = threadIdx.x & 31;
+    const int base0 = threadIdx.x & ~31;
+    if (prologue == 1) {
+        if (threadIdx.x < MK_MAXB) rowstat[threadIdx.x] = 0.f;
+        __syncthreads();
+        for (int base = base0; base < total; base += MK_THREADS) {
+            const int idx = base + lane;
+            float part = 0.f;
+            if (idx < total) {
+                const int m = idx / words, c = idx - m * words;
+                const uint4 raw = mk_ldcg16(in + static_cast<size_t>(m) * ld + c * 8);
+                const float2 f0 = unpack2<bf16>(raw.x), f1 = unpack2<bf16>(raw.y), f2 = unpack2<bf16>(raw.z), f3 = unpack2<bf16>(raw.w);
+                part = f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 8);
+            part += __shfl_xor_sync(0xffffffffu, part, 4);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
+        }
+        __syncthreads();
+    }
+    for (int base = base0; base < total; base += MK_THREADS) {
+        const int idx = base + lane;
+        float part = 0.f;
+        int m = 0, c = 0;
+        if (idx < total) {
+            m = idx / words;
+            c = idx - m * words;
+            const bf16 *src = in + static_cast<size_t>(m) * ld + c * 8;
+            uint4 raw = mk_ldcg16(src);
+            if (prologue != 0) {
+                const uint4 aux = prologue == 2 ? mk_ldcg16(src + up_off) : *reinterpret_cast<const uint4 *>(norm_w + c * 8);
+                const uint32_t xin[4] = {raw.x, raw.y, raw.z, raw.w};
+                const uint32_t yin[4] = {aux.x, aux.y, aux.z, aux.w};
+                uint32_t o[4];
+                const float inv = prologue == 1 ? rsqrtf(rowstat[m] / static_cast<float>(N) + eps) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 xv = unpack2<bf16>(xin[i]), yv = unpack2<bf16>(yin[i]);
+                    float r0, r1;
+                    if (prologue == 1) {
+                        r0 = xv.x * inv * yv.x;
+                        r1 = xv.y * inv * yv.y;
+                    } else {
+                        r0 = (xv.x / (1.0f + expf(-xv.x))) * yv.x;
+                        r1 = (xv.y / (1.0f + expf(-xv.y))) * yv.y;
+                    }
+                    o[i] = pack2<bf16>(r0, r1);
+                }
+                raw = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            uint4 p;
+            p.x = __byte_perm(raw.x, raw.z, 0x5410);
+            p.y = __byte_perm(raw.x, raw.z, 0x7632);
+            p.z = __byte_perm(raw.y, raw.w, 0x5410);
+            p.w = __byte_perm(raw.y, raw.w, 0x7632);
+            const int pos = (c & ~15) | ((c & 3) << 2) | ((c >> 2) & 3);
+            act[static_cast<size_t>(pos) * B + m] = p;
+            const float2 f0 = unpack2<bf16>(raw.x), f1 = unpack2<bf16>(raw.y), f2 = unpack2<bf16>(raw.z), f3 = unpack2<bf16>(raw.w);
+            part = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 8);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        if (idx < total && (c & 15) == 0) asum[(c >> 4) * B + m] = part;
+    }
+    __syncthreads();
+}
+
+// One projection: out[m, k] (= res[m, k] +) sum_n act[m, n] * dequant(w[k, n]) for this CTA's rows.
+// When amax is non-null the CTA also records the arg-max of its logits rows per request.
+template <int RING>
+__device__ void mk_stream(const MkArgs &a, int sp, Ring<RING> &ring, Cursor &cur, const bf16 *in, int ld, int up_off, int prologue,
+                          const bf16 *norm_w, bf16 *out, const bf16 *res, unsigned char *dyn) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const SPhase p = mk_sphase(a, sp);
+    const SRange r = mk_range(p, warp);
+    const int B = a.B;
+    const int words = p.N / 8;
+    uint4 *act = reinterpret_cast<uint4 *>(dyn);
+    float *asum = reinterpret_cast<float *>(dyn + static_cast<size_t>(words) * B * 16);
+    float *rowstat = asum + ((r.G * B + 3) & ~3);
+    float *entries = rowstat + 16;  // [(chunks + MK_WARPS) entries][16 rows][8 cols]
+    mk_stage(in, ld, up_off, p.N, B, prologue, norm_w, a.eps, act, asum, rowstat);
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int acc_chunk = -1;
+    auto flush = [&]() {
+        if (acc_chunk >= 0) {
+            float *e = entries + static_cast<size_t>(acc_chunk + warp) * 128;
+            e[g * 8 + 2 * t] = acc[0];
+            e[g * 8 + 2 * t + 1] = acc[1];
+            e[(g + 8) * 8 + 2 * t] = acc[2];
+            e[(g + 8) * 8 + 2 * t + 1] = acc[3];
+        }
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    };
+    for (int i = r.begin; i < r.end; ++i) {
+        const int chunk = i / r.G;
+        const int u = i - chunk * r.G;
+        if (chunk != acc_chunk) {
+            flush();
+            acc_chunk = chunk;
+        }
+        mk_wait<RING - 2>();
+        __syncwarp();
+        const unsigned char *slot0 = ring.base + (ring.consumed % RING) * MK_SLOT;
+        const int row0 = r.r0 + chunk * 16 + g, row1 = row0 + 8;
+        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
+        float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(slot0 + MK_CODE);
+        if (row0 < r.r1) {
+            w0 = *reinterpret_cast<const uint4 *>(slot0 + g * 64 + t * 16);
+            const int par = static_cast<int>((static_cast<long long>(row0) * r.G + u) & 1);
+            const float2 sp2 = unpack2<bf16>(sw[g]), cp2 = unpack2<bf16>(sw[16 + g]);
+            s0 = par ? sp2.y : sp2.x;
+            c0 = (par ? cp2.y : cp2.x) - 128.f * s0;
+        }
+        if (row1 < r.r1) {
+            w1 = *reinterpret_cast<const uint4 *>(slot0 + (g + 8) * 64 + t * 16);
+            const int par = static_cast<int>((static_cast<long long>(row1) * r.G + u) & 1);
+            const float2 sp2 = unpack2<bf16>(sw[g + 8]), cp2 = unpack2<bf16>(sw[16 + g + 8]);
+            s1 = par ? sp2.y : sp2.x;
+            c1 = (par ? cp2.y : cp2.x) - 128.f * s1;
+        }
+        __syncwarp();
+        ring.consumed += 1;
+        mk_issue<RING>(a, ring, cur, warp, lane);
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t x0[4] = {w0.x, w0.y, w0.z, w0.w};
+        const uint32_t x1[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            constexpr uint32_t MASK = 0x000F000Fu, MAGIC = 0x43004300u;
+            const uint32_t a0 = (x0[j] & MASK) | MAGIC, a1 = ((x0[j] >> 4) & MASK) | MAGIC;
+            const uint32_t a2 = ((x0[j] >> 8) & MASK) | MAGIC, a3 = ((x0[j] >> 12) & MASK) | MAGIC;
+            const uint32_t b0 = (x1[j] & MASK) | MAGIC, b1 = ((x1[j] >> 4) & MASK) | MAGIC;
+            const uint32_t b2 = ((x1[j] >> 8) & MASK) | MAGIC, b3 = ((x1[j] >> 12) & MASK) | MAGIC;
+            uint4 bf = make_uint4(0u, 0u, 0u, 0u);
+            if (g < B) bf = act[static_cast<size_t>(16 * u + 4 * j + t) * B + g];
+            mk_mma(d, a0, b0, a1, b1, bf.x, bf.y);
+            mk_mma(d, a2, b2, a3, b3, bf.z, bf.w);
+        }
+        const int m0 = 2 * t;
+        const float as0 = m0 < B ? asum[u * B + m0] : 0.f;
+        const float as1 = m0 + 1 < B ? asum[u * B + m0 + 1] : 0.f;
+        acc[0] += s0 * d[0] + c0 * as0;
+        acc[1] += s0 * d[1] + c0 * as1;
+        acc[2] += s1 * d[2] + c1 * as0;
+        acc[3] += s1 * d[3] + c1 * as1;
+    }
+    flush();
+    __syncthreads();
+
+    // ---- deterministic reduction of the entries of each chunk (in warp order) + epilogue
+    const int items = r.chunks * r.G;
+    for (int o = threadIdx.x; o < r.chunks * 16 * B; o += MK_THREADS) {
+        const int m = o / (r.chunks * 16);  // request-major so that consecutive threads store consecutive features
+        const int rr = o - m * (r.chunks * 16);
+        const int chunk = rr >> 4, row = rr & 15;
+        const int k = r.r0 + rr;
+        if (k < r.r1) {
+            float v = 0.f;
+            for (int w = 0; w < MK_WARPS; ++w) {
+                const int wb = static_cast<int>(static_cast<long long>(items) * w / MK_WARPS);
+                const int we = static_cast<int>(static_cast<long long>(items) * (w + 1) / MK_WARPS);
+                if (wb < we && wb < (chunk + 1) * r.G && we > chunk * r.G) v += entries[static_cast<size_t>(chunk + w) * 128 + row * 8 + m];
+            }
+            bf16 vb = __float2bfloat16_rn(v);
+            if (res != nullptr) vb = __float2bfloat16_rn(mk_bf(res[static_cast<size_t>(m) * p.K + k]) + mk_bf(vb));
+            out[static_cast<size_t>(m) * p.K + k] = vb;
+        }
+    }
+    __syncthreads();
+}
+
+struct BestPair {
+    float v;
+    int i;
+};
+__device__ __forceinline__ BestPair mk_better(BestPair a, BestPair b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+
+// Arg-max of the logits rows [r0, r1) this CTA has just written, one result per request.
+__device__ void mk_cta_argmax(const MkArgs &a, int r0, int r1, float *scratch_v, int *scratch_i) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int m = 0; m < a.B; ++m) {
+        BestPair mine{-CUDART_INF_F, 0x7fffffff};
+        const bf16 *row = static_cast<const bf16 *>(a.logits) + static_cast<size_t>(m) * a.V;
+        for (int k = r0 + threadIdx.x; k < r1; k += MK_THREADS) mine = mk_better(mine, BestPair{mk_bf(row[k]), k});
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            BestPair other{__shfl_xor_sync(0xffffffffu, mine.v, o), __shfl_xor_sync(0xffffffffu, mine.i, o)};
+            mine = mk_better(mine, other);
+        }
+        if (lane == 0) scratch_v[warp] = mine.v, scratch_i[warp] = mine.i;
+        __syncthreads();
+        if (warp == 0) {
+            BestPair r{lane < MK_WARPS ? scratch_v[lane] : -CUDART_INF_F, lane < MK_WARPS ? scratch_i[lane] : 0x7fffffff};
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                BestPair other{__shfl_xor_sync(0xffffffffu, r.v, o), __shfl_xor_sync(0xffffffffu, r.i, o)};
+                r = mk_better(r, other);
+            }
+            if (lane == 0) a.amax_val[blockIdx.x * a.B + m] = r.v, a.amax_idx[blockIdx.x * a.B + m] = r.i;
+        }
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------- attention --
+// One CTA per (request, kv head, split); 16 lanes per token, 8 dims per lane, L == 1.
+__device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *dyn) {
+    const int D = a.D, G = a.Hq / a.Hkv;
+    const int items = a.B * a.Hkv * a.nsplit;
+    if (static_cast<int>(blockIdx.x) >= items) return;
+    const int split = blockIdx.x % a.nsplit;
+    const int kvh = (blockIdx.x / a.nsplit) % a.Hkv;
+    const int b = blockIdx.x / (a.nsplit * a.Hkv);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ctx = min(a.context_lens[b], a.max_pages * a.page_size);
+    const int qkv_w = (a.Hq + 2 * a.Hkv) * D;
+
+    float *q_s = reinterpret_cast<float *>(dyn);                  // [G][128] pre-scaled
+    bf16 *k_cur = reinterpret_cast<bf16 *>(q_s + 4 * 128);         // [128]
+    bf16 *v_cur = k_cur + 128;                                     // [128]
+    float *m_s = reinterpret_cast<float *>(v_cur + 128);           // [MK_WARPS][4]
+    float *l_s = m_s + MK_WARPS * 4;
+    float *o_s = l_s + MK_WARPS * 4;                               // [MK_WARPS][4][128]
+
+    // ---- per-head q/k RMSNorm + RoPE (rounded like rms_norm -> rope), V copy; heads: G q, 1 k, 1 v
+    if (warp < G + 2) {
+        const bool is_q = warp < G, is_k = warp == G;
+        const int head_off = is_q ? (kvh * G + warp) * D : (is_k ? (a.Hq + kvh) * D : (a.Hq + a.Hkv + kvh) * D);
+        const bf16 *src = static_cast<const bf16 *>(a.qkv) + static_cast<size_t>(b) * qkv_w + head_off;
+        // lane owns pairs (i, i+64) for i = lane, lane+32   (D == 128)
+        float re[2], im[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            re[h] = mk_bf(__ldcg(src + lane + 32 * h));
+            im[h] = mk_bf(__ldcg(src + lane + 32 * h + 64));
+        }
+        if (is_q || is_k) {
+            float ss = re[0] * re[0] + im[0] * im[0] + re[1] * re[1] + im[1] * im[1];
+            ss = warp_sum(ss);
+            const float inv = rsqrtf(ss / static_cast<float>(D) + a.eps);
+            const bf16 *w = static_cast<const bf16 *>(is_q ? l.q_norm : l.k_norm);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                const float nre = mk_round(re[h] * inv * mk_bf(w[i]));
+                const float nim = mk_round(im[h] * inv * mk_bf(w[i + 64]));
+                const double inv_freq = exp2(-static_cast<double>(i) / 64.0 * log2(static_cast<double>(a.rope_base)));
+                const float angle = static_cast<float>(static_cast<double>(a.offsets[b]) * inv_freq);
+                float s, c;
+                sincosf(angle, &s, &c);
+                const bf16 ore = __float2bfloat16_rn(nre * c - nim * s), oim = __float2bfloat16_rn(nim * c + nre * s);
+                if (is_q) {
+                    q_s[warp * 128 + i] = mk_bf(ore) * a.attn_scale * MK_LOG2E;
+                    q_s[warp * 128 + i + 64] = mk_bf(oim) * a.attn_scale * MK_LOG2E;
+                } else {
+                    k_cur[i] = ore, k_cur[i + 64] = oim;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) v_cur[lane + 32 * h] = __float2bfloat16_rn(re[h]), v_cur[lane + 32 * h + 64] = __float2bfloat16_rn(im[h]);
+        }
+    }
+    __syncthreads();
+    const int begin = split * a.tokens_per_split;
+    const int end = min(ctx, begin + a.tokens_per_split);
+    const int cur_tok = ctx - 1;
+    // the split that owns the newest token appends it to the cache (paged_cache_update semantics)
+    if (ctx > 0 && cur_tok >= begin && cur_tok < end && threadIdx.x < 2 * (D / 8)) {
+        const int lp = cur_tok / a.page_size;
+        const int pid = l.table[static_cast<size_t>(b) * a.max_pages + lp];
+        if (pid >= 0 && pid < a.num_pages) {
+            const bool kk = threadIdx.x < D / 8;
+            const int ch = kk ? threadIdx.x : threadIdx.x - D / 8;
+            bf16 *dst = static_cast<bf16 *>(kk ? l.k_pages : l.v_pages) + ((static_cast<size_t>(pid) * a.Hkv + kvh) * a.page_size + (cur_tok - lp * a.page_size)) * D + ch * 8;
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>((kk ? k_cur : v_cur) + ch * 8);
+        }
+    }
+
+    // ---- online softmax over this split; lane group = 16 lanes, 8 dims per lane
+    const int grp = lane >> 4, c8 = lane & 15;
+    float acc[4][8], mm[4], ll[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        mm[r] = MK_NEG, ll[r] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
+    }
+    const int stride = MK_WARPS * 2;
+    for (int base = begin + warp * 2 + grp; base < end; base += 2 * stride) {
+        uint4 kr[2], vr[2];
+        bool ok[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // two tokens per iteration, all loads issued before any use
+            const int tok = base + h * stride;
+            ok[h] = tok < end;
+            kr[h] = vr[h] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[h]) {
+                if (tok == cur_tok) {
+                    kr[h] = *reinterpret_cast<const uint4 *>(k_cur + c8 * 8);
+                    vr[h] = *reinterpret_cast<const uint4 *>(v_cur + c8 * 8);
+                } else {
+                    const int lp = tok / a.page_size;
+                    const int pid = l.table[static_cast<size_t>(b) * a.max_pages + lp];
+                    ok[h] = pid >= 0 && pid < a.num_pages;
+                    if (ok[h]) {
+                        const size_t off = ((static_cast<size_t>(pid) * a.Hkv + kvh) * a.page_size + (tok - lp * a.page_size)) * D + c8 * 8;
+                        kr[h] = ldg_stream(static_cast<const bf16 *>(l.k_pages) + off);
+                        vr[h] = ldg_stream(static_cast<const bf16 *>(l.v_pages) + off);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t kw[4] = {kr[h].x, kr[h].y, kr[h].z, kr[h].w};
+            const uint32_t vw[4] = {vr[h].x, vr[h].y, vr[h].z, vr[h].w};
+            float kf[8], vf[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack2<bf16>(kw[i]), e = unpack2<bf16>(vw[i]);
+                kf[2 * i] = f.x, kf[2 * i + 1] = f.y, vf[2 * i] = e.x, vf[2 * i + 1] = e.y;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (r < G) {
+                    const float4 qa = *reinterpret_cast<const float4 *>(q_s + r * 128 + c8 * 8);
+                    const float4 qb = *reinterpret_cast<const float4 *>(q_s + r * 128 + c8 * 8 + 4);
+                    float s = qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3] + qb.x * kf[4] + qb.y * kf[5] + qb.z * kf[6] + qb.w * kf[7];
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    s += __shfl_xor_sync(0xffffffffu, s, 4);
+                    s += __shfl_xor_sync(0xffffffffu, s, 8);
+                    if (!ok[h]) s = -CUDART_INF_F;
+                    const float nm = fmaxf(mm[r], s);
+                    const float corr = exp2f(mm[r] - nm), pr = exp2f(s - nm);
+                    ll[r] = ll[r] * corr + pr;
+                    mm[r] = nm;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[r][i] = acc[r][i] * corr + pr * vf[i];
+                }
+            }
+        }
+    }
+    // ---- merge the 2 lane groups of every warp (shuffle), then the warps through shared memory
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r < G) {
+            const float mo = __shfl_xor_sync(0xffffffffu, mm[r], 16), lo = __shfl_xor_sync(0xffffffffu, ll[r], 16);
+            const float nm = fmaxf(mm[r], mo);
+            const float fs = exp2f(mm[r] - nm), fo = exp2f(mo - nm);
+            ll[r] = ll[r] * fs + lo * fo;
+            mm[r] = nm;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[r][i] = acc[r][i] * fs + __shfl_xor_sync(0xffffffffu, acc[r][i], 16) * fo;
+            if (grp == 0) {
+                float *o = o_s + (static_cast<size_t>(warp) * 4 + r) * 128 + c8 * 8;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = acc[r][i];
+                if (c8 == 0) m_s[warp * 4 + r] = mm[r], l_s[warp * 4 + r] = ll[r];
+            }
+        }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < G * 128; o += MK_THREADS) {
+        const int r = o >> 7, d = o & 127;
+        float gm = MK_NEG;
+        for (int s = 0; s < MK_WARPS; ++s) gm = fmaxf(gm, m_s[s * 4 + r]);
+        float gl = 0.f, acc_o = 0.f;
+        for (int s = 0; s < MK_WARPS; ++s) {
+            const float f = exp2f(m_s[s * 4 + r] - gm);
+            gl += l_s[s * 4 + r] * f;
+            acc_o += o_s[(static_cast<size_t>(s) * 4 + r) * 128 + d] * f;
+        }
+        const int head = kvh * G + r;
+        if (a.nsplit == 1) {
+            static_cast<bf16 *>(a.y)[(static_cast<size_t>(b) * a.Hq + head) * D + d] = __float2bfloat16_rn(gl == 0.f ? 0.f : acc_o / gl);
+        } else {
+            const size_t row = (static_cast<size_t>(b) * a.Hq + head) * a.nsplit + split;
+            a.attn_ws[row * (D + 2) + d] = acc_o;
+            if (d == 0) a.attn_ws[row * (D + 2) + D] = gm, a.attn_ws[row * (D + 2) + D + 1] = gl;
+        }
+    }
+}
+
+__device__ void mk_attention_merge(const MkArgs &a) {
+    const int D = a.D;
+    const int heads = a.B * a.Hq;
+    const int warp_global = blockIdx.x * MK_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    for (int h = warp_global; h < heads; h += gridDim.x * MK_WARPS) {
+        const float *base = a.attn_ws + static_cast<size_t>(h) * a.nsplit * (D + 2);
+        float gm = MK_NEG;
+        for (int s = 0; s < a.nsplit; ++s) gm = fmaxf(gm, __ldcg(base + s * (D + 2) + D));
+        float gl = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < a.nsplit; ++s) {
+            const float f = exp2f(__ldcg(base + s * (D + 2) + D) - gm);
+            gl += __ldcg(base + s * (D + 2) + D + 1) * f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] += __ldcg(base + s * (D + 2) + lane + 32 * i) * f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) static_cast<bf16 *>(a.y)[static_cast<size_t>(h) * D + lane + 32 * i] = __float2bfloat16_rn(gl == 0.f ? 0.f : o[i] / gl);
+    }
+}
+
+// ------------------------------------------------------------------ kernel --
+template <int RING>
+__global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs a) {
+    extern __shared__ __align__(128) unsigned char mk_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *dyn = mk_smem_raw + static_cast<size_t>(MK_WARPS) * RING * MK_SLOT;
+    __shared__ float amax_v[MK_WARPS];
+    __shared__ int amax_i[MK_WARPS];
+    unsigned epoch = 0;
+
+    Ring<RING> ring;
+    ring.base = mk_smem_raw + static_cast<size_t>(warp) * RING * MK_SLOT;
+    ring.base_s = mk_smem(ring.base);
+    ring.issued = ring.consumed = 0;
+    Cursor cur;
+    cur.sp = 0, cur.i = 0;
+    mk_cursor_load(a, cur, warp);
+#pragma unroll
+    for (int i = 0; i < RING - 1; ++i) mk_issue<RING>(a, ring, cur, warp, lane);  // weights first: they depend on nothing
+
+    // ---- phase 0: embedding rows -> xa (quantized_matmul.metal:58-89); feature words dealt across the grid
+    {
+        const int words = a.H / 8;
+        for (int idx = blockIdx.x * MK_THREADS + threadIdx.x; idx < a.B * words; idx += gridDim.x * MK_THREADS) {
+            const int m = idx / words, wc = idx - m * words;
+            const int row = a.tokens[m];
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (row >= 0 && row < a.V) {
+                const uint32_t packed = static_cast<const uint32_t *>(a.w_emb)[static_cast<size_t>(row) * words + wc];
+                const size_t gidx = static_cast<size_t>(row) * (a.H / 128) + wc / 16;
+                const float s = mk_bf(static_cast<const bf16 *>(a.s_emb)[gidx]), bb = mk_bf(static_cast<const bf16 *>(a.b_emb)[gidx]);
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = static_cast<float>((packed >> (4 * j)) & 0xFu) * s + bb;
+                o.x = pack2<bf16>(v[0], v[1]), o.y = pack2<bf16>(v[2], v[3]), o.z = pack2<bf16>(v[4], v[5]), o.w = pack2<bf16>(v[6], v[7]);
+            }
+            *reinterpret_cast<uint4 *>(static_cast<bf16 *>(a.xa) + static_cast<size_t>(m) * a.H + wc * 8) = o;
+        }
+    }
+    mk_grid_sync(a.sync_counter, epoch);
+
+    bf16 *x = static_cast<bf16 *>(a.xa), *x_alt = static_cast<bf16 *>(a.xb);
+    bf16 *qkv = static_cast<bf16 *>(a.qkv), *yb = static_cast<bf16 *>(a.y), *gu = static_cast<bf16 *>(a.gu);
+    for (int layer = 0; layer < a.n_layers; ++layer) {
+        const MkLayer &l = a.layers[layer];
+        mk_stream<RING>(a, 4 * layer + 0, ring, cur, x, a.H, 0, 1, static_cast<const bf16 *>(l.ln1), qkv, nullptr, dyn);
+        mk_grid_sync(a.sync_counter, epoch);
+        mk_attention(a, l, dyn);
+        mk_grid_sync(a.sync_counter, epoch);
+        if (a.nsplit > 1) {
+            mk_attention_merge(a);
+            mk_grid_sync(a.sync_counter, epoch);
+        }
+        mk_stream<RING>(a, 4 * layer + 1, ring, cur, yb, a.Hq * a.D, 0, 0, nullptr, x_alt, x, dyn);
+        mk_grid_sync(a.sync_counter, epoch);
+        mk_stream<RING>(a, 4 * layer + 2, ring, cur, x_alt, a.H, 0, 1, static_cast<const bf16 *>(l.ln2), gu, nullptr, dyn);
+        mk_grid_sync(a.sync_counter, epoch);
+        mk_stream<RING>(a, 4 * layer + 3, ring, cur, gu, 2 * a.I, a.I, 2, nullptr, x, x_alt, dyn);
+        mk_grid_sync(a.sync_counter, epoch);
+    }
+    // ---- final norm + (tied) head, then greedy arg-max
+    {
+        const int sp = 4 * a.n_layers;
+        mk_stream<RING>(a, sp, ring, cur, x, a.H, 0, 1, static_cast<const bf16 *>(a.final_norm), static_cast<bf16 *>(a.logits), nullptr, dyn);
+        const SPhase p = mk_sphase(a, sp);
+        const SRange r = mk_range(p, warp);
+        mk_cta_argmax(a, r.r0, r.r1, amax_v, amax_i);
+    }
+    mk_grid_sync(a.sync_counter, epoch);
+    if (blockIdx.x == 0 && warp == 0) {
+        const int step = *a.step_counter;
+        for (int m = 0; m < a.B; ++m) {
+            BestPair r{-CUDART_INF_F, 0x7fffffff};
+            for (int c = lane; c < static_cast<int>(gridDim.x); c += 32) r = mk_better(r, BestPair{__ldcg(a.amax_val + c * a.B + m), __ldcg(a.amax_idx + c * a.B + m)});
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                BestPair other{__shfl_xor_sync(0xffffffffu, r.v, o), __shfl_xor_sync(0xffffffffu, r.i, o)};
+                r = mk_better(r, other);
+            }
+            if (lane == 0) {
+                const int tok = r.i == 0x7fffffff ? 0 : r.i;
+                a.next_tokens[m] = tok;
+                if (a.advance) {
+                    const bool active = a.context_lens[m] > 0;
+                    if (active) a.tokens[m] = tok, a.offsets[m] += 1, a.context_lens[m] += 1;
+                    if (step < a.log_capacity) a.out_log[static_cast<size_t>(step) * a.B + m] = active ? tok : -1;
+                }
+            }
+        }
+        if (lane == 0 && a.advance) *a.step_counter = step + 1;
+    }
+    mk_wait<0>();
+    // ---- leave the barrier counters clean for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned ticket = atomicAdd(a.exit_counter, 1u);
+        if (ticket == gridDim.x - 1) {
+            *a.sync_counter = 0u;
+            *a.exit_counter = 0u;
+            __threadfence();
+        }
+    }
+}
+
+// -------------------------------------------------------------- host side --
+size_t mk_dyn_bytes(const MkArgs &a, int grid) {
+    // act staging + group sums + row stats + partial-sum entries, maximised over the five projection shapes
+    auto need = [&](int N, int K) {
+        const size_t rows = static_cast<size_t>((static_cast<long long>(K) + grid - 1) / grid) + 1;
+        const size_t chunks = (rows + 15) / 16 + 1;
+        return static_cast<size_t>(N / 8) * a.B * 16 + (static_cast<size_t>((N / 128) * a.B + 3) & ~3u) * 4 + 64 + (chunks + MK_WARPS) * 512;
+    };
+    size_t best = need(a.H, (a.Hq + 2 * a.Hkv) * a.D);
+    best = std::max(best, need(a.Hq * a.D, a.H));
+    best = std::max(best, need(a.H, 2 * a.I));
+    best = std::max(best, need(a.I, a.H));
+    best = std::max(best, need(a.H, a.V));
+    // attention scratch: q (4 heads fp32) + k/v rows + per lane-group (m, l, o)
+    const size_t attn = 4 * 128 * 4 + 2 * 128 * 2 + static_cast<size_t>(MK_WARPS) * 4 * (2 + 128) * 4;
+    return std::max(best, attn);
+}
+
+template <int RING>
+static int mk_launch_t(const MkArgs &a, cudaStream_t st, int *grid_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int sms = sm_count();
+    const int grid = sms;  // one CTA per SM
+    const size_t smem = static_cast<size_t>(MK_WARPS) * RING * MK_SLOT + mk_dyn_bytes(a, grid);
+    if (smem > 227 * 1024) return -1;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(decode_megakernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return fail(TL_ECUDA, "decode_step: cannot raise shared memory limit");
+        configured = true;
+    }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel<RING>, MK_THREADS, smem);
+    if (per_sm < 1) return fail(TL_ECUDA, "decode_step: kernel does not fit on an SM (smem %zu)", smem);
+    MkArgs args = a;
+    args.ring = RING;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(MK_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, decode_megakernel<RING>, args);
+    if (e != cudaSuccess) return fail(TL_ECUDA, "decode_step: launch failed: %s", cudaGetErrorString(e));
+    if (grid_out) *grid_out = grid;
+    count_launch();
+    return check_launch("decode_megakernel");
+}
+
+int launch_decode_megakernel(const MkArgs &a, cudaStream_t st) {
+    if (a.B < 1 || a.B > MK_MAXB) return fail(TL_EINVAL, "decode_step: batch must be 1..8");
+    if (a.D != 128 || a.Hq % a.Hkv != 0 || a.Hq / a.Hkv > 4) return fail(TL_EINVAL, "decode_step: needs head_dim 128 and at most 4 query heads per KV head");
+    if (a.H % 128 != 0 || a.I % 128 != 0 || (a.Hq * a.D) % 128 != 0) return fail(TL_EINVAL, "decode_step: widths must be multiples of 128");
+    int rc = mk_launch_t<8>(a, st, nullptr);
+    if (rc == -1) rc = mk_launch_t<6>(a, st, nullptr);
+    if (rc == -1) rc = mk_launch_t<4>(a, st, nullptr);
+    if (rc == -1) rc = mk_launch_t<3>(a, st, nullptr);
+    if (rc == -1) return fail(TL_EINVAL, "decode_step: activations do not fit in shared memory for batch %d", a.B);
+    return rc;
+}
+
+int mk_grid_size() { return sm_count(); }
+
+}  // namespace tl

@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "../../include/tiny_llm_b200.h"
+
 namespace tl {
 
 // elementwise.cu
@@ -54,6 +56,10 @@ int w4a16_gemm_split(int M, int N, int K, int use_split_k);
 size_t w4a16_gemm_workspace(int M, int N, int K, int dtype, int use_split_k);
 int launch_w4a16_gemm(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N,
                       int K, int dtype, int use_split_k, void *ws, size_t ws_bytes, cudaStream_t st);
+
+// decode_megakernel.cu
+int launch_decode_megakernel(const tl_decode_args &a, cudaStream_t st);
+int mk_grid_size();
 
 // attention_decode.cu
 int launch_decode_attention(const void *q, const void *k, const void *v, const float *mask, void *out, int q_rows,

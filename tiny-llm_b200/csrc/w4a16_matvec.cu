@@ -735,11 +735,15 @@ template <typename T>
 static int stream3_t(StreamArgs args, cudaStream_t st) {
     if (!aligned16(args.p0) || !aligned16(args.b) || (args.p1 && !aligned16(args.p1)) || (args.lda % 8) != 0)
         return fail(TL_EINVAL, "quantized_matmul: operands must be 16-byte aligned");
-    const size_t budget = 150 * 1024;
-    int rpp = 8;
-    if (args.M > 16 && static_cast<size_t>(args.N) * 32 * 2 <= budget)
+    // rows of `a` handled per pass: as many as fit in shared memory next to the weight rings
+    const size_t budget = 224 * 1024 - stream3_smem_bytes(args.N, 0, 4) - 2048;
+    const size_t per_row = static_cast<size_t>(args.N) * 2 + static_cast<size_t>(args.N / 128) * 4;
+    const int fit = static_cast<int>(budget / per_row);
+    if (fit < 1) return fail(TL_EINVAL, "quantized_matmul: reduction length %d does not fit in shared memory", args.N);
+    int rpp = fit < 8 ? fit : 8;
+    if (args.M > 16 && fit >= 32)
         rpp = 32;
-    else if (args.M > 8 && static_cast<size_t>(args.N) * 16 * 2 <= budget)
+    else if (args.M > 8 && fit >= 16)
         rpp = 16;
     args.rows_per_pass = rpp;
     if (rpp == 32) return stream3_launch<T, 4>(args, st);
