@@ -186,6 +186,9 @@ typedef struct tl_decode_args {
     unsigned *sync_counter, *exit_counter;          /* zero-initialised, self-cleaning */
     int nsplit, tokens_per_split;                   /* KV split of the attention phase */
     int ring;                                       /* filled in by the launcher */
+    const double *rope_inv_freq;                    /* [D/2]: base^(-i/(D/2)), formed in double on the host */
+    long long *prof;                                /* optional [2 * prof_capacity]: (tag, SM clock) stamps of CTA 0 */
+    int prof_capacity;
 } tl_decode_args;
 
 /* Number of CTAs the step kernel launches (sizes amax_val / amax_idx). */

@@ -69,17 +69,39 @@ __device__ __forceinline__ void mk_mma(float (&d)[4], uint32_t a0, uint32_t a1, 
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// D = A*B with a zero accumulator input: the eight MMAs of one 128-column group are issued as
+// INDEPENDENT instructions (legacy mma.sync has a long latency on sm_100; a dependent chain of
+// eight costs ~4x more than eight back-to-back issues) and summed afterwards.
+__device__ __forceinline__ void mk_mma0(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
 __device__ __forceinline__ uint4 mk_ldcg16(const void *p) { return __ldcg(reinterpret_cast<const uint4 *>(p)); }
 __device__ __forceinline__ float mk_bf(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float mk_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// Optional in-kernel timeline (CTA 0, thread 0): (tag, clock64) pairs.
+struct Prof {
+    long long *buf;
+    int n, cap;
+    __device__ __forceinline__ void stamp(int tag) {
+        if (buf != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && n < cap) {
+            buf[2 * n] = tag;
+            buf[2 * n + 1] = clock64();
+            n += 1;
+        }
+    }
+};
 
 // Grid-wide barrier: monotonically increasing arrival counter, self-cleaned at kernel exit.
 __device__ __forceinline__ void mk_grid_sync(unsigned *counter, unsigned &epoch) {
     __syncthreads();
     epoch += 1;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
+        // release-increment / acquire-poll: orders this CTA's phase output before the arrival and
+        // the other CTAs' output after the observation (the barrier above made them thread 0's)
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         const unsigned target = epoch * gridDim.x;
         unsigned spins = 0;
         while (true) {
@@ -88,7 +110,6 @@ __device__ __forceinline__ void mk_grid_sync(unsigned *counter, unsigned &epoch)
             if (seen >= target) break;
             if (++spins > (1u << 22)) __trap();  // ~seconds: a lost CTA must not hang the GPU
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -277,7 +298,7 @@ __device__ void mk_stage(const bf16 *in, int ld, int up_off, int N, int B, int p
 // When amax is non-null the CTA also records the arg-max of its logits rows per request.
 template <int RING>
 __device__ void mk_stream(const MkArgs &a, int sp, Ring<RING> &ring, Cursor &cur, const bf16 *in, int ld, int up_off, int prologue,
-                          const bf16 *norm_w, bf16 *out, const bf16 *res, unsigned char *dyn) {
+                          const bf16 *norm_w, bf16 *out, const bf16 *res, unsigned char *dyn, Prof &prof) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const SPhase p = mk_sphase(a, sp);
@@ -289,6 +310,7 @@ __device__ void mk_stream(const MkArgs &a, int sp, Ring<RING> &ring, Cursor &cur
     float *rowstat = asum + ((r.G * B + 3) & ~3);
     float *entries = rowstat + 16;  // [(chunks + MK_WARPS) entries][16 rows][8 cols]
     mk_stage(in, ld, up_off, p.N, B, prologue, norm_w, a.eps, act, asum, rowstat);
+    prof.stamp(100 + sp * 10 + 1);
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int acc_chunk = -1;
@@ -333,7 +355,7 @@ __device__ void mk_stream(const MkArgs &a, int sp, Ring<RING> &ring, Cursor &cur
         __syncwarp();
         ring.consumed += 1;
         mk_issue<RING>(a, ring, cur, warp, lane);
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        float dd[8][4];
         const uint32_t x0[4] = {w0.x, w0.y, w0.z, w0.w};
         const uint32_t x1[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
@@ -345,9 +367,13 @@ __device__ void mk_stream(const MkArgs &a, int sp, Ring<RING> &ring, Cursor &cur
             const uint32_t b2 = ((x1[j] >> 8) & MASK) | MAGIC, b3 = ((x1[j] >> 12) & MASK) | MAGIC;
             uint4 bf = make_uint4(0u, 0u, 0u, 0u);
             if (g < B) bf = act[static_cast<size_t>(16 * u + 4 * j + t) * B + g];
-            mk_mma(d, a0, b0, a1, b1, bf.x, bf.y);
-            mk_mma(d, a2, b2, a3, b3, bf.z, bf.w);
+            mk_mma0(dd[2 * j], a0, b0, a1, b1, bf.x, bf.y);
+            mk_mma0(dd[2 * j + 1], a2, b2, a3, b3, bf.z, bf.w);
         }
+        float d[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            d[c] = ((dd[0][c] + dd[1][c]) + (dd[2][c] + dd[3][c])) + ((dd[4][c] + dd[5][c]) + (dd[6][c] + dd[7][c]));
         const int m0 = 2 * t;
         const float as0 = m0 < B ? asum[u * B + m0] : 0.f;
         const float as1 = m0 + 1 < B ? asum[u * B + m0 + 1] : 0.f;
@@ -357,7 +383,9 @@ __device__ void mk_stream(const MkArgs &a, int sp, Ring<RING> &ring, Cursor &cur
         acc[3] += s1 * d[3] + c1 * as1;
     }
     flush();
+    prof.stamp(100 + sp * 10 + 2);
     __syncthreads();
+    prof.stamp(100 + sp * 10 + 3);
 
     // ---- deterministic reduction of the entries of each chunk (in warp order) + epilogue
     const int items = r.chunks * r.G;
@@ -374,7 +402,7 @@ __device__ void mk_stream(const MkArgs &a, int sp, Ring<RING> &ring, Cursor &cur
                 if (wb < we && wb < (chunk + 1) * r.G && we > chunk * r.G) v += entries[static_cast<size_t>(chunk + w) * 128 + row * 8 + m];
             }
             bf16 vb = __float2bfloat16_rn(v);
-            if (res != nullptr) vb = __float2bfloat16_rn(mk_bf(res[static_cast<size_t>(m) * p.K + k]) + mk_bf(vb));
+            if (res != nullptr) vb = __float2bfloat16_rn(mk_bf(__ldcg(res + static_cast<size_t>(m) * p.K + k)) + mk_bf(vb));  // L2: written by other phases
             out[static_cast<size_t>(m) * p.K + k] = vb;
         }
     }
@@ -456,8 +484,7 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
                 const int i = lane + 32 * h;
                 const float nre = mk_round(re[h] * inv * mk_bf(w[i]));
                 const float nim = mk_round(im[h] * inv * mk_bf(w[i + 64]));
-                const double inv_freq = exp2(-static_cast<double>(i) / 64.0 * log2(static_cast<double>(a.rope_base)));
-                const float angle = static_cast<float>(static_cast<double>(a.offsets[b]) * inv_freq);
+                const float angle = static_cast<float>(static_cast<double>(a.offsets[b]) * a.rope_inv_freq[i]);
                 float s, c;
                 sincosf(angle, &s, &c);
                 const bf16 ore = __float2bfloat16_rn(nre * c - nim * s), oim = __float2bfloat16_rn(nim * c + nre * s);
@@ -499,12 +526,14 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
     }
     const int stride = MK_WARPS * 2;
-    for (int base = begin + warp * 2 + grp; base < end; base += 2 * stride) {
+    // NOTE: the trip count must be warp-uniform (full-mask shuffles inside): the lane group is folded
+    // into the token index, not into the loop bounds.
+    for (int base = begin + warp * 2; base < end; base += 2 * stride) {
         uint4 kr[2], vr[2];
         bool ok[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // two tokens per iteration, all loads issued before any use
-            const int tok = base + h * stride;
+            const int tok = base + grp + h * stride;
             ok[h] = tok < end;
             kr[h] = vr[h] = make_uint4(0u, 0u, 0u, 0u);
             if (ok[h]) {
@@ -625,6 +654,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
     __shared__ float amax_v[MK_WARPS];
     __shared__ int amax_i[MK_WARPS];
     unsigned epoch = 0;
+    Prof prof{a.prof, 0, a.prof_capacity};
+    prof.stamp(1);
 
     Ring<RING> ring;
     ring.base = mk_smem_raw + static_cast<size_t>(warp) * RING * MK_SLOT;
@@ -655,31 +686,44 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
             *reinterpret_cast<uint4 *>(static_cast<bf16 *>(a.xa) + static_cast<size_t>(m) * a.H + wc * 8) = o;
         }
     }
+    prof.stamp(2);
     mk_grid_sync(a.sync_counter, epoch);
+    prof.stamp(3);
 
     bf16 *x = static_cast<bf16 *>(a.xa), *x_alt = static_cast<bf16 *>(a.xb);
     bf16 *qkv = static_cast<bf16 *>(a.qkv), *yb = static_cast<bf16 *>(a.y), *gu = static_cast<bf16 *>(a.gu);
     for (int layer = 0; layer < a.n_layers; ++layer) {
         const MkLayer &l = a.layers[layer];
-        mk_stream<RING>(a, 4 * layer + 0, ring, cur, x, a.H, 0, 1, static_cast<const bf16 *>(l.ln1), qkv, nullptr, dyn);
+        mk_stream<RING>(a, 4 * layer + 0, ring, cur, x, a.H, 0, 1, static_cast<const bf16 *>(l.ln1), qkv, nullptr, dyn, prof);
+        prof.stamp(100 + (4 * layer) * 10 + 4);
         mk_grid_sync(a.sync_counter, epoch);
+        prof.stamp(100 + (4 * layer) * 10 + 5);
         mk_attention(a, l, dyn);
+        prof.stamp(100 + (4 * layer) * 10 + 6);
         mk_grid_sync(a.sync_counter, epoch);
+        prof.stamp(100 + (4 * layer) * 10 + 7);
         if (a.nsplit > 1) {
             mk_attention_merge(a);
             mk_grid_sync(a.sync_counter, epoch);
         }
-        mk_stream<RING>(a, 4 * layer + 1, ring, cur, yb, a.Hq * a.D, 0, 0, nullptr, x_alt, x, dyn);
+        mk_stream<RING>(a, 4 * layer + 1, ring, cur, yb, a.Hq * a.D, 0, 0, nullptr, x_alt, x, dyn, prof);
+        prof.stamp(100 + (4 * layer + 1) * 10 + 4);
         mk_grid_sync(a.sync_counter, epoch);
-        mk_stream<RING>(a, 4 * layer + 2, ring, cur, x_alt, a.H, 0, 1, static_cast<const bf16 *>(l.ln2), gu, nullptr, dyn);
+        prof.stamp(100 + (4 * layer + 1) * 10 + 5);
+        mk_stream<RING>(a, 4 * layer + 2, ring, cur, x_alt, a.H, 0, 1, static_cast<const bf16 *>(l.ln2), gu, nullptr, dyn, prof);
+        prof.stamp(100 + (4 * layer + 2) * 10 + 4);
         mk_grid_sync(a.sync_counter, epoch);
-        mk_stream<RING>(a, 4 * layer + 3, ring, cur, gu, 2 * a.I, a.I, 2, nullptr, x, x_alt, dyn);
+        prof.stamp(100 + (4 * layer + 2) * 10 + 5);
+        mk_stream<RING>(a, 4 * layer + 3, ring, cur, gu, 2 * a.I, a.I, 2, nullptr, x, x_alt, dyn, prof);
+        prof.stamp(100 + (4 * layer + 3) * 10 + 4);
         mk_grid_sync(a.sync_counter, epoch);
+        prof.stamp(100 + (4 * layer + 3) * 10 + 5);
     }
     // ---- final norm + (tied) head, then greedy arg-max
     {
         const int sp = 4 * a.n_layers;
-        mk_stream<RING>(a, sp, ring, cur, x, a.H, 0, 1, static_cast<const bf16 *>(a.final_norm), static_cast<bf16 *>(a.logits), nullptr, dyn);
+        mk_stream<RING>(a, sp, ring, cur, x, a.H, 0, 1, static_cast<const bf16 *>(a.final_norm), static_cast<bf16 *>(a.logits), nullptr, dyn, prof);
+        prof.stamp(90001);
         const SPhase p = mk_sphase(a, sp);
         const SRange r = mk_range(p, warp);
         mk_cta_argmax(a, r.r0, r.r1, amax_v, amax_i);
@@ -707,6 +751,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
         }
         if (lane == 0 && a.advance) *a.step_counter = step + 1;
     }
+    prof.stamp(99999);
     mk_wait<0>();
     // ---- leave the barrier counters clean for the next launch
     __syncthreads();
@@ -746,10 +791,11 @@ static int mk_launch_t(const MkArgs &a, cudaStream_t st, int *grid_out) {
     const int sms = sm_count();
     const int grid = sms;  // one CTA per SM
     const size_t smem = static_cast<size_t>(MK_WARPS) * RING * MK_SLOT + mk_dyn_bytes(a, grid);
-    if (smem > 227 * 1024) return -1;
+    constexpr size_t kMaxDyn = 226 * 1024;  // 227 KiB opt-in limit minus this kernel's static shared memory
+    if (smem > kMaxDyn) return -1;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(decode_megakernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(decode_megakernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDyn)) != cudaSuccess)
             return fail(TL_ECUDA, "decode_step: cannot raise shared memory limit");
         configured = true;
     }

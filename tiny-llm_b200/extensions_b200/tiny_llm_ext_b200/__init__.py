@@ -541,7 +541,7 @@ class DecodeArgs(ctypes.Structure):
         + [(n, _VP) for n in ("tokens", "offsets", "context_lens", "next_tokens", "out_log", "step_counter")]
         + [("log_capacity", _I), ("advance", _I)]
         + [(n, _VP) for n in ("xa", "xb", "qkv", "y", "gu", "logits", "attn_ws", "amax_val", "amax_idx", "sync_counter", "exit_counter")]
-        + [("nsplit", _I), ("tokens_per_split", _I), ("ring", _I)]
+        + [("nsplit", _I), ("tokens_per_split", _I), ("ring", _I), ("rope_inv_freq", _VP), ("prof", _VP), ("prof_capacity", _I)]
     )
 
 

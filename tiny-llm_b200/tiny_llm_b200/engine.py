@@ -90,6 +90,10 @@ class MegaStep:
         a.log_capacity = engine.log_capacity
         for name in ("xa", "xb", "qkv", "y", "gu", "logits", "attn_ws", "amax_val", "amax_idx"):
             setattr(a, name, getattr(self, name).data_ptr())
+        half = D // 2
+        self.rope_inv_freq = torch.pow(torch.tensor(float(attn.rope.base), dtype=torch.float64),
+                                       -torch.arange(half, dtype=torch.float64) / half).to(dev)
+        a.rope_inv_freq = self.rope_inv_freq.data_ptr()
         a.sync_counter = self.counters.data_ptr()
         a.exit_counter = self.counters.data_ptr() + 4
         self.args = a
