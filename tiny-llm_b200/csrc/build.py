@@ -19,8 +19,11 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent
 ROOT = CSRC.parent.parent
 OUT_DIR = CSRC.parent / "extensions_b200" / "tiny_llm_ext_b200"
-LIB = OUT_DIR / "libtiny_llm_b200.so"
-BUILD = CSRC / "build"
+# Experiment builds: TL_DEFINES="-DS4_DEPTH_SMALL=3 ..." TL_LIB_SUFFIX=_d3 python build.py
+# -> libtiny_llm_b200_d3.so next to the product library (tools/kbench.py --lib selects it).
+SUFFIX = os.environ.get("TL_LIB_SUFFIX", "")
+LIB = OUT_DIR / f"libtiny_llm_b200{SUFFIX}.so"
+BUILD = CSRC / f"build{SUFFIX}"
 
 SOURCES = [
     "c_abi.cu",
@@ -38,6 +41,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-I", str(ROOT / "include"),
+    *os.environ.get("TL_DEFINES", "").split(),
 ]
 
 

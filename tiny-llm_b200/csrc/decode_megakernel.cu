@@ -13,19 +13,19 @@
 //
 // with a grid-wide barrier between phases (every phase consumes a full
 // activation vector produced by all CTAs of the previous one).  The point of
-// the design is what happens ACROSS the barriers: every warp owns a private
-// cp.async ring (RING x 1 KiB weight groups + their scales) whose fill cursor
-// walks the concatenated work list of ALL streaming phases, independent of the
-// consume cursor.  While a warp waits at a barrier or re-stages activations,
-// its ring already holds the first groups of the next projection, so HBM keeps
-// streaming through the synchronisation bubbles.
+// the design is what happens ACROSS the barriers: every warp keeps MK_DEPTH
+// weight units (2 KiB each) in flight in registers, and the cursor that issues
+// those loads walks the concatenated work list of ALL streaming phases,
+// independent of the consumer.  While a warp waits at a barrier or re-stages
+// activations, the first units of the next projection are already on their way
+// (16 warps x 8 KiB x 148 SMs = 19 MB in flight: a third of a layer).
 //
 // Work split of a projection [K rows x N]: CTA c owns rows [K*c/C, K*(c+1)/C)
-// (all CTAs stream the same number of bytes), in 16-row chunks x N/128 groups;
-// the (chunk, group) items are dealt to the CTA's warps as contiguous ranges.
-// A warp accumulates a chunk in registers (mma.sync on exact (128+q) codes, as
-// in w4a16_matvec.cu) and parks its partial sum in shared-memory entry
-// (chunk + warp); entries of a chunk are summed in warp order: deterministic.
+// (all CTAs stream the same number of bytes), in 16-row chunks x N/(128 U) units;
+// the (chunk, unit) pairs are dealt to the CTA's warps as contiguous ranges.
+// A warp accumulates a chunk in registers (w4a16_item.cuh: mma.sync on exact
+// (128+q) codes) and parks its partial sum in shared-memory entry (chunk + warp);
+// entries of a chunk are summed in warp order: deterministic.
 //
 // Arithmetic and rounding points are those of the operator sequence
 // (rms_norm -> quantized_matmul -> ... , see engine.py::_forward_unfused).
@@ -34,13 +34,12 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "w4a16_item.cuh"
 
 namespace tl {
 
 constexpr int MK_WARPS = 16;
 constexpr int MK_THREADS = MK_WARPS * 32;
-constexpr int MK_CODE = 1024;              // 16 rows x 64 B packed codes
-constexpr int MK_SLOT = MK_CODE + 128;     // + 16 scale words + 16 bias words
 constexpr int MK_MAXB = 8;
 constexpr float MK_LOG2E = 1.44269504089f;
 constexpr float MK_NEG = -1e30f;
@@ -52,31 +51,6 @@ typedef tl_decode_layer MkLayer;
 typedef tl_decode_args MkArgs;
 
 // ------------------------------------------------------------- primitives --
-__device__ __forceinline__ uint32_t mk_smem(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mk_cp16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void mk_cp4(uint32_t dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void mk_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void mk_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void mk_mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-// D = A*B with a zero accumulator input: the eight MMAs of one 128-column group are issued as
-// INDEPENDENT instructions (legacy mma.sync has a long latency on sm_100; a dependent chain of
-// eight costs ~4x more than eight back-to-back issues) and summed afterwards.
-__device__ __forceinline__ void mk_mma0(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
-}
 __device__ __forceinline__ uint4 mk_ldcg16(const void *p) { return __ldcg(reinterpret_cast<const uint4 *>(p)); }
 __device__ __forceinline__ float mk_bf(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float mk_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
@@ -139,267 +113,162 @@ __device__ __forceinline__ SPhase mk_sphase(const MkArgs &a, int sp) {
     return p;
 }
 
-// Rows of this CTA and the item range of this warp for one streaming phase.
+// Rows of this CTA and the unit range of this warp for one streaming phase.  A unit is U
+// consecutive 128-column groups of one 16-row chunk (w4a16_item.cuh).
 struct SRange {
-    int r0, r1, G, chunks, begin, end;  // items [begin, end) in chunk-major order
+    int r0, r1, P, chunks, begin, end;  // units [begin, end) in chunk-major order, P units per chunk
 };
+template <int U>
 __device__ __forceinline__ SRange mk_range(const SPhase &p, int warp) {
     SRange r;
-    r.r0 = static_cast<int>(static_cast<long long>(p.K) * blockIdx.x / gridDim.x);
-    r.r1 = static_cast<int>(static_cast<long long>(p.K) * (blockIdx.x + 1) / gridDim.x);
-    r.G = p.N / 128;
-    r.chunks = (r.r1 - r.r0 + 15) / 16;
-    const int items = r.chunks * r.G;
-    r.begin = static_cast<int>(static_cast<long long>(items) * warp / MK_WARPS);
-    r.end = static_cast<int>(static_cast<long long>(items) * (warp + 1) / MK_WARPS);
+    // K * gridDim.x < 2^31 (checked by the launcher): 32-bit divisions only
+    r.r0 = static_cast<int>(static_cast<unsigned>(p.K) * blockIdx.x / gridDim.x);
+    r.r1 = static_cast<int>(static_cast<unsigned>(p.K) * (blockIdx.x + 1) / gridDim.x);
+    r.P = p.N / (128 * U);
+    r.chunks = (r.r1 - r.r0 + 15) >> 4;
+    const unsigned units = r.chunks * r.P;
+    r.begin = static_cast<int>(units * warp / MK_WARPS);
+    r.end = static_cast<int>(units * (warp + 1) / MK_WARPS);
     return r;
 }
 
-// Fill cursor of a warp's ring: walks (streaming phase, item) pairs of the whole step.
-struct Cursor {
-    int sp, i;  // phase and absolute item index inside the phase's CTA item space
-    SPhase p;
-    SRange r;
+// Per-warp register pipeline: DEPTH weight units in flight, filled by a cursor that walks the
+// (streaming phase, unit) pairs of the WHOLE step, so the first units of the next projection are
+// already on their way while the warp sits in a grid barrier or re-stages activations.
+constexpr int MK_DEPTH = 4;
+template <int U>
+struct Pipe {
+    W4Unit<U> buf[MK_DEPTH];
+    int slot;                            // buffer the consumer takes next
+    int sp, i, end;                      // load cursor: phase, next unit, end of this warp's range
+    int u, P, row_base, r1, G;           // unit inside its chunk, units per chunk, chunk rows, CTA row end
+    const unsigned char *w, *tab;        // phase weights; this lane's scale (lanes 0-15) or bias table
+    const unsigned char *p0, *p8, *sb;   // this lane's addresses for the next unit
 };
-__device__ __forceinline__ void mk_cursor_load(const MkArgs &a, Cursor &c, int warp) {
+
+template <int U>
+__device__ __forceinline__ void mk_chunk_ptrs(Pipe<U> &c, int lane) {  // rows past the CTA's range are clamped
+    const int g = lane >> 2, t = lane & 3;
+    const int last = c.r1 - 1;
+    const size_t row_bytes = static_cast<size_t>(c.G) * 64;
+    c.p0 = c.w + min(c.row_base + g, last) * row_bytes + c.u * (U * 64) + t * 16;
+    c.p8 = c.w + min(c.row_base + g + 8, last) * row_bytes + c.u * (U * 64) + t * 16;
+    c.sb = c.tab + (static_cast<size_t>(min(c.row_base + (lane & 15), last)) * c.G + c.u * U) * 2;
+}
+
+// Position the load cursor on the first unit of phase c.sp (or a later one) that belongs to this warp.
+template <int U>
+__device__ __forceinline__ void mk_cursor_phase(const MkArgs &a, Pipe<U> &c, int warp, int lane) {
     while (c.sp < mk_num_sphases(a)) {
-        c.p = mk_sphase(a, c.sp);
-        c.r = mk_range(c.p, warp);
-        if (c.i < c.r.begin) c.i = c.r.begin;
-        if (c.i < c.r.end) return;
+        const SPhase p = mk_sphase(a, c.sp);
+        const SRange r = mk_range<U>(p, warp);
+        if (r.begin < r.end) {
+            c.i = r.begin, c.end = r.end, c.P = r.P, c.r1 = r.r1, c.G = p.N / 128;
+            const int chunk = r.begin / r.P;
+            c.u = r.begin - chunk * r.P;
+            c.row_base = r.r0 + chunk * 16;
+            c.w = reinterpret_cast<const unsigned char *>(p.w);
+            c.tab = reinterpret_cast<const unsigned char *>(lane < 16 ? p.s : p.b);
+            mk_chunk_ptrs<U>(c, lane);
+            return;
+        }
         c.sp += 1;
-        c.i = 0;
     }
 }
 
-template <int RING>
-struct Ring {
-    unsigned char *base;
-    uint32_t base_s;
-    unsigned issued, consumed;
-};
-
-template <int RING>
-__device__ __forceinline__ void mk_issue(const MkArgs &a, Ring<RING> &ring, Cursor &c, int warp, int lane) {
+template <int U>
+__device__ __forceinline__ void mk_load_next(const MkArgs &a, Pipe<U> &c, W4Unit<U> &un, int warp, int lane) {
     if (c.sp < mk_num_sphases(a)) {
-        const int chunk = c.i / c.r.G;
-        const int u = c.i - chunk * c.r.G;
-        const int row_base = c.r.r0 + chunk * 16;
-        const uint32_t slot = ring.base_s + (ring.issued % RING) * MK_SLOT;
-        const int crow = row_base + (lane >> 1);
-        if (crow < c.r.r1) {
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(c.p.w) + static_cast<size_t>(crow) * (c.p.N / 2) + u * 64 + (lane & 1) * 32;
-            const uint32_t dst = slot + (lane >> 1) * 64 + (lane & 1) * 32;
-            mk_cp16(dst, src);
-            mk_cp16(dst + 16, src + 16);
-        }
-        const int prow = row_base + (lane & 15);
-        if (prow < c.r.r1) {
-            const long long e = static_cast<long long>(prow) * c.r.G + u;
-            const unsigned char *table = reinterpret_cast<const unsigned char *>(lane < 16 ? c.p.s : c.p.b);
-            const uint32_t pdst = slot + MK_CODE + lane * 4;
-            if ((e | 1) < static_cast<long long>(c.p.K) * c.r.G) {
-                mk_cp4(pdst, table + ((e >> 1) << 2));
-            } else {
-                const uint16_t v = *reinterpret_cast<const uint16_t *>(table + e * 2);
-                *reinterpret_cast<uint32_t *>(ring.base + (ring.issued % RING) * MK_SLOT + MK_CODE + lane * 4) =
-                    (e & 1) ? (static_cast<uint32_t>(v) << 16) : static_cast<uint32_t>(v);
-            }
-        }
+        w4_load<U>(un, c.p0, c.p8, c.sb);
         c.i += 1;
-        if (c.i >= c.r.end) {
+        if (c.i == c.end) {
             c.sp += 1;
-            c.i = 0;
-            mk_cursor_load(a, c, warp);
+            mk_cursor_phase<U>(a, c, warp, lane);
+        } else if (++c.u == c.P) {
+            c.u = 0;
+            c.row_base += 16;
+            mk_chunk_ptrs<U>(c, lane);
+        } else {
+            c.p0 += U * 64;
+            c.p8 += U * 64;
+            c.sb += U * 2;
         }
     }
-    mk_commit();
-    ring.issued += 1;
-}
-
-// Stage the activation rows of a streaming phase into shared memory in MMA-fragment order.
-// prologue 0: plain; 1: rms_norm(x, w, eps); 2: swiglu(gate, up) with up = in + up_off.
-__device__ void mk_stage(const bf16 *in, int ld, int up_off, int N, int B, int prologue, const bf16 *norm_w, float eps, uint4 *act,
-                         float *asum, float *rowstat) {
-    const int words = N / 8;
-    const int total = B * words;
-    const int lane = threadIdx.x & 31;
-    const int base0 = threadIdx.x & ~31;
-    if (prologue == 1) {
-        if (threadIdx.x < MK_MAXB) rowstat[threadIdx.x] = 0.f;
-        __syncthreads();
-        for (int base = base0; base < total; base += MK_THREADS) {
-            const int idx = base + lane;
-            float part = 0.f;
-            if (idx < total) {
-                const int m = idx / words, c = idx - m * words;
-                const uint4 raw = mk_ldcg16(in + static_cast<size_t>(m) * ld + c * 8);
-                const float2 f0 = unpack2<bf16>(raw.x), f1 = unpack2<bf16>(raw.y), f2 = unpack2<bf16>(raw.z), f3 = unpack2<bf16>(raw.w);
-                part = f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
-            }
-            part += __shfl_xor_sync(0xffffffffu, part, 8);
-            part += __shfl_xor_sync(0xffffffffu, part, 4);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
-        }
-        __syncthreads();
-    }
-    for (int base = base0; base < total; base += MK_THREADS) {
-        const int idx = base + lane;
-        float part = 0.f;
-        int m = 0, c = 0;
-        if (idx < total) {
-            m = idx / words;
-            c = idx - m * words;
-            const bf16 *src = in + static_cast<size_t>(m) * ld + c * 8;
-            uint4 raw = mk_ldcg16(src);
-            if (prologue != 0) {
-                const uint4 aux = prologue == 2 ? mk_ldcg16(src + up_off) : *reinterpret_cast<const uint4 *>(norm_w + c * 8);
-                const uint32_t xin[4] = {raw.x, raw.y, raw.z, raw.w};
-                const uint32_t yin[4] = {aux.x, aux.y, aux.z, aux.w};
-                uint32_t o[4];
-                const float inv = prologue == 1 ? rsqrtf(rowstat[m] / static_cast<float>(N) + eps) : 0.f;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 xv = unpack2<bf16>(xin[i]), yv = unpack2<bf16>(yin[i]);
-                    float r0, r1;
-                    if (prologue == 1) {
-                        r0 = xv.x * inv * yv.x;
-                        r1 = xv.y * inv * yv.y;
-                    } else {
-                        r0 = (xv.x / (1.0f + expf(-xv.x))) * yv.x;
-                        r1 = (xv.y / (1.0f + expf(-xv.y))) * yv.y;
-                    }
-                    o[i] = pack2<bf16>(r0, r1);
-                }
-                raw = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-            uint4 p;
-            p.x = __byte_perm(raw.x, raw.z, 0x5410);
-            p.y = __byte_perm(raw.x, raw.z, 0x7632);
-            p.z = __byte_perm(raw.y, raw.w, 0x5410);
-            p.w = __byte_perm(raw.y, raw.w, 0x7632);
-            const int pos = (c & ~15) | ((c & 3) << 2) | ((c >> 2) & 3);
-            act[static_cast<size_t>(pos) * B + m] = p;
-            const float2 f0 = unpack2<bf16>(raw.x), f1 = unpack2<bf16>(raw.y), f2 = unpack2<bf16>(raw.z), f3 = unpack2<bf16>(raw.w);
-            part = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
-        }
-        part += __shfl_xor_sync(0xffffffffu, part, 8);
-        part += __shfl_xor_sync(0xffffffffu, part, 4);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        if (idx < total && (c & 15) == 0) asum[(c >> 4) * B + m] = part;
-    }
-    __syncthreads();
 }
 
 // One projection: out[m, k] (= res[m, k] +) sum_n act[m, n] * dequant(w[k, n]) for this CTA's rows.
-// When amax is non-null the CTA also records the arg-max of its logits rows per request.
-template <int RING>
-__device__ void mk_stream(const MkArgs &a, int sp, Ring<RING> &ring, Cursor &cur, const bf16 *in, int ld, int up_off, int prologue,
-                          const bf16 *norm_w, bf16 *out, const bf16 *res, unsigned char *dyn, Prof &prof) {
+// prologue 0: plain; 1: rms_norm(x, norm_w, eps); 2: swiglu(gate, up) with up = in + up_off.
+template <int MP, int U>
+__device__ void mk_stream(const MkArgs &a, int sp, Pipe<U> &pipe, const bf16 *in, int ld, int up_off, int prologue, const bf16 *norm_w,
+                          bf16 *out, const bf16 *res, unsigned char *dyn, Prof &prof) {
+    constexpr int MPA = w4_mpa(MP);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const SPhase p = mk_sphase(a, sp);
-    const SRange r = mk_range(p, warp);
+    const SRange r = mk_range<U>(p, warp);
     const int B = a.B;
-    const int words = p.N / 8;
+    const int words = p.N / 8, G = p.N / 128;
     uint4 *act = reinterpret_cast<uint4 *>(dyn);
-    float *asum = reinterpret_cast<float *>(dyn + static_cast<size_t>(words) * B * 16);
-    float *rowstat = asum + ((r.G * B + 3) & ~3);
-    float *entries = rowstat + 16;  // [(chunks + MK_WARPS) entries][16 rows][8 cols]
-    mk_stage(in, ld, up_off, p.N, B, prologue, norm_w, a.eps, act, asum, rowstat);
+    float *asum = reinterpret_cast<float *>(dyn + static_cast<size_t>(words) * MP * 16);
+    float *rowstat = asum + G * MPA;
+    float *entries = rowstat + 32;  // [(chunks + MK_WARPS) entries][16 rows][8 cols]
+    w4_stage<bf16, MP, MK_THREADS>(in, ld, prologue == 2 ? in + up_off : norm_w, prologue, p.N, B, a.eps, act, asum, rowstat);
     prof.stamp(100 + sp * 10 + 1);
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int acc_chunk = -1;
-    auto flush = [&]() {
-        if (acc_chunk >= 0) {
-            float *e = entries + static_cast<size_t>(acc_chunk + warp) * 128;
-            e[g * 8 + 2 * t] = acc[0];
-            e[g * 8 + 2 * t + 1] = acc[1];
-            e[(g + 8) * 8 + 2 * t] = acc[2];
-            e[(g + 8) * 8 + 2 * t + 1] = acc[3];
-        }
-        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    int chunk = r.begin / r.P;
+    int u = r.begin - chunk * r.P;
+    const uint4 *act0 = w4_act_lane<MP>(act, g, t);
+    const float *asum0 = w4_asum_lane<MP>(asum, t);
+    const uint4 *actp = act0 + u * U * w4_act_group_stride<MP>();
+    const float *asump = asum0 + u * U * w4_asum_group_stride<MP>();
+    auto flush = [&]() {  // park this warp's partial sums of `chunk` in entry (chunk + warp)
+        float *e = entries + static_cast<size_t>(chunk + warp) * 128;
+        e[g * 8 + 2 * t] = acc[0][0];
+        e[g * 8 + 2 * t + 1] = acc[0][1];
+        e[(g + 8) * 8 + 2 * t] = acc[0][2];
+        e[(g + 8) * 8 + 2 * t + 1] = acc[0][3];
+        acc[0][0] = acc[0][1] = acc[0][2] = acc[0][3] = 0.f;
     };
-    for (int i = r.begin; i < r.end; ++i) {
-        const int chunk = i / r.G;
-        const int u = i - chunk * r.G;
-        if (chunk != acc_chunk) {
-            flush();
-            acc_chunk = chunk;
-        }
-        mk_wait<RING - 2>();
-        __syncwarp();
-        const unsigned char *slot0 = ring.base + (ring.consumed % RING) * MK_SLOT;
-        const int row0 = r.r0 + chunk * 16 + g, row1 = row0 + 8;
-        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
-        float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>(slot0 + MK_CODE);
-        if (row0 < r.r1) {
-            w0 = *reinterpret_cast<const uint4 *>(slot0 + g * 64 + t * 16);
-            const int par = static_cast<int>((static_cast<long long>(row0) * r.G + u) & 1);
-            const float2 sp2 = unpack2<bf16>(sw[g]), cp2 = unpack2<bf16>(sw[16 + g]);
-            s0 = par ? sp2.y : sp2.x;
-            c0 = (par ? cp2.y : cp2.x) - 128.f * s0;
-        }
-        if (row1 < r.r1) {
-            w1 = *reinterpret_cast<const uint4 *>(slot0 + (g + 8) * 64 + t * 16);
-            const int par = static_cast<int>((static_cast<long long>(row1) * r.G + u) & 1);
-            const float2 sp2 = unpack2<bf16>(sw[g + 8]), cp2 = unpack2<bf16>(sw[16 + g + 8]);
-            s1 = par ? sp2.y : sp2.x;
-            c1 = (par ? cp2.y : cp2.x) - 128.f * s1;
-        }
-        __syncwarp();
-        ring.consumed += 1;
-        mk_issue<RING>(a, ring, cur, warp, lane);
-        float dd[8][4];
-        const uint32_t x0[4] = {w0.x, w0.y, w0.z, w0.w};
-        const uint32_t x1[4] = {w1.x, w1.y, w1.z, w1.w};
+    int i = r.begin;
+    while (i < r.end) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            constexpr uint32_t MASK = 0x000F000Fu, MAGIC = 0x43004300u;
-            const uint32_t a0 = (x0[j] & MASK) | MAGIC, a1 = ((x0[j] >> 4) & MASK) | MAGIC;
-            const uint32_t a2 = ((x0[j] >> 8) & MASK) | MAGIC, a3 = ((x0[j] >> 12) & MASK) | MAGIC;
-            const uint32_t b0 = (x1[j] & MASK) | MAGIC, b1 = ((x1[j] >> 4) & MASK) | MAGIC;
-            const uint32_t b2 = ((x1[j] >> 8) & MASK) | MAGIC, b3 = ((x1[j] >> 12) & MASK) | MAGIC;
-            uint4 bf = make_uint4(0u, 0u, 0u, 0u);
-            if (g < B) bf = act[static_cast<size_t>(16 * u + 4 * j + t) * B + g];
-            mk_mma0(dd[2 * j], a0, b0, a1, b1, bf.x, bf.y);
-            mk_mma0(dd[2 * j + 1], a2, b2, a3, b3, bf.z, bf.w);
+        for (int k = 0; k < MK_DEPTH; ++k) {
+            if (pipe.slot == k && i < r.end) {  // warp-uniform; k is a compile-time register index
+                w4_consume<bf16, MP, U>(pipe.buf[k], actp, asump, g, acc);
+                mk_load_next<U>(a, pipe, pipe.buf[k], warp, lane);
+                pipe.slot = (k + 1) % MK_DEPTH;
+                i += 1;
+                actp += U * w4_act_group_stride<MP>();
+                asump += U * w4_asum_group_stride<MP>();
+                if (++u == r.P) {
+                    flush();
+                    u = 0;
+                    chunk += 1;
+                    actp = act0;
+                    asump = asum0;
+                }
+            }
         }
-        float d[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            d[c] = ((dd[0][c] + dd[1][c]) + (dd[2][c] + dd[3][c])) + ((dd[4][c] + dd[5][c]) + (dd[6][c] + dd[7][c]));
-        const int m0 = 2 * t;
-        const float as0 = m0 < B ? asum[u * B + m0] : 0.f;
-        const float as1 = m0 + 1 < B ? asum[u * B + m0 + 1] : 0.f;
-        acc[0] += s0 * d[0] + c0 * as0;
-        acc[1] += s0 * d[1] + c0 * as1;
-        acc[2] += s1 * d[2] + c1 * as0;
-        acc[3] += s1 * d[3] + c1 * as1;
     }
-    flush();
+    if (u != 0) flush();
     prof.stamp(100 + sp * 10 + 2);
     __syncthreads();
     prof.stamp(100 + sp * 10 + 3);
 
     // ---- deterministic reduction of the entries of each chunk (in warp order) + epilogue
-    const int items = r.chunks * r.G;
+    const unsigned units = r.chunks * r.P;
     for (int o = threadIdx.x; o < r.chunks * 16 * B; o += MK_THREADS) {
         const int m = o / (r.chunks * 16);  // request-major so that consecutive threads store consecutive features
         const int rr = o - m * (r.chunks * 16);
-        const int chunk = rr >> 4, row = rr & 15;
+        const int ch = rr >> 4, row = rr & 15;
         const int k = r.r0 + rr;
         if (k < r.r1) {
             float v = 0.f;
             for (int w = 0; w < MK_WARPS; ++w) {
-                const int wb = static_cast<int>(static_cast<long long>(items) * w / MK_WARPS);
-                const int we = static_cast<int>(static_cast<long long>(items) * (w + 1) / MK_WARPS);
-                if (wb < we && wb < (chunk + 1) * r.G && we > chunk * r.G) v += entries[static_cast<size_t>(chunk + w) * 128 + row * 8 + m];
+                const int wb = static_cast<int>(units * w / MK_WARPS);
+                const int we = static_cast<int>(units * (w + 1) / MK_WARPS);
+                if (wb < we && wb < (ch + 1) * r.P && we > ch * r.P) v += entries[static_cast<size_t>(ch + w) * 128 + row * 8 + m];
             }
             bf16 vb = __float2bfloat16_rn(v);
             if (res != nullptr) vb = __float2bfloat16_rn(mk_bf(__ldcg(res + static_cast<size_t>(m) * p.K + k)) + mk_bf(vb));  // L2: written by other phases
@@ -646,26 +515,22 @@ __device__ void mk_attention_merge(const MkArgs &a) {
 }
 
 // ------------------------------------------------------------------ kernel --
-template <int RING>
+template <int MP, int U>
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs a) {
     extern __shared__ __align__(128) unsigned char mk_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *dyn = mk_smem_raw + static_cast<size_t>(MK_WARPS) * RING * MK_SLOT;
+    unsigned char *dyn = mk_smem_raw;
     __shared__ float amax_v[MK_WARPS];
     __shared__ int amax_i[MK_WARPS];
     unsigned epoch = 0;
     Prof prof{a.prof, 0, a.prof_capacity};
     prof.stamp(1);
 
-    Ring<RING> ring;
-    ring.base = mk_smem_raw + static_cast<size_t>(warp) * RING * MK_SLOT;
-    ring.base_s = mk_smem(ring.base);
-    ring.issued = ring.consumed = 0;
-    Cursor cur;
-    cur.sp = 0, cur.i = 0;
-    mk_cursor_load(a, cur, warp);
+    Pipe<U> pipe;
+    pipe.slot = 0, pipe.sp = 0;
+    mk_cursor_phase<U>(a, pipe, warp, lane);
 #pragma unroll
-    for (int i = 0; i < RING - 1; ++i) mk_issue<RING>(a, ring, cur, warp, lane);  // weights first: they depend on nothing
+    for (int k = 0; k < MK_DEPTH; ++k) mk_load_next<U>(a, pipe, pipe.buf[k], warp, lane);  // weights first: they depend on nothing
 
     // ---- phase 0: embedding rows -> xa (quantized_matmul.metal:58-89); feature words dealt across the grid
     {
@@ -692,43 +557,41 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
 
     bf16 *x = static_cast<bf16 *>(a.xa), *x_alt = static_cast<bf16 *>(a.xb);
     bf16 *qkv = static_cast<bf16 *>(a.qkv), *yb = static_cast<bf16 *>(a.y), *gu = static_cast<bf16 *>(a.gu);
-    for (int layer = 0; layer < a.n_layers; ++layer) {
-        const MkLayer &l = a.layers[layer];
-        mk_stream<RING>(a, 4 * layer + 0, ring, cur, x, a.H, 0, 1, static_cast<const bf16 *>(l.ln1), qkv, nullptr, dyn, prof);
-        prof.stamp(100 + (4 * layer) * 10 + 4);
-        mk_grid_sync(a.sync_counter, epoch);
-        prof.stamp(100 + (4 * layer) * 10 + 5);
-        mk_attention(a, l, dyn);
-        prof.stamp(100 + (4 * layer) * 10 + 6);
-        mk_grid_sync(a.sync_counter, epoch);
-        prof.stamp(100 + (4 * layer) * 10 + 7);
-        if (a.nsplit > 1) {
-            mk_attention_merge(a);
-            mk_grid_sync(a.sync_counter, epoch);
+    // One mk_stream call site for all 4L+1 projections (the streaming loop must stay in the
+    // instruction cache; five inlined copies did not).
+    const int head = 4 * a.n_layers;
+    for (int sp = 0; sp <= head; ++sp) {
+        const int kind = sp < head ? (sp & 3) : 4;
+        const MkLayer &l = a.layers[sp < head ? (sp >> 2) : a.n_layers - 1];
+        const bf16 *in = x, *norm_w = nullptr, *res = nullptr;
+        bf16 *out = qkv;
+        int ld = a.H, up_off = 0, prologue = 1;
+        switch (kind) {
+            case 0: norm_w = static_cast<const bf16 *>(l.ln1); break;
+            case 1: in = yb, ld = a.Hq * a.D, prologue = 0, out = x_alt, res = x; break;
+            case 2: in = x_alt, norm_w = static_cast<const bf16 *>(l.ln2), out = gu; break;
+            case 3: in = gu, ld = 2 * a.I, up_off = a.I, prologue = 2, out = x, res = x_alt; break;
+            default: norm_w = static_cast<const bf16 *>(a.final_norm), out = static_cast<bf16 *>(a.logits); break;
         }
-        mk_stream<RING>(a, 4 * layer + 1, ring, cur, yb, a.Hq * a.D, 0, 0, nullptr, x_alt, x, dyn, prof);
-        prof.stamp(100 + (4 * layer + 1) * 10 + 4);
+        mk_stream<MP, U>(a, sp, pipe, in, ld, up_off, prologue, norm_w, out, res, dyn, prof);
+        if (kind == 4) {  // greedy arg-max partials of this CTA's logits rows
+            const SRange r = mk_range<U>(mk_sphase(a, sp), warp);
+            mk_cta_argmax(a, r.r0, r.r1, amax_v, amax_i);
+        }
+        prof.stamp(100 + sp * 10 + 4);
         mk_grid_sync(a.sync_counter, epoch);
-        prof.stamp(100 + (4 * layer + 1) * 10 + 5);
-        mk_stream<RING>(a, 4 * layer + 2, ring, cur, x_alt, a.H, 0, 1, static_cast<const bf16 *>(l.ln2), gu, nullptr, dyn, prof);
-        prof.stamp(100 + (4 * layer + 2) * 10 + 4);
-        mk_grid_sync(a.sync_counter, epoch);
-        prof.stamp(100 + (4 * layer + 2) * 10 + 5);
-        mk_stream<RING>(a, 4 * layer + 3, ring, cur, gu, 2 * a.I, a.I, 2, nullptr, x, x_alt, dyn, prof);
-        prof.stamp(100 + (4 * layer + 3) * 10 + 4);
-        mk_grid_sync(a.sync_counter, epoch);
-        prof.stamp(100 + (4 * layer + 3) * 10 + 5);
+        prof.stamp(100 + sp * 10 + 5);
+        if (kind == 0) {
+            mk_attention(a, l, dyn);
+            prof.stamp(100 + sp * 10 + 6);
+            mk_grid_sync(a.sync_counter, epoch);
+            prof.stamp(100 + sp * 10 + 7);
+            if (a.nsplit > 1) {
+                mk_attention_merge(a);
+                mk_grid_sync(a.sync_counter, epoch);
+            }
+        }
     }
-    // ---- final norm + (tied) head, then greedy arg-max
-    {
-        const int sp = 4 * a.n_layers;
-        mk_stream<RING>(a, sp, ring, cur, x, a.H, 0, 1, static_cast<const bf16 *>(a.final_norm), static_cast<bf16 *>(a.logits), nullptr, dyn, prof);
-        prof.stamp(90001);
-        const SPhase p = mk_sphase(a, sp);
-        const SRange r = mk_range(p, warp);
-        mk_cta_argmax(a, r.r0, r.r1, amax_v, amax_i);
-    }
-    mk_grid_sync(a.sync_counter, epoch);
     if (blockIdx.x == 0 && warp == 0) {
         const int step = *a.step_counter;
         for (int m = 0; m < a.B; ++m) {
@@ -752,7 +615,6 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
         if (lane == 0 && a.advance) *a.step_counter = step + 1;
     }
     prof.stamp(99999);
-    mk_wait<0>();
     // ---- leave the barrier counters clean for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -767,12 +629,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
 }
 
 // -------------------------------------------------------------- host side --
-size_t mk_dyn_bytes(const MkArgs &a, int grid) {
+size_t mk_dyn_bytes(const MkArgs &a, int grid, int MP) {
     // act staging + group sums + row stats + partial-sum entries, maximised over the five projection shapes
+    const int MPA = MP < 8 ? 8 : MP;
     auto need = [&](int N, int K) {
         const size_t rows = static_cast<size_t>((static_cast<long long>(K) + grid - 1) / grid) + 1;
         const size_t chunks = (rows + 15) / 16 + 1;
-        return static_cast<size_t>(N / 8) * a.B * 16 + (static_cast<size_t>((N / 128) * a.B + 3) & ~3u) * 4 + 64 + (chunks + MK_WARPS) * 512;
+        return static_cast<size_t>(N / 8) * MP * 16 + static_cast<size_t>(N / 128) * MPA * 4 + 128 + (chunks + MK_WARPS) * 512;
     };
     size_t best = need(a.H, (a.Hq + 2 * a.Hkv) * a.D);
     best = std::max(best, need(a.Hq * a.D, a.H));
@@ -784,26 +647,21 @@ size_t mk_dyn_bytes(const MkArgs &a, int grid) {
     return std::max(best, attn);
 }
 
-template <int RING>
-static int mk_launch_t(const MkArgs &a, cudaStream_t st, int *grid_out) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const int sms = sm_count();
-    const int grid = sms;  // one CTA per SM
-    const size_t smem = static_cast<size_t>(MK_WARPS) * RING * MK_SLOT + mk_dyn_bytes(a, grid);
+template <int MP, int U>
+static int mk_launch_t(const MkArgs &a, cudaStream_t st) {
+    const int grid = sm_count();  // one CTA per SM
+    const size_t smem = mk_dyn_bytes(a, grid, MP);
     constexpr size_t kMaxDyn = 226 * 1024;  // 227 KiB opt-in limit minus this kernel's static shared memory
-    if (smem > kMaxDyn) return -1;
+    if (smem > kMaxDyn) return fail(TL_EINVAL, "decode_step: activations do not fit in shared memory for batch %d", a.B);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(decode_megakernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDyn)) != cudaSuccess)
+        if (cudaFuncSetAttribute(decode_megakernel<MP, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDyn)) != cudaSuccess)
             return fail(TL_ECUDA, "decode_step: cannot raise shared memory limit");
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel<MP, U>, MK_THREADS, smem);
+        if (per_sm < 1) return fail(TL_ECUDA, "decode_step: kernel does not fit on an SM (smem %zu)", smem);
         configured = true;
     }
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_megakernel<RING>, MK_THREADS, smem);
-    if (per_sm < 1) return fail(TL_ECUDA, "decode_step: kernel does not fit on an SM (smem %zu)", smem);
-    MkArgs args = a;
-    args.ring = RING;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(MK_THREADS);
@@ -814,23 +672,29 @@ static int mk_launch_t(const MkArgs &a, cudaStream_t st, int *grid_out) {
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, decode_megakernel<RING>, args);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, decode_megakernel<MP, U>, a);
     if (e != cudaSuccess) return fail(TL_ECUDA, "decode_step: launch failed: %s", cudaGetErrorString(e));
-    if (grid_out) *grid_out = grid;
     count_launch();
     return check_launch("decode_megakernel");
+}
+
+template <int U>
+static int mk_launch_u(const MkArgs &a, cudaStream_t st) {
+    switch (w4_pad_cols(a.B)) {
+        case 1: return mk_launch_t<1, U>(a, st);
+        case 2: return mk_launch_t<2, U>(a, st);
+        case 4: return mk_launch_t<4, U>(a, st);
+        default: return mk_launch_t<8, U>(a, st);
+    }
 }
 
 int launch_decode_megakernel(const MkArgs &a, cudaStream_t st) {
     if (a.B < 1 || a.B > MK_MAXB) return fail(TL_EINVAL, "decode_step: batch must be 1..8");
     if (a.D != 128 || a.Hq % a.Hkv != 0 || a.Hq / a.Hkv > 4) return fail(TL_EINVAL, "decode_step: needs head_dim 128 and at most 4 query heads per KV head");
     if (a.H % 128 != 0 || a.I % 128 != 0 || (a.Hq * a.D) % 128 != 0) return fail(TL_EINVAL, "decode_step: widths must be multiples of 128");
-    int rc = mk_launch_t<8>(a, st, nullptr);
-    if (rc == -1) rc = mk_launch_t<6>(a, st, nullptr);
-    if (rc == -1) rc = mk_launch_t<4>(a, st, nullptr);
-    if (rc == -1) rc = mk_launch_t<3>(a, st, nullptr);
-    if (rc == -1) return fail(TL_EINVAL, "decode_step: activations do not fit in shared memory for batch %d", a.B);
-    return rc;
+    // pairs of groups per unit need 4-byte aligned scale pairs: every reduction width a multiple of 256
+    const bool pairs = a.H % 256 == 0 && a.I % 256 == 0 && (a.Hq * a.D) % 256 == 0;
+    return pairs ? mk_launch_u<2>(a, st) : mk_launch_u<1>(a, st);
 }
 
 int mk_grid_size() { return sm_count(); }

@@ -1,0 +1,322 @@
+// Shared building blocks of the W4A16 weight-streaming kernels (w4a16_matvec.cu and
+// decode_megakernel.cu): activation staging, the register-pipelined weight unit and the
+// tensor-core consumer.
+//
+// Why this shape (measured on B200, profiles/r01_kbench_*): the first three streaming kernels
+// all stalled at ~2 TB/s no matter how the bytes were fetched.  SASS of the cp.async-ring
+// version showed 334 instructions per 1-KiB weight group per warp - the kernel was
+// instruction-issue bound, not memory bound.  The budget below is ~100 per KiB:
+//
+//   * weights go global -> registers (ld.global.nc, 128-bit, immediate offsets from one running
+//     pointer per row); no shared-memory ring, so no LDGSTS, no wait_group/syncwarp, no slot math;
+//   * a lane turns four codes into two exact bf16 (128+q) pairs with ONE lop3 each (mask in the
+//     constant bank, magic in a register) plus a shift for three of the four nibble positions;
+//   * the B fragments of a unit are four 128-bit shared loads at compile-time offsets from one
+//     running address (the padded column count MP is a template parameter);
+//   * scales/biases: one 32-bit load per LANE per unit (16 rows x {scale,bias}), distributed with
+//     four shuffles; the "-128 * sum(a)" correction enters as the accumulator input of the first
+//     MMA, so the epilogue is two FMAs per output.
+//
+// Layouts (16-byte units):  act[((u*4 + j)*MP + col)*4 + t]   u = 128-column group, j = word of
+// the lane's 128-bit weight load, col = activation row, t = lane & 3;  asum[u*MPA + col].
+#pragma once
+
+#include "common.cuh"
+
+namespace tl {
+
+// Opaque to ptxas (constant memory may be rewritten by the host), which keeps (x & mask) | magic
+// a single LOP3 with the mask read from the constant bank.
+static __constant__ uint32_t k_w4_mask = 0x000F000Fu;
+// Experiment switch: x >> s as the high word of x * 2^(32-s) (IMAD.HI, FMA pipe) instead of SHF
+// (ALU pipe).  Measured slower on B200 (lm_head 56 -> 69 us): kept only for the record.
+#ifndef W4_SHR_IMADHI
+#define W4_SHR_IMADHI 0
+#endif
+static __constant__ uint32_t k_w4_shr[3] = {1u << 28, 1u << 24, 1u << 20};
+template <int S>
+__device__ __forceinline__ uint32_t w4_shr(uint32_t x) {
+#if W4_SHR_IMADHI
+    return __umulhi(x, k_w4_shr[S / 4 - 1]);
+#else
+    return x >> S;
+#endif
+}
+
+template <typename T>
+struct W4Num;
+template <>
+struct W4Num<__nv_bfloat16> {
+    static constexpr uint32_t MAGIC = 0x43004300u;  // bf16 128.0 in both halves: code q -> 128 + q exactly
+    static constexpr float NEG_OFFSET = -128.f;
+    static __device__ __forceinline__ float lo(uint32_t w) { return __uint_as_float(w << 16); }
+    static __device__ __forceinline__ float hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+    static __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    // D = A*B + {c0, c1, c0, c1}
+    static __device__ __forceinline__ void mma_c(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                 uint32_t b1, float c0, float c1) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+                     : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1));
+    }
+};
+template <>
+struct W4Num<__half> {
+    static constexpr uint32_t MAGIC = 0x64006400u;  // fp16 1024.0 in both halves
+    static constexpr float NEG_OFFSET = -1024.f;
+    static __device__ __forceinline__ float lo(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xffffu))); }
+    static __device__ __forceinline__ float hi(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16))); }
+    static __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    static __device__ __forceinline__ void mma_c(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                 uint32_t b1, float c0, float c1) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+                     : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1));
+    }
+};
+
+__device__ __forceinline__ uint32_t w4_lop(uint32_t x, uint32_t mask, uint32_t magic) {  // (x & mask) | magic
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(mask), "r"(magic));
+    return r;
+}
+
+__host__ __device__ constexpr int w4_mpa(int MP) { return MP < 8 ? 8 : MP; }
+__host__ __device__ constexpr int w4_pad_cols(int m) { return m <= 1 ? 1 : (m <= 2 ? 2 : (m <= 4 ? 4 : (m <= 8 ? 8 : (m <= 16 ? 16 : 32)))); }
+
+// A unit = U consecutive 128-column groups of one 16-row tile.  Lane (g = lane >> 2, t = lane & 3)
+// holds, per group, 16 bytes of row g and of row g + 8 (words 4t..4t+3 of the group), and ONE
+// scale/bias word: lanes 0-15 the scales of rows 0-15, lanes 16-31 the biases.
+template <int U>
+struct W4Unit {
+    uint4 w[2 * U];
+    uint32_t sb;
+};
+
+template <int U>
+__device__ __forceinline__ void w4_load(W4Unit<U> &un, const unsigned char *p0, const unsigned char *p8, const unsigned char *psb) {
+#pragma unroll
+    for (int it = 0; it < U; ++it) {
+        un.w[2 * it] = ldg_stream(p0 + it * 64);
+        un.w[2 * it + 1] = ldg_stream(p8 + it * 64);
+    }
+    if (U == 2) {
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(un.sb) : "l"(psb));
+    } else {
+        unsigned short v;
+        asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(psb));
+        un.sb = v;
+    }
+}
+
+// acc[mt][0..3] += dequantised (16 rows x U groups) . activations, for MMA column tiles mt.
+// actp / asump: this lane's base pointers for the unit's first group (see layouts above).
+template <typename T, int MP, int U>
+__device__ __forceinline__ void w4_consume(const W4Unit<U> &un, const uint4 *actp, const float *asump, int g,
+                                           float (&acc)[(MP + 7) / 8][4]) {
+    constexpr int MT = (MP + 7) / 8;
+    constexpr int MPA = w4_mpa(MP);
+    const uint32_t mask = k_w4_mask;
+    const uint32_t magic = W4Num<T>::MAGIC;
+    const uint32_t s0w = __shfl_sync(0xffffffffu, un.sb, g);
+    const uint32_t s8w = __shfl_sync(0xffffffffu, un.sb, g + 8);
+    const uint32_t b0w = __shfl_sync(0xffffffffu, un.sb, g + 16);
+    const uint32_t b8w = __shfl_sync(0xffffffffu, un.sb, g + 24);
+#pragma unroll
+    for (int it = 0; it < U; ++it) {
+        const float s0 = it == 0 ? W4Num<T>::lo(s0w) : W4Num<T>::hi(s0w);
+        const float s8 = it == 0 ? W4Num<T>::lo(s8w) : W4Num<T>::hi(s8w);
+        const float b0 = it == 0 ? W4Num<T>::lo(b0w) : W4Num<T>::hi(b0w);
+        const float b8 = it == 0 ? W4Num<T>::lo(b8w) : W4Num<T>::hi(b8w);
+        const uint32_t x0[4] = {un.w[2 * it].x, un.w[2 * it].y, un.w[2 * it].z, un.w[2 * it].w};
+        const uint32_t x1[4] = {un.w[2 * it + 1].x, un.w[2 * it + 1].y, un.w[2 * it + 1].z, un.w[2 * it + 1].w};
+        float d[MT][4];
+        float2 as[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) as[mt] = *reinterpret_cast<const float2 *>(asump + it * MPA + mt * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t a0 = w4_lop(x0[j], mask, magic), a1 = w4_lop(w4_shr<4>(x0[j]), mask, magic);
+            const uint32_t a2 = w4_lop(w4_shr<8>(x0[j]), mask, magic), a3 = w4_lop(w4_shr<12>(x0[j]), mask, magic);
+            const uint32_t c0 = w4_lop(x1[j], mask, magic), c1 = w4_lop(w4_shr<4>(x1[j]), mask, magic);
+            const uint32_t c2 = w4_lop(w4_shr<8>(x1[j]), mask, magic), c3 = w4_lop(w4_shr<12>(x1[j]), mask, magic);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const uint4 bf = actp[(it * 4 + j) * MP * 4 + mt * 32];
+                if (j == 0)
+                    W4Num<T>::mma_c(d[mt], a0, c0, a1, c1, bf.x, bf.y, as[mt].x * W4Num<T>::NEG_OFFSET, as[mt].y * W4Num<T>::NEG_OFFSET);
+                else
+                    W4Num<T>::mma(d[mt], a0, c0, a1, c1, bf.x, bf.y);
+                W4Num<T>::mma(d[mt], a2, c2, a3, c3, bf.z, bf.w);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            acc[mt][0] = fmaf(b0, as[mt].x, fmaf(s0, d[mt][0], acc[mt][0]));
+            acc[mt][1] = fmaf(b0, as[mt].y, fmaf(s0, d[mt][1], acc[mt][1]));
+            acc[mt][2] = fmaf(b8, as[mt].x, fmaf(s8, d[mt][2], acc[mt][2]));
+            acc[mt][3] = fmaf(b8, as[mt].y, fmaf(s8, d[mt][3], acc[mt][3]));
+        }
+    }
+}
+
+// This lane's base pointers into the staged activations (group 0).
+template <int MP>
+__device__ __forceinline__ const uint4 *w4_act_lane(const uint4 *act, int g, int t) {
+    const int col = MP >= 8 ? g : (g & (MP - 1));  // columns >= the real row count hold don't-care data
+    return act + col * 4 + t;
+}
+template <int MP>
+__device__ __forceinline__ const float *w4_asum_lane(const float *asum, int t) {
+    return asum + 2 * t;
+}
+// Strides (in elements of the respective pointer) of one 128-column group.
+template <int MP>
+__device__ __forceinline__ constexpr int w4_act_group_stride() { return 16 * MP; }
+template <int MP>
+__device__ __forceinline__ constexpr int w4_asum_group_stride() { return w4_mpa(MP); }
+
+enum { W4_PRO_NONE = 0, W4_PRO_RMSNORM = 1, W4_PRO_SWIGLU = 2 };
+
+// Stage Mp rows of activations (N columns, row stride lda) into act/asum, applying the prologue
+//   RMSNORM : a = T(x * rsqrt(mean(x^2) + eps) * w)   (aux = norm weight, week2_kernels.metal:41-47)
+//   SWIGLU  : a = T(g / (1 + exp(-g)) * u)            (aux = up rows, same stride; :115-116)
+// with every rounding point of the unfused operator sequence.  Inputs are read through L2
+// (ld.global.cg): in the persistent kernel they were written by other CTAs of the same launch.
+// Ends with __syncthreads(); rowstat needs 32 floats.
+template <typename T, int MP, int NT>
+__device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int prologue, int N, int Mp, float eps, uint4 *act,
+                                         float *asum, float *rowstat) {
+    constexpr int MPA = w4_mpa(MP);
+    constexpr int CACHE = 4;
+    const int words = N / 8;
+    const int total = Mp * words;
+    const int lane = threadIdx.x & 31;
+    const int base0 = threadIdx.x & ~31;
+    const bool cached = total <= CACHE * NT;
+    const bool rms = prologue == W4_PRO_RMSNORM;
+    uint4 held[CACHE];
+    auto chunk_src = [&](int idx, int &m, int &c) -> const T * {
+        m = idx / words;
+        c = idx - m * words;
+        return in + static_cast<size_t>(m) * lda + c * 8;
+    };
+    auto half_warp_sum = [](float v) {
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        return v;
+    };
+    auto square_sum = [](const uint4 &raw) {
+        const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
+        return f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
+    };
+    auto emit = [&](int idx, uint4 raw) {  // idx may be >= total (lane padding): contributes nothing
+        float part = 0.f;
+        int m = 0, c = 0;
+        if (idx < total) {
+            const T *src = chunk_src(idx, m, c);
+            if (prologue != W4_PRO_NONE) {
+                const uint4 auxv = rms ? *reinterpret_cast<const uint4 *>(aux + c * 8) : __ldcg(reinterpret_cast<const uint4 *>(aux + (src - in)));
+                const uint32_t xin[4] = {raw.x, raw.y, raw.z, raw.w};
+                const uint32_t yin[4] = {auxv.x, auxv.y, auxv.z, auxv.w};
+                uint32_t o[4];
+                const float inv = rms ? rsqrtf(rowstat[m] / static_cast<float>(N) + eps) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 xv = unpack2<T>(xin[i]), yv = unpack2<T>(yin[i]);
+                    float r0, r1;
+                    if (rms) {
+                        r0 = xv.x * inv * yv.x;
+                        r1 = xv.y * inv * yv.y;
+                    } else {
+                        r0 = (xv.x / (1.0f + expf(-xv.x))) * yv.x;
+                        r1 = (xv.y / (1.0f + expf(-xv.y))) * yv.y;
+                    }
+                    o[i] = pack2<T>(r0, r1);
+                }
+                raw = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            // element order [0,4,1,5,2,6,3,7]: the B-fragment registers {(e0,e4),(e1,e5),(e2,e6),(e3,e7)}
+            // match the k-slots the lop3 extraction assigns to the nibbles of one packed word
+            uint4 p;
+            p.x = __byte_perm(raw.x, raw.z, 0x5410);
+            p.y = __byte_perm(raw.x, raw.z, 0x7632);
+            p.z = __byte_perm(raw.y, raw.w, 0x5410);
+            p.w = __byte_perm(raw.y, raw.w, 0x7632);
+            const int u = c >> 4, j = c & 3, t = (c >> 2) & 3;
+            act[((u * 4 + j) * MP + m) * 4 + t] = p;
+            const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
+            part = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+        }
+        part = half_warp_sum(part);  // the 16 chunks of one group live in 16 consecutive lanes
+        if (idx < total && (c & 15) == 0) asum[(c >> 4) * MPA + m] = part;
+    };
+    if (cached) {
+#pragma unroll
+        for (int j = 0; j < CACHE; ++j) {
+            const int idx = base0 + j * NT + lane;
+            held[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (idx < total) {
+                int m, c;
+                held[j] = __ldcg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
+            }
+        }
+    }
+    if (rms) {
+        if (threadIdx.x < 32) rowstat[threadIdx.x] = 0.f;
+        __syncthreads();
+        // a warp's 32 chunks belong to at most two rows (words % 16 == 0): reduce per half-warp
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < CACHE; ++j) {
+                const int idx = base0 + j * NT + lane;
+                if (base0 + j * NT < total) {
+                    const float part = half_warp_sum(idx < total ? square_sum(held[j]) : 0.f);
+                    if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
+                }
+            }
+        } else {
+            for (int base = base0; base < total; base += NT) {
+                const int idx = base + lane;
+                float part = 0.f;
+                if (idx < total) {
+                    int m, c;
+                    part = square_sum(__ldcg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c))));
+                }
+                part = half_warp_sum(part);
+                if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
+            }
+        }
+        __syncthreads();
+    }
+    if (cached) {
+#pragma unroll
+        for (int j = 0; j < CACHE; ++j)
+            if (base0 + j * NT < total) emit(base0 + j * NT + lane, held[j]);
+    } else {
+        for (int base = base0; base < total; base += NT) {
+            const int idx = base + lane;
+            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+            if (idx < total) {
+                int m, c;
+                raw = __ldcg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
+            }
+            emit(idx, raw);
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace tl

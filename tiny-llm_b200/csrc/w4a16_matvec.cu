@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "w4a16_item.cuh"
 
 namespace tl {
 
@@ -320,34 +321,38 @@ int launch_w4a16_stream(const void *scales, const void *biases, const void *a, c
 }
 
 // ---------------------------------------------------------------------------
-// v3: per-warp cp.async rings.
+// v4: register-pipelined streaming (see w4a16_item.cuh for the instruction budget).
 //
-// Measured on B200 (profiles/r01_kbench_*): v1 (register prefetch, 2 KB in flight
-// per warp) reached 31 % of HBM peak on the tied head; v2 (one producer warp issuing
-// 256-byte cp.async.bulk rows into a CTA ring) was slower still - small bulk copies
-// are issue-limited.  v3 gives every warp a PRIVATE ring of RING 1-KiB slots (one
-// 16-row x 128-column weight group each) filled with 16-byte cp.async: 8 KiB in
-// flight per warp, 128+ KiB per SM, no mbarriers and no cross-warp traffic on the
-// load path.  A tile's reduction dimension is split over a team of TW warps
-// (TW = 1..8, chosen so that small projections still put >= 16 warps on every SM);
-// only that team synchronises (named barrier) to combine its partial sums.
+// History, all measured on B200 (profiles/r01_kbench_*): v1 (register prefetch, 2 KB in flight
+// per warp), v2 (producer warp + 256-byte cp.async.bulk ring) and v3 (per-warp cp.async rings)
+// all stalled near 2 TB/s: SASS showed ~330 instructions per KiB of weights, i.e. the kernels
+// were issue bound.  v4 keeps 2-4 units (U x 1 KiB each) per warp in flight in REGISTERS,
+// walks global memory with running pointers, and spends ~100 instructions per KiB.
 //
-// Weights never depend on the previous kernel: each warp fills its ring BEFORE
-// griddepcontrol.wait, so with programmatic dependent launch the HBM stream of
-// kernel n+1 starts while kernel n drains.
+// A tile (16 output rows) is reduced by a team of TW warps (TW = 1..16, chosen so that small
+// projections still give every warp of the chip a unit); only that team synchronises (named
+// barrier) to combine its partial sums, in warp order (deterministic).
+//
+// Weights never depend on the previous kernel: each warp issues its first DEPTH units BEFORE
+// griddepcontrol.wait, so with programmatic dependent launch the HBM stream of kernel n+1
+// starts while kernel n drains.
 //
 // Optional fusions that keep every rounding point of the unfused call sequence
 // (so results match rms_norm -> matvec, swiglu -> matvec, matvec -> add):
 //   prologue RMSNORM : a = T(x * rsqrt(mean(x^2)+eps) * w)   (week2_kernels.metal:41-47)
 //   prologue SWIGLU  : a = T(g / (1 + exp(-g)) * u)          (week2_kernels.metal:115-116)
 //   epilogue RESIDUAL: out = T(float(res) + float(T(acc)))   (qwen3_week3.py:204-206)
-constexpr int S3_WARPS = 8;
-constexpr int S3_THREADS = S3_WARPS * 32;
-constexpr int S3_RING = 8;              // slots per warp
-constexpr int S3_CODE_BYTES = 1024;     // 16 rows x 64 B of packed codes
-constexpr int S3_SLOT_BYTES = 1024 + 128;  // + 16 scale words + 16 bias words (4 B each, see issue())
+#ifndef S4_NWARPS
+#define S4_NWARPS 16
+#endif
+#ifndef S4_DEPTH_SMALL
+#define S4_DEPTH_SMALL 4
+#endif
+constexpr int S4_WARPS = S4_NWARPS;
+constexpr int S4_THREADS = S4_WARPS * 32;
+constexpr int S4_CTAS_PER_SM = 16 / S4_WARPS;  // 128 registers per thread either way
 
-enum { PRO_NONE = 0, PRO_RMSNORM = 1, PRO_SWIGLU = 2 };
+enum { PRO_NONE = W4_PRO_NONE, PRO_RMSNORM = W4_PRO_RMSNORM, PRO_SWIGLU = W4_PRO_SWIGLU };
 enum { EPI_NONE = 0, EPI_RESIDUAL = 1 };
 
 struct StreamArgs {
@@ -361,379 +366,198 @@ struct StreamArgs {
     int rows_per_pass, team_warps;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <typename T, int MT>
-__global__ void __launch_bounds__(S3_THREADS) w4a16_stream3_kernel(const StreamArgs args) {
-    extern __shared__ __align__(128) unsigned char smem3_raw[];
+// MP: activation rows per pass padded to a power of two (template: shared-memory offsets of the
+// B fragments become immediates).  U: 128-column groups per unit (2 when N % 256 == 0).
+template <typename T, int MP, int U, bool TEAM>
+__global__ void __launch_bounds__(S4_THREADS, S4_CTAS_PER_SM) w4a16_stream4_kernel(const StreamArgs args) {
+    constexpr int MT = (MP + 7) / 8;
+    constexpr int MPA = w4_mpa(MP);
+    constexpr int S4_DEPTH = (MP <= 8 ? S4_DEPTH_SMALL : (MP == 16 ? 3 : 2));
+    extern __shared__ __align__(128) unsigned char smem4_raw[];
     const int N = args.N, K = args.K;
     const int pass = blockIdx.y;
     const int Mp = min(args.rows_per_pass, args.M - pass * args.rows_per_pass);
     const int words = N / 8;
     const int G = N / 128;
-    const int TW = args.team_warps;
+    const int P = G / U;  // units per tile
+    const int TW = TEAM ? args.team_warps : 1;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int team = warp / TW;
     const int wit = warp - team * TW;
-    const int teams = S3_WARPS / TW;
+    const int teams = S4_WARPS / TW;
     const int g = lane >> 2, t = lane & 3;
 
-    // shared layout: rings [8 warps][RING][1 KiB] | act | asum | row stats | red
-    unsigned char *ring = smem3_raw + static_cast<size_t>(warp) * S3_RING * S3_SLOT_BYTES;
-    uint4 *act = reinterpret_cast<uint4 *>(smem3_raw + static_cast<size_t>(S3_WARPS) * S3_RING * S3_SLOT_BYTES);
-    float *asum = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(act) + static_cast<size_t>(words) * Mp * 16);
-    float *rowstat = asum + ((G * Mp + 3) & ~3);
+    // shared layout: act [words*MP] x 16 B | asum [G*MPA] | row stats [32] | red [warps][16][8*MT]
+    uint4 *act = reinterpret_cast<uint4 *>(smem4_raw);
+    float *asum = reinterpret_cast<float *>(smem4_raw + static_cast<size_t>(words) * MP * 16);
+    float *rowstat = asum + G * MPA;
     float *red = rowstat + 32;
-    const uint32_t ring_s = smem_u32(ring);
 
     griddep_launch();
 
-    // ---- this warp's work list: tiles of its team, groups u = wit, wit+TW, ... of each tile
+    // ---- this warp's work list: tiles of its team, units wit, wit+TW, ... of each tile
     const int tiles = (K + 15) / 16;
     const int team_id = blockIdx.x * teams + team;
     const int team_count = gridDim.x * teams;
-    const int gpw = (G - wit + TW - 1) / TW;  // groups of one tile that belong to this warp
+    const int upw = (P - wit + TW - 1) / TW;  // units of one tile that belong to this warp (>= 1: TW <= P)
     const int my_tiles = team_id < tiles ? (tiles - team_id + team_count - 1) / team_count : 0;
-    const int total_items = my_tiles * gpw;
-    const unsigned char *bbytes = reinterpret_cast<const unsigned char *>(args.b);
-    const int crow = lane >> 1;         // row of the tile this lane copies
-    const int chalf = (lane & 1) * 32;  // which 32 bytes of the row's 64
+    const int total_units = my_tiles * upw;
 
-    // Scales/biases ride in the same ring: a 2-byte value cannot be cp.async'ed on its own, so the
-    // aligned 4-byte word that contains it is copied and the consumer picks the half by parity.
-    const unsigned char *sbytes = reinterpret_cast<const unsigned char *>(args.scales);
-    const unsigned char *cbytes = reinterpret_cast<const unsigned char *>(args.biases);
-    const long long sb_elems = static_cast<long long>(K) * G;
-    auto issue = [&](int item) {  // item -> (tile, group); one commit group per item, always
-        if (item < total_items) {
-            const int tile = team_id + (item / gpw) * team_count;
-            const int u = wit + (item % gpw) * TW;
-            const int row = min(tile * 16 + crow, K - 1);
-            const unsigned char *src = bbytes + static_cast<size_t>(row) * (N / 2) + u * 64 + chalf;
-            const uint32_t slot = ring_s + (item % S3_RING) * S3_SLOT_BYTES;
-            const uint32_t dst = slot + crow * 64 + chalf;
-            cp_async16(dst, src);
-            cp_async16(dst + 16, src + 16);
-            const int prow = min(tile * 16 + (lane & 15), K - 1);
-            const long long e = static_cast<long long>(prow) * G + u;
-            const unsigned char *table = lane < 16 ? sbytes : cbytes;
-            const uint32_t pdst = slot + S3_CODE_BYTES + lane * 4;
-            if ((e | 1) < sb_elems) {
-                cp_async4(pdst, table + ((e >> 1) << 2));
-            } else {  // last element of an odd-sized table: its pair would cross the end, copy synchronously
-                const uint16_t v = *reinterpret_cast<const uint16_t *>(table + e * 2);
-                *reinterpret_cast<uint32_t *>(ring + (item % S3_RING) * S3_SLOT_BYTES + S3_CODE_BYTES + lane * 4) =
-                    (e & 1) ? (static_cast<uint32_t>(v) << 16) : static_cast<uint32_t>(v);
+    // ---- load cursor (runs S4_DEPTH units ahead of the consumer)
+    const unsigned char *bbytes = reinterpret_cast<const unsigned char *>(args.b);
+    const unsigned char *sbtable = reinterpret_cast<const unsigned char *>(lane < 16 ? args.scales : args.biases);
+    const size_t row_bytes = static_cast<size_t>(N) / 2;
+    const unsigned char *l_p0, *l_p8, *l_sb;
+    int l_tile = team_id, l_in_tile = 0, l_left = total_units;
+    auto tile_ptrs = [&](int tile) {  // rows past K are clamped: loaded, multiplied, never stored
+        const int r0 = min(tile * 16 + g, K - 1), r8 = min(tile * 16 + g + 8, K - 1);
+        const int rs = min(tile * 16 + (lane & 15), K - 1);
+        l_p0 = bbytes + r0 * row_bytes + wit * (U * 64) + t * 16;
+        l_p8 = bbytes + r8 * row_bytes + wit * (U * 64) + t * 16;
+        l_sb = sbtable + (static_cast<size_t>(rs) * G + wit * U) * 2;
+    };
+    tile_ptrs(l_tile);
+    auto load_next = [&](W4Unit<U> &un) {
+        if (l_left > 0) {
+            w4_load<U>(un, l_p0, l_p8, l_sb);
+            l_left -= 1;
+            if (++l_in_tile == upw) {
+                l_in_tile = 0;
+                l_tile += team_count;
+                tile_ptrs(l_tile);
+            } else {
+                l_p0 += TW * (U * 64);
+                l_p8 += TW * (U * 64);
+                l_sb += TW * (U * 2);
             }
         }
-        cp_async_commit();
     };
+    W4Unit<U> buf[S4_DEPTH];
 #pragma unroll
-    for (int i = 0; i < S3_RING - 1; ++i) issue(i);  // fill the ring before touching activations
+    for (int k = 0; k < S4_DEPTH; ++k) load_next(buf[k]);  // in flight before the activations exist
 
     griddep_wait();  // activations (and the residual) come from the previous kernel
     const T *p0 = static_cast<const T *>(args.p0) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda;
     const T *p1 = args.prologue == PRO_SWIGLU
                       ? static_cast<const T *>(args.p1) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda
                       : static_cast<const T *>(args.p1);
-    // ---- stage activations: each 8-element chunk is loaded ONCE (kept in registers across the
-    // row-statistics barrier when the tile is small enough), transformed by the prologue, rounded
-    // to T, permuted into MMA-fragment order and written to shared memory with its group sum.
-    {
-        constexpr int CACHE = 4;
-        const int total = Mp * words;
-        const bool cached = total <= CACHE * S3_THREADS;
-        const bool rms = args.prologue == PRO_RMSNORM;
-        uint4 held[CACHE];
-        auto chunk_src = [&](int idx, int &m, int &c) -> const T * {
-            m = idx / words;
-            c = idx - m * words;
-            return p0 + static_cast<size_t>(m) * args.lda + c * 8;
-        };
-        auto half_warp_sum = [](float v) {
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            return v;
-        };
-        auto square_sum = [](const uint4 &raw) {
-            const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
-            return f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
-        };
-        auto emit = [&](int idx, uint4 raw) {  // idx may be >= total (lane padding): contributes nothing
-            float part = 0.f;
-            int m = 0, c = 0;
-            if (idx < total) {
-                const T *src = chunk_src(idx, m, c);
-                if (args.prologue != PRO_NONE) {
-                    const uint4 aux = *reinterpret_cast<const uint4 *>(
-                        args.prologue == PRO_SWIGLU ? p1 + (src - p0) : p1 + c * 8);
-                    const uint32_t xin[4] = {raw.x, raw.y, raw.z, raw.w};
-                    const uint32_t yin[4] = {aux.x, aux.y, aux.z, aux.w};
-                    uint32_t o[4];
-                    const float inv = rms ? rsqrtf(rowstat[m] / static_cast<float>(N) + args.eps) : 0.f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 xv = unpack2<T>(xin[i]), yv = unpack2<T>(yin[i]);
-                        float r0, r1;
-                        if (rms) {
-                            r0 = xv.x * inv * yv.x;
-                            r1 = xv.y * inv * yv.y;
-                        } else {
-                            r0 = (xv.x / (1.0f + expf(-xv.x))) * yv.x;
-                            r1 = (xv.y / (1.0f + expf(-xv.y))) * yv.y;
-                        }
-                        o[i] = pack2<T>(r0, r1);
-                    }
-                    raw = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-                uint4 p;
-                p.x = __byte_perm(raw.x, raw.z, 0x5410);
-                p.y = __byte_perm(raw.x, raw.z, 0x7632);
-                p.z = __byte_perm(raw.y, raw.w, 0x5410);
-                p.w = __byte_perm(raw.y, raw.w, 0x7632);
-                // 4x4 transpose of the chunk order inside a group: the four lanes of an MMA group
-                // then read 64 contiguous bytes per sub-step (no bank conflicts).
-                const int pos = (c & ~15) | ((c & 3) << 2) | ((c >> 2) & 3);
-                act[static_cast<size_t>(pos) * Mp + m] = p;
-                const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
-                part = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
-            }
-            part = half_warp_sum(part);  // 16 consecutive chunks (one group) live in 16 consecutive lanes
-            if (idx < total && (c & 15) == 0) asum[(c >> 4) * Mp + m] = part;
-        };
-        const int base0 = threadIdx.x & ~31;
-        if (cached) {
-#pragma unroll
-            for (int j = 0; j < CACHE; ++j) {
-                const int idx = base0 + j * S3_THREADS + lane;
-                held[j] = make_uint4(0u, 0u, 0u, 0u);
-                if (idx < total) {
-                    int m, c;
-                    held[j] = *reinterpret_cast<const uint4 *>(chunk_src(idx, m, c));
-                }
-            }
-        }
-        if (rms) {
-            if (threadIdx.x < 32) rowstat[threadIdx.x] = 0.f;
-            __syncthreads();
-            // a warp's 32 chunks belong to at most two rows (words % 16 == 0): reduce per half-warp
-            if (cached) {
-#pragma unroll
-                for (int j = 0; j < CACHE; ++j) {
-                    const int idx = base0 + j * S3_THREADS + lane;
-                    if (base0 + j * S3_THREADS < total) {
-                        const float part = half_warp_sum(idx < total ? square_sum(held[j]) : 0.f);
-                        if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
-                    }
-                }
-            } else {
-                for (int base = base0; base < total; base += S3_THREADS) {
-                    const int idx = base + lane;
-                    float part = 0.f;
-                    if (idx < total) {
-                        int m, c;
-                        part = square_sum(*reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
-                    }
-                    part = half_warp_sum(part);
-                    if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
-                }
-            }
-            __syncthreads();
-        }
-        if (cached) {
-#pragma unroll
-            for (int j = 0; j < CACHE; ++j)
-                if (base0 + j * S3_THREADS < total) emit(base0 + j * S3_THREADS + lane, held[j]);
-        } else {
-            for (int base = base0; base < total; base += S3_THREADS) {
-                const int idx = base + lane;
-                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-                if (idx < total) {
-                    int m, c;
-                    raw = *reinterpret_cast<const uint4 *>(chunk_src(idx, m, c));
-                }
-                emit(idx, raw);
-            }
-        }
-    }
-    __syncthreads();
+    w4_stage<T, MP, S4_THREADS>(p0, args.lda, p1, args.prologue, N, Mp, args.eps, act, asum, rowstat);
 
     T *out = static_cast<T *>(args.out) + static_cast<size_t>(pass) * args.rows_per_pass * K;
     const T *res = args.epilogue == EPI_RESIDUAL ? static_cast<const T *>(args.residual) + static_cast<size_t>(pass) * args.rows_per_pass * K
                                                  : nullptr;
     float *team_red = red + static_cast<size_t>(team) * TW * 16 * 8 * MT;
+    float *wred = team_red + static_cast<size_t>(wit) * 16 * 8 * MT;
     const int team_threads = TW * 32;
     const int ttid = threadIdx.x - team * team_threads;
 
-    int item = 0;
-    for (int ti = 0; ti < my_tiles; ++ti) {
-        const int tile = team_id + ti * team_count;
-        const int row0 = min(tile * 16 + g, K - 1);
-        const int row1 = min(tile * 16 + g + 8, K - 1);
-        float acc[MT][4];
+    const uint4 *act0 = w4_act_lane<MP>(act, g, t) + wit * U * w4_act_group_stride<MP>();
+    const float *asum0 = w4_asum_lane<MP>(asum, t) + wit * U * w4_asum_group_stride<MP>();
+    const uint4 *actp = act0;
+    const float *asump = asum0;
+    const int act_step = TW * U * w4_act_group_stride<MP>();
+    const int asum_step = TW * U * w4_asum_group_stride<MP>();
+
+    float acc[MT][4];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
-        for (int u = wit; u < G; u += TW, ++item) {
-            cp_async_wait<S3_RING - 2>();  // the oldest outstanding group (this item) has landed
-            __syncwarp();
-            const unsigned char *slot0 = ring + (item % S3_RING) * S3_SLOT_BYTES;
-            const unsigned char *slot = slot0 + t * 16;
-            const uint4 w0 = *reinterpret_cast<const uint4 *>(slot + g * 64);
-            const uint4 w1 = *reinterpret_cast<const uint4 *>(slot + (g + 8) * 64);
-            const uint32_t *sw = reinterpret_cast<const uint32_t *>(slot0 + S3_CODE_BYTES);
-            const int par0 = static_cast<int>((static_cast<long long>(row0) * G + u) & 1);
-            const int par1 = static_cast<int>((static_cast<long long>(row1) * G + u) & 1);
-            const float2 sp0 = unpack2<T>(sw[g]), sp1 = unpack2<T>(sw[g + 8]);
-            const float2 cp0 = unpack2<T>(sw[16 + g]), cp1 = unpack2<T>(sw[16 + g + 8]);
-            const float s0 = par0 ? sp0.y : sp0.x, s1 = par1 ? sp1.y : sp1.x;
-            const float c0 = (par0 ? cp0.y : cp0.x) - Mma<T>::OFFSET * s0;
-            const float c1 = (par1 ? cp1.y : cp1.x) - Mma<T>::OFFSET * s1;
-            __syncwarp();                   // every lane has read the slot the next issue may overwrite ...
-            issue(item + S3_RING - 1);      // ... which is slot (item - 1) % RING, consumed one iteration ago
-            // The MMAs of one group are independent instructions (two accumulator sets per column
-            // tile, summed afterwards): legacy mma.sync has a long latency on sm_100 and a dependent
-            // chain of eight is ~4x slower than back-to-back issue.
-            constexpr int CH = MT == 1 ? 8 : (MT == 2 ? 4 : 2);  // independent accumulator sets per column tile
-            float dd[MT][CH][4];
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int c = 0; c < CH; ++c) dd[mt][c][0] = dd[mt][c][1] = dd[mt][c][2] = dd[mt][c][3] = 0.f;
-            const uint32_t x0[4] = {w0.x, w0.y, w0.z, w0.w};
-            const uint32_t x1[4] = {w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                constexpr uint32_t MASK = 0x000F000Fu;
-                const uint32_t a0 = (x0[j] & MASK) | Mma<T>::MAGIC;
-                const uint32_t a1 = ((x0[j] >> 4) & MASK) | Mma<T>::MAGIC;
-                const uint32_t a2 = ((x0[j] >> 8) & MASK) | Mma<T>::MAGIC;
-                const uint32_t a3 = ((x0[j] >> 12) & MASK) | Mma<T>::MAGIC;
-                const uint32_t b0 = (x1[j] & MASK) | Mma<T>::MAGIC;
-                const uint32_t b1 = ((x1[j] >> 4) & MASK) | Mma<T>::MAGIC;
-                const uint32_t b2 = ((x1[j] >> 8) & MASK) | Mma<T>::MAGIC;
-                const uint32_t b3 = ((x1[j] >> 12) & MASK) | Mma<T>::MAGIC;
-                const int chunk = 16 * u + 4 * j + t;
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const int col = mt * 8 + g;
-                    uint4 bf = make_uint4(0u, 0u, 0u, 0u);
-                    if (col < Mp) bf = act[static_cast<size_t>(chunk) * Mp + col];
-                    Mma<T>::mma(dd[mt][(2 * j) % CH], a0, b0, a1, b1, bf.x, bf.y);
-                    Mma<T>::mma(dd[mt][(2 * j + 1) % CH], a2, b2, a3, b3, bf.z, bf.w);
-                }
-            }
-            float d[MT][4];
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float sum = 0.f;
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) sum += dd[mt][k][c];
-                    d[mt][c] = sum;
-                }
+    for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+    int c_tile = team_id, c_in_tile = 0;
+
+    // ---- end of a tile: store 16 x Mp outputs.  Without teams a warp owns the whole reduction and
+    // stores straight from its accumulators (small code: this block is inlined once per pipeline slot
+    // and the hot loop has to stay inside the instruction cache); a team first combines its partial
+    // sums through shared memory, in warp order.
+    auto store_one = [&](int m, int k, float v) {
+        if (m < Mp && k < K) {
+            T vb = from_f<T>(v);
+            if (res != nullptr) vb = from_f<T>(to_f(res[static_cast<size_t>(m) * K + k]) + to_f(vb));
+            out[static_cast<size_t>(m) * K + k] = vb;
+        }
+    };
+    auto finish_tile = [&]() {
+        if (!TEAM) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const int m0 = mt * 8 + 2 * t;
-                const float as0 = m0 < Mp ? asum[u * Mp + m0] : 0.f;
-                const float as1 = m0 + 1 < Mp ? asum[u * Mp + m0 + 1] : 0.f;
-                acc[mt][0] += s0 * d[mt][0] + c0 * as0;
-                acc[mt][1] += s0 * d[mt][1] + c0 * as1;
-                acc[mt][2] += s1 * d[mt][2] + c1 * as0;
-                acc[mt][3] += s1 * d[mt][3] + c1 * as1;
+                const int m0 = mt * 8 + 2 * t, k0 = c_tile * 16 + g;
+                store_one(m0, k0, acc[mt][0]);
+                store_one(m0 + 1, k0, acc[mt][1]);
+                store_one(m0, k0 + 8, acc[mt][2]);
+                store_one(m0 + 1, k0 + 8, acc[mt][3]);
+                acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
             }
+            return;
         }
-        // ---- combine the team's partial sums and store 16 x (8*MT) outputs
-        float *wred = team_red + static_cast<size_t>(wit) * 16 * 8 * MT;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             wred[g * 8 * MT + mt * 8 + 2 * t] = acc[mt][0];
             wred[g * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][1];
             wred[(g + 8) * 8 * MT + mt * 8 + 2 * t] = acc[mt][2];
             wred[(g + 8) * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][3];
+            acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
         }
-        if (TW == 1)
-            __syncwarp();
-        else
-            named_barrier(1 + team, team_threads);
+        named_barrier(1 + team, team_threads);
         for (int o = ttid; o < 16 * 8 * MT; o += team_threads) {
             const int m = o >> 4, r = o & 15;  // consecutive threads -> consecutive output features
-            const int k = tile * 16 + r;
-            if (m < Mp && k < K) {
-                float v = 0.f;
-                for (int w = 0; w < TW; ++w) v += team_red[(w * 16 + r) * 8 * MT + m];
-                T vb = from_f<T>(v);
-                if (res != nullptr) vb = from_f<T>(to_f(res[static_cast<size_t>(m) * K + k]) + to_f(vb));
-                out[static_cast<size_t>(m) * K + k] = vb;
+            float v = 0.f;
+            for (int w = 0; w < TW; ++w) v += team_red[(w * 16 + r) * 8 * MT + m];
+            store_one(m, c_tile * 16 + r, v);
+        }
+        named_barrier(1 + team, team_threads);
+    };
+
+    for (int n = 0; n < total_units; n += S4_DEPTH) {
+#pragma unroll
+        for (int k = 0; k < S4_DEPTH; ++k) {
+            if (n + k < total_units) {  // warp-uniform
+                w4_consume<T, MP, U>(buf[k], actp, asump, g, acc);
+                load_next(buf[k]);
+                actp += act_step;
+                asump += asum_step;
+                if (++c_in_tile == upw) {
+                    finish_tile();
+                    c_in_tile = 0;
+                    c_tile += team_count;
+                    actp = act0;
+                    asump = asum0;
+                }
             }
         }
-        if (TW == 1)
-            __syncwarp();
-        else
-            named_barrier(1 + team, team_threads);
     }
-    cp_async_wait<0>();
 }
 
 static bool g_use_pdl = false;
 void set_use_pdl(bool on) { g_use_pdl = on; }
 bool use_pdl() { return g_use_pdl; }
 
-static size_t stream3_smem_bytes(int N, int Mp, int MT) {
-    size_t bytes = static_cast<size_t>(S3_WARPS) * S3_RING * S3_SLOT_BYTES;
-    bytes += static_cast<size_t>(N / 8) * Mp * 16;
-    bytes += static_cast<size_t>(((N / 128) * Mp + 3) & ~3) * 4;
+static size_t stream4_smem_bytes(int N, int MP) {
+    const int MT = (MP + 7) / 8, MPA = MP < 8 ? 8 : MP;
+    size_t bytes = static_cast<size_t>(N / 8) * MP * 16;
+    bytes += static_cast<size_t>(N / 128) * MPA * 4;
     bytes += 32 * 4;
-    bytes += static_cast<size_t>(S3_WARPS) * 16 * 8 * MT * 4;
+    bytes += static_cast<size_t>(S4_WARPS) * 16 * 8 * MT * 4;
     return bytes;
 }
+constexpr size_t S4_SMEM_MAX = 226 * 1024;
 
-template <typename T, int MT>
-static int stream3_launch(StreamArgs args, cudaStream_t st) {
-    const int Mp = args.rows_per_pass < args.M ? args.rows_per_pass : args.M;
-    const size_t smem = stream3_smem_bytes(args.N, Mp, MT);
-    if (smem > 224 * 1024)
-        return fail(TL_EINVAL, "quantized_matmul: activations do not fit in shared memory (N=%d, rows=%d)", args.N, Mp);
+template <typename T, int MP, int U, bool TEAM>
+static int stream4_launch_k(StreamArgs args, int grid_x, size_t smem, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(w4a16_stream3_kernel<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(w4a16_stream4_kernel<T, MP, U, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(S4_SMEM_MAX));
         if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
         configured = true;
     }
-    const int tiles = ceil_div(args.K, 16);
-    const int G = args.N / 128;
-    const int sms = sm_count();
-    // team width: split a tile's reduction over TW warps until the launch offers ~16 warps per SM
-    int tw = 1;
-    while (tw < S3_WARPS && tiles * tw < sms * 16 && tw * 2 <= G) tw *= 2;
-    args.team_warps = tw;
-    const int teams_per_cta = S3_WARPS / tw;
-    int ctas_per_sm = static_cast<int>((224 * 1024) / (smem + 1024));
-    ctas_per_sm = ctas_per_sm > 3 ? 3 : (ctas_per_sm < 1 ? 1 : ctas_per_sm);
-    const int want = ceil_div(tiles, teams_per_cta);
-    const int cap = sms * ctas_per_sm;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(want < cap ? want : cap, ceil_div(args.M, args.rows_per_pass));
-    cfg.blockDim = dim3(S3_THREADS);
+    cfg.gridDim = dim3(grid_x, ceil_div(args.M, args.rows_per_pass));
+    cfg.blockDim = dim3(S4_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -741,30 +565,56 @@ static int stream3_launch(StreamArgs args, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream3_kernel<T, MT>, args);
-    if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream3: launch failed: %s", cudaGetErrorString(e));
-    TL_LAUNCH_CHECK("w4a16_stream3");
+    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream4_kernel<T, MP, U, TEAM>, args);
+    if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream4: launch failed: %s", cudaGetErrorString(e));
+    TL_LAUNCH_CHECK("w4a16_stream4");
     return TL_OK;
 }
 
+template <typename T, int MP, int U>
+static int stream4_launch(StreamArgs args, cudaStream_t st) {
+    const size_t smem = stream4_smem_bytes(args.N, MP);
+    if (smem > S4_SMEM_MAX)
+        return fail(TL_EINVAL, "quantized_matmul: activations do not fit in shared memory (N=%d, rows=%d)", args.N, MP);
+    const int tiles = ceil_div(args.K, 16);
+    const int P = (args.N / 128) / U;
+    const int sms = sm_count();
+    // team width: split a tile's reduction over TW warps until every warp of the chip has a unit
+    int tw = 1;
+    while (tw < S4_WARPS && tiles * tw < sms * 16 && tw * 2 <= P) tw *= 2;
+    args.team_warps = tw;
+    const int teams_per_cta = S4_WARPS / tw;
+    const int want = ceil_div(tiles, teams_per_cta);
+    int ctas_per_sm = static_cast<int>(S4_SMEM_MAX / (smem + 1024));
+    ctas_per_sm = ctas_per_sm > S4_CTAS_PER_SM ? S4_CTAS_PER_SM : (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+    const int cap = sms * ctas_per_sm;
+    const int grid_x = want < cap ? want : cap;
+    return tw > 1 ? stream4_launch_k<T, MP, U, true>(args, grid_x, smem, st) : stream4_launch_k<T, MP, U, false>(args, grid_x, smem, st);
+}
+
+template <typename T, int U>
+static int stream4_u(StreamArgs args, cudaStream_t st) {
+    // rows of `a` handled per pass: as many (power of two, <= 32) as fit in shared memory
+    int rpp = w4_pad_cols(args.M < 32 ? args.M : 32);
+    while (rpp > 1 && stream4_smem_bytes(args.N, rpp) > S4_SMEM_MAX) rpp /= 2;
+    args.rows_per_pass = rpp;
+    switch (rpp) {
+        case 1: return stream4_launch<T, 1, U>(args, st);
+        case 2: return stream4_launch<T, 2, U>(args, st);
+        case 4: return stream4_launch<T, 4, U>(args, st);
+        case 8: return stream4_launch<T, 8, U>(args, st);
+        case 16: return stream4_launch<T, 16, U>(args, st);
+        default: return stream4_launch<T, 32, U>(args, st);
+    }
+}
+
 template <typename T>
-static int stream3_t(StreamArgs args, cudaStream_t st) {
+static int stream4_t(StreamArgs args, cudaStream_t st) {
     if (!aligned16(args.p0) || !aligned16(args.b) || (args.p1 && !aligned16(args.p1)) || (args.lda % 8) != 0)
         return fail(TL_EINVAL, "quantized_matmul: operands must be 16-byte aligned");
-    // rows of `a` handled per pass: as many as fit in shared memory next to the weight rings
-    const size_t budget = 224 * 1024 - stream3_smem_bytes(args.N, 0, 4) - 2048;
-    const size_t per_row = static_cast<size_t>(args.N) * 2 + static_cast<size_t>(args.N / 128) * 4;
-    const int fit = static_cast<int>(budget / per_row);
-    if (fit < 1) return fail(TL_EINVAL, "quantized_matmul: reduction length %d does not fit in shared memory", args.N);
-    int rpp = fit < 8 ? fit : 8;
-    if (args.M > 16 && fit >= 32)
-        rpp = 32;
-    else if (args.M > 8 && fit >= 16)
-        rpp = 16;
-    args.rows_per_pass = rpp;
-    if (rpp == 32) return stream3_launch<T, 4>(args, st);
-    if (rpp == 16) return stream3_launch<T, 2>(args, st);
-    return stream3_launch<T, 1>(args, st);
+    const bool pairs = (args.N % 256) == 0 && (reinterpret_cast<uintptr_t>(args.scales) & 3u) == 0 &&
+                       (reinterpret_cast<uintptr_t>(args.biases) & 3u) == 0;
+    return (pairs && args.M <= 16) ? stream4_u<T, 2>(args, st) : stream4_u<T, 1>(args, st);  // 32 rows x pairs would spill
 }
 
 int launch_w4a16_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *p1,
@@ -777,8 +627,8 @@ int launch_w4a16_fused(const void *scales, const void *biases, const void *b, vo
     args.M = M, args.N = N, args.K = K, args.lda = lda;
     args.prologue = prologue, args.epilogue = epilogue, args.eps = eps;
     switch (dtype) {
-        case TL_F16: return stream3_t<__half>(args, st);
-        case TL_BF16: return stream3_t<__nv_bfloat16>(args, st);
+        case TL_F16: return stream4_t<__half>(args, st);
+        case TL_BF16: return stream4_t<__nv_bfloat16>(args, st);
     }
     return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
 }

@@ -570,4 +570,5 @@ def device_info() -> tuple[int, int, int]:
     return sms.value, major.value, minor.value
 
 
-load_library()
+# TL_LIB selects an experiment build (tiny-llm_b200/csrc/build.py with TL_LIB_SUFFIX); default: the in-tree product library.
+load_library(os.environ.get("TL_LIB") or None)

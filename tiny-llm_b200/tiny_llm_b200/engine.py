@@ -25,6 +25,8 @@ front and the engine re-captures if a slab pointer changes.
 
 from __future__ import annotations
 
+import os
+
 from types import SimpleNamespace
 
 import numpy as np
@@ -204,6 +206,9 @@ class DecodeEngine:
                 for b in model.layers_inner
             ]
         # persistent == None: use the whole-step kernel whenever the model shape allows it
+        # (TL_PERSISTENT=0 forces the CUDA-graph path for A/B measurements)
+        if persistent is None and os.environ.get("TL_PERSISTENT", "1") == "0":
+            persistent = False
         self.persistent = (persistent is not False) and MegaStep.supported(self)
         self._mega = MegaStep(self) if self.persistent else None
 

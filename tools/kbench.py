@@ -110,15 +110,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "kbench.json"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--lib", default=None, help="alternative libtiny_llm_b200*.so (experiment builds)")
+    ap.add_argument("--only", default=None, help="comma-separated matvec shape names; skips attention and small ops")
     args = ap.parse_args()
     import os
 
+    if args.lib:
+        ext.load_library(args.lib)
     if os.environ.get("TL_PDL", "0") == "1":
         ext.set_pdl(True)
     peak = peak_gbs()
     report = {"hbm_peak_gbs": peak, "gpu": torch.cuda.get_device_name(0), "matvec": [], "attention": [], "small_ops_us": {}}
     shapes = [("q", 2560, 4096), ("kv", 2560, 1024), ("o", 4096, 2560), ("gate_up", 2560, 9728), ("down", 9728, 2560), ("lm_head", 2560, 151936)]
     batches = [1, 8] if args.quick else [1, 2, 4, 8, 16, 32]
+    if args.only:
+        shapes = [s for s in shapes if s[0] in args.only.split(",")]
     for name, N, K in shapes:
         copies = max(2, min(48, int(300e6 // (K * N // 2)) + 1))
         for M in batches:
@@ -126,7 +132,7 @@ def main():
             gbs = nbytes / us / 1e3
             report["matvec"].append(dict(name=name, M=M, N=N, K=K, us=round(us, 2), gbs=round(gbs, 1), frac=round(gbs / peak, 3)))
             print(f"matvec {name:8s} M={M:2d} {N}->{K}: {us:8.2f} us  {gbs:7.1f} GB/s  {gbs / peak:5.1%}", flush=True)
-    for B, S in ([(1, 1024), (1, 8192)] if args.quick else [(1, 128), (1, 1024), (1, 4096), (1, 8192), (8, 4096), (32, 2048), (64, 8192)]):
+    for B, S in [] if args.only else ([(1, 1024), (1, 8192)] if args.quick else [(1, 128), (1, 1024), (1, 4096), (1, 8192), (8, 4096), (32, 2048), (64, 8192)]):
         try:
             us, nbytes = attention_case(B, S)
         except torch.OutOfMemoryError:
@@ -135,7 +141,7 @@ def main():
         gbs = nbytes / us / 1e3
         report["attention"].append(dict(B=B, S=S, us=round(us, 2), gbs=round(gbs, 1), frac=round(gbs / peak, 3)))
         print(f"paged decode attention B={B:2d} S={S:5d}: {us:9.2f} us  {gbs:7.1f} GB/s  {gbs / peak:5.1%}", flush=True)
-    report["small_ops_us"] = {k: round(v, 2) for k, v in small_ops().items()}
+    report["small_ops_us"] = {} if args.only else {k: round(v, 2) for k, v in small_ops().items()}
     print("small ops (us):", report["small_ops_us"], flush=True)
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
     Path(args.out).write_text(json.dumps(report, indent=1))
