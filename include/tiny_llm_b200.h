@@ -152,6 +152,22 @@ int tl_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, co
                                   void *q_out, void *key_pages, void *value_pages, int batch, int num_heads,
                                   int num_kv_heads, int head_dim, float base, float eps, int num_pages, int page_size,
                                   int max_pages, int dtype, void *stream);
+/* Fused decode attention, L == 1 (bf16, head_dim 128, <= 4 query heads per KV head): per-head
+ * q/k RMSNorm + RoPE, append of the newest K/V row and paged GQA attention in ONE launch (plus a
+ * merge launch when the context is split over several CTAs).  Replaces, with the same rounding
+ * points, the call sequence rms_norm, rms_norm, rope, rope, paged_cache_update, paged_attention
+ * of /root/reference/src/tiny_llm_ref/qwen3_week3.py:62-105.  qkv [B, (Hq + 2 Hkv) * 128] is the
+ * row-concatenated projection output; context_lens are post-append; rope_inv_freq holds the 64
+ * float64 frequencies base^(-i/64); out [B, Hq * 128]; max_context bounds every context_lens[b]
+ * (it fixes the split count, so a captured launch stays valid as the contexts grow);
+ * workspace: tl_decode_attention_fused_workspace() floats. */
+size_t tl_decode_attention_fused_workspace(int batch, int num_heads, int num_kv_heads);
+int tl_decode_attention_fused(const void *qkv, const void *q_norm_weight, const void *k_norm_weight,
+                              const int32_t *offsets, const int32_t *block_table, const int32_t *context_lens,
+                              const double *rope_inv_freq, void *key_pages, void *value_pages, void *out,
+                              float *workspace, int batch, int num_heads, int num_kv_heads, int head_dim, float eps,
+                              float scale, int num_pages, int page_size, int max_pages, int max_context, int dtype,
+                              void *stream);
 /* ---- whole-step persistent decode kernel -------------------------------------
  * One cooperative launch runs a complete decode step (L == 1, bf16, W4A16, paged
  * KV, batch 1..8, head_dim 128, <= 4 query heads per KV head) of the Week-3

@@ -79,6 +79,39 @@ def test_fused_qk_norm_rope_append_equals_the_unfused_sequence(dev):
     assert torch.equal(kp[untouched.to(dev)], kp_ref[untouched.to(dev)])
 
 
+@pytest.mark.parametrize("contexts,page", [([17, 1, 33], 16), ([131, 256, 257], 128), ([700, 5, 1030], 64), ([4100], 128)])
+@pytest.mark.parametrize("Hq,Hkv", [(32, 8), (4, 2), (2, 2)])
+def test_fused_decode_attention_equals_the_operator_sequence(dev, contexts, page, Hq, Hkv):
+    """q/k norm + rope + append + paged attention in one launch (and its split/merge form for long
+    contexts) against the per-operator kernels on the same cache."""
+    g = torch.Generator().manual_seed(sum(contexts) + Hq)
+    B, D = len(contexts), 128
+    max_pages = (max(contexts) + page - 1) // page + 1
+    P = B * max_pages + 2
+    qkv = torch.randn(B, (Hq + 2 * Hkv) * D, generator=g).to(BF16).to(dev)
+    qw = (1 + 0.1 * torch.randn(D, generator=g)).to(BF16).to(dev)
+    kw = (1 + 0.1 * torch.randn(D, generator=g)).to(BF16).to(dev)
+    ctx = torch.tensor(contexts, dtype=torch.int32, device=dev)
+    offsets = (ctx - 1).clamp_min(0).to(torch.int32)
+    perm = torch.randperm(P, generator=g)
+    bt = torch.full((B, max_pages), -1, dtype=torch.int32)
+    for b, c in enumerate(contexts):
+        n = (c + page - 1) // page
+        bt[b, :n] = perm[b * max_pages : b * max_pages + n].to(torch.int32)
+    bt = bt.to(dev)
+    kp = torch.randn(P, Hkv, page, D, generator=g).to(BF16).to(dev)
+    vp = torch.randn(P, Hkv, page, D, generator=g).to(BF16).to(dev)
+    kp_ref, vp_ref = kp.clone(), vp.clone()
+    scale = D**-0.5
+    q = ext.decode_qk_norm_rope_append(qkv, qw, kw, offsets, bt, ctx, kp_ref, vp_ref, Hq, Hkv, 1e6, 1e-6)
+    want = ext.paged_attention(q.view(B * Hq, 1, D), kp_ref, vp_ref, bt, ctx, scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
+    freq = ext.rope_inv_freq_table(D, 1e6, dev)
+    got = ext.decode_attention_fused(qkv, qw, kw, offsets, bt, ctx, freq, kp, vp, Hq, Hkv, 1e-6, scale, max(contexts) + 7)
+    assert torch.equal(kp, kp_ref) and torch.equal(vp, vp_ref), "the appended rows are the same bits"
+    # probabilities stay fp32 in both; the summation order over tokens differs
+    torch.testing.assert_close(got.float().view(B * Hq, D), want.float().view(B * Hq, D), rtol=2**-7, atol=4e-3)
+
+
 @pytest.fixture(scope="module")
 def tiny_gpu(dev):
     return synthetic_qwen3("tiny-d128", seed=0, realistic=True, max_position_embeddings=512, device=dev)

@@ -121,11 +121,14 @@ struct SRange {
 template <int U>
 __device__ __forceinline__ SRange mk_range(const SPhase &p, int warp) {
     SRange r;
-    // K * gridDim.x < 2^31 (checked by the launcher): 32-bit divisions only
-    r.r0 = static_cast<int>(static_cast<unsigned>(p.K) * blockIdx.x / gridDim.x);
-    r.r1 = static_cast<int>(static_cast<unsigned>(p.K) * (blockIdx.x + 1) / gridDim.x);
+    // Whole 16-row chunks per CTA: a chunk shared by two CTAs would cost both of them a full tile of
+    // tensor-core work for a few rows each (K = 2560 over 148 CTAs did exactly that).
+    const unsigned all = static_cast<unsigned>(p.K + 15) >> 4;  // all * gridDim.x < 2^31: 32-bit divisions only
+    const int c0 = static_cast<int>(all * blockIdx.x / gridDim.x), c1 = static_cast<int>(all * (blockIdx.x + 1) / gridDim.x);
+    r.r0 = c0 * 16;
+    r.r1 = min(p.K, c1 * 16);
     r.P = p.N / (128 * U);
-    r.chunks = (r.r1 - r.r0 + 15) >> 4;
+    r.chunks = c1 - c0;
     const unsigned units = r.chunks * r.P;
     r.begin = static_cast<int>(units * warp / MK_WARPS);
     r.end = static_cast<int>(units * (warp + 1) / MK_WARPS);
@@ -135,12 +138,15 @@ __device__ __forceinline__ SRange mk_range(const SPhase &p, int warp) {
 // Per-warp register pipeline: DEPTH weight units in flight, filled by a cursor that walks the
 // (streaming phase, unit) pairs of the WHOLE step, so the first units of the next projection are
 // already on their way while the warp sits in a grid barrier or re-stages activations.
-constexpr int MK_DEPTH = 4;
+#ifndef MK_DEPTH_N
+#define MK_DEPTH_N 4
+#endif
+constexpr int MK_DEPTH = MK_DEPTH_N;
 template <int U>
 struct Pipe {
     W4Unit<U> buf[MK_DEPTH];
     int slot;                            // buffer the consumer takes next
-    int sp, i, end;                      // load cursor: phase, next unit, end of this warp's range
+    int sp, i, end, hold;                // load cursor: phase, next unit, end of this warp's range; parked at an o_proj phase
     int u, P, row_base, r1, G;           // unit inside its chunk, units per chunk, chunk rows, CTA row end
     const unsigned char *w, *tab;        // phase weights; this lane's scale (lanes 0-15) or bias table
     const unsigned char *p0, *p8, *sb;   // this lane's addresses for the next unit
@@ -156,10 +162,17 @@ __device__ __forceinline__ void mk_chunk_ptrs(Pipe<U> &c, int lane) {  // rows p
     c.sb = c.tab + (static_cast<size_t>(min(c.row_base + (lane & 15), last)) * c.G + c.u * U) * 2;
 }
 
-// Position the load cursor on the first unit of phase c.sp (or a later one) that belongs to this warp.
+// Position the load cursor on the first unit of phase c.sp (or a later one) that belongs to this
+// warp.  The cursor never walks into an o_proj phase on its own (resume == false): the attention
+// phase in front of it wants the registers, so the pipeline is drained there and refilled after.
 template <int U>
-__device__ __forceinline__ void mk_cursor_phase(const MkArgs &a, Pipe<U> &c, int warp, int lane) {
+__device__ __forceinline__ void mk_cursor_phase(const MkArgs &a, Pipe<U> &c, int warp, int lane, bool resume) {
     while (c.sp < mk_num_sphases(a)) {
+        if (!resume && (c.sp & 3) == 1 && c.sp < 4 * a.n_layers) {
+            c.hold = 1;
+            return;
+        }
+        resume = false;
         const SPhase p = mk_sphase(a, c.sp);
         const SRange r = mk_range<U>(p, warp);
         if (r.begin < r.end) {
@@ -176,14 +189,16 @@ __device__ __forceinline__ void mk_cursor_phase(const MkArgs &a, Pipe<U> &c, int
     }
 }
 
-template <int U>
+// FORCE: always define `un` (a dummy load when the cursor is parked or exhausted), so that the
+// pipeline registers are provably dead before a refill.
+template <int U, bool FORCE>
 __device__ __forceinline__ void mk_load_next(const MkArgs &a, Pipe<U> &c, W4Unit<U> &un, int warp, int lane) {
-    if (c.sp < mk_num_sphases(a)) {
+    if (c.sp < mk_num_sphases(a) && !c.hold) {
         w4_load<U>(un, c.p0, c.p8, c.sb);
         c.i += 1;
         if (c.i == c.end) {
             c.sp += 1;
-            mk_cursor_phase<U>(a, c, warp, lane);
+            mk_cursor_phase<U>(a, c, warp, lane, false);
         } else if (++c.u == c.P) {
             c.u = 0;
             c.row_base += 16;
@@ -193,7 +208,22 @@ __device__ __forceinline__ void mk_load_next(const MkArgs &a, Pipe<U> &c, W4Unit
             c.p8 += U * 64;
             c.sb += U * 2;
         }
+    } else if (FORCE) {
+        const unsigned char *dummy = static_cast<const unsigned char *>(a.w_head);
+        w4_load<U>(un, dummy, dummy, static_cast<const unsigned char *>(a.s_head));
     }
+}
+
+// (Re)start the pipeline: every buffer is rewritten, the consumer restarts at buffer 0.
+template <int U>
+__device__ __forceinline__ void mk_refill(const MkArgs &a, Pipe<U> &c, int warp, int lane, bool resume) {
+    c.slot = 0;
+    if (resume && c.hold) {  // only the o_proj phase itself releases a parked cursor
+        c.hold = 0;
+        mk_cursor_phase<U>(a, c, warp, lane, true);
+    }
+#pragma unroll
+    for (int k = 0; k < MK_DEPTH; ++k) mk_load_next<U, true>(a, c, c.buf[k], warp, lane);
 }
 
 // One projection: out[m, k] (= res[m, k] +) sum_n act[m, n] * dequant(w[k, n]) for this CTA's rows.
@@ -236,7 +266,7 @@ __device__ void mk_stream(const MkArgs &a, int sp, Pipe<U> &pipe, const bf16 *in
         for (int k = 0; k < MK_DEPTH; ++k) {
             if (pipe.slot == k && i < r.end) {  // warp-uniform; k is a compile-time register index
                 w4_consume<bf16, MP, U>(pipe.buf[k], actp, asump, g, acc);
-                mk_load_next<U>(a, pipe, pipe.buf[k], warp, lane);
+                mk_load_next<U, false>(a, pipe, pipe.buf[k], warp, lane);
                 pipe.slot = (k + 1) % MK_DEPTH;
                 i += 1;
                 actp += U * w4_act_group_stride<MP>();
@@ -312,8 +342,28 @@ __device__ void mk_cta_argmax(const MkArgs &a, int r0, int r1, float *scratch_v,
 }
 
 // --------------------------------------------------------------- attention --
-// One CTA per (request, kv head, split); 16 lanes per token, 8 dims per lane, L == 1.
-__device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *dyn) {
+// One CTA per (request, kv head, split), L == 1.  The phase is pure latency (8 CTAs x 64 KB of
+// K/V at context 128), so it is organised around dependent round trips and wide parallelism, not
+// bandwidth.  Per round of up to MK_ATT_TOK tokens:
+//   A  page ids of the round -> shared; warps 0..G+1 already hold their q/k/v head rows, norm
+//      weights and rope frequencies in registers (loaded before anything else)
+//   B  cp.async ALL K/V rows of the round into shared memory (row stride 528 B: bank spread)
+//   C  while those are in flight: q/k RMSNorm + RoPE (rounded like rms_norm -> rope), V copy
+//   S  scores = Q K^T on the tensor cores: mma.sync m16n8k16, A = the G query heads (rows >= G
+//      zero), B = K rows straight from shared memory; 8 tokens per MMA tile, 16 warps
+//   M  one warp per head: max / exp2 / sum over the round's tokens (fp32)
+//   V  out = P V on CUDA cores with fp32 probabilities: thread = (head, 8 dims, token subset)
+//   then the running (max, sum, out) of thread (head, dim) absorbs the round.
+constexpr int MK_ATT_TOK = 256;     // K/V rows staged per round
+constexpr int MK_KV_STRIDE = 528;   // bytes per staged token: K row | V row | 16 B pad
+constexpr size_t MK_ATT_BYTES = 4 * 128 * 2 + 2 * 128 * 2 + 4 * MK_ATT_TOK * 4 + 64 + 8 * 4 * 128 * 4 + (MK_ATT_TOK + 4) * 4 +
+                                static_cast<size_t>(MK_ATT_TOK) * MK_KV_STRIDE;
+
+__device__ __forceinline__ void mk_cp16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+
+__device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *dyn, Prof &prof) {
     const int D = a.D, G = a.Hq / a.Hkv;
     const int items = a.B * a.Hkv * a.nsplit;
     if (static_cast<int>(blockIdx.x) >= items) return;
@@ -321,174 +371,204 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
     const int kvh = (blockIdx.x / a.nsplit) % a.Hkv;
     const int b = blockIdx.x / (a.nsplit * a.Hkv);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ctx = min(a.context_lens[b], a.max_pages * a.page_size);
     const int qkv_w = (a.Hq + 2 * a.Hkv) * D;
 
-    float *q_s = reinterpret_cast<float *>(dyn);                  // [G][128] pre-scaled
-    bf16 *k_cur = reinterpret_cast<bf16 *>(q_s + 4 * 128);         // [128]
-    bf16 *v_cur = k_cur + 128;                                     // [128]
-    float *m_s = reinterpret_cast<float *>(v_cur + 128);           // [MK_WARPS][4]
-    float *l_s = m_s + MK_WARPS * 4;
-    float *o_s = l_s + MK_WARPS * 4;                               // [MK_WARPS][4][128]
+    bf16 *q_s = reinterpret_cast<bf16 *>(dyn);                      // [4][128] rope output (unscaled)
+    bf16 *k_cur = q_s + 4 * 128;                                    // [128] newest token
+    bf16 *v_cur = k_cur + 128;                                      // [128]
+    float *s_s = reinterpret_cast<float *>(v_cur + 128);            // [4][MK_ATT_TOK] scores, then probabilities
+    float *st_s = s_s + 4 * MK_ATT_TOK;                             // m[4], l[4] of the round
+    float *op_s = st_s + 16;                                        // [8 subsets][4][128] partial outputs
+    int *pg_s = reinterpret_cast<int *>(op_s + 8 * 4 * 128);        // page ids of the round
+    unsigned char *kv_s = reinterpret_cast<unsigned char *>(pg_s + MK_ATT_TOK + 4);  // [MK_ATT_TOK][528]
 
-    // ---- per-head q/k RMSNorm + RoPE (rounded like rms_norm -> rope), V copy; heads: G q, 1 k, 1 v
-    if (warp < G + 2) {
-        const bool is_q = warp < G, is_k = warp == G;
+    // ---- head rows for the q path (registers; used after the K/V copies are in flight)
+    const bool qpath = warp < G + 2;
+    const bool is_q = warp < G, is_k = warp == G;
+    float re[2] = {0.f, 0.f}, im[2] = {0.f, 0.f}, wre[2] = {0.f, 0.f}, wim[2] = {0.f, 0.f};
+    double freq[2] = {0.0, 0.0};
+    int position = 0;
+    if (qpath) {
         const int head_off = is_q ? (kvh * G + warp) * D : (is_k ? (a.Hq + kvh) * D : (a.Hq + a.Hkv + kvh) * D);
         const bf16 *src = static_cast<const bf16 *>(a.qkv) + static_cast<size_t>(b) * qkv_w + head_off;
-        // lane owns pairs (i, i+64) for i = lane, lane+32   (D == 128)
-        float re[2], im[2];
+        const bf16 *w = static_cast<const bf16 *>(is_q ? l.q_norm : l.k_norm);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h) {  // lane owns pairs (i, i+64) for i = lane, lane+32   (D == 128)
             re[h] = mk_bf(__ldcg(src + lane + 32 * h));
             im[h] = mk_bf(__ldcg(src + lane + 32 * h + 64));
-        }
-        if (is_q || is_k) {
-            float ss = re[0] * re[0] + im[0] * im[0] + re[1] * re[1] + im[1] * im[1];
-            ss = warp_sum(ss);
-            const float inv = rsqrtf(ss / static_cast<float>(D) + a.eps);
-            const bf16 *w = static_cast<const bf16 *>(is_q ? l.q_norm : l.k_norm);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane + 32 * h;
-                const float nre = mk_round(re[h] * inv * mk_bf(w[i]));
-                const float nim = mk_round(im[h] * inv * mk_bf(w[i + 64]));
-                const float angle = static_cast<float>(static_cast<double>(a.offsets[b]) * a.rope_inv_freq[i]);
-                float s, c;
-                sincosf(angle, &s, &c);
-                const bf16 ore = __float2bfloat16_rn(nre * c - nim * s), oim = __float2bfloat16_rn(nim * c + nre * s);
-                if (is_q) {
-                    q_s[warp * 128 + i] = mk_bf(ore) * a.attn_scale * MK_LOG2E;
-                    q_s[warp * 128 + i + 64] = mk_bf(oim) * a.attn_scale * MK_LOG2E;
-                } else {
-                    k_cur[i] = ore, k_cur[i + 64] = oim;
-                }
+            if (is_q || is_k) {
+                wre[h] = mk_bf(w[lane + 32 * h]);
+                wim[h] = mk_bf(w[lane + 32 * h + 64]);
+                freq[h] = a.rope_inv_freq[lane + 32 * h];
             }
-        } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) v_cur[lane + 32 * h] = __float2bfloat16_rn(re[h]), v_cur[lane + 32 * h + 64] = __float2bfloat16_rn(im[h]);
         }
+        position = a.offsets[b];
     }
-    __syncthreads();
+    const int ctx = min(a.context_lens[b], a.max_pages * a.page_size);
     const int begin = split * a.tokens_per_split;
     const int end = min(ctx, begin + a.tokens_per_split);
     const int cur_tok = ctx - 1;
-    // the split that owns the newest token appends it to the cache (paged_cache_update semantics)
-    if (ctx > 0 && cur_tok >= begin && cur_tok < end && threadIdx.x < 2 * (D / 8)) {
-        const int lp = cur_tok / a.page_size;
-        const int pid = l.table[static_cast<size_t>(b) * a.max_pages + lp];
-        if (pid >= 0 && pid < a.num_pages) {
+    const int gidx = warp * 2 + (lane >> 4), c8 = lane & 15;   // copy mapping: lane group of 16 per token row
+    const int g = lane >> 2, t = lane & 3;                      // MMA fragment coordinates
+    const int oh = threadIdx.x >> 7, od = threadIdx.x & 127;    // owner of out[head oh][dim od]
+    const float scale2 = a.attn_scale * MK_LOG2E;
+    float m_run = MK_NEG, l_run = 0.f, o_run = 0.f;
+    prof.stamp(50001);
+
+    for (int rb = begin; rb < end || rb == begin; rb += MK_ATT_TOK) {  // one pass even for an empty split (q path, barriers)
+        const int rend = min(end, rb + MK_ATT_TOK);
+        const int cnt = max(rend - rb, 0);
+        const int lp0 = rb / a.page_size;
+        const int npg = cnt > 0 ? (rend - 1) / a.page_size - lp0 + 1 : 0;
+        if (static_cast<int>(threadIdx.x) < npg) pg_s[threadIdx.x] = l.table[static_cast<size_t>(b) * a.max_pages + lp0 + threadIdx.x];
+        __syncthreads();
+        prof.stamp(50002);
+        // ---- B: all K/V rows of the round in flight
+#pragma unroll
+        for (int j = 0; j < MK_ATT_TOK / 32; ++j) {
+            const int slot = j * 32 + gidx;
+            const int tok = rb + slot;
+            if (tok < rend && tok != cur_tok) {
+                const int lp = tok / a.page_size;
+                const int pid = pg_s[lp - lp0];
+                if (pid >= 0 && pid < a.num_pages) {
+                    const size_t off = ((static_cast<size_t>(pid) * a.Hkv + kvh) * a.page_size + (tok - lp * a.page_size)) * D + c8 * 8;
+                    mk_cp16(kv_s + slot * MK_KV_STRIDE + c8 * 16, static_cast<const bf16 *>(l.k_pages) + off);
+                    mk_cp16(kv_s + slot * MK_KV_STRIDE + 256 + c8 * 16, static_cast<const bf16 *>(l.v_pages) + off);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        prof.stamp(50003);
+        // ---- C: q path (first round only)
+        if (rb == begin && qpath) {
+            if (is_q || is_k) {
+                float ss = re[0] * re[0] + im[0] * im[0] + re[1] * re[1] + im[1] * im[1];
+                ss = warp_sum(ss);
+                const float inv = rsqrtf(ss / static_cast<float>(D) + a.eps);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = lane + 32 * h;
+                    const float nre = mk_round(re[h] * inv * wre[h]);
+                    const float nim = mk_round(im[h] * inv * wim[h]);
+                    const float angle = static_cast<float>(static_cast<double>(position) * freq[h]);
+                    float sn, cs;
+                    sincosf(angle, &sn, &cs);
+                    const bf16 ore = __float2bfloat16_rn(nre * cs - nim * sn), oim = __float2bfloat16_rn(nim * cs + nre * sn);
+                    bf16 *dst = is_q ? q_s + warp * 128 : k_cur;
+                    dst[i] = ore, dst[i + 64] = oim;
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) v_cur[lane + 32 * h] = __float2bfloat16_rn(re[h]), v_cur[lane + 32 * h + 64] = __float2bfloat16_rn(im[h]);
+            }
+        }
+        prof.stamp(50004);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // q_s / k_cur / v_cur and every lane's K/V pieces are visible
+        // the newest token: its K/V rows join the staged rows, and the split that owns it appends it
+        // to the cache (paged_cache_update semantics)
+        if (ctx > 0 && cur_tok >= rb && cur_tok < rend && threadIdx.x < 2 * (D / 8)) {
             const bool kk = threadIdx.x < D / 8;
             const int ch = kk ? threadIdx.x : threadIdx.x - D / 8;
-            bf16 *dst = static_cast<bf16 *>(kk ? l.k_pages : l.v_pages) + ((static_cast<size_t>(pid) * a.Hkv + kvh) * a.page_size + (cur_tok - lp * a.page_size)) * D + ch * 8;
-            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>((kk ? k_cur : v_cur) + ch * 8);
+            const uint4 row = *reinterpret_cast<const uint4 *>((kk ? k_cur : v_cur) + ch * 8);
+            *reinterpret_cast<uint4 *>(kv_s + (cur_tok - rb) * MK_KV_STRIDE + (kk ? 0 : 256) + ch * 16) = row;
+            const int lp = cur_tok / a.page_size;
+            const int pid = pg_s[lp - lp0];
+            if (pid >= 0 && pid < a.num_pages) {
+                bf16 *dst = static_cast<bf16 *>(kk ? l.k_pages : l.v_pages) + ((static_cast<size_t>(pid) * a.Hkv + kvh) * a.page_size + (cur_tok - lp * a.page_size)) * D + ch * 8;
+                *reinterpret_cast<uint4 *>(dst) = row;
+            }
         }
-    }
-
-    // ---- online softmax over this split; lane group = 16 lanes, 8 dims per lane
-    const int grp = lane >> 4, c8 = lane & 15;
-    float acc[4][8], mm[4], ll[4];
+        __syncthreads();
+        prof.stamp(50005);
+        // ---- S: scores of 8 tokens x G heads per MMA tile
+        for (int tile = warp; tile * 8 < cnt; tile += MK_WARPS) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            const unsigned char *krow = kv_s + (tile * 8 + g) * MK_KV_STRIDE + t * 4;
+            const bf16 *qrow = q_s + (g < G ? g : 0) * 128 + 2 * t;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        mm[r] = MK_NEG, ll[r] = 0.f;
+            for (int ks = 0; ks < 8; ++ks) {
+                uint32_t a0 = *reinterpret_cast<const uint32_t *>(qrow + ks * 16);
+                uint32_t a2 = *reinterpret_cast<const uint32_t *>(qrow + ks * 16 + 8);
+                if (g >= G) a0 = a2 = 0u;
+                const uint32_t b0 = *reinterpret_cast<const uint32_t *>(krow + ks * 32);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t *>(krow + ks * 32 + 16);
+                W4Num<bf16>::mma(d, a0, 0u, a2, 0u, b0, b1);
+            }
+            if (g < G) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[r][i] = 0.f;
-    }
-    const int stride = MK_WARPS * 2;
-    // NOTE: the trip count must be warp-uniform (full-mask shuffles inside): the lane group is folded
-    // into the token index, not into the loop bounds.
-    for (int base = begin + warp * 2; base < end; base += 2 * stride) {
-        uint4 kr[2], vr[2];
-        bool ok[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {  // two tokens per iteration, all loads issued before any use
-            const int tok = base + grp + h * stride;
-            ok[h] = tok < end;
-            kr[h] = vr[h] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok[h]) {
-                if (tok == cur_tok) {
-                    kr[h] = *reinterpret_cast<const uint4 *>(k_cur + c8 * 8);
-                    vr[h] = *reinterpret_cast<const uint4 *>(v_cur + c8 * 8);
-                } else {
-                    const int lp = tok / a.page_size;
-                    const int pid = l.table[static_cast<size_t>(b) * a.max_pages + lp];
-                    ok[h] = pid >= 0 && pid < a.num_pages;
-                    if (ok[h]) {
-                        const size_t off = ((static_cast<size_t>(pid) * a.Hkv + kvh) * a.page_size + (tok - lp * a.page_size)) * D + c8 * 8;
-                        kr[h] = ldg_stream(static_cast<const bf16 *>(l.k_pages) + off);
-                        vr[h] = ldg_stream(static_cast<const bf16 *>(l.v_pages) + off);
+                for (int e = 0; e < 2; ++e) {
+                    const int slot = tile * 8 + 2 * t + e;
+                    bool ok = slot < cnt;
+                    if (ok) {
+                        const int pid = pg_s[(rb + slot) / a.page_size - lp0];
+                        ok = pid >= 0 && pid < a.num_pages;
+                    }
+                    s_s[g * MK_ATT_TOK + slot] = ok ? d[e] * scale2 : -CUDART_INF_F;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- M: per head max / exp2 / sum over the round
+        const int cnt8 = (cnt + 7) & ~7;  // S wrote whole tiles
+        if (warp < G) {
+            float mx = MK_NEG;
+            for (int i = lane; i < cnt8; i += 32) mx = fmaxf(mx, s_s[warp * MK_ATT_TOK + i]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int i = lane; i < cnt8; i += 32) {
+                const float pr = exp2f(s_s[warp * MK_ATT_TOK + i] - mx);
+                s_s[warp * MK_ATT_TOK + i] = pr;
+                sum += pr;
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) st_s[warp] = mx, st_s[4 + warp] = sum;
+        }
+        __syncthreads();
+        // ---- V: partial outputs, thread = (token subset, 8 dims, head)
+        {
+            const int sub = threadIdx.x & 7, d8 = (threadIdx.x >> 3) & 15;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (oh < G) {
+                for (int slot = sub; slot < cnt8; slot += 8) {
+                    const float pr = s_s[oh * MK_ATT_TOK + slot];
+                    if (pr != 0.f) {  // masked / padded slots hold no valid V row
+                        const uint4 vr = *reinterpret_cast<const uint4 *>(kv_s + slot * MK_KV_STRIDE + 256 + d8 * 16);
+                        const float2 f0 = unpack2<bf16>(vr.x), f1 = unpack2<bf16>(vr.y), f2 = unpack2<bf16>(vr.z), f3 = unpack2<bf16>(vr.w);
+                        acc[0] += pr * f0.x, acc[1] += pr * f0.y, acc[2] += pr * f1.x, acc[3] += pr * f1.y;
+                        acc[4] += pr * f2.x, acc[5] += pr * f2.y, acc[6] += pr * f3.x, acc[7] += pr * f3.y;
                     }
                 }
             }
+            float *o = op_s + (sub * 4 + oh) * 128 + d8 * 8;
+            *reinterpret_cast<float4 *>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4 *>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
+        __syncthreads();
+        prof.stamp(50006);
+        if (oh < G) {
+            float o_r = 0.f;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint32_t kw[4] = {kr[h].x, kr[h].y, kr[h].z, kr[h].w};
-            const uint32_t vw[4] = {vr[h].x, vr[h].y, vr[h].z, vr[h].w};
-            float kf[8], vf[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack2<bf16>(kw[i]), e = unpack2<bf16>(vw[i]);
-                kf[2 * i] = f.x, kf[2 * i + 1] = f.y, vf[2 * i] = e.x, vf[2 * i + 1] = e.y;
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (r < G) {
-                    const float4 qa = *reinterpret_cast<const float4 *>(q_s + r * 128 + c8 * 8);
-                    const float4 qb = *reinterpret_cast<const float4 *>(q_s + r * 128 + c8 * 8 + 4);
-                    float s = qa.x * kf[0] + qa.y * kf[1] + qa.z * kf[2] + qa.w * kf[3] + qb.x * kf[4] + qb.y * kf[5] + qb.z * kf[6] + qb.w * kf[7];
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    s += __shfl_xor_sync(0xffffffffu, s, 8);
-                    if (!ok[h]) s = -CUDART_INF_F;
-                    const float nm = fmaxf(mm[r], s);
-                    const float corr = exp2f(mm[r] - nm), pr = exp2f(s - nm);
-                    ll[r] = ll[r] * corr + pr;
-                    mm[r] = nm;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[r][i] = acc[r][i] * corr + pr * vf[i];
-                }
-            }
+            for (int sub = 0; sub < 8; ++sub) o_r += op_s[(sub * 4 + oh) * 128 + od];
+            const float m_r = st_s[oh], l_r = st_s[4 + oh];
+            const float nm = fmaxf(m_run, m_r);
+            const float fr = exp2f(m_run - nm), fn = exp2f(m_r - nm);
+            o_run = o_run * fr + o_r * fn;
+            l_run = l_run * fr + l_r * fn;
+            m_run = nm;
         }
+        __syncthreads();  // the round's page ids, rows and scores are dead: the next round may overwrite them
     }
-    // ---- merge the 2 lane groups of every warp (shuffle), then the warps through shared memory
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        if (r < G) {
-            const float mo = __shfl_xor_sync(0xffffffffu, mm[r], 16), lo = __shfl_xor_sync(0xffffffffu, ll[r], 16);
-            const float nm = fmaxf(mm[r], mo);
-            const float fs = exp2f(mm[r] - nm), fo = exp2f(mo - nm);
-            ll[r] = ll[r] * fs + lo * fo;
-            mm[r] = nm;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[r][i] = acc[r][i] * fs + __shfl_xor_sync(0xffffffffu, acc[r][i], 16) * fo;
-            if (grp == 0) {
-                float *o = o_s + (static_cast<size_t>(warp) * 4 + r) * 128 + c8 * 8;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = acc[r][i];
-                if (c8 == 0) m_s[warp * 4 + r] = mm[r], l_s[warp * 4 + r] = ll[r];
-            }
-        }
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < G * 128; o += MK_THREADS) {
-        const int r = o >> 7, d = o & 127;
-        float gm = MK_NEG;
-        for (int s = 0; s < MK_WARPS; ++s) gm = fmaxf(gm, m_s[s * 4 + r]);
-        float gl = 0.f, acc_o = 0.f;
-        for (int s = 0; s < MK_WARPS; ++s) {
-            const float f = exp2f(m_s[s * 4 + r] - gm);
-            gl += l_s[s * 4 + r] * f;
-            acc_o += o_s[(static_cast<size_t>(s) * 4 + r) * 128 + d] * f;
-        }
-        const int head = kvh * G + r;
+    prof.stamp(50007);
+    if (oh < G) {
+        const int head = kvh * G + oh;
         if (a.nsplit == 1) {
-            static_cast<bf16 *>(a.y)[(static_cast<size_t>(b) * a.Hq + head) * D + d] = __float2bfloat16_rn(gl == 0.f ? 0.f : acc_o / gl);
+            static_cast<bf16 *>(a.y)[(static_cast<size_t>(b) * a.Hq + head) * D + od] = __float2bfloat16_rn(l_run == 0.f ? 0.f : o_run / l_run);
         } else {
             const size_t row = (static_cast<size_t>(b) * a.Hq + head) * a.nsplit + split;
-            a.attn_ws[row * (D + 2) + d] = acc_o;
-            if (d == 0) a.attn_ws[row * (D + 2) + D] = gm, a.attn_ws[row * (D + 2) + D + 1] = gl;
+            a.attn_ws[row * (D + 2) + od] = o_run;
+            if (od == 0) a.attn_ws[row * (D + 2) + D] = m_run, a.attn_ws[row * (D + 2) + D + 1] = l_run;
         }
     }
 }
@@ -527,10 +607,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
     prof.stamp(1);
 
     Pipe<U> pipe;
-    pipe.slot = 0, pipe.sp = 0;
-    mk_cursor_phase<U>(a, pipe, warp, lane);
-#pragma unroll
-    for (int k = 0; k < MK_DEPTH; ++k) mk_load_next<U>(a, pipe, pipe.buf[k], warp, lane);  // weights first: they depend on nothing
+    pipe.sp = 0, pipe.hold = 0;
+    mk_cursor_phase<U>(a, pipe, warp, lane, false);
+    mk_refill<U>(a, pipe, warp, lane, false);  // weights first: they depend on nothing
 
     // ---- phase 0: embedding rows -> xa (quantized_matmul.metal:58-89); feature words dealt across the grid
     {
@@ -573,6 +652,19 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
             case 3: in = gu, ld = 2 * a.I, up_off = a.I, prologue = 2, out = x, res = x_alt; break;
             default: norm_w = static_cast<const bf16 *>(a.final_norm), out = static_cast<bf16 *>(a.logits); break;
         }
+        if (kind == 1) {  // attention sits in front of o_proj; the weight pipeline is empty here (see mk_cursor_phase)
+            mk_attention(a, l, dyn, prof);
+            prof.stamp(100 + (sp - 1) * 10 + 6);
+            // restart the weight stream BEFORE the barrier: the 140 CTAs without an attention item get
+            // here at once, and everyone's first o_proj units fly while the grid synchronises
+            mk_refill<U>(a, pipe, warp, lane, true);
+            mk_grid_sync(a.sync_counter, epoch);
+            prof.stamp(100 + (sp - 1) * 10 + 7);
+            if (a.nsplit > 1) {
+                mk_attention_merge(a);
+                mk_grid_sync(a.sync_counter, epoch);
+            }
+        }
         mk_stream<MP, U>(a, sp, pipe, in, ld, up_off, prologue, norm_w, out, res, dyn, prof);
         if (kind == 4) {  // greedy arg-max partials of this CTA's logits rows
             const SRange r = mk_range<U>(mk_sphase(a, sp), warp);
@@ -581,16 +673,6 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
         prof.stamp(100 + sp * 10 + 4);
         mk_grid_sync(a.sync_counter, epoch);
         prof.stamp(100 + sp * 10 + 5);
-        if (kind == 0) {
-            mk_attention(a, l, dyn);
-            prof.stamp(100 + sp * 10 + 6);
-            mk_grid_sync(a.sync_counter, epoch);
-            prof.stamp(100 + sp * 10 + 7);
-            if (a.nsplit > 1) {
-                mk_attention_merge(a);
-                mk_grid_sync(a.sync_counter, epoch);
-            }
-        }
     }
     if (blockIdx.x == 0 && warp == 0) {
         const int step = *a.step_counter;
@@ -642,9 +724,7 @@ size_t mk_dyn_bytes(const MkArgs &a, int grid, int MP) {
     best = std::max(best, need(a.H, 2 * a.I));
     best = std::max(best, need(a.I, a.H));
     best = std::max(best, need(a.H, a.V));
-    // attention scratch: q (4 heads fp32) + k/v rows + per lane-group (m, l, o)
-    const size_t attn = 4 * 128 * 4 + 2 * 128 * 2 + static_cast<size_t>(MK_WARPS) * 4 * (2 + 128) * 4;
-    return std::max(best, attn);
+    return std::max(best, MK_ATT_BYTES + 64);
 }
 
 template <int MP, int U>
@@ -695,6 +775,67 @@ int launch_decode_megakernel(const MkArgs &a, cudaStream_t st) {
     // pairs of groups per unit need 4-byte aligned scale pairs: every reduction width a multiple of 256
     const bool pairs = a.H % 256 == 0 && a.I % 256 == 0 && (a.Hq * a.D) % 256 == 0;
     return pairs ? mk_launch_u<2>(a, st) : mk_launch_u<1>(a, st);
+}
+
+// ---- the attention phase as a kernel of its own (CUDA-graph decode path) ----
+__global__ void __launch_bounds__(MK_THREADS, 1) decode_attention_fused_kernel(const MkArgs a, const MkLayer l) {
+    extern __shared__ __align__(128) unsigned char att_smem_raw[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the o_proj stream may prefetch its weights now
+    Prof prof{nullptr, 0, 0};
+    mk_attention(a, l, att_smem_raw, prof);
+}
+__global__ void __launch_bounds__(MK_THREADS, 1) decode_attention_merge_kernel(const MkArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    mk_attention_merge(a);
+}
+
+static int attention_max_split(int batch, int num_kv_heads) {
+    const int s = sm_count() / (batch * num_kv_heads);
+    return s < 1 ? 1 : s;
+}
+size_t decode_attention_fused_workspace(int batch, int num_heads, int num_kv_heads) {
+    return static_cast<size_t>(batch) * num_heads * attention_max_split(batch, num_kv_heads) * (128 + 2);
+}
+
+int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, const void *k_norm_weight, const int32_t *offsets,
+                                  const int32_t *block_table, const int32_t *context_lens, const double *rope_inv_freq,
+                                  void *key_pages, void *value_pages, void *out, float *workspace, int batch, int num_heads,
+                                  int num_kv_heads, int head_dim, float eps, float scale, int num_pages, int page_size,
+                                  int max_pages, int max_context, int dtype, cudaStream_t st) {
+    if (batch == 0) return TL_OK;
+    if (dtype != TL_BF16 || head_dim != 128 || num_kv_heads < 1 || num_heads % num_kv_heads != 0 || num_heads / num_kv_heads > 4)
+        return fail(TL_EINVAL, "decode_attention_fused: needs bfloat16, head_dim 128 and at most 4 query heads per KV head");
+    MkArgs a{};
+    MkLayer l{};
+    a.B = batch, a.Hq = num_heads, a.Hkv = num_kv_heads, a.D = head_dim;
+    a.eps = eps, a.attn_scale = scale;
+    a.page_size = page_size, a.max_pages = max_pages, a.num_pages = num_pages;
+    a.offsets = const_cast<int32_t *>(offsets), a.context_lens = const_cast<int32_t *>(context_lens);
+    a.rope_inv_freq = rope_inv_freq;
+    a.qkv = const_cast<void *>(qkv), a.y = out, a.attn_ws = workspace;
+    const int max_split = attention_max_split(batch, num_kv_heads);
+    int tps = (max_context < 1 ? 1 : max_context + max_split - 1) / max_split;
+    tps = tps < MK_ATT_TOK ? MK_ATT_TOK : tps;
+    tps = (tps + 63) / 64 * 64;
+    a.tokens_per_split = tps;
+    a.nsplit = (max_context + tps - 1) / tps;
+    a.nsplit = a.nsplit < 1 ? 1 : (a.nsplit > max_split ? max_split : a.nsplit);
+    l.q_norm = q_norm_weight, l.k_norm = k_norm_weight, l.table = block_table;
+    l.k_pages = key_pages, l.v_pages = value_pages;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MK_ATT_BYTES + 64)) != cudaSuccess)
+            return fail(TL_ECUDA, "decode_attention_fused: cannot raise shared memory limit");
+        configured = true;
+    }
+    decode_attention_fused_kernel<<<batch * num_kv_heads * a.nsplit, MK_THREADS, MK_ATT_BYTES + 64, st>>>(a, l);
+    TL_LAUNCH_CHECK("decode_attention_fused");
+    if (a.nsplit > 1) {
+        const int heads = batch * num_heads;
+        decode_attention_merge_kernel<<<(heads + MK_WARPS - 1) / MK_WARPS, MK_THREADS, 0, st>>>(a);
+        TL_LAUNCH_CHECK("decode_attention_merge");
+    }
+    return TL_OK;
 }
 
 int mk_grid_size() { return sm_count(); }

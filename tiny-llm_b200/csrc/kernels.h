@@ -60,6 +60,12 @@ int launch_w4a16_gemm(const void *scales, const void *biases, const void *a, con
 // decode_megakernel.cu
 int launch_decode_megakernel(const tl_decode_args &a, cudaStream_t st);
 int mk_grid_size();
+size_t decode_attention_fused_workspace(int batch, int num_heads, int num_kv_heads);
+int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, const void *k_norm_weight, const int32_t *offsets,
+                                  const int32_t *block_table, const int32_t *context_lens, const double *rope_inv_freq,
+                                  void *key_pages, void *value_pages, void *out, float *workspace, int batch, int num_heads,
+                                  int num_kv_heads, int head_dim, float eps, float scale, int num_pages, int page_size,
+                                  int max_pages, int max_context, int dtype, cudaStream_t st);
 
 // attention_decode.cu
 int launch_decode_attention(const void *q, const void *k, const void *v, const float *mask, void *out, int q_rows,

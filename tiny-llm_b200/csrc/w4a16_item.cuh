@@ -205,7 +205,7 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
     const int base0 = threadIdx.x & ~31;
     const bool cached = total <= CACHE * NT;
     const bool rms = prologue == W4_PRO_RMSNORM;
-    uint4 held[CACHE];
+    uint4 held[CACHE], held_aux[CACHE];  // both operands of the prologue are fetched in ONE round trip
     auto chunk_src = [&](int idx, int &m, int &c) -> const T * {
         m = idx / words;
         c = idx - m * words;
@@ -222,13 +222,17 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
         const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
         return f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
     };
-    auto emit = [&](int idx, uint4 raw) {  // idx may be >= total (lane padding): contributes nothing
+    auto aux_load = [&](int idx) {
+        int m, c;
+        const T *src = chunk_src(idx, m, c);
+        return rms ? *reinterpret_cast<const uint4 *>(aux + c * 8) : __ldcg(reinterpret_cast<const uint4 *>(aux + (src - in)));
+    };
+    auto emit = [&](int idx, uint4 raw, uint4 auxv) {  // idx may be >= total (lane padding): contributes nothing
         float part = 0.f;
         int m = 0, c = 0;
         if (idx < total) {
-            const T *src = chunk_src(idx, m, c);
+            chunk_src(idx, m, c);
             if (prologue != W4_PRO_NONE) {
-                const uint4 auxv = rms ? *reinterpret_cast<const uint4 *>(aux + c * 8) : __ldcg(reinterpret_cast<const uint4 *>(aux + (src - in)));
                 const uint32_t xin[4] = {raw.x, raw.y, raw.z, raw.w};
                 const uint32_t yin[4] = {auxv.x, auxv.y, auxv.z, auxv.w};
                 uint32_t o[4];
@@ -267,10 +271,11 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
 #pragma unroll
         for (int j = 0; j < CACHE; ++j) {
             const int idx = base0 + j * NT + lane;
-            held[j] = make_uint4(0u, 0u, 0u, 0u);
+            held[j] = held_aux[j] = make_uint4(0u, 0u, 0u, 0u);
             if (idx < total) {
                 int m, c;
                 held[j] = __ldcg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
+                if (prologue != W4_PRO_NONE) held_aux[j] = aux_load(idx);
             }
         }
     }
@@ -304,16 +309,17 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
     if (cached) {
 #pragma unroll
         for (int j = 0; j < CACHE; ++j)
-            if (base0 + j * NT < total) emit(base0 + j * NT + lane, held[j]);
+            if (base0 + j * NT < total) emit(base0 + j * NT + lane, held[j], held_aux[j]);
     } else {
         for (int base = base0; base < total; base += NT) {
             const int idx = base + lane;
-            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+            uint4 raw = make_uint4(0u, 0u, 0u, 0u), auxv = raw;
             if (idx < total) {
                 int m, c;
                 raw = __ldcg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
+                if (prologue != W4_PRO_NONE) auxv = aux_load(idx);
             }
-            emit(idx, raw);
+            emit(idx, raw, auxv);
         }
     }
     __syncthreads();

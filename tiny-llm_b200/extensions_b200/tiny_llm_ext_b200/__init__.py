@@ -84,6 +84,8 @@ _SIGNATURES = {
     "tl_decode_advance": (_I, [_VP] * 6 + [_I, _I, _VP]),
     "tl_quantized_matmul_fused": (_I, [_VP] * 7 + [_I] * 6 + [_F, _I, _VP]),
     "tl_decode_qk_norm_rope_append": (_I, [_VP] * 9 + [_I] * 4 + [_F, _F] + [_I] * 4 + [_VP]),
+    "tl_decode_attention_fused_workspace": (_SZ, [_I, _I, _I]),
+    "tl_decode_attention_fused": (_I, [_VP] * 11 + [_I] * 4 + [_F, _F] + [_I] * 5 + [_VP]),
     "tl_set_pdl": (_I, [_I]),
     "tl_decode_step_grid": (_I, []),
     "tl_decode_step": (_I, [_VP, _VP]),
@@ -519,6 +521,52 @@ def decode_qk_norm_rope_append(qkv, q_norm_weight, k_norm_weight, offsets, block
         )
     )
     return q_out
+
+
+def rope_inv_freq_table(head_dim: int, base: float, device) -> torch.Tensor:
+    """float64 [head_dim / 2] frequencies base^(-i / (head_dim / 2)) (rope.py:13-15 forms them the same way)."""
+    half = head_dim // 2
+    return torch.pow(torch.tensor(float(base), dtype=torch.float64), -torch.arange(half, dtype=torch.float64) / half).to(device)
+
+
+def decode_attention_fused_workspace(batch: int, num_heads: int, num_kv_heads: int) -> int:
+    return int(_lib.tl_decode_attention_fused_workspace(int(batch), int(num_heads), int(num_kv_heads)))
+
+
+def decode_attention_fused(qkv, q_norm_weight, k_norm_weight, offsets, block_table, context_lens, rope_inv_freq, key_pages,
+                           value_pages, num_heads, num_kv_heads, eps, scale, max_context, out=None, workspace=None, stream=None):
+    """One decode step of attention for ``qkv [B, (Hq + 2 Hkv) * 128]`` (bf16): per-head q/k RMSNorm +
+    RoPE, append of the newest K/V row, paged GQA attention (context_lens are post-append) ->
+    ``[B, Hq * 128]``.  ``max_context`` bounds every context length (it fixes the split count)."""
+    B = qkv.shape[0]
+    P, Hkv, page_size, D = key_pages.shape
+    if qkv.dim() != 2 or qkv.shape[1] != (num_heads + 2 * num_kv_heads) * D or Hkv != num_kv_heads:
+        raise RuntimeError("decode_attention_fused: qkv must be [B, (Hq + 2*Hkv) * D]")
+    if qkv.dtype != key_pages.dtype or value_pages.dtype != key_pages.dtype or q_norm_weight.dtype != qkv.dtype or k_norm_weight.dtype != qkv.dtype:
+        raise RuntimeError("decode_attention_fused: dtype mismatch")
+    if rope_inv_freq.dtype != torch.float64 or rope_inv_freq.numel() != D // 2:
+        raise RuntimeError("decode_attention_fused: rope_inv_freq must be float64 [head_dim / 2]")
+    if block_table.dim() != 2 or block_table.shape[0] != B or block_table.dtype != torch.int32 or context_lens.dtype != torch.int32:
+        raise RuntimeError("decode_attention_fused: block_table must be int32 [B, max_pages] and context_lens int32 [B]")
+    _gpu("decode_attention_fused", qkv, q_norm_weight, k_norm_weight, offsets, block_table, context_lens, rope_inv_freq, key_pages, value_pages)
+    _contig("decode_attention_fused", qkv=qkv, offsets=offsets, block_table=block_table, context_lens=context_lens,
+            key_pages=key_pages, value_pages=value_pages, rope_inv_freq=rope_inv_freq)
+    if out is None:
+        out = torch.empty((B, num_heads * D), dtype=qkv.dtype, device=qkv.device)
+    need = decode_attention_fused_workspace(B, num_heads, num_kv_heads)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.float32, device=qkv.device)
+    elif workspace.dtype != torch.float32 or workspace.numel() < need or not workspace.is_cuda:
+        raise RuntimeError("decode_attention_fused: workspace must hold decode_attention_fused_workspace() float32 values")
+    _check(
+        _lib.tl_decode_attention_fused(
+            qkv.data_ptr(), q_norm_weight.data_ptr(), k_norm_weight.data_ptr(), offsets.data_ptr(), block_table.data_ptr(),
+            context_lens.data_ptr(), rope_inv_freq.data_ptr(), key_pages.data_ptr(), value_pages.data_ptr(), out.data_ptr(),
+            workspace.data_ptr(), B, int(num_heads), int(num_kv_heads), D, float(eps), float(scale), P, page_size,
+            block_table.shape[1], int(max_context), _DTYPE_CODE[qkv.dtype], _stream_ptr(stream, qkv),
+        )
+    )
+    return out
 
 
 class DecodeLayer(ctypes.Structure):

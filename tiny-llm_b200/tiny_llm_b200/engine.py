@@ -161,6 +161,7 @@ class DecodeEngine:
         self.device = torch.device(device)
         self.page_size = model.page_size
         self.max_pages = (max_seq_len + self.page_size - 1) // self.page_size
+        self.max_seq_len = self.max_pages * self.page_size
         self.n_layers = model.num_hidden_layers
         attn = model.layers_inner[0].self_attn
         self.Hq, self.Hkv, self.D = attn.num_heads, attn.num_kv_heads, attn.head_dim
@@ -205,6 +206,15 @@ class DecodeEngine:
                 )
                 for b in model.layers_inner
             ]
+        # one-launch attention (q/k norm + rope + append + paged GQA) when the head layout allows it
+        attn0 = model.layers_inner[0].self_attn
+        self._attention_fused = (self.fused and self.D == 128 and self.Hq // self.Hkv <= 4
+                                 and model.embedding.weight.scales.dtype == torch.bfloat16
+                                 and not getattr(attn0.rope, "traditional", False)
+                                 and os.environ.get("TL_ATTENTION_FUSED", "1") != "0")
+        if self._attention_fused:
+            self._rope_inv_freq = ext.rope_inv_freq_table(self.D, attn0.rope.base, self.device)
+            self._attn_ws = torch.empty(ext.decode_attention_fused_workspace(self.B, self.Hq, self.Hkv), dtype=torch.float32, device=self.device)
         # persistent == None: use the whole-step kernel whenever the model shape allows it
         # (TL_PERSISTENT=0 forces the CUDA-graph path for A/B measurements)
         if persistent is None and os.environ.get("TL_PERSISTENT", "1") == "0":
@@ -273,11 +283,17 @@ class DecodeEngine:
             ln1, ln2 = block.input_layernorm, block.post_attention_layernorm
             qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, x, ln1._weight_as(x.dtype, x.device),
                                              prologue=ext.PRO_RMSNORM, eps=ln1.eps)
-            q = ext.decode_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
-                                               self.offsets, self.tables[i], self.context_lens, pool._key_pages, pool._value_pages,
-                                               Hq, Hkv, at.rope.base, at.q_norm.eps)
-            y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i], self.context_lens,
-                                    at.scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
+            if self._attention_fused:
+                y = ext.decode_attention_fused(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
+                                               self.offsets, self.tables[i], self.context_lens, self._rope_inv_freq,
+                                               pool._key_pages, pool._value_pages, Hq, Hkv, at.q_norm.eps, at.scale,
+                                               self.max_seq_len, workspace=self._attn_ws)
+            else:
+                q = ext.decode_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
+                                                   self.offsets, self.tables[i], self.context_lens, pool._key_pages, pool._value_pages,
+                                                   Hq, Hkv, at.rope.base, at.q_norm.eps)
+                y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i], self.context_lens,
+                                        at.scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
             x = ext.quantized_matmul_fused(at.wo.scales, at.wo.biases, at.wo.weight, y.view(B, Hq * D), residual=x, epilogue=ext.EPI_RESIDUAL)
             gu = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, x, ln2._weight_as(x.dtype, x.device),
                                             prologue=ext.PRO_RMSNORM, eps=ln2.eps)

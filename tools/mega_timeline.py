@@ -64,13 +64,15 @@ def main():
     for tag, clk in stamps:
         dt = (clk - prev) / mhz
         prev = clk
-        if tag >= 100 and tag < 90000:
+        if 50000 <= tag < 60000:
+            name = "attn:" + {1: "loads-issued", 2: "page-ids+sync", 3: "kv-copies-issued", 4: "q-path", 5: "wait+sync", 6: "softmax", 7: "merge-groups+sync"}.get(tag - 50000, str(tag))
+        elif tag >= 100 and tag < 90000:
             sp, kind = (tag - 100) // 10, (tag - 100) % 10
             name = ["qkv", "o", "gate_up", "down"][sp % 4] + ":" + KIND.get(kind, str(kind))
         else:
             name = {1: "start", 2: "ring-fill+embed", 3: "grid-sync(embed)", 90001: "head", 99999: "argmax+sync"}.get(tag, str(tag))
         agg[name] += dt
-        if len(rows) < 40:
+        if len(rows) < 60:
             rows.append((name, round(dt, 2)))
     print("event-timed step: %.3f ms; stamped span: %.1f us" % (total_ms, (stamps[-1][1] - t0) / mhz))
     print("first events (us):", rows)
