@@ -242,7 +242,7 @@ __device__ void mk_stream(const MkArgs &a, int sp, Pipe<U> &pipe, const bf16 *in
     float *asum = reinterpret_cast<float *>(dyn + static_cast<size_t>(words) * MP * 16);
     float *rowstat = asum + G * MPA;
     float *entries = rowstat + 32;  // [(chunks + MK_WARPS) entries][16 rows][8 cols]
-    w4_stage<bf16, MP, MK_THREADS>(in, ld, prologue == 2 ? in + up_off : norm_w, prologue, p.N, B, a.eps, act, asum, rowstat);
+    w4_stage<bf16, MP, MK_THREADS>(in, ld, prologue == 2 ? in + up_off : norm_w, prologue, p.N, B, a.eps, act, asum, rowstat, []() {});
     prof.stamp(100 + sp * 10 + 1);
 
     float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};

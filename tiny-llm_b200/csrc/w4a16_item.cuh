@@ -194,9 +194,13 @@ enum { W4_PRO_NONE = 0, W4_PRO_RMSNORM = 1, W4_PRO_SWIGLU = 2 };
 // with every rounding point of the unfused operator sequence.  Inputs are read through L2
 // (ld.global.cg): in the persistent kernel they were written by other CTAs of the same launch.
 // Ends with __syncthreads(); rowstat needs 32 floats.
-template <typename T, int MP, int NT>
+// after_loads() runs right after the activation loads have been ISSUED (register-cached path):
+// the streaming kernel uses it to launch the rest of its weight prefetch behind them - loads
+// return roughly in issue order per SM, and activations stuck behind 128 KiB of weights were the
+// largest fixed cost of a small projection.
+template <typename T, int MP, int NT, typename AfterLoads>
 __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int prologue, int N, int Mp, float eps, uint4 *act,
-                                         float *asum, float *rowstat) {
+                                         float *asum, float *rowstat, AfterLoads &&after_loads) {
     constexpr int MPA = w4_mpa(MP);
     constexpr int CACHE = 4;
     const int words = N / 8;
@@ -279,6 +283,7 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
             }
         }
     }
+    after_loads();
     if (rms) {
         if (threadIdx.x < 32) rowstat[threadIdx.x] = 0.f;
         __syncthreads();

@@ -321,19 +321,24 @@ int launch_w4a16_stream(const void *scales, const void *biases, const void *a, c
 }
 
 // ---------------------------------------------------------------------------
-// v4: register-pipelined streaming (see w4a16_item.cuh for the instruction budget).
+// v5: register-pipelined streaming, contiguous rows per CTA (see w4a16_item.cuh for the
+// instruction budget of the inner loop).
 //
-// History, all measured on B200 (profiles/r01_kbench_*): v1 (register prefetch, 2 KB in flight
-// per warp), v2 (producer warp + 256-byte cp.async.bulk ring) and v3 (per-warp cp.async rings)
-// all stalled near 2 TB/s: SASS showed ~330 instructions per KiB of weights, i.e. the kernels
-// were issue bound.  v4 keeps 2-4 units (U x 1 KiB each) per warp in flight in REGISTERS,
-// walks global memory with running pointers, and spends ~100 instructions per KiB.
+// History, all measured on B200 (profiles/r01_kbench_*, tools/s4_timeline.py):
+//   v1 (register prefetch, 2 KB in flight per warp), v2 (producer warp + 256-byte cp.async.bulk
+//   ring) and v3 (per-warp cp.async rings) stalled near 2 TB/s: ~330 instructions per KiB of
+//   weights - issue bound.  v4 (register pipeline, ~120 instructions per KiB) reached 3.9 TB/s on
+//   the tied head but dealt 16-row tiles to fixed-size warp teams: 1216 tiles over 1184 teams
+//   made 32 teams work twice as long as the rest (gate|up: 11 us instead of 6), and every tile
+//   ended with two named barriers and a dependent residual load.
+// v5 gives CTA c the contiguous rows of chunks [C*c/grid, C*(c+1)/grid) (C = K/16 chunks, all
+// CTAs within one chunk of each other) and deals the CTA's (chunk, unit) pairs to its 16 warps as
+// equal contiguous ranges.  A warp accumulates a chunk in registers and parks the partial sums in
+// shared-memory entry (chunk + warp); after ONE block barrier the entries of every chunk are summed
+// in warp order (deterministic), the residual (prefetched before the stream starts) is added and
+// the outputs are stored.
 //
-// A tile (16 output rows) is reduced by a team of TW warps (TW = 1..16, chosen so that small
-// projections still give every warp of the chip a unit); only that team synchronises (named
-// barrier) to combine its partial sums, in warp order (deterministic).
-//
-// Weights never depend on the previous kernel: each warp issues its first DEPTH units BEFORE
+// Weights never depend on the previous kernel: each warp requests its first units BEFORE
 // griddepcontrol.wait, so with programmatic dependent launch the HBM stream of kernel n+1
 // starts while kernel n drains.
 //
@@ -342,15 +347,32 @@ int launch_w4a16_stream(const void *scales, const void *biases, const void *a, c
 //   prologue RMSNORM : a = T(x * rsqrt(mean(x^2)+eps) * w)   (week2_kernels.metal:41-47)
 //   prologue SWIGLU  : a = T(g / (1 + exp(-g)) * u)          (week2_kernels.metal:115-116)
 //   epilogue RESIDUAL: out = T(float(res) + float(T(acc)))   (qwen3_week3.py:204-206)
-#ifndef S4_NWARPS
-#define S4_NWARPS 16
+constexpr int S5_WARPS = 16;
+constexpr int S5_THREADS = S5_WARPS * 32;
+#ifndef S5_DEPTH_SMALL
+#define S5_DEPTH_SMALL 4
 #endif
-#ifndef S4_DEPTH_SMALL
-#define S4_DEPTH_SMALL 4
+// Debug build (-DS4_PROF=1, tools/s4_timeline.py): per-launch globaltimer stamps of CTA 0.
+#ifndef S4_PROF
+#define S4_PROF 0
 #endif
-constexpr int S4_WARPS = S4_NWARPS;
-constexpr int S4_THREADS = S4_WARPS * 32;
-constexpr int S4_CTAS_PER_SM = 16 / S4_WARPS;  // 128 registers per thread either way
+#if S4_PROF
+constexpr int S4_PROF_SLOTS = 4096, S4_PROF_FIELDS = 8;
+__device__ unsigned long long g_s4_prof[S4_PROF_SLOTS * S4_PROF_FIELDS];
+__device__ unsigned int g_s4_prof_next;
+__device__ __forceinline__ unsigned long long s4_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define S4_STAMP(field)                                                                        \
+    do {                                                                                       \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && s4_slot < S4_PROF_SLOTS) \
+            g_s4_prof[s4_slot * S4_PROF_FIELDS + (field)] = s4_now();                          \
+    } while (0)
+#else
+#define S4_STAMP(field) do { } while (0)
+#endif
 
 enum { PRO_NONE = W4_PRO_NONE, PRO_RMSNORM = W4_PRO_RMSNORM, PRO_SWIGLU = W4_PRO_SWIGLU };
 enum { EPI_NONE = 0, EPI_RESIDUAL = 1 };
@@ -363,201 +385,226 @@ struct StreamArgs {
     int M, N, K, lda;
     int prologue, epilogue;
     float eps;
-    int rows_per_pass, team_warps;
+    int rows_per_pass;
 };
 
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void named_barrier(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 // MP: activation rows per pass padded to a power of two (template: shared-memory offsets of the
 // B fragments become immediates).  U: 128-column groups per unit (2 when N % 256 == 0).
-template <typename T, int MP, int U, bool TEAM>
-__global__ void __launch_bounds__(S4_THREADS, S4_CTAS_PER_SM) w4a16_stream4_kernel(const StreamArgs args) {
+template <typename T, int MP, int U>
+__global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const StreamArgs args) {
     constexpr int MT = (MP + 7) / 8;
     constexpr int MPA = w4_mpa(MP);
-    constexpr int S4_DEPTH = (MP <= 8 ? S4_DEPTH_SMALL : (MP == 16 ? 3 : 2));
-    extern __shared__ __align__(128) unsigned char smem4_raw[];
+    constexpr int DEPTH = (MP <= 8 ? S5_DEPTH_SMALL : (MP == 16 ? 3 : 2));  // units per warp in the register pipeline
+    constexpr int ENTRY = 16 * 8 * MT;                                      // floats per (chunk, warp) partial sum
+    extern __shared__ __align__(128) unsigned char smem5_raw[];
+    __shared__ int warp_begin[S5_WARPS + 1];
     const int N = args.N, K = args.K;
     const int pass = blockIdx.y;
     const int Mp = min(args.rows_per_pass, args.M - pass * args.rows_per_pass);
     const int words = N / 8;
     const int G = N / 128;
-    const int P = G / U;  // units per tile
-    const int TW = TEAM ? args.team_warps : 1;
+    const int P = G / U;  // units per chunk
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int team = warp / TW;
-    const int wit = warp - team * TW;
-    const int teams = S4_WARPS / TW;
     const int g = lane >> 2, t = lane & 3;
 
-    // shared layout: act [words*MP] x 16 B | asum [G*MPA] | row stats [32] | red [warps][16][8*MT]
-    uint4 *act = reinterpret_cast<uint4 *>(smem4_raw);
-    float *asum = reinterpret_cast<float *>(smem4_raw + static_cast<size_t>(words) * MP * 16);
+    // shared layout: act [words*MP] x 16 B | asum [G*MPA] | row stats [32] | entries [(chunks + warps)][16][8*MT]
+    uint4 *act = reinterpret_cast<uint4 *>(smem5_raw);
+    float *asum = reinterpret_cast<float *>(smem5_raw + static_cast<size_t>(words) * MP * 16);
     float *rowstat = asum + G * MPA;
-    float *red = rowstat + 32;
+    float *entries = rowstat + 32;
 
     griddep_launch();
+#if S4_PROF
+    __shared__ unsigned int s4_slot_s;
+    if (threadIdx.x == 0) s4_slot_s = (blockIdx.x == 0 && blockIdx.y == 0) ? atomicAdd(&g_s4_prof_next, 1u) : 0xffffffffu;
+    __syncthreads();
+    const unsigned int s4_slot = s4_slot_s;
+    S4_STAMP(0);
+#endif
 
-    // ---- this warp's work list: tiles of its team, units wit, wit+TW, ... of each tile
-    const int tiles = (K + 15) / 16;
-    const int team_id = blockIdx.x * teams + team;
-    const int team_count = gridDim.x * teams;
-    const int upw = (P - wit + TW - 1) / TW;  // units of one tile that belong to this warp (>= 1: TW <= P)
-    const int my_tiles = team_id < tiles ? (tiles - team_id + team_count - 1) / team_count : 0;
-    const int total_units = my_tiles * upw;
+    // ---- rows of this CTA (whole 16-row chunks) and units of this warp
+    const unsigned all = static_cast<unsigned>(K + 15) >> 4;  // all * gridDim.x < 2^31 (K < 2^24 rows)
+    const int c0 = static_cast<int>(all * blockIdx.x / gridDim.x), c1 = static_cast<int>(all * (blockIdx.x + 1) / gridDim.x);
+    const int chunks = c1 - c0;
+    const int r0 = c0 * 16, r1 = min(K, c1 * 16);
+    const unsigned units = static_cast<unsigned>(chunks) * P;
+    const int begin = static_cast<int>(units * warp / S5_WARPS), end = static_cast<int>(units * (warp + 1) / S5_WARPS);
+    if (threadIdx.x <= S5_WARPS) warp_begin[threadIdx.x] = static_cast<int>(units * threadIdx.x / S5_WARPS);
 
-    // ---- load cursor (runs S4_DEPTH units ahead of the consumer)
+    // ---- load cursor (runs DEPTH units ahead of the consumer)
     const unsigned char *bbytes = reinterpret_cast<const unsigned char *>(args.b);
     const unsigned char *sbtable = reinterpret_cast<const unsigned char *>(lane < 16 ? args.scales : args.biases);
     const size_t row_bytes = static_cast<size_t>(N) / 2;
     const unsigned char *l_p0, *l_p8, *l_sb;
-    int l_tile = team_id, l_in_tile = 0, l_left = total_units;
-    auto tile_ptrs = [&](int tile) {  // rows past K are clamped: loaded, multiplied, never stored
-        const int r0 = min(tile * 16 + g, K - 1), r8 = min(tile * 16 + g + 8, K - 1);
-        const int rs = min(tile * 16 + (lane & 15), K - 1);
-        l_p0 = bbytes + r0 * row_bytes + wit * (U * 64) + t * 16;
-        l_p8 = bbytes + r8 * row_bytes + wit * (U * 64) + t * 16;
-        l_sb = sbtable + (static_cast<size_t>(rs) * G + wit * U) * 2;
+    int l_i = begin, l_chunk = begin / P;
+    int l_u = begin - l_chunk * P;
+    auto chunk_ptrs = [&]() {  // rows past K are clamped: loaded, multiplied, never stored
+        const int base = r0 + l_chunk * 16;
+        const int q0 = min(base + g, K - 1), q8 = min(base + g + 8, K - 1), qs = min(base + (lane & 15), K - 1);
+        l_p0 = bbytes + q0 * row_bytes + l_u * (U * 64) + t * 16;
+        l_p8 = bbytes + q8 * row_bytes + l_u * (U * 64) + t * 16;
+        l_sb = sbtable + (static_cast<size_t>(qs) * G + l_u * U) * 2;
     };
-    tile_ptrs(l_tile);
+    chunk_ptrs();
     auto load_next = [&](W4Unit<U> &un) {
-        if (l_left > 0) {
+        if (l_i < end) {
             w4_load<U>(un, l_p0, l_p8, l_sb);
-            l_left -= 1;
-            if (++l_in_tile == upw) {
-                l_in_tile = 0;
-                l_tile += team_count;
-                tile_ptrs(l_tile);
+            l_i += 1;
+            if (++l_u == P) {
+                l_u = 0;
+                l_chunk += 1;
+                chunk_ptrs();
             } else {
-                l_p0 += TW * (U * 64);
-                l_p8 += TW * (U * 64);
-                l_sb += TW * (U * 2);
+                l_p0 += U * 64;
+                l_p8 += U * 64;
+                l_sb += U * 2;
             }
         }
     };
-    W4Unit<U> buf[S4_DEPTH];
+    W4Unit<U> buf[DEPTH];
 #pragma unroll
-    for (int k = 0; k < S4_DEPTH; ++k) load_next(buf[k]);  // in flight before the activations exist
+    for (int k = 0; k < DEPTH; ++k) load_next(buf[k]);  // in flight before the activations exist
+    S4_STAMP(1);
 
     griddep_wait();  // activations (and the residual) come from the previous kernel
+    S4_STAMP(2);
     const T *p0 = static_cast<const T *>(args.p0) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda;
     const T *p1 = args.prologue == PRO_SWIGLU
                       ? static_cast<const T *>(args.p1) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda
                       : static_cast<const T *>(args.p1);
-    w4_stage<T, MP, S4_THREADS>(p0, args.lda, p1, args.prologue, N, Mp, args.eps, act, asum, rowstat);
-
     T *out = static_cast<T *>(args.out) + static_cast<size_t>(pass) * args.rows_per_pass * K;
     const T *res = args.epilogue == EPI_RESIDUAL ? static_cast<const T *>(args.residual) + static_cast<size_t>(pass) * args.rows_per_pass * K
                                                  : nullptr;
-    float *team_red = red + static_cast<size_t>(team) * TW * 16 * 8 * MT;
-    float *wred = team_red + static_cast<size_t>(wit) * 16 * 8 * MT;
-    const int team_threads = TW * 32;
-    const int ttid = threadIdx.x - team * team_threads;
+    // the residual of this thread's first output: requested now, needed after the stream
+    const int outs = chunks * 16 * Mp;
+    float res_first = 0.f;
+    if (res != nullptr && static_cast<int>(threadIdx.x) < outs) {
+        const int m = threadIdx.x / (chunks * 16), rr = threadIdx.x - m * (chunks * 16);
+        if (r0 + rr < r1) res_first = to_f(res[static_cast<size_t>(m) * K + r0 + rr]);
+    }
+    w4_stage<T, MP, S5_THREADS>(p0, args.lda, p1, args.prologue, N, Mp, args.eps, act, asum, rowstat, []() {});
+    S4_STAMP(3);
 
-    const uint4 *act0 = w4_act_lane<MP>(act, g, t) + wit * U * w4_act_group_stride<MP>();
-    const float *asum0 = w4_asum_lane<MP>(asum, t) + wit * U * w4_asum_group_stride<MP>();
-    const uint4 *actp = act0;
-    const float *asump = asum0;
-    const int act_step = TW * U * w4_act_group_stride<MP>();
-    const int asum_step = TW * U * w4_asum_group_stride<MP>();
-
+    const uint4 *act0 = w4_act_lane<MP>(act, g, t);
+    const float *asum0 = w4_asum_lane<MP>(asum, t);
+    int chunk = begin / P;
+    int u = begin - chunk * P;
+    const uint4 *actp = act0 + u * U * w4_act_group_stride<MP>();
+    const float *asump = asum0 + u * U * w4_asum_group_stride<MP>();
     float acc[MT][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
-    int c_tile = team_id, c_in_tile = 0;
-
-    // ---- end of a tile: store 16 x Mp outputs.  Without teams a warp owns the whole reduction and
-    // stores straight from its accumulators (small code: this block is inlined once per pipeline slot
-    // and the hot loop has to stay inside the instruction cache); a team first combines its partial
-    // sums through shared memory, in warp order.
-    auto store_one = [&](int m, int k, float v) {
-        if (m < Mp && k < K) {
-            T vb = from_f<T>(v);
-            if (res != nullptr) vb = from_f<T>(to_f(res[static_cast<size_t>(m) * K + k]) + to_f(vb));
-            out[static_cast<size_t>(m) * K + k] = vb;
-        }
-    };
-    auto finish_tile = [&]() {
-        if (!TEAM) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int m0 = mt * 8 + 2 * t, k0 = c_tile * 16 + g;
-                store_one(m0, k0, acc[mt][0]);
-                store_one(m0 + 1, k0, acc[mt][1]);
-                store_one(m0, k0 + 8, acc[mt][2]);
-                store_one(m0 + 1, k0 + 8, acc[mt][3]);
-                acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
-            }
-            return;
-        }
+    auto flush = [&]() {  // park this warp's partial sums of `chunk` in entry (chunk + warp)
+        float *e = entries + static_cast<size_t>(chunk + warp) * ENTRY;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-            wred[g * 8 * MT + mt * 8 + 2 * t] = acc[mt][0];
-            wred[g * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][1];
-            wred[(g + 8) * 8 * MT + mt * 8 + 2 * t] = acc[mt][2];
-            wred[(g + 8) * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][3];
+            e[g * 8 * MT + mt * 8 + 2 * t] = acc[mt][0];
+            e[g * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][1];
+            e[(g + 8) * 8 * MT + mt * 8 + 2 * t] = acc[mt][2];
+            e[(g + 8) * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][3];
             acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
         }
-        named_barrier(1 + team, team_threads);
-        for (int o = ttid; o < 16 * 8 * MT; o += team_threads) {
-            const int m = o >> 4, r = o & 15;  // consecutive threads -> consecutive output features
-            float v = 0.f;
-            for (int w = 0; w < TW; ++w) v += team_red[(w * 16 + r) * 8 * MT + m];
-            store_one(m, c_tile * 16 + r, v);
-        }
-        named_barrier(1 + team, team_threads);
     };
-
-    for (int n = 0; n < total_units; n += S4_DEPTH) {
+    for (int i = begin; i < end; i += DEPTH) {
 #pragma unroll
-        for (int k = 0; k < S4_DEPTH; ++k) {
-            if (n + k < total_units) {  // warp-uniform
+        for (int k = 0; k < DEPTH; ++k) {
+            if (i + k < end) {  // warp-uniform; k is a compile-time register index
                 w4_consume<T, MP, U>(buf[k], actp, asump, g, acc);
                 load_next(buf[k]);
-                actp += act_step;
-                asump += asum_step;
-                if (++c_in_tile == upw) {
-                    finish_tile();
-                    c_in_tile = 0;
-                    c_tile += team_count;
+                actp += U * w4_act_group_stride<MP>();
+                asump += U * w4_asum_group_stride<MP>();
+                if (++u == P) {
+                    flush();
+                    u = 0;
+                    chunk += 1;
                     actp = act0;
                     asump = asum0;
                 }
             }
         }
     }
+    if (u != 0) flush();
+    S4_STAMP(4);
+    __syncthreads();
+    S4_STAMP(6);
+
+    // ---- sum the entries of each chunk in warp order, add the residual, store
+    for (int o = threadIdx.x; o < outs; o += S5_THREADS) {
+        const int m = o / (chunks * 16);  // request-major: consecutive threads store consecutive features
+        const int rr = o - m * (chunks * 16);
+        const int ch = rr >> 4, row = rr & 15;
+        const int k = r0 + rr;
+        if (k < r1) {
+            float v = 0.f;
+            const int lo = ch * P, hi = lo + P;
+            for (int w = 0; w < S5_WARPS; ++w)
+                if (warp_begin[w] < hi && warp_begin[w + 1] > lo && warp_begin[w] < warp_begin[w + 1])
+                    v += entries[static_cast<size_t>(ch + w) * ENTRY + row * 8 * MT + m];
+            T vb = from_f<T>(v);
+            if (res != nullptr) {
+                const float rv = o == static_cast<int>(threadIdx.x) ? res_first : to_f(res[static_cast<size_t>(m) * K + k]);
+                vb = from_f<T>(rv + to_f(vb));
+            }
+            out[static_cast<size_t>(m) * K + k] = vb;
+        }
+    }
+    S4_STAMP(5);
 }
+
+#if S4_PROF
+extern "C" int tl_debug_s4_prof(unsigned long long *host_out, int max_slots) {
+    unsigned int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_s4_prof_next, sizeof(n));
+    if (static_cast<int>(n) > max_slots) n = max_slots;
+    if (n > S4_PROF_SLOTS) n = S4_PROF_SLOTS;
+    cudaMemcpyFromSymbol(host_out, g_s4_prof, static_cast<size_t>(n) * S4_PROF_FIELDS * sizeof(unsigned long long));
+    unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_s4_prof_next, &zero, sizeof(zero));
+    return static_cast<int>(n);
+}
+#endif
 
 static bool g_use_pdl = false;
 void set_use_pdl(bool on) { g_use_pdl = on; }
 bool use_pdl() { return g_use_pdl; }
 
-static size_t stream4_smem_bytes(int N, int MP) {
+constexpr size_t S5_SMEM_MAX = 226 * 1024;
+static size_t stream5_smem_bytes(int N, int K, int MP, int grid) {
     const int MT = (MP + 7) / 8, MPA = MP < 8 ? 8 : MP;
+    const int all = (K + 15) / 16;
+    const int chunks = (all + grid - 1) / grid;
     size_t bytes = static_cast<size_t>(N / 8) * MP * 16;
     bytes += static_cast<size_t>(N / 128) * MPA * 4;
     bytes += 32 * 4;
-    bytes += static_cast<size_t>(S4_WARPS) * 16 * 8 * MT * 4;
+    bytes += static_cast<size_t>(chunks + S5_WARPS) * 16 * 8 * MT * 4;
     return bytes;
 }
-constexpr size_t S4_SMEM_MAX = 226 * 1024;
+static int stream5_grid(int K) {
+    const int all = (K + 15) / 16, sms = sm_count();
+    return all < sms ? all : sms;
+}
 
-template <typename T, int MP, int U, bool TEAM>
-static int stream4_launch_k(StreamArgs args, int grid_x, size_t smem, cudaStream_t st) {
+template <typename T, int MP, int U>
+static int stream5_launch(StreamArgs args, cudaStream_t st) {
+    const int grid_x = stream5_grid(args.K);
+    const size_t smem = stream5_smem_bytes(args.N, args.K, MP, grid_x);
+    if (smem > S5_SMEM_MAX)
+        return fail(TL_EINVAL, "quantized_matmul: activations do not fit in shared memory (N=%d, K=%d, rows=%d)", args.N, args.K, MP);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(w4a16_stream4_kernel<T, MP, U, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(S4_SMEM_MAX));
+        cudaError_t e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(S5_SMEM_MAX));
         if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid_x, ceil_div(args.M, args.rows_per_pass));
-    cfg.blockDim = dim3(S4_THREADS);
+    cfg.blockDim = dim3(S5_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -565,56 +612,37 @@ static int stream4_launch_k(StreamArgs args, int grid_x, size_t smem, cudaStream
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream4_kernel<T, MP, U, TEAM>, args);
-    if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream4: launch failed: %s", cudaGetErrorString(e));
-    TL_LAUNCH_CHECK("w4a16_stream4");
+    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream5_kernel<T, MP, U>, args);
+    if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream5: launch failed: %s", cudaGetErrorString(e));
+    TL_LAUNCH_CHECK("w4a16_stream5");
     return TL_OK;
 }
 
-template <typename T, int MP, int U>
-static int stream4_launch(StreamArgs args, cudaStream_t st) {
-    const size_t smem = stream4_smem_bytes(args.N, MP);
-    if (smem > S4_SMEM_MAX)
-        return fail(TL_EINVAL, "quantized_matmul: activations do not fit in shared memory (N=%d, rows=%d)", args.N, MP);
-    const int tiles = ceil_div(args.K, 16);
-    const int P = (args.N / 128) / U;
-    const int sms = sm_count();
-    // team width: split a tile's reduction over TW warps until every warp of the chip has a unit
-    int tw = 1;
-    while (tw < S4_WARPS && tiles * tw < sms * 16 && tw * 2 <= P) tw *= 2;
-    args.team_warps = tw;
-    const int teams_per_cta = S4_WARPS / tw;
-    const int want = ceil_div(tiles, teams_per_cta);
-    int ctas_per_sm = static_cast<int>(S4_SMEM_MAX / (smem + 1024));
-    ctas_per_sm = ctas_per_sm > S4_CTAS_PER_SM ? S4_CTAS_PER_SM : (ctas_per_sm < 1 ? 1 : ctas_per_sm);
-    const int cap = sms * ctas_per_sm;
-    const int grid_x = want < cap ? want : cap;
-    return tw > 1 ? stream4_launch_k<T, MP, U, true>(args, grid_x, smem, st) : stream4_launch_k<T, MP, U, false>(args, grid_x, smem, st);
-}
-
 template <typename T, int U>
-static int stream4_u(StreamArgs args, cudaStream_t st) {
+static int stream5_u(StreamArgs args, cudaStream_t st) {
     // rows of `a` handled per pass: as many (power of two, <= 32) as fit in shared memory
     int rpp = w4_pad_cols(args.M < 32 ? args.M : 32);
-    while (rpp > 1 && stream4_smem_bytes(args.N, rpp) > S4_SMEM_MAX) rpp /= 2;
+    const int grid_x = stream5_grid(args.K);
+    while (rpp > 1 && stream5_smem_bytes(args.N, args.K, rpp, grid_x) > S5_SMEM_MAX) rpp /= 2;
     args.rows_per_pass = rpp;
     switch (rpp) {
-        case 1: return stream4_launch<T, 1, U>(args, st);
-        case 2: return stream4_launch<T, 2, U>(args, st);
-        case 4: return stream4_launch<T, 4, U>(args, st);
-        case 8: return stream4_launch<T, 8, U>(args, st);
-        case 16: return stream4_launch<T, 16, U>(args, st);
-        default: return stream4_launch<T, 32, U>(args, st);
+        case 1: return stream5_launch<T, 1, U>(args, st);
+        case 2: return stream5_launch<T, 2, U>(args, st);
+        case 4: return stream5_launch<T, 4, U>(args, st);
+        case 8: return stream5_launch<T, 8, U>(args, st);
+        case 16: return stream5_launch<T, 16, U>(args, st);
+        default: return stream5_launch<T, 32, U>(args, st);
     }
 }
 
 template <typename T>
-static int stream4_t(StreamArgs args, cudaStream_t st) {
+static int stream5_t(StreamArgs args, cudaStream_t st) {
     if (!aligned16(args.p0) || !aligned16(args.b) || (args.p1 && !aligned16(args.p1)) || (args.lda % 8) != 0)
         return fail(TL_EINVAL, "quantized_matmul: operands must be 16-byte aligned");
+    if (args.K >= (1 << 24)) return fail(TL_EINVAL, "quantized_matmul: more than 2^24 output features");
     const bool pairs = (args.N % 256) == 0 && (reinterpret_cast<uintptr_t>(args.scales) & 3u) == 0 &&
                        (reinterpret_cast<uintptr_t>(args.biases) & 3u) == 0;
-    return (pairs && args.M <= 16) ? stream4_u<T, 2>(args, st) : stream4_u<T, 1>(args, st);  // 32 rows x pairs would spill
+    return (pairs && args.M <= 16) ? stream5_u<T, 2>(args, st) : stream5_u<T, 1>(args, st);  // 32 rows x pairs would spill
 }
 
 int launch_w4a16_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *p1,
@@ -627,8 +655,8 @@ int launch_w4a16_fused(const void *scales, const void *biases, const void *b, vo
     args.M = M, args.N = N, args.K = K, args.lda = lda;
     args.prologue = prologue, args.epilogue = epilogue, args.eps = eps;
     switch (dtype) {
-        case TL_F16: return stream4_t<__half>(args, st);
-        case TL_BF16: return stream4_t<__nv_bfloat16>(args, st);
+        case TL_F16: return stream5_t<__half>(args, st);
+        case TL_BF16: return stream5_t<__nv_bfloat16>(args, st);
     }
     return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
 }
