@@ -136,10 +136,15 @@ size_t tl_argmax_workspace(int rows, int vocab);
  *            TL_PRO_SWIGLU  : a = swiglu(p0 = gate [M, N], p1 = up [M, N])
  *   epilogue TL_EPI_NONE    : out = result
  *            TL_EPI_RESIDUAL: out = residual [M, K] + result
+ *            TL_EPI_SWIGLU_PAIRS: out [M, K/2]; the weight rows are gate and up rows interleaved in
+ *                             blocks of 8 (rows 16c..16c+7 = gate 8c..8c+7, rows 16c+8..16c+15 = up
+ *                             8c..8c+7; K % 16 == 0) and out[m, 8c+r] = swiglu(T(gate), T(up)): the
+ *                             MLP activation leaves the gate|up projection already combined
+ *                             (week2_kernels.metal:115-116 applied to the rounded projection outputs)
  * lda is the row stride (elements) of p0 (and of p1 for SWIGLU), so gate/up may
  * be the two halves of one [M, 2N] buffer. */
 enum { TL_PRO_NONE = 0, TL_PRO_RMSNORM = 1, TL_PRO_SWIGLU = 2 };
-enum { TL_EPI_NONE = 0, TL_EPI_RESIDUAL = 1 };
+enum { TL_EPI_NONE = 0, TL_EPI_RESIDUAL = 1, TL_EPI_SWIGLU_PAIRS = 2 };
 int tl_quantized_matmul_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0,
                               const void *p1, const void *residual, int M, int N, int K, int lda, int prologue,
                               int epilogue, float eps, int dtype, void *stream);
@@ -173,7 +178,8 @@ int tl_decode_attention_fused(const void *qkv, const void *q_norm_weight, const 
  * KV, batch 1..8, head_dim 128, <= 4 query heads per KV head) of the Week-3
  * model: the call sequence of qwen3_week3.py:320-338 at L == 1 plus the greedy
  * sampler of batch.py:8-13, with the same rounding points as the per-operator
- * launchers.  q|k|v and gate|up projections are passed row-concatenated.
+ * launchers.  q|k|v are passed row-concatenated; gate|up interleaved in blocks of
+ * 8 rows (the TL_EPI_SWIGLU_PAIRS layout), gu holds swiglu(gate, up) [B, I].
  * `layers` points to DEVICE memory holding n_layers tl_decode_layer records;
  * every other pointer is a device pointer too.  block tables are per layer. */
 typedef struct tl_decode_layer {

@@ -51,6 +51,23 @@ def test_fused_projection_equals_the_unfused_operator_sequence(dev, M, N, K):
     assert torch.equal(got, ext.add(res, want))
 
 
+@pytest.mark.parametrize("M", [1, 5, 8, 16])
+@pytest.mark.parametrize("N,inter", [(2560, 9728), (256, 384), (1024, 40)])
+def test_swiglu_pairs_epilogue_equals_projection_then_swiglu(dev, M, N, inter):
+    """gate|up rows interleaved in blocks of 8: the projection emits swiglu(gate, up) itself."""
+    g = torch.Generator().manual_seed(M + N + inter)
+    wg, sg, bg = packed(inter, N, g, dev)
+    wu, su, bu = packed(inter, N, g, dev)
+    x = (torch.randn(M, N, generator=g) * 2).to(BF16).to(dev)
+    want = ext.swiglu(ext.quantized_matmul(sg, bg, 128, 4, x, wg, True), ext.quantized_matmul(su, bu, 128, 4, x, wu, True))
+    w, s, b = ext.interleave_gate_up(wg, wu), ext.interleave_gate_up(sg, su), ext.interleave_gate_up(bg, bu)
+    got = ext.quantized_matmul_fused(s, b, w, x, epilogue=ext.EPI_SWIGLU_PAIRS)
+    assert got.shape == (M, inter)
+    # the 2*inter-row projection deals its rows to CTAs and warps differently from the two
+    # inter-row projections, so the fp32 partial sums meet in a different order: one bf16 ulp
+    torch.testing.assert_close(got.float(), want.float(), rtol=2**-7, atol=2e-3 * float(want.float().abs().max()))
+
+
 def test_fused_qk_norm_rope_append_equals_the_unfused_sequence(dev):
     g = torch.Generator().manual_seed(3)
     B, Hq, Hkv, D, page, P = 3, 32, 8, 128, 16, 7

@@ -234,8 +234,10 @@ int tl_quantized_matmul_fused(const void *scales, const void *biases, const void
     if (dtype != TL_F16 && dtype != TL_BF16) return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
     if (M < 0 || N <= 0 || K < 0 || lda < N) return fail(TL_EINVAL, "quantized_matmul_fused: bad shape");
     if (N % 128 != 0) return fail(TL_EINVAL, "quantized_matmul: N must be divisible by group_size");
-    if (prologue < TL_PRO_NONE || prologue > TL_PRO_SWIGLU || epilogue < TL_EPI_NONE || epilogue > TL_EPI_RESIDUAL)
+    if (prologue < TL_PRO_NONE || prologue > TL_PRO_SWIGLU || epilogue < TL_EPI_NONE || epilogue > TL_EPI_SWIGLU_PAIRS)
         return fail(TL_EINVAL, "quantized_matmul_fused: unknown prologue/epilogue");
+    if (epilogue == TL_EPI_SWIGLU_PAIRS && K % 16 != 0)
+        return fail(TL_EINVAL, "quantized_matmul_fused: interleaved gate|up rows need K %% 16 == 0");
     if (M == 0 || K == 0) return TL_OK;
     if (!scales || !biases || !b || !out || !p0 || (prologue != TL_PRO_NONE && !p1) || (epilogue == TL_EPI_RESIDUAL && !residual))
         return fail(TL_EINVAL, "quantized_matmul_fused: null pointer");

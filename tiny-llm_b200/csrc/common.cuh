@@ -94,6 +94,36 @@ __device__ __forceinline__ uint4 ldg_stream(const void *p) {
     return r;
 }
 
+// L2 (ld.global.cg) loads of data another CTA or the previous kernel has just written.  They are
+// VOLATILE asm with a memory clobber on purpose: the CUDA header versions (__ldcg) are plain asm
+// without a clobber, which the compiler may hoist above griddepcontrol.wait / a grid barrier -
+// observed: q rows read before the projection that produces them had finished.
+__device__ __forceinline__ uint4 ld_cg(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_cg(const float *p) {
+    float r;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ int ld_cg(const int *p) {
+    int r;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ __nv_bfloat16 ld_cg(const __nv_bfloat16 *p) {
+    unsigned short r;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+    return __ushort_as_bfloat16(r);
+}
+__device__ __forceinline__ __half ld_cg(const __half *p) {
+    unsigned short r;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
+    return __ushort_as_half(r);
+}
+
 }  // namespace tl
 
 #define TL_LAUNCH_CHECK(name)                    \

@@ -30,6 +30,7 @@
 // Arithmetic and rounding points are those of the operator sequence
 // (rms_norm -> quantized_matmul -> ... , see engine.py::_forward_unfused).
 #include <algorithm>
+#include <stdlib.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -51,7 +52,7 @@ typedef tl_decode_layer MkLayer;
 typedef tl_decode_args MkArgs;
 
 // ------------------------------------------------------------- primitives --
-__device__ __forceinline__ uint4 mk_ldcg16(const void *p) { return __ldcg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ uint4 mk_ldcg16(const void *p) { return ld_cg(reinterpret_cast<const uint4 *>(p)); }
 __device__ __forceinline__ float mk_bf(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float mk_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
@@ -230,7 +231,7 @@ __device__ __forceinline__ void mk_refill(const MkArgs &a, Pipe<U> &c, int warp,
 // prologue 0: plain; 1: rms_norm(x, norm_w, eps); 2: swiglu(gate, up) with up = in + up_off.
 template <int MP, int U>
 __device__ void mk_stream(const MkArgs &a, int sp, Pipe<U> &pipe, const bf16 *in, int ld, int up_off, int prologue, const bf16 *norm_w,
-                          bf16 *out, const bf16 *res, unsigned char *dyn, Prof &prof) {
+                          bf16 *out, const bf16 *res, bool swiglu_pairs, unsigned char *dyn, Prof &prof) {
     constexpr int MPA = w4_mpa(MP);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -288,6 +289,26 @@ __device__ void mk_stream(const MkArgs &a, int sp, Pipe<U> &pipe, const bf16 *in
 
     // ---- deterministic reduction of the entries of each chunk (in warp order) + epilogue
     const unsigned units = r.chunks * r.P;
+    if (swiglu_pairs) {  // gate rows 0-7 / up rows 8-15 of every chunk (engine.py::_interleave_gate_up) -> 8 activations
+        auto chunk_sum = [&](int ch, int row, int m) {
+            float v = 0.f;
+            for (int w = 0; w < MK_WARPS; ++w) {
+                const int wb = static_cast<int>(units * w / MK_WARPS);
+                const int we = static_cast<int>(units * (w + 1) / MK_WARPS);
+                if (wb < we && wb < (ch + 1) * r.P && we > ch * r.P) v += entries[static_cast<size_t>(ch + w) * 128 + row * 8 + m];
+            }
+            return v;
+        };
+        for (int o = threadIdx.x; o < r.chunks * 8 * B; o += MK_THREADS) {
+            const int m = o / (r.chunks * 8);
+            const int rr = o - m * (r.chunks * 8);
+            const int ch = rr >> 3, row = rr & 7;
+            const float gate = mk_round(chunk_sum(ch, row, m)), up = mk_round(chunk_sum(ch, row + 8, m));
+            out[static_cast<size_t>(m) * (p.K / 2) + (r.r0 >> 1) + rr] = __float2bfloat16_rn((gate / (1.0f + expf(-gate))) * up);
+        }
+        __syncthreads();
+        return;
+    }
     for (int o = threadIdx.x; o < r.chunks * 16 * B; o += MK_THREADS) {
         const int m = o / (r.chunks * 16);  // request-major so that consecutive threads store consecutive features
         const int rr = o - m * (r.chunks * 16);
@@ -301,7 +322,7 @@ __device__ void mk_stream(const MkArgs &a, int sp, Pipe<U> &pipe, const bf16 *in
                 if (wb < we && wb < (ch + 1) * r.P && we > ch * r.P) v += entries[static_cast<size_t>(ch + w) * 128 + row * 8 + m];
             }
             bf16 vb = __float2bfloat16_rn(v);
-            if (res != nullptr) vb = __float2bfloat16_rn(mk_bf(__ldcg(res + static_cast<size_t>(m) * p.K + k)) + mk_bf(vb));  // L2: written by other phases
+            if (res != nullptr) vb = __float2bfloat16_rn(mk_bf(ld_cg(res + static_cast<size_t>(m) * p.K + k)) + mk_bf(vb));  // L2: written by other phases
             out[static_cast<size_t>(m) * p.K + k] = vb;
         }
     }
@@ -363,6 +384,10 @@ __device__ __forceinline__ void mk_cp16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
 }
 
+// DEPWAIT (stand-alone kernel under programmatic dependent launch): everything that does not read
+// this step's qkv row - page ids, the K/V rows of older tokens - is requested BEFORE
+// griddepcontrol.wait, i.e. while the qkv projection is still draining.
+template <bool DEPWAIT>
 __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *dyn, Prof &prof) {
     const int D = a.D, G = a.Hq / a.Hkv;
     const int items = a.B * a.Hkv * a.nsplit;
@@ -388,14 +413,21 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
     float re[2] = {0.f, 0.f}, im[2] = {0.f, 0.f}, wre[2] = {0.f, 0.f}, wim[2] = {0.f, 0.f};
     double freq[2] = {0.0, 0.0};
     int position = 0;
+    auto load_q = [&]() {
+        if (qpath) {
+            const int head_off = is_q ? (kvh * G + warp) * D : (is_k ? (a.Hq + kvh) * D : (a.Hq + a.Hkv + kvh) * D);
+            const bf16 *src = static_cast<const bf16 *>(a.qkv) + static_cast<size_t>(b) * qkv_w + head_off;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // lane owns pairs (i, i+64) for i = lane, lane+32   (D == 128)
+                re[h] = mk_bf(ld_cg(src + lane + 32 * h));
+                im[h] = mk_bf(ld_cg(src + lane + 32 * h + 64));
+            }
+        }
+    };
     if (qpath) {
-        const int head_off = is_q ? (kvh * G + warp) * D : (is_k ? (a.Hq + kvh) * D : (a.Hq + a.Hkv + kvh) * D);
-        const bf16 *src = static_cast<const bf16 *>(a.qkv) + static_cast<size_t>(b) * qkv_w + head_off;
         const bf16 *w = static_cast<const bf16 *>(is_q ? l.q_norm : l.k_norm);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {  // lane owns pairs (i, i+64) for i = lane, lane+32   (D == 128)
-            re[h] = mk_bf(__ldcg(src + lane + 32 * h));
-            im[h] = mk_bf(__ldcg(src + lane + 32 * h + 64));
+        for (int h = 0; h < 2; ++h) {
             if (is_q || is_k) {
                 wre[h] = mk_bf(w[lane + 32 * h]);
                 wim[h] = mk_bf(w[lane + 32 * h + 64]);
@@ -404,6 +436,7 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         }
         position = a.offsets[b];
     }
+    if (!DEPWAIT) load_q();
     const int ctx = min(a.context_lens[b], a.max_pages * a.page_size);
     const int begin = split * a.tokens_per_split;
     const int end = min(ctx, begin + a.tokens_per_split);
@@ -440,6 +473,10 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         prof.stamp(50003);
+        if (DEPWAIT && rb == begin) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");  // the qkv row of this step exists now
+            load_q();
+        }
         // ---- C: q path (first round only)
         if (rb == begin && qpath) {
             if (is_q || is_k) {
@@ -581,13 +618,13 @@ __device__ void mk_attention_merge(const MkArgs &a) {
     for (int h = warp_global; h < heads; h += gridDim.x * MK_WARPS) {
         const float *base = a.attn_ws + static_cast<size_t>(h) * a.nsplit * (D + 2);
         float gm = MK_NEG;
-        for (int s = 0; s < a.nsplit; ++s) gm = fmaxf(gm, __ldcg(base + s * (D + 2) + D));
+        for (int s = 0; s < a.nsplit; ++s) gm = fmaxf(gm, ld_cg(base + s * (D + 2) + D));
         float gl = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
         for (int s = 0; s < a.nsplit; ++s) {
-            const float f = exp2f(__ldcg(base + s * (D + 2) + D) - gm);
-            gl += __ldcg(base + s * (D + 2) + D + 1) * f;
+            const float f = exp2f(ld_cg(base + s * (D + 2) + D) - gm);
+            gl += ld_cg(base + s * (D + 2) + D + 1) * f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] += __ldcg(base + s * (D + 2) + lane + 32 * i) * f;
+            for (int i = 0; i < 4; ++i) o[i] += ld_cg(base + s * (D + 2) + lane + 32 * i) * f;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) static_cast<bf16 *>(a.y)[static_cast<size_t>(h) * D + lane + 32 * i] = __float2bfloat16_rn(gl == 0.f ? 0.f : o[i] / gl);
@@ -648,12 +685,12 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
         switch (kind) {
             case 0: norm_w = static_cast<const bf16 *>(l.ln1); break;
             case 1: in = yb, ld = a.Hq * a.D, prologue = 0, out = x_alt, res = x; break;
-            case 2: in = x_alt, norm_w = static_cast<const bf16 *>(l.ln2), out = gu; break;
-            case 3: in = gu, ld = 2 * a.I, up_off = a.I, prologue = 2, out = x, res = x_alt; break;
+            case 2: in = x_alt, norm_w = static_cast<const bf16 *>(l.ln2), out = gu; break;  // emits swiglu(gate, up) [B, I]
+            case 3: in = gu, ld = a.I, prologue = 0, out = x, res = x_alt; break;
             default: norm_w = static_cast<const bf16 *>(a.final_norm), out = static_cast<bf16 *>(a.logits); break;
         }
         if (kind == 1) {  // attention sits in front of o_proj; the weight pipeline is empty here (see mk_cursor_phase)
-            mk_attention(a, l, dyn, prof);
+            mk_attention<false>(a, l, dyn, prof);
             prof.stamp(100 + (sp - 1) * 10 + 6);
             // restart the weight stream BEFORE the barrier: the 140 CTAs without an attention item get
             // here at once, and everyone's first o_proj units fly while the grid synchronises
@@ -665,7 +702,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
                 mk_grid_sync(a.sync_counter, epoch);
             }
         }
-        mk_stream<MP, U>(a, sp, pipe, in, ld, up_off, prologue, norm_w, out, res, dyn, prof);
+        mk_stream<MP, U>(a, sp, pipe, in, ld, up_off, prologue, norm_w, out, res, kind == 2, dyn, prof);
         if (kind == 4) {  // greedy arg-max partials of this CTA's logits rows
             const SRange r = mk_range<U>(mk_sphase(a, sp), warp);
             mk_cta_argmax(a, r.r0, r.r1, amax_v, amax_i);
@@ -678,7 +715,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_megakernel(const MkArgs 
         const int step = *a.step_counter;
         for (int m = 0; m < a.B; ++m) {
             BestPair r{-CUDART_INF_F, 0x7fffffff};
-            for (int c = lane; c < static_cast<int>(gridDim.x); c += 32) r = mk_better(r, BestPair{__ldcg(a.amax_val + c * a.B + m), __ldcg(a.amax_idx + c * a.B + m)});
+            for (int c = lane; c < static_cast<int>(gridDim.x); c += 32) r = mk_better(r, BestPair{ld_cg(a.amax_val + c * a.B + m), ld_cg(a.amax_idx + c * a.B + m)});
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 BestPair other{__shfl_xor_sync(0xffffffffu, r.v, o), __shfl_xor_sync(0xffffffffu, r.i, o)};
@@ -772,6 +809,7 @@ int launch_decode_megakernel(const MkArgs &a, cudaStream_t st) {
     if (a.B < 1 || a.B > MK_MAXB) return fail(TL_EINVAL, "decode_step: batch must be 1..8");
     if (a.D != 128 || a.Hq % a.Hkv != 0 || a.Hq / a.Hkv > 4) return fail(TL_EINVAL, "decode_step: needs head_dim 128 and at most 4 query heads per KV head");
     if (a.H % 128 != 0 || a.I % 128 != 0 || (a.Hq * a.D) % 128 != 0) return fail(TL_EINVAL, "decode_step: widths must be multiples of 128");
+    if (a.H % 16 != 0 || ((a.Hq + 2 * a.Hkv) * a.D) % 16 != 0) return fail(TL_EINVAL, "decode_step: projection heights must be multiples of 16");
     // pairs of groups per unit need 4-byte aligned scale pairs: every reduction width a multiple of 256
     const bool pairs = a.H % 256 == 0 && a.I % 256 == 0 && (a.Hq * a.D) % 256 == 0;
     return pairs ? mk_launch_u<2>(a, st) : mk_launch_u<1>(a, st);
@@ -782,10 +820,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_attention_fused_kernel(c
     extern __shared__ __align__(128) unsigned char att_smem_raw[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the o_proj stream may prefetch its weights now
     Prof prof{nullptr, 0, 0};
-    mk_attention(a, l, att_smem_raw, prof);
+    mk_attention<true>(a, l, att_smem_raw, prof);
 }
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_attention_merge_kernel(const MkArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     mk_attention_merge(a);
 }
 
@@ -815,7 +854,7 @@ int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, co
     a.qkv = const_cast<void *>(qkv), a.y = out, a.attn_ws = workspace;
     const int max_split = attention_max_split(batch, num_kv_heads);
     int tps = (max_context < 1 ? 1 : max_context + max_split - 1) / max_split;
-    tps = tps < MK_ATT_TOK ? MK_ATT_TOK : tps;
+    tps = tps < 2 * MK_ATT_TOK ? 2 * MK_ATT_TOK : tps;  // a split (extra merge launch) only pays beyond two rounds
     tps = (tps + 63) / 64 * 64;
     a.tokens_per_split = tps;
     a.nsplit = (max_context + tps - 1) / tps;
@@ -828,11 +867,25 @@ int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, co
             return fail(TL_ECUDA, "decode_attention_fused: cannot raise shared memory limit");
         configured = true;
     }
-    decode_attention_fused_kernel<<<batch * num_kv_heads * a.nsplit, MK_THREADS, MK_ATT_BYTES + 64, st>>>(a, l);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(batch * num_kv_heads * a.nsplit);
+    cfg.blockDim = dim3(MK_THREADS);
+    cfg.dynamicSmemBytes = MK_ATT_BYTES + 64;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl() ? 1 : 0;  // without the attribute griddepcontrol.wait returns at once
+    cudaError_t e = cudaLaunchKernelEx(&cfg, decode_attention_fused_kernel, a, l);
+    if (e != cudaSuccess) return fail(TL_ECUDA, "decode_attention_fused: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("decode_attention_fused");
     if (a.nsplit > 1) {
         const int heads = batch * num_heads;
-        decode_attention_merge_kernel<<<(heads + MK_WARPS - 1) / MK_WARPS, MK_THREADS, 0, st>>>(a);
+        cfg.gridDim = dim3((heads + MK_WARPS - 1) / MK_WARPS);
+        cfg.dynamicSmemBytes = 0;
+        e = cudaLaunchKernelEx(&cfg, decode_attention_merge_kernel, a);
+        if (e != cudaSuccess) return fail(TL_ECUDA, "decode_attention_merge: launch failed: %s", cudaGetErrorString(e));
         TL_LAUNCH_CHECK("decode_attention_merge");
     }
     return TL_OK;

@@ -229,7 +229,7 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
     auto aux_load = [&](int idx) {
         int m, c;
         const T *src = chunk_src(idx, m, c);
-        return rms ? *reinterpret_cast<const uint4 *>(aux + c * 8) : __ldcg(reinterpret_cast<const uint4 *>(aux + (src - in)));
+        return rms ? *reinterpret_cast<const uint4 *>(aux + c * 8) : ld_cg(reinterpret_cast<const uint4 *>(aux + (src - in)));
     };
     auto emit = [&](int idx, uint4 raw, uint4 auxv) {  // idx may be >= total (lane padding): contributes nothing
         float part = 0.f;
@@ -278,7 +278,7 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
             held[j] = held_aux[j] = make_uint4(0u, 0u, 0u, 0u);
             if (idx < total) {
                 int m, c;
-                held[j] = __ldcg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
+                held[j] = ld_cg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
                 if (prologue != W4_PRO_NONE) held_aux[j] = aux_load(idx);
             }
         }
@@ -303,7 +303,7 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
                 float part = 0.f;
                 if (idx < total) {
                     int m, c;
-                    part = square_sum(__ldcg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c))));
+                    part = square_sum(ld_cg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c))));
                 }
                 part = half_warp_sum(part);
                 if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
@@ -321,7 +321,7 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
             uint4 raw = make_uint4(0u, 0u, 0u, 0u), auxv = raw;
             if (idx < total) {
                 int m, c;
-                raw = __ldcg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
+                raw = ld_cg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
                 if (prologue != W4_PRO_NONE) auxv = aux_load(idx);
             }
             emit(idx, raw, auxv);

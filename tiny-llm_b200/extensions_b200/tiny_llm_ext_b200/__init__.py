@@ -462,7 +462,7 @@ def decode_advance(tokens, next_tokens, offsets, context_lens, out_log, step_cou
 
 
 PRO_NONE, PRO_RMSNORM, PRO_SWIGLU = 0, 1, 2
-EPI_NONE, EPI_RESIDUAL = 0, 1
+EPI_NONE, EPI_RESIDUAL, EPI_SWIGLU_PAIRS = 0, 1, 2
 
 
 def quantized_matmul_fused(scales, biases, b, p0, p1=None, residual=None, prologue=PRO_NONE, epilogue=EPI_NONE, eps=0.0,
@@ -486,8 +486,10 @@ def quantized_matmul_fused(scales, biases, b, p0, p1=None, residual=None, prolog
         raise RuntimeError("quantized_matmul_fused: norm weight must be [N]")
     if epilogue == EPI_RESIDUAL and (residual is None or tuple(residual.shape) != (M, K) or not residual.is_contiguous()):
         raise RuntimeError("quantized_matmul_fused: residual must be contiguous [M, K]")
+    if epilogue == EPI_SWIGLU_PAIRS and K % 16:
+        raise RuntimeError("quantized_matmul_fused: interleaved gate|up rows need K % 16 == 0")
     if out is None:
-        out = torch.empty((M, K), dtype=p0.dtype, device=p0.device)
+        out = torch.empty((M, K // 2 if epilogue == EPI_SWIGLU_PAIRS else K), dtype=p0.dtype, device=p0.device)
     _check(
         _lib.tl_quantized_matmul_fused(
             scales.data_ptr(), biases.data_ptr(), b.data_ptr(), out.data_ptr(), p0.data_ptr(),
@@ -496,6 +498,15 @@ def quantized_matmul_fused(scales, biases, b, p0, p1=None, residual=None, prolog
         )
     )
     return out
+
+
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """Row layout EPI_SWIGLU_PAIRS expects: blocks of 8 gate rows followed by the matching 8 up rows."""
+    K = gate.shape[0]
+    if gate.shape != up.shape or K % 8:
+        raise RuntimeError("interleave_gate_up: gate and up must share a shape with rows % 8 == 0")
+    tail = gate.shape[1:]
+    return torch.stack((gate.reshape(K // 8, 8, *tail), up.reshape(K // 8, 8, *tail)), dim=1).reshape(2 * K, *tail).contiguous()
 
 
 def decode_qk_norm_rope_append(qkv, q_norm_weight, k_norm_weight, offsets, block_table, context_lens, key_pages, value_pages,

@@ -51,6 +51,20 @@ def _concat_weights(parts):
     )
 
 
+def _interleave_gate_up(gate, up):
+    """gate|up rows in blocks of 8 (``ext.interleave_gate_up``): the streaming kernel's
+    EPI_SWIGLU_PAIRS epilogue then emits swiglu(gate, up) directly, so the MLP activation never
+    makes a round trip through memory as two separate vectors."""
+    as_i32 = lambda w: w.view(torch.int32) if w.dtype == torch.uint32 else w
+    return SimpleNamespace(
+        weight=ext.interleave_gate_up(as_i32(gate.weight), as_i32(up.weight)),
+        scales=ext.interleave_gate_up(gate.scales, up.scales),
+        biases=ext.interleave_gate_up(gate.biases, up.biases),
+        group_size=gate.group_size,
+        bits=gate.bits,
+    )
+
+
 class MegaStep:
     """Argument block + scratch of the whole-step persistent kernel (``tl_decode_step``)."""
 
@@ -111,6 +125,8 @@ class MegaStep:
     @staticmethod
     def supported(engine: "DecodeEngine") -> bool:
         m = engine.model
+        if m.layers_inner[0].mlp.hidden_dim % 8:
+            return False
         if not (engine.fused and engine.D == 128 and engine.B <= 8 and engine.Hq // engine.Hkv <= 4):
             return False
         if m.hidden_size % 128 or m.layers_inner[0].mlp.hidden_dim % 128:
@@ -202,7 +218,7 @@ class DecodeEngine:
             self._packed = [
                 SimpleNamespace(
                     qkv=_concat_weights([b.self_attn.wq, b.self_attn.wk, b.self_attn.wv]),
-                    gate_up=_concat_weights([b.mlp.w_gate, b.mlp.w_up]),
+                    gate_up=_interleave_gate_up(b.mlp.w_gate, b.mlp.w_up),
                 )
                 for b in model.layers_inner
             ]
@@ -215,10 +231,10 @@ class DecodeEngine:
         if self._attention_fused:
             self._rope_inv_freq = ext.rope_inv_freq_table(self.D, attn0.rope.base, self.device)
             self._attn_ws = torch.empty(ext.decode_attention_fused_workspace(self.B, self.Hq, self.Hkv), dtype=torch.float32, device=self.device)
-        # persistent == None: use the whole-step kernel whenever the model shape allows it
-        # (TL_PERSISTENT=0 forces the CUDA-graph path for A/B measurements)
-        if persistent is None and os.environ.get("TL_PERSISTENT", "1") == "0":
-            persistent = False
+        if persistent is None:
+            # measured on B200 (Qwen3-4B, batch 1): CUDA-graph + PDL path 1.55 ms/token, whole-step
+            # kernel 2.44 ms/token -> the graph path is the default, TL_PERSISTENT=1 opts in
+            persistent = os.environ.get("TL_PERSISTENT", "0") == "1"
         self.persistent = (persistent is not False) and MegaStep.supported(self)
         self._mega = MegaStep(self) if self.persistent else None
 
@@ -295,11 +311,10 @@ class DecodeEngine:
                 y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i], self.context_lens,
                                         at.scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
             x = ext.quantized_matmul_fused(at.wo.scales, at.wo.biases, at.wo.weight, y.view(B, Hq * D), residual=x, epilogue=ext.EPI_RESIDUAL)
-            gu = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, x, ln2._weight_as(x.dtype, x.device),
-                                            prologue=ext.PRO_RMSNORM, eps=ln2.eps)
+            act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, x, ln2._weight_as(x.dtype, x.device),
+                                             prologue=ext.PRO_RMSNORM, eps=ln2.eps, epilogue=ext.EPI_SWIGLU_PAIRS)  # [B, inter]
             wd = block.mlp.w_down
-            x = ext.quantized_matmul_fused(wd.scales, wd.biases, wd.weight, gu[:, :inter], gu[:, inter:], residual=x,
-                                           prologue=ext.PRO_SWIGLU, epilogue=ext.EPI_RESIDUAL)
+            x = ext.quantized_matmul_fused(wd.scales, wd.biases, wd.weight, act, residual=x, epilogue=ext.EPI_RESIDUAL)
         head = m.w_lm_head if m.w_lm_head is not None else m.embedding.weight
         logits = ext.quantized_matmul_fused(head.scales, head.biases, head.weight, x, m.norm._weight_as(x.dtype, x.device),
                                             prologue=ext.PRO_RMSNORM, eps=m.norm.eps)

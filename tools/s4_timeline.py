@@ -22,7 +22,7 @@ sys.path[:0] = [str(ROOT), str(ROOT / "tiny-llm_b200")]
 
 from extensions_b200 import tiny_llm_ext_b200 as ext  # noqa: E402
 
-SHAPES = [("qkv", 2560, 6144, "rms"), ("o", 4096, 2560, "res"), ("gate_up", 2560, 19456, "rms"), ("down", 9728, 2560, "swiglu")]
+SHAPES = [("qkv", 2560, 6144, "rms"), ("o", 4096, 2560, "res"), ("gate_up", 2560, 19456, "rms"), ("down", 9728, 2560, "res")]
 
 
 def main():
@@ -50,9 +50,9 @@ def main():
             w, s, b = ws["o"][i]
             h2 = ext.quantized_matmul_fused(s, b, w, y, residual=h, epilogue=ext.EPI_RESIDUAL)
             w, s, b = ws["gate_up"][i]
-            gu = ext.quantized_matmul_fused(s, b, w, h2, nw, prologue=ext.PRO_RMSNORM, eps=1e-6)
+            act = ext.quantized_matmul_fused(s, b, w, h2, nw, prologue=ext.PRO_RMSNORM, eps=1e-6, epilogue=ext.EPI_SWIGLU_PAIRS)
             w, s, b = ws["down"][i]
-            h = ext.quantized_matmul_fused(s, b, w, gu[:, :9728], gu[:, 9728:], residual=h2, prologue=ext.PRO_SWIGLU, epilogue=ext.EPI_RESIDUAL)
+            h = ext.quantized_matmul_fused(s, b, w, act, residual=h2, epilogue=ext.EPI_RESIDUAL)
 
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
