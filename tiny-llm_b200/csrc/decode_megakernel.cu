@@ -547,6 +547,7 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
             }
         }
         __syncthreads();
+        prof.stamp(50008);
         // ---- M: per head max / exp2 / sum over the round
         const int cnt8 = (cnt + 7) & ~7;  // S wrote whole tiles
         if (warp < G) {
@@ -563,6 +564,7 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
             if (lane == 0) st_s[warp] = mx, st_s[4 + warp] = sum;
         }
         __syncthreads();
+        prof.stamp(50009);
         // ---- V: partial outputs, thread = (token subset, 8 dims, head)
         {
             const int sub = threadIdx.x & 7, d8 = (threadIdx.x >> 3) & 15;

@@ -65,7 +65,7 @@ def main():
         dt = (clk - prev) / mhz
         prev = clk
         if 50000 <= tag < 60000:
-            name = "attn:" + {1: "loads-issued", 2: "page-ids+sync", 3: "kv-copies-issued", 4: "q-path", 5: "wait+sync", 6: "softmax", 7: "merge-groups+sync"}.get(tag - 50000, str(tag))
+            name = "attn:" + {1: "loads-issued", 2: "page-ids+sync", 3: "kv-copies-issued", 4: "q-path", 5: "wait+sync", 6: "PV+sync", 7: "absorb-round", 8: "scores(mma)+sync", 9: "softmax-stats+sync"}.get(tag - 50000, str(tag))
         elif tag >= 100 and tag < 90000:
             sp, kind = (tag - 100) // 10, (tag - 100) % 10
             name = ["qkv", "o", "gate_up", "down"][sp % 4] + ":" + KIND.get(kind, str(kind))
