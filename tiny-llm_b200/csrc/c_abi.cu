@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "trace.cuh"
 
 namespace tl {
 
@@ -281,6 +282,14 @@ int tl_decode_attention_fused(const void *qkv, const void *q_norm_weight, const 
                                          key_pages, value_pages, out, workspace, batch, num_heads, num_kv_heads, head_dim, eps,
                                          scale, num_pages, page_size, max_pages, max_context, dtype, as_stream(stream));
 }
+
+#if TL_TRACE
+extern "C" int tl_debug_trace(unsigned long long *device_events, unsigned int *device_count, unsigned int capacity) {
+    trace_bind_matvec(device_events, device_count, capacity);
+    trace_bind_attention(device_events, device_count, capacity);
+    return TL_OK;
+}
+#endif
 
 int tl_decode_step_grid(void) { return mk_grid_size(); }
 

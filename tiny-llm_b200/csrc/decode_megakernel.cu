@@ -36,6 +36,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "w4a16_item.cuh"
+#include "trace.cuh"
 
 namespace tl {
 
@@ -437,8 +438,14 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         position = a.offsets[b];
     }
     if (!DEPWAIT) load_q();
-    const int ctx = min(a.context_lens[b], a.max_pages * a.page_size);
+    // page ids of the first round do not need the context length: request them together with it
     const int begin = split * a.tokens_per_split;
+    {
+        const int lp_first = begin / a.page_size + static_cast<int>(threadIdx.x);
+        if (static_cast<int>(threadIdx.x) <= MK_ATT_TOK && lp_first < a.max_pages)
+            pg_s[threadIdx.x] = l.table[static_cast<size_t>(b) * a.max_pages + lp_first];
+    }
+    const int ctx = min(a.context_lens[b], a.max_pages * a.page_size);
     const int end = min(ctx, begin + a.tokens_per_split);
     const int cur_tok = ctx - 1;
     const int gidx = warp * 2 + (lane >> 4), c8 = lane & 15;   // copy mapping: lane group of 16 per token row
@@ -453,28 +460,37 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         const int cnt = max(rend - rb, 0);
         const int lp0 = rb / a.page_size;
         const int npg = cnt > 0 ? (rend - 1) / a.page_size - lp0 + 1 : 0;
-        if (static_cast<int>(threadIdx.x) < npg) pg_s[threadIdx.x] = l.table[static_cast<size_t>(b) * a.max_pages + lp0 + threadIdx.x];
+        if (rb != begin && static_cast<int>(threadIdx.x) < npg) pg_s[threadIdx.x] = l.table[static_cast<size_t>(b) * a.max_pages + lp0 + threadIdx.x];
         __syncthreads();
         prof.stamp(50002);
         // ---- B: all K/V rows of the round in flight
+        {
+            int lpi = (rb + gidx) / a.page_size;        // logical page and row inside it of this lane group's next token,
+            int row = rb + gidx - lpi * a.page_size;    // advanced by 32 tokens per step without further divisions
+            const size_t head_rows = static_cast<size_t>(a.Hkv) * a.page_size;
+            unsigned char *dst = kv_s + gidx * MK_KV_STRIDE + c8 * 16;
 #pragma unroll
-        for (int j = 0; j < MK_ATT_TOK / 32; ++j) {
-            const int slot = j * 32 + gidx;
-            const int tok = rb + slot;
-            if (tok < rend && tok != cur_tok) {
-                const int lp = tok / a.page_size;
-                const int pid = pg_s[lp - lp0];
-                if (pid >= 0 && pid < a.num_pages) {
-                    const size_t off = ((static_cast<size_t>(pid) * a.Hkv + kvh) * a.page_size + (tok - lp * a.page_size)) * D + c8 * 8;
-                    mk_cp16(kv_s + slot * MK_KV_STRIDE + c8 * 16, static_cast<const bf16 *>(l.k_pages) + off);
-                    mk_cp16(kv_s + slot * MK_KV_STRIDE + 256 + c8 * 16, static_cast<const bf16 *>(l.v_pages) + off);
+            for (int j = 0; j < MK_ATT_TOK / 32; ++j) {
+                const int tok = rb + j * 32 + gidx;
+                if (tok < rend && tok != cur_tok) {
+                    const int pid = pg_s[lpi - lp0];
+                    if (pid >= 0 && pid < a.num_pages) {
+                        const size_t off = ((pid * head_rows + static_cast<size_t>(kvh) * a.page_size + row) << 7) + c8 * 8;  // D == 128
+                        mk_cp16(dst, static_cast<const bf16 *>(l.k_pages) + off);
+                        mk_cp16(dst + 256, static_cast<const bf16 *>(l.v_pages) + off);
+                    }
                 }
+                dst += 32 * MK_KV_STRIDE;
+                row += 32;
+                while (row >= a.page_size) row -= a.page_size, lpi += 1;
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         prof.stamp(50003);
         if (DEPWAIT && rb == begin) {
+            TL_TRACE_STAMP(21);
             asm volatile("griddepcontrol.wait;" ::: "memory");  // the qkv row of this step exists now
+            TL_TRACE_STAMP(22);
             load_q();
         }
         // ---- C: q path (first round only)
@@ -519,9 +535,10 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         }
         __syncthreads();
         prof.stamp(50005);
+        if (DEPWAIT) TL_TRACE_STAMP(23);
         // ---- S: scores of 8 tokens x G heads per MMA tile
         for (int tile = warp; tile * 8 < cnt; tile += MK_WARPS) {
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};  // two independent MMA chains
             const unsigned char *krow = kv_s + (tile * 8 + g) * MK_KV_STRIDE + t * 4;
             const bf16 *qrow = q_s + (g < G ? g : 0) * 128 + 2 * t;
 #pragma unroll
@@ -531,8 +548,12 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
                 if (g >= G) a0 = a2 = 0u;
                 const uint32_t b0 = *reinterpret_cast<const uint32_t *>(krow + ks * 32);
                 const uint32_t b1 = *reinterpret_cast<const uint32_t *>(krow + ks * 32 + 16);
-                W4Num<bf16>::mma(d, a0, 0u, a2, 0u, b0, b1);
+                if (ks & 1)
+                    W4Num<bf16>::mma(d2, a0, 0u, a2, 0u, b0, b1);
+                else
+                    W4Num<bf16>::mma(d, a0, 0u, a2, 0u, b0, b1);
             }
+            d[0] += d2[0], d[1] += d2[1];
             if (g < G) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -568,17 +589,23 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         // ---- V: partial outputs, thread = (token subset, 8 dims, head)
         {
             const int sub = threadIdx.x & 7, d8 = (threadIdx.x >> 3) & 15;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (oh < G) {
-                for (int slot = sub; slot < cnt8; slot += 8) {
-                    const float pr = s_s[oh * MK_ATT_TOK + slot];
+                auto add_slot = [&](int slot, float (&dst)[8]) {
+                    const float pr = slot < cnt8 ? s_s[oh * MK_ATT_TOK + slot] : 0.f;
                     if (pr != 0.f) {  // masked / padded slots hold no valid V row
                         const uint4 vr = *reinterpret_cast<const uint4 *>(kv_s + slot * MK_KV_STRIDE + 256 + d8 * 16);
                         const float2 f0 = unpack2<bf16>(vr.x), f1 = unpack2<bf16>(vr.y), f2 = unpack2<bf16>(vr.z), f3 = unpack2<bf16>(vr.w);
-                        acc[0] += pr * f0.x, acc[1] += pr * f0.y, acc[2] += pr * f1.x, acc[3] += pr * f1.y;
-                        acc[4] += pr * f2.x, acc[5] += pr * f2.y, acc[6] += pr * f3.x, acc[7] += pr * f3.y;
+                        dst[0] += pr * f0.x, dst[1] += pr * f0.y, dst[2] += pr * f1.x, dst[3] += pr * f1.y;
+                        dst[4] += pr * f2.x, dst[5] += pr * f2.y, dst[6] += pr * f3.x, dst[7] += pr * f3.y;
                     }
+                };
+                for (int slot = sub; slot < cnt8; slot += 16) {  // two token rows per iteration, independent chains
+                    add_slot(slot, acc);
+                    add_slot(slot + 8, acc2);
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += acc2[i];
             }
             float *o = op_s + (sub * 4 + oh) * 128 + d8 * 8;
             *reinterpret_cast<float4 *>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -821,9 +848,14 @@ int launch_decode_megakernel(const MkArgs &a, cudaStream_t st) {
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_attention_fused_kernel(const MkArgs a, const MkLayer l) {
     extern __shared__ __align__(128) unsigned char att_smem_raw[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the o_proj stream may prefetch its weights now
+    TL_TRACE_STAMP(20);
     Prof prof{nullptr, 0, 0};
     mk_attention<true>(a, l, att_smem_raw, prof);
+    TL_TRACE_STAMP(29);
 }
+#if TL_TRACE
+void trace_bind_attention(unsigned long long *buf, unsigned int *n, unsigned int cap) { trace_bind(buf, n, cap); }
+#endif
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_attention_merge_kernel(const MkArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");

@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "w4a16_item.cuh"
+#include "trace.cuh"
 
 namespace tl {
 
@@ -354,28 +355,6 @@ constexpr int S5_THREADS = S5_WARPS * 32;
 #ifndef S5_DEPTH_SMALL
 #define S5_DEPTH_SMALL 4
 #endif
-// Debug build (-DS4_PROF=1, tools/s4_timeline.py): per-launch globaltimer stamps of CTA 0.
-#ifndef S4_PROF
-#define S4_PROF 0
-#endif
-#if S4_PROF
-constexpr int S4_PROF_SLOTS = 4096, S4_PROF_FIELDS = 8;
-__device__ unsigned long long g_s4_prof[S4_PROF_SLOTS * S4_PROF_FIELDS];
-__device__ unsigned int g_s4_prof_next;
-__device__ __forceinline__ unsigned long long s4_now() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-#define S4_STAMP(field)                                                                        \
-    do {                                                                                       \
-        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && s4_slot < S4_PROF_SLOTS) \
-            g_s4_prof[s4_slot * S4_PROF_FIELDS + (field)] = s4_now();                          \
-    } while (0)
-#else
-#define S4_STAMP(field) do { } while (0)
-#endif
-
 enum { PRO_NONE = W4_PRO_NONE, PRO_RMSNORM = W4_PRO_RMSNORM, PRO_SWIGLU = W4_PRO_SWIGLU };
 enum { EPI_NONE = 0, EPI_RESIDUAL = 1, EPI_SWIGLU_PAIRS = 2 };
 
@@ -420,13 +399,7 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
     float *entries = rowstat + 32;
 
     griddep_launch();
-#if S4_PROF
-    __shared__ unsigned int s4_slot_s;
-    if (threadIdx.x == 0) s4_slot_s = (blockIdx.x == 0 && blockIdx.y == 0) ? atomicAdd(&g_s4_prof_next, 1u) : 0xffffffffu;
-    __syncthreads();
-    const unsigned int s4_slot = s4_slot_s;
-    S4_STAMP(0);
-#endif
+    TL_TRACE_STAMP(10);
 
     // ---- rows of this CTA (whole 16-row chunks) and units of this warp
     const unsigned all = static_cast<unsigned>(K + 15) >> 4;  // all * gridDim.x < 2^31 (K < 2^24 rows)
@@ -470,10 +443,10 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
     W4Unit<U> buf[DEPTH];
 #pragma unroll
     for (int k = 0; k < DEPTH; ++k) load_next(buf[k]);  // in flight before the activations exist
-    S4_STAMP(1);
+    TL_TRACE_STAMP(11);
 
     griddep_wait();  // activations (and the residual) come from the previous kernel
-    S4_STAMP(2);
+    TL_TRACE_STAMP(12);
     const T *p0 = static_cast<const T *>(args.p0) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda;
     const T *p1 = args.prologue == PRO_SWIGLU
                       ? static_cast<const T *>(args.p1) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda
@@ -489,7 +462,7 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
         if (r0 + rr < r1) res_first = to_f(res[static_cast<size_t>(m) * K + r0 + rr]);
     }
     w4_stage<T, MP, S5_THREADS>(p0, args.lda, p1, args.prologue, N, Mp, args.eps, act, asum, rowstat, []() {});
-    S4_STAMP(3);
+    TL_TRACE_STAMP(13);
 
     const uint4 *act0 = w4_act_lane<MP>(act, g, t);
     const float *asum0 = w4_asum_lane<MP>(asum, t);
@@ -530,9 +503,9 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
         }
     }
     if (u != 0) flush();
-    S4_STAMP(4);
+    TL_TRACE_STAMP(14);
     __syncthreads();
-    S4_STAMP(6);
+    TL_TRACE_STAMP(16);
 
     auto chunk_sum = [&](int ch, int row, int m) {  // entries of one output in warp order
         float v = 0.f;
@@ -550,7 +523,7 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
             const float gate = to_f(from_f<T>(chunk_sum(ch, row, m))), up = to_f(from_f<T>(chunk_sum(ch, row + 8, m)));
             out[static_cast<size_t>(m) * (K / 2) + c0 * 8 + rr] = from_f<T>((gate / (1.0f + expf(-gate))) * up);
         }
-        S4_STAMP(5);
+        TL_TRACE_STAMP(15);
         return;
     }
     // ---- sum the entries of each chunk in warp order, add the residual, store
@@ -568,21 +541,11 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
             out[static_cast<size_t>(m) * K + k] = vb;
         }
     }
-    S4_STAMP(5);
+    TL_TRACE_STAMP(15);
 }
 
-#if S4_PROF
-extern "C" int tl_debug_s4_prof(unsigned long long *host_out, int max_slots) {
-    unsigned int n = 0;
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(&n, g_s4_prof_next, sizeof(n));
-    if (static_cast<int>(n) > max_slots) n = max_slots;
-    if (n > S4_PROF_SLOTS) n = S4_PROF_SLOTS;
-    cudaMemcpyFromSymbol(host_out, g_s4_prof, static_cast<size_t>(n) * S4_PROF_FIELDS * sizeof(unsigned long long));
-    unsigned int zero = 0;
-    cudaMemcpyToSymbol(g_s4_prof_next, &zero, sizeof(zero));
-    return static_cast<int>(n);
-}
+#if TL_TRACE
+void trace_bind_matvec(unsigned long long *buf, unsigned int *n, unsigned int cap) { trace_bind(buf, n, cap); }
 #endif
 
 // Programmatic dependent launch is on by default (tl_set_pdl(0) or TL_PDL=0 turns it off): every
