@@ -378,7 +378,7 @@ __device__ void mk_cta_argmax(const MkArgs &a, int r0, int r1, float *scratch_v,
 //   then the running (max, sum, out) of thread (head, dim) absorbs the round.
 constexpr int MK_ATT_TOK = 256;     // K/V rows staged per round
 constexpr int MK_KV_STRIDE = 528;   // bytes per staged token: K row | V row | 16 B pad
-constexpr size_t MK_ATT_BYTES = 4 * 128 * 2 + 2 * 128 * 2 + 4 * MK_ATT_TOK * 4 + 64 + 8 * 4 * 128 * 4 + (MK_ATT_TOK + 4) * 4 +
+constexpr size_t MK_ATT_BYTES = 4 * 128 * 2 + 2 * 128 * 2 + 4 * MK_ATT_TOK * 4 + 256 * 4 + (MK_ATT_TOK + 4) * 4 +
                                 static_cast<size_t>(MK_ATT_TOK) * MK_KV_STRIDE;
 
 __device__ __forceinline__ void mk_cp16(void *dst, const void *src) {
@@ -403,9 +403,8 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
     bf16 *k_cur = q_s + 4 * 128;                                    // [128] newest token
     bf16 *v_cur = k_cur + 128;                                      // [128]
     float *s_s = reinterpret_cast<float *>(v_cur + 128);            // [4][MK_ATT_TOK] scores, then probabilities
-    float *st_s = s_s + 4 * MK_ATT_TOK;                             // m[4], l[4] of the round
-    float *op_s = st_s + 16;                                        // [8 subsets][4][128] partial outputs
-    int *pg_s = reinterpret_cast<int *>(op_s + 8 * 4 * 128);        // page ids of the round
+    float *st_s = s_s + 4 * MK_ATT_TOK;                             // per (head, tile): max [4][32], then sum [4][32]
+    int *pg_s = reinterpret_cast<int *>(st_s + 256);                // page ids of the round
     unsigned char *kv_s = reinterpret_cast<unsigned char *>(pg_s + MK_ATT_TOK + 4);  // [MK_ATT_TOK][528]
 
     // ---- head rows for the q path (registers; used after the K/V copies are in flight)
@@ -452,7 +451,7 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
     const int g = lane >> 2, t = lane & 3;                      // MMA fragment coordinates
     const int oh = threadIdx.x >> 7, od = threadIdx.x & 127;    // owner of out[head oh][dim od]
     const float scale2 = a.attn_scale * MK_LOG2E;
-    float m_run = MK_NEG, l_run = 0.f, o_run = 0.f;
+    float m_run = MK_NEG, l_run = 0.f, o_run[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // kept by the (threadIdx & 7) == 0 lanes
     prof.stamp(50001);
 
     for (int rb = begin; rb < end || rb == begin; rb += MK_ATT_TOK) {  // one pass even for an empty split (q path, barriers)
@@ -536,7 +535,7 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         __syncthreads();
         prof.stamp(50005);
         if (DEPWAIT) TL_TRACE_STAMP(23);
-        // ---- S: scores of 8 tokens x G heads per MMA tile
+        // ---- S: scores of 8 tokens x G heads per MMA tile, with the tile's softmax statistics
         for (int tile = warp; tile * 8 < cnt; tile += MK_WARPS) {
             float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};  // two independent MMA chains
             const unsigned char *krow = kv_s + (tile * 8 + g) * MK_KV_STRIDE + t * 4;
@@ -553,88 +552,85 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
                 else
                     W4Num<bf16>::mma(d, a0, 0u, a2, 0u, b0, b1);
             }
-            d[0] += d2[0], d[1] += d2[1];
-            if (g < G) {
+            // lane (g, t) holds head g, tokens 2t and 2t+1 of the tile
+            float sc[2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int slot = tile * 8 + 2 * t + e;
-                    bool ok = slot < cnt;
-                    if (ok) {
-                        const int pid = pg_s[(rb + slot) / a.page_size - lp0];
-                        ok = pid >= 0 && pid < a.num_pages;
-                    }
-                    s_s[g * MK_ATT_TOK + slot] = ok ? d[e] * scale2 : -CUDART_INF_F;
+            for (int e = 0; e < 2; ++e) {
+                const int slot = tile * 8 + 2 * t + e;
+                bool ok = slot < cnt;
+                if (ok) {
+                    const int pid = pg_s[(rb + slot) / a.page_size - lp0];
+                    ok = pid >= 0 && pid < a.num_pages;
                 }
+                sc[e] = ok ? (d[e] + d2[e]) * scale2 : -CUDART_INF_F;
+            }
+            float mx = fmaxf(sc[0], sc[1]);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float ref = mx == -CUDART_INF_F ? 0.f : mx;  // a fully masked tile: probabilities 0, not NaN
+            const float p0 = exp2f(sc[0] - ref), p1 = exp2f(sc[1] - ref);
+            float ls = p0 + p1;
+            ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+            ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+            if (g < G) {
+                *reinterpret_cast<float2 *>(s_s + g * MK_ATT_TOK + tile * 8 + 2 * t) = make_float2(p0, p1);
+                if (t == 0) st_s[g * 32 + tile] = mx == -CUDART_INF_F ? MK_NEG : mx, st_s[128 + g * 32 + tile] = ls;
             }
         }
         __syncthreads();
         prof.stamp(50008);
-        // ---- M: per head max / exp2 / sum over the round
-        const int cnt8 = (cnt + 7) & ~7;  // S wrote whole tiles
-        if (warp < G) {
-            float mx = MK_NEG;
-            for (int i = lane; i < cnt8; i += 32) mx = fmaxf(mx, s_s[warp * MK_ATT_TOK + i]);
-            mx = warp_max(mx);
-            float sum = 0.f;
-            for (int i = lane; i < cnt8; i += 32) {
-                const float pr = exp2f(s_s[warp * MK_ATT_TOK + i] - mx);
-                s_s[warp * MK_ATT_TOK + i] = pr;
-                sum += pr;
-            }
-            sum = warp_sum(sum);
-            if (lane == 0) st_s[warp] = mx, st_s[4 + warp] = sum;
-        }
-        __syncthreads();
-        prof.stamp(50009);
-        // ---- V: partial outputs, thread = (token subset, 8 dims, head)
+        // ---- V: thread = (token of the tile, 8 dims, head); one staged row per tile, then a shuffle
+        // reduction over the 8 tokens of a tile position; the sub == 0 lane keeps the running state
         {
             const int sub = threadIdx.x & 7, d8 = (threadIdx.x >> 3) & 15;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int ntile = (cnt + 7) >> 3;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float m_r = MK_NEG, l_r = 0.f;
             if (oh < G) {
-                auto add_slot = [&](int slot, float (&dst)[8]) {
-                    const float pr = slot < cnt8 ? s_s[oh * MK_ATT_TOK + slot] : 0.f;
+                for (int tile = 0; tile < ntile; ++tile) m_r = fmaxf(m_r, st_s[oh * 32 + tile]);
+                for (int tile = 0; tile < ntile; ++tile) {
+                    const float f = exp2f(st_s[oh * 32 + tile] - m_r);
+                    l_r += st_s[128 + oh * 32 + tile] * f;
+                    const int slot = tile * 8 + sub;
+                    const float pr = s_s[oh * MK_ATT_TOK + slot] * f;
                     if (pr != 0.f) {  // masked / padded slots hold no valid V row
                         const uint4 vr = *reinterpret_cast<const uint4 *>(kv_s + slot * MK_KV_STRIDE + 256 + d8 * 16);
                         const float2 f0 = unpack2<bf16>(vr.x), f1 = unpack2<bf16>(vr.y), f2 = unpack2<bf16>(vr.z), f3 = unpack2<bf16>(vr.w);
-                        dst[0] += pr * f0.x, dst[1] += pr * f0.y, dst[2] += pr * f1.x, dst[3] += pr * f1.y;
-                        dst[4] += pr * f2.x, dst[5] += pr * f2.y, dst[6] += pr * f3.x, dst[7] += pr * f3.y;
+                        acc[0] += pr * f0.x, acc[1] += pr * f0.y, acc[2] += pr * f1.x, acc[3] += pr * f1.y;
+                        acc[4] += pr * f2.x, acc[5] += pr * f2.y, acc[6] += pr * f3.x, acc[7] += pr * f3.y;
                     }
-                };
-                for (int slot = sub; slot < cnt8; slot += 16) {  // two token rows per iteration, independent chains
-                    add_slot(slot, acc);
-                    add_slot(slot + 8, acc2);
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += acc2[i];
             }
-            float *o = op_s + (sub * 4 + oh) * 128 + d8 * 8;
-            *reinterpret_cast<float4 *>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            *reinterpret_cast<float4 *>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        }
-        __syncthreads();
-        prof.stamp(50006);
-        if (oh < G) {
-            float o_r = 0.f;
 #pragma unroll
-            for (int sub = 0; sub < 8; ++sub) o_r += op_s[(sub * 4 + oh) * 128 + od];
-            const float m_r = st_s[oh], l_r = st_s[4 + oh];
-            const float nm = fmaxf(m_run, m_r);
-            const float fr = exp2f(m_run - nm), fn = exp2f(m_r - nm);
-            o_run = o_run * fr + o_r * fn;
-            l_run = l_run * fr + l_r * fn;
-            m_run = nm;
+            for (int off = 1; off < 8; off <<= 1)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+            if (oh < G && sub == 0) {
+                const float nm = fmaxf(m_run, m_r);
+                const float fr = exp2f(m_run - nm), fn = exp2f(m_r - nm);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o_run[i] = o_run[i] * fr + acc[i] * fn;
+                l_run = l_run * fr + l_r * fn;
+                m_run = nm;
+            }
         }
+        prof.stamp(50006);
         __syncthreads();  // the round's page ids, rows and scores are dead: the next round may overwrite them
     }
     prof.stamp(50007);
-    if (oh < G) {
-        const int head = kvh * G + oh;
+    if (oh < G && (threadIdx.x & 7) == 0) {  // this lane owns out[head oh][8 dims]
+        const int head = kvh * G + oh, d0 = ((threadIdx.x >> 3) & 15) * 8;
         if (a.nsplit == 1) {
-            static_cast<bf16 *>(a.y)[(static_cast<size_t>(b) * a.Hq + head) * D + od] = __float2bfloat16_rn(l_run == 0.f ? 0.f : o_run / l_run);
+            const float inv = l_run == 0.f ? 0.f : 1.0f / l_run;
+            uint4 o;
+            o.x = pack2<bf16>(o_run[0] * inv, o_run[1] * inv), o.y = pack2<bf16>(o_run[2] * inv, o_run[3] * inv);
+            o.z = pack2<bf16>(o_run[4] * inv, o_run[5] * inv), o.w = pack2<bf16>(o_run[6] * inv, o_run[7] * inv);
+            *reinterpret_cast<uint4 *>(static_cast<bf16 *>(a.y) + (static_cast<size_t>(b) * a.Hq + head) * D + d0) = o;
         } else {
             const size_t row = (static_cast<size_t>(b) * a.Hq + head) * a.nsplit + split;
-            a.attn_ws[row * (D + 2) + od] = o_run;
-            if (od == 0) a.attn_ws[row * (D + 2) + D] = m_run, a.attn_ws[row * (D + 2) + D + 1] = l_run;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a.attn_ws[row * (D + 2) + d0 + i] = o_run[i];
+            if (d0 == 0) a.attn_ws[row * (D + 2) + D] = m_run, a.attn_ws[row * (D + 2) + D + 1] = l_run;
         }
     }
 }
