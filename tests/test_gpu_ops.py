@@ -291,7 +291,8 @@ PAGED_CASES = [
     (BF16, 128, 128, 32, 8, 1, [1]), (BF16, 128, 128, 32, 8, 1, [128]), (BF16, 128, 128, 32, 8, 1, [129]),
     (BF16, 128, 128, 32, 8, 1, [1000, 0, 17, 4097]), (BF16, 128, 128, 32, 8, 4, [900, 4]), (BF16, 128, 128, 32, 8, 8, [300]),
     (BF16, 128, 128, 16, 8, 1, [2500]), (BF16, 128, 16, 8, 8, 2, [77, 130]), (BF16, 128, 128, 32, 8, 128, [128]),
-    (BF16, 128, 128, 32, 8, 40, [300]), (BF16, 64, 16, 4, 2, 1, [50]), (BF16, 64, 16, 4, 2, 5, [50]), (F32, 128, 8, 2, 1, 12, [40]),
+    (BF16, 128, 128, 32, 8, 40, [300]), (BF16, 128, 16, 8, 2, 70, [70, 200]), (BF16, 128, 128, 32, 8, 257, [600]),
+    (BF16, 128, 64, 8, 8, 64, [64, 0, 500]), (BF16, 128, 32, 4, 1, 100, [40, 100]), (BF16, 64, 16, 4, 2, 1, [50]), (BF16, 64, 16, 4, 2, 5, [50]), (F32, 128, 8, 2, 1, 12, [40]),
 ]
 
 
@@ -314,6 +315,29 @@ def test_paged_attention_matches_oracle(dev, case, causal):
     for b, n in enumerate(lens):
         if n == 0:
             assert torch.count_nonzero(got[b * Hq : (b + 1) * Hq]) == 0, "idle slot must be exact zeros"
+
+
+def test_full_size_prefill_attention_properties(dev):
+    """Config-3 size (Hq 32, Hkv 8, D 128, page 128, a 4096-token prompt in one chunk) through the
+    tensor-core flash kernel: constant V rows come back unchanged (softmax weights sum to one), and
+    identical K rows make every query the causal running mean of V."""
+    g = gen(43)
+    S, page, Hq, Hkv, D = 4096, 128, 32, 8, 128
+    pages = S // page
+    bt = torch.randperm(pages, generator=g).reshape(1, pages).to(torch.int32).to(dev)
+    cl = torch.tensor([S], dtype=torch.int32, device=dev)
+    q = torch.randn(Hq, S, D, generator=g).to(BF16).to(dev)
+    kp = torch.randn(pages, Hkv, page, D, generator=g).to(BF16).to(dev)
+    v_row = torch.randn(Hkv, 1, D, generator=g).to(BF16)
+    vp = v_row[None].expand(pages, Hkv, page, D).contiguous().to(dev)
+    out = ext.paged_attention(q, kp, vp, bt, cl, D**-0.5, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
+    want = v_row.repeat_interleave(Hq // Hkv, dim=0).expand(Hq, S, D)
+    assert_close(out, want, rtol=4 * ULP[BF16], atol=1e-6, msg="constant V")
+    vp2 = torch.randn(pages, Hkv, page, D, generator=g).to(BF16).to(dev)
+    out2 = ext.paged_attention(q, torch.zeros_like(kp), vp2, bt, cl, D**-0.5, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
+    dense = vp2[bt[0].long()].permute(1, 0, 2, 3).reshape(Hkv, S, D).float()
+    running = dense.cumsum(dim=1) / torch.arange(1, S + 1, device=dev, dtype=torch.float32)[None, :, None]
+    assert_close(out2, running.repeat_interleave(Hq // Hkv, dim=0), rtol=2e-2, atol=4e-3, msg="causal running mean of V")
 
 
 def test_full_size_decode_attention_properties(dev):

@@ -16,6 +16,8 @@
 // sees keys < clamp(ctx - L + l + 1, 0, ctx)   (paged_attention.metal:158-160).
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -527,6 +529,10 @@ int launch_paged_decode(const void *q, const void *kp, const void *vp, const int
                         int is_causal, int num_kv_heads, int num_heads, int dtype, void *ws, size_t ws_bytes,
                         cudaStream_t st) {
     const bool fast = dtype == TL_BF16 && D == GQA_D && aligned16(q) && aligned16(kp) && aligned16(vp);
+    static const bool fa_off = [] { const char *e = getenv("TL_PREFILL_FA"); return e != nullptr && e[0] == '0'; }();
+    if (fast && !fa_off && rows <= 65535)  // tensor-core flash kernel (attention_prefill.cu); TL_PREFILL_FA=0: CUDA-core control
+        return launch_paged_prefill_fa(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal, num_kv_heads,
+                                       num_heads, st);
     if (fast)
         return launch_paged_gqa(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal,
                                 num_kv_heads, num_heads, true, ws, ws_bytes, st);
@@ -541,6 +547,10 @@ int launch_paged_prefill(const void *q, const void *kp, const void *vp, const in
                          int rows, int L, int D, int num_pages, int page_size, int max_pages, float scale,
                          int is_causal, int num_kv_heads, int num_heads, int dtype, cudaStream_t st) {
     const bool fast = dtype == TL_BF16 && D == GQA_D && aligned16(q) && aligned16(kp) && aligned16(vp);
+    static const bool fa_off = [] { const char *e = getenv("TL_PREFILL_FA"); return e != nullptr && e[0] == '0'; }();
+    if (fast && !fa_off && rows <= 65535)  // tensor-core flash kernel (attention_prefill.cu); TL_PREFILL_FA=0: CUDA-core control
+        return launch_paged_prefill_fa(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal, num_kv_heads,
+                                       num_heads, st);
     if (fast)
         return launch_paged_gqa(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal,
                                 num_kv_heads, num_heads, false, nullptr, 0, st);

@@ -31,6 +31,7 @@ SOURCES = [
     "w4a16_matvec.cu",
     "w4a16_gemm.cu",
     "attention_decode.cu",
+    "attention_prefill.cu",
     "decode_megakernel.cu",
 ]
 

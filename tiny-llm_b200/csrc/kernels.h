@@ -82,6 +82,9 @@ int launch_paged_decode(const void *q, const void *kp, const void *vp, const int
                         cudaStream_t st);
 
 // attention_prefill.cu
+int launch_paged_prefill_fa(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out, int rows,
+                            int L, int num_pages, int page_size, int max_pages, float scale, int is_causal, int num_kv_heads,
+                            int num_heads, cudaStream_t st);
 int launch_paged_prefill(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out,
                          int rows, int L, int D, int num_pages, int page_size, int max_pages, float scale,
                          int is_causal, int num_kv_heads, int num_heads, int dtype, cudaStream_t st);
