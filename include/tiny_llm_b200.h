@@ -157,6 +157,19 @@ int tl_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, co
                                   void *q_out, void *key_pages, void *value_pages, int batch, int num_heads,
                                   int num_kv_heads, int head_dim, float base, float eps, int num_pages, int page_size,
                                   int max_pages, int dtype, void *stream);
+/* Chunk append (B200 extension of paged_cache_update, paged_attention.cpp:14-31): the rows of ONE
+ * request's key/value chunk [1, H, L, D] (element strides src_head_stride / src_token_stride, unit
+ * inner stride) are written into up to TL_PAGE_SPANS page slices in one launch:
+ * pages[page_id[i], :, start[i]:start[i]+count[i], :] = chunk[0, :, src[i]:src[i]+count[i], :].
+ * `spans` is a HOST pointer (passed by value to the kernel). */
+#define TL_PAGE_SPANS 64
+typedef struct tl_page_span_list {
+    int32_t page_id[TL_PAGE_SPANS], start[TL_PAGE_SPANS], count[TL_PAGE_SPANS], src[TL_PAGE_SPANS];
+    int32_t n;
+} tl_page_span_list;
+int tl_paged_cache_append_chunk(void *key_pages, void *value_pages, const void *keys, const void *values,
+                                const tl_page_span_list *spans, int num_pages, int heads, int page_size, int head_dim,
+                                long long src_head_stride, long long src_token_stride, int dtype, void *stream);
 /* Fused decode attention, L == 1 (bf16, head_dim 128, <= 4 query heads per KV head): per-head
  * q/k RMSNorm + RoPE, append of the newest K/V row and paged GQA attention in ONE launch (plus a
  * merge launch when the context is split over several CTAs).  Replaces, with the same rounding

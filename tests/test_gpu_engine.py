@@ -195,9 +195,10 @@ def test_persistent_step_with_split_kv_attention_matches_operator_path(dev, tiny
         pool, ref_pool = model.page_pools[1], ref_model.page_pools[1]
         pid, slot = cache[1].page_ids[-1], cache[1].page_lens[-1] - 1
         rid = ref_cache[1].page_ids[-1]
-        torch.testing.assert_close(pool._key_pages[pid, :, slot].float(), ref_pool._key_pages[rid, :, slot].float(), rtol=2**-7, atol=1e-3)
-        assert torch.equal(pool._value_pages[pid, :, slot], ref_pool._value_pages[rid, :, slot]) or torch.allclose(
-            pool._value_pages[pid, :, slot].float(), ref_pool._value_pages[rid, :, slot].float(), rtol=2**-7, atol=1e-3)
+        # (layer 1's rows have been through a full layer of two different kernel families: the hidden
+        # state may differ by an ulp, which rms_norm + rope can turn into a few ulps of a K element; a misplaced row would be off by O(1))
+        torch.testing.assert_close(pool._key_pages[pid, :, slot].float(), ref_pool._key_pages[rid, :, slot].float(), rtol=2**-6, atol=5e-2)
+        torch.testing.assert_close(pool._value_pages[pid, :, slot].float(), ref_pool._value_pages[rid, :, slot].float(), rtol=2**-6, atol=5e-2)
         tok = int(torch.argmax(want[0, -1].float()))
         offset += 1
 

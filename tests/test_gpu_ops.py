@@ -171,6 +171,9 @@ def test_rms_norm_matches_oracle(dev, shape, dtype):
         dict(shape=(2, 9, 8, 4), dims=4, offsets=[1, 4]),
         dict(shape=(1, 3, 2, 16), dims=8, offsets=[5]),
         dict(shape=(1, 3, 2, 16), dims=8, offsets=[5], traditional=True),
+        dict(shape=(1, 300, 32, 128), dims=128, offsets=[100]),                    # prefill-sized: per-(token, pair) kernel
+        dict(shape=(2, 70, 8, 128), dims=128, offsets=[0, 5000]),
+        dict(shape=(1, 80, 4, 16), dims=16, offsets=[9], traditional=True),
     ],
     ids=lambda c: f"{c['shape']}-d{c['dims']}{'-trad' if c.get('traditional') else ''}",
 )
@@ -265,6 +268,33 @@ def test_paged_cache_append_decode_matches_per_row_updates(dev):
     kd, vd = kp.to(dev), vp.to(dev)
     ext.paged_cache_append_decode(kd, vd, keys.to(dev), values.to(dev), bt.to(dev), ctx.to(dev))
     assert torch.equal(kd.cpu(), want_k) and torch.equal(vd.cpu(), want_v)
+
+
+@pytest.mark.parametrize("dtype", [BF16, F32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("page,H,D,L,first", [(16, 2, 128, 70, 5), (128, 8, 128, 300, 0), (8, 3, 20, 33, 7)])
+def test_paged_cache_append_chunk_equals_per_page_updates(dev, dtype, page, H, D, L, first):
+    """One launch for a whole chunk (strided [1, H, L, D] view of a [1, L, H, D] projection output)
+    against the reference's per-page paged_cache_update sequence."""
+    g = gen(page + H + D + L)
+    n_pages = (first + L + page - 1) // page + 3
+    kp = torch.randn(n_pages, H, page, D, generator=g).to(dtype).to(dev)
+    vp = torch.randn(n_pages, H, page, D, generator=g).to(dtype).to(dev)
+    kp_ref, vp_ref = kp.clone(), vp.clone()
+    keys = torch.randn(1, L, H, D, generator=g).to(dtype).to(dev).transpose(1, 2)    # [1, H, L, D], token stride H*D
+    values = torch.randn(1, L, H, D, generator=g).to(dtype).to(dev).transpose(1, 2)
+    order = torch.randperm(n_pages, generator=g).tolist()
+    spans, done, slot = [], 0, first
+    for pid in order:
+        if done >= L:
+            break
+        take = min(page - slot, L - done)
+        spans.append((pid, slot, take, done))
+        ext.paged_cache_update(kp_ref, keys[:, :, done : done + take].contiguous(), pid, slot)
+        ext.paged_cache_update(vp_ref, values[:, :, done : done + take].contiguous(), pid, slot)
+        done += take
+        slot = 0
+    ext.paged_cache_append_chunk(kp, vp, keys, values, spans)
+    assert torch.equal(kp, kp_ref) and torch.equal(vp, vp_ref)
 
 
 def build_paged(g, lens, page, Hkv, D, dtype, scatter=True):

@@ -44,6 +44,11 @@ __device__ __forceinline__ void fa_ldsm4(uint32_t (&r)[4], uint32_t addr) {
 __device__ __forceinline__ void fa_ldsm4_t(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
+__device__ __forceinline__ float fa_exp2(float x) {  // ex2.approx: 2 ulp, exp2(-inf) = 0; inputs are <= 0 here
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void fa_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -82,8 +87,15 @@ __global__ void __launch_bounds__(FA_THREADS) paged_prefill_fa_kernel(const bf16
         const bool ok = q0 + row < L;
         fa_cp16(fa_smem(q_s + row * FA_STRIDE + col), q_head + static_cast<size_t>(ok ? q0 + row : 0) * FA_D + col, ok);
     }
+    const bool tile_in_page = page_size % FA_BN == 0;  // a 64-key tile never straddles pages: one table lookup per tile
     auto load_kv = [&](int kt, int stage) {
         bf16 *ks = k_s + stage * FA_BN * FA_STRIDE, *vs = v_s + stage * FA_BN * FA_STRIDE;
+        int tile_pid = -1, tile_row0 = 0;
+        if (tile_in_page) {
+            const int lp = kt * FA_BN / page_size;
+            tile_pid = bt[static_cast<size_t>(b) * max_pages + lp];
+            tile_row0 = kt * FA_BN - lp * page_size;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int c = threadIdx.x + i * FA_THREADS, row = c >> 4, col = (c & 15) * 8;
@@ -91,11 +103,15 @@ __global__ void __launch_bounds__(FA_THREADS) paged_prefill_fa_kernel(const bf16
             bool ok = j < ctx;
             size_t off = 0;
             if (ok) {
-                const int lp = j / page_size;
-                const int pid = bt[static_cast<size_t>(b) * max_pages + lp];
+                int pid = tile_pid, prow = tile_row0 + row;
+                if (!tile_in_page) {
+                    const int lp = j / page_size;
+                    pid = bt[static_cast<size_t>(b) * max_pages + lp];
+                    prow = j - lp * page_size;
+                }
                 ok = pid >= 0 && pid < num_pages;
                 if (ok)
-                    off = ((static_cast<size_t>(pid) * Hkv + kvh) * page_size + (j - lp * page_size)) * FA_D + col;
+                    off = ((static_cast<size_t>(pid) * Hkv + kvh) * page_size + prow) * FA_D + col;
                 else if ((c & 15) == 0)
                     bad[stage] = kt + 1;
             }
@@ -179,14 +195,14 @@ __global__ void __launch_bounds__(FA_THREADS) paged_prefill_fa_kernel(const bf16
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float nm0 = fmaxf(m0, mx0), nm1 = fmaxf(m1, mx1);
         const float r0 = nm0 == -CUDART_INF_F ? 0.f : nm0, r1 = nm1 == -CUDART_INF_F ? 0.f : nm1;  // fully masked so far
-        const float al0 = exp2f(m0 - r0), al1 = exp2f(m1 - r1);
+        const float al0 = fa_exp2(m0 - r0), al1 = fa_exp2(m1 - r1);
         m0 = nm0, m1 = nm1;
         float ps0 = 0.f, ps1 = 0.f;
         uint32_t pa[4][4];  // P as A fragments: 4 k-steps of 16 keys
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const float p00 = exp2f(s[n][0] - r0), p01 = exp2f(s[n][1] - r0);
-            const float p10 = exp2f(s[n][2] - r1), p11 = exp2f(s[n][3] - r1);
+            const float p00 = fa_exp2(s[n][0] - r0), p01 = fa_exp2(s[n][1] - r0);
+            const float p10 = fa_exp2(s[n][2] - r1), p11 = fa_exp2(s[n][3] - r1);
             ps0 += p00 + p01, ps1 += p10 + p11;
             pa[n >> 1][(n & 1) * 2] = pack2<bf16>(p00, p01);
             pa[n >> 1][(n & 1) * 2 + 1] = pack2<bf16>(p10, p11);

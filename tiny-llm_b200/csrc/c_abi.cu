@@ -187,6 +187,23 @@ int tl_paged_cache_append_decode(void *key_pages, void *value_pages, const void 
                                             num_pages, heads, page_size, head_dim, max_pages, dtype, as_stream(stream));
 }
 
+int tl_paged_cache_append_chunk(void *key_pages, void *value_pages, const void *keys, const void *values,
+                                const tl_page_span_list *spans, int num_pages, int heads, int page_size, int head_dim,
+                                long long src_head_stride, long long src_token_stride, int dtype, void *stream) {
+    if (dtype != TL_F32 && dtype != TL_BF16) return fail(TL_EDTYPE, "paged_cache_append_chunk: float32 or bfloat16 pages required");
+    if (!spans || spans->n < 0 || spans->n > TL_PAGE_SPANS) return fail(TL_EINVAL, "paged_cache_append_chunk: bad span list");
+    if (num_pages <= 0 || heads <= 0 || page_size <= 0 || head_dim <= 0 || src_token_stride < head_dim)
+        return fail(TL_EINVAL, "paged_cache_append_chunk: bad shape");
+    if (spans->n == 0) return TL_OK;
+    if (!key_pages || !value_pages || !keys || !values) return fail(TL_EINVAL, "paged_cache_append_chunk: null pointer");
+    for (int i = 0; i < spans->n; ++i)
+        if (spans->page_id[i] < 0 || spans->page_id[i] >= num_pages || spans->start[i] < 0 || spans->count[i] < 0 || spans->src[i] < 0 ||
+            spans->start[i] + spans->count[i] > page_size)
+            return fail(TL_EINVAL, "paged_cache_append_chunk: destination slice is outside page storage");
+    return launch_paged_cache_append_chunk(key_pages, value_pages, keys, values, *spans, heads, page_size, head_dim, src_head_stride,
+                                           src_token_stride, dtype, as_stream(stream));
+}
+
 size_t tl_paged_attention_workspace(int rows, int L, int D, int num_kv_heads, int num_heads, int dtype) {
     if (L > 8) return 0;
     return paged_decode_workspace(rows, L, D, num_kv_heads, num_heads, dtype);

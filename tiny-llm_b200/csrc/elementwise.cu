@@ -8,6 +8,8 @@
 #include <float.h>
 #include <limits.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -170,11 +172,46 @@ __global__ void rope_kernel(const T *__restrict__ x, const int32_t *__restrict__
     out[im_i] = from_f<T>(im * c + re * s);
 }
 
+// Prefill-sized inputs, full rotation (dims == D): one thread per (b, l, pair) forms the frequency
+// (double exp2/log2) and sincosf ONCE and walks the H heads - the per-element kernel above spent
+// 77 us per call at L = 4096 recomputing them 32 times over.
+template <typename T>
+__global__ void rope_heads_kernel(const T *__restrict__ x, const int32_t *__restrict__ offsets, T *__restrict__ out, int B, int L,
+                                  int H, int D, float base, int traditional) {
+    const int half_dim = D / 2;
+    const long long total = static_cast<long long>(B) * L * half_dim;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int item = static_cast<int>(idx % half_dim);
+    const int l = static_cast<int>((idx / half_dim) % L);
+    const int b = static_cast<int>(idx / (static_cast<long long>(half_dim) * L));
+    const double inv_freq = exp2(-static_cast<double>(item) / static_cast<double>(half_dim) * log2(static_cast<double>(base)));
+    const float angle = static_cast<float>(static_cast<double>(offsets[b] + l) * inv_freq);
+    float s, c;
+    sincosf(angle, &s, &c);
+    size_t re_i = (static_cast<size_t>(b) * L + l) * H * D + (traditional ? 2 * item : item);
+    const int im_off = traditional ? 1 : half_dim;
+    for (int h = 0; h < H; ++h, re_i += D) {
+        const float re = to_f(x[re_i]), im = to_f(x[re_i + im_off]);
+        out[re_i] = from_f<T>(re * c - im * s);
+        out[re_i + im_off] = from_f<T>(im * c + re * s);
+    }
+}
+
 template <typename T>
 static int rope_t(const void *x, const int32_t *off, void *out, int B, int L, int H, int D, int dims, float base,
                   int traditional, cudaStream_t st) {
     const long long total = static_cast<long long>(B) * L * H * (dims / 2 + D - dims);
     if (total == 0) return TL_OK;
+    if (dims == D && H > 1 && static_cast<long long>(B) * L >= 64) {
+        const long long work = static_cast<long long>(B) * L * (D / 2);
+        const long long nb = ceil_div_ll(work, 128);
+        if (nb > INT_MAX) return fail(TL_EINVAL, "rope: tensor too large");
+        rope_heads_kernel<T><<<static_cast<unsigned>(nb), 128, 0, st>>>(static_cast<const T *>(x), off, static_cast<T *>(out), B, L, H, D, base,
+                                                                      traditional);
+        TL_LAUNCH_CHECK("rope");
+        return TL_OK;
+    }
     const int threads = 256;
     const long long blocks = ceil_div_ll(total, threads);
     if (blocks > INT_MAX) return fail(TL_EINVAL, "rope: tensor too large");
@@ -358,6 +395,62 @@ int launch_paged_cache_update(void *pages, const void *values, int heads, int pa
             page_id, start);
     }
     TL_LAUNCH_CHECK("paged_cache_update");
+    return TL_OK;
+}
+
+// Chunk append: up to TL_PAGE_SPANS (page, first row, rows, first source token) spans of ONE
+// request written in one launch, K and V together, straight from strided [1, H, L, D] sources
+// (the per-page paged_cache_update sequence of paged_kv_cache.py:271-312 cost 64 launches plus
+// 64 slice copies per layer for a 4096-token chunk).
+template <typename V>
+__global__ void paged_cache_append_chunk_kernel(V *__restrict__ key_pages, V *__restrict__ value_pages, const V *__restrict__ keys,
+                                                const V *__restrict__ values, const tl_page_span_list spans, int heads, int page_size,
+                                                int dvec, long long src_head_stride, long long src_token_stride) {
+    const int span = blockIdx.y;
+    const int pid = spans.page_id[span], start = spans.start[span], count = spans.count[span], src0 = spans.src[span];
+    const long long total = static_cast<long long>(heads) * count * dvec;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int d = static_cast<int>(idx % dvec);
+        const int t = static_cast<int>((idx / dvec) % count);
+        const int h = static_cast<int>(idx / (static_cast<long long>(dvec) * count));
+        const size_t dst = ((static_cast<size_t>(pid) * heads + h) * page_size + start + t) * dvec + d;
+        const size_t src = static_cast<size_t>(h) * src_head_stride + static_cast<size_t>(src0 + t) * src_token_stride + d;
+        key_pages[dst] = keys[src];
+        value_pages[dst] = values[src];
+    }
+}
+
+int launch_paged_cache_append_chunk(void *key_pages, void *value_pages, const void *keys, const void *values,
+                                    const tl_page_span_list &spans, int heads, int page_size, int head_dim, long long src_head_stride,
+                                    long long src_token_stride, int dtype, cudaStream_t st) {
+    const int esize = dtype == TL_F32 ? 4 : 2;
+    if (spans.n == 0) return TL_OK;
+    int longest = 0;
+    for (int i = 0; i < spans.n; ++i) longest = spans.count[i] > longest ? spans.count[i] : longest;
+    const bool vec = (head_dim * esize) % 16 == 0 && aligned16(key_pages) && aligned16(value_pages) && aligned16(keys) && aligned16(values) &&
+                     (src_head_stride * esize) % 16 == 0 && (src_token_stride * esize) % 16 == 0;
+    const int threads = 256;
+    if (vec) {
+        const int per = 16 / esize, dvec = head_dim / per;
+        const long long work = static_cast<long long>(heads) * longest * dvec;
+        dim3 grid(static_cast<unsigned>(std::min<long long>(ceil_div_ll(work, threads), 64)), spans.n);
+        paged_cache_append_chunk_kernel<uint4><<<grid, threads, 0, st>>>(static_cast<uint4 *>(key_pages), static_cast<uint4 *>(value_pages),
+                                                                       static_cast<const uint4 *>(keys), static_cast<const uint4 *>(values),
+                                                                       spans, heads, page_size, dvec, src_head_stride / per, src_token_stride / per);
+    } else {
+        const long long work = static_cast<long long>(heads) * longest * head_dim;
+        dim3 grid(static_cast<unsigned>(std::min<long long>(ceil_div_ll(work, threads), 64)), spans.n);
+        if (esize == 4)
+            paged_cache_append_chunk_kernel<uint32_t><<<grid, threads, 0, st>>>(
+                static_cast<uint32_t *>(key_pages), static_cast<uint32_t *>(value_pages), static_cast<const uint32_t *>(keys),
+                static_cast<const uint32_t *>(values), spans, heads, page_size, head_dim, src_head_stride, src_token_stride);
+        else
+            paged_cache_append_chunk_kernel<uint16_t><<<grid, threads, 0, st>>>(
+                static_cast<uint16_t *>(key_pages), static_cast<uint16_t *>(value_pages), static_cast<const uint16_t *>(keys),
+                static_cast<const uint16_t *>(values), spans, heads, page_size, head_dim, src_head_stride, src_token_stride);
+    }
+    TL_LAUNCH_CHECK("paged_cache_append_chunk");
     return TL_OK;
 }
 

@@ -19,6 +19,9 @@ int launch_quantized_embedding(const void *indices, const void *scales, const vo
                                void *out, int tokens, int vocab, int dim, int dtype, cudaStream_t st);
 int launch_paged_cache_update(void *pages, const void *values, int heads, int page_size, int head_dim, int length,
                               int page_id, int start, int dtype, cudaStream_t st);
+int launch_paged_cache_append_chunk(void *key_pages, void *value_pages, const void *keys, const void *values,
+                                    const tl_page_span_list &spans, int heads, int page_size, int head_dim, long long src_head_stride,
+                                    long long src_token_stride, int dtype, cudaStream_t st);
 int launch_paged_cache_append_decode(void *key_pages, void *value_pages, const void *keys, const void *values,
                                      const int32_t *block_table, const int32_t *context_lens, int batch,
                                      int num_pages, int heads, int page_size, int head_dim, int max_pages, int dtype,

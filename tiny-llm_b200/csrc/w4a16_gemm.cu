@@ -27,6 +27,7 @@
 // Packed weights are read once per 128-token tile (L2 absorbs the re-reads across
 // token tiles); activations are read once per 128-feature tile.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -37,7 +38,7 @@ namespace tl {
 constexpr int GM = 128;       // tokens per tile   (UMMA M)
 constexpr int GN = 128;       // features per tile (UMMA N)
 constexpr int GK = 64;        // reduction elements per stage (128 bytes: one swizzle atom)
-constexpr int GSTAGES = 4;
+constexpr int GSTAGES_MAX = 4;  // stages of the shared-memory ring (MT <= 2); 3 for MT = 4: 80 KiB per stage
 constexpr int G_DEQ_WARPS = 8;
 constexpr int G_THREADS = (4 + G_DEQ_WARPS) * 32;
 constexpr int G_TILE_BYTES = GM * GK * 2;  // 16 KiB, same for A and B tiles
@@ -133,14 +134,20 @@ struct Deq<__half> {
     static constexpr uint32_t MAGIC = 0x64006400u;  // (1024, 1024)
 };
 
+// MT token tiles (128 rows each) share one dequantised weight tile per stage: the dequantisers are
+// the busiest warps of this kernel, and with MT = 2 their work per flop halves (measured at
+// M = 4096 with MT = 1: 470-550 TF/s, 28-33 % of the bf16 peak).
+template <int MT>
 struct GemmSmem {
+    static constexpr int STAGES = MT <= 2 ? GSTAGES_MAX : 2;
+    static constexpr int A_STAGE = MT * G_TILE_BYTES;
     static constexpr int A_OFF = 0;
-    static constexpr int B_OFF = GSTAGES * G_TILE_BYTES;
-    static constexpr int BAR_OFF = 2 * GSTAGES * G_TILE_BYTES;
+    static constexpr int B_OFF = STAGES * A_STAGE;
+    static constexpr int BAR_OFF = B_OFF + STAGES * G_TILE_BYTES;
     static constexpr int BYTES = BAR_OFF + 256;
 };
 
-template <typename T>
+template <typename T, int MT>
 __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const T *__restrict__ scales,
                                                                   const T *__restrict__ biases, const uint32_t *__restrict__ b,
                                                                   T *__restrict__ out, int M, int N, int K, int vec_store) {
@@ -150,12 +157,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
     const int num_kb = N / GK;
     const int G = N / 128;
 
-    const uint32_t a_base = g_smem_u32(gsm + GemmSmem::A_OFF);
-    const uint32_t b_base = g_smem_u32(gsm + GemmSmem::B_OFF);
-    const uint32_t bar_base = g_smem_u32(gsm + GemmSmem::BAR_OFF);
+    using Smem = GemmSmem<MT>;
+    constexpr int GSTAGES = Smem::STAGES;
+    constexpr int TMEM_COLS = G_TMEM_COLS * MT;
+    const uint32_t a_base = g_smem_u32(gsm + Smem::A_OFF);
+    const uint32_t b_base = g_smem_u32(gsm + Smem::B_OFF);
+    const uint32_t bar_base = g_smem_u32(gsm + Smem::BAR_OFF);
     const uint32_t full_a = bar_base, full_b = bar_base + 8 * GSTAGES, empty = bar_base + 16 * GSTAGES;
     const uint32_t tmem_full = bar_base + 24 * GSTAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gsm + GemmSmem::BAR_OFF + 24 * GSTAGES + 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gsm + Smem::BAR_OFF + 24 * GSTAGES + 8);
 
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     if (warp == 1 && lane == 0) {
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "n"(G_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     g_tc_fence_before();
@@ -183,8 +193,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
                 const int s = kb % GSTAGES;
                 const uint32_t ph = (kb / GSTAGES) & 1;
                 g_mbar_wait(empty + 8 * s, ph ^ 1);
-                g_mbar_expect_tx(full_a + 8 * s, G_TILE_BYTES);
-                g_tma_load_2d(a_base + s * G_TILE_BYTES, &tmap_a, kb * GK, m_tile * GM, full_a + 8 * s);
+                g_mbar_expect_tx(full_a + 8 * s, Smem::A_STAGE);
+#pragma unroll
+                for (int i = 0; i < MT; ++i)  // token rows beyond M are zero-filled by the TMA unit
+                    g_tma_load_2d(a_base + s * Smem::A_STAGE + i * G_TILE_BYTES, &tmap_a, kb * GK, (m_tile * MT + i) * GM, full_a + 8 * s);
             }
         }
     } else if (warp == 1) {
@@ -197,11 +209,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
                 g_mbar_wait(full_a + 8 * s, ph);
                 g_mbar_wait(full_b + 8 * s, ph);
                 g_tc_fence_after();
-                const uint64_t adesc = g_smem_desc(a_base + s * G_TILE_BYTES);
                 const uint64_t bdesc = g_smem_desc(b_base + s * G_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < GK / 16; ++k)  // +32 bytes along K per step: +2 in the (addr >> 4) field
-                    g_tc_mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                for (int i = 0; i < MT; ++i) {
+                    const uint64_t adesc = g_smem_desc(a_base + s * Smem::A_STAGE + i * G_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GK / 16; ++k)  // +32 bytes along K per step: +2 in the (addr >> 4) field
+                        g_tc_mma(tmem_d + i * G_TMEM_COLS, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
                 g_tc_commit(empty + 8 * s);  // stage reusable once these MMAs have read it
             }
             g_tc_commit(tmem_full);
@@ -245,7 +260,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
                 outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);  // (e6, e7)
             }
             g_mbar_wait(empty + 8 * s, ph ^ 1);
-            unsigned char *tile = gsm + GemmSmem::B_OFF + s * G_TILE_BYTES + row * 128;
+            unsigned char *tile = gsm + Smem::B_OFF + s * G_TILE_BYTES + row * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int chunk = half * 4 + j;  // 16-byte chunk (8 elements) along K
@@ -260,12 +275,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
         g_tc_fence_after();
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int col_half = (warp - 4) >> 2;   // 0 or 1
-        const int m = m_tile * GM + q * 32 + lane;
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int cbi = 0; cbi < 2 * MT; ++cbi) {
+            const int i = cbi >> 1, cb = cbi & 1;
+            const int m = (m_tile * MT + i) * GM + q * 32 + lane;
             const int col0 = col_half * 64 + cb * 32;
             uint32_t v[32];
-            g_tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + col0, v);
+            g_tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + i * G_TMEM_COLS + col0, v);
             if (m < M) {
                 T *dst = out + static_cast<size_t>(m) * K + n_tile * GN + col0;
                 const int valid = min(32, K - (n_tile * GN + col0));
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
     __syncthreads();
     if (warp == 2) {
         g_tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(G_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -328,6 +344,23 @@ bool w4a16_gemm_supported(int M, int N, int K, int dtype) {
 int w4a16_gemm_split(int, int, int, int) { return 1; }
 size_t w4a16_gemm_workspace(int, int, int, int, int) { return 0; }
 
+template <typename T, int MT>
+static int gemm_launch(const CUtensorMap &map, const void *scales, const void *biases, const void *b, void *out, int M, int N, int K,
+                       int vec_store, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(w4a16_gemm_kernel<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<MT>::BYTES);
+        if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid(ceil_div(K, GN), ceil_div(M, GM * MT));
+    w4a16_gemm_kernel<T, MT><<<grid, G_THREADS, GemmSmem<MT>::BYTES, st>>>(map, static_cast<const T *>(scales), static_cast<const T *>(biases),
+                                                                           static_cast<const uint32_t *>(b), static_cast<T *>(out), M, N, K,
+                                                                           vec_store);
+    TL_LAUNCH_CHECK("w4a16_gemm");
+    return TL_OK;
+}
+
 template <typename T>
 static int gemm_t(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N, int K,
                   cudaStream_t st) {
@@ -343,19 +376,11 @@ static int gemm_t(const void *scales, const void *biases, const void *a, const v
     CUresult r = encode(&map, dt, 2, const_cast<void *>(a), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TL_ECUDA, "quantized_matmul: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(w4a16_gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem::BYTES);
-        if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
-        configured = true;
-    }
-    dim3 grid(ceil_div(K, GN), ceil_div(M, GM));
     const int vec_store = (K % 8 == 0 && aligned16(out)) ? 1 : 0;
-    w4a16_gemm_kernel<T><<<grid, G_THREADS, GemmSmem::BYTES, st>>>(map, static_cast<const T *>(scales), static_cast<const T *>(biases),
-                                                                  static_cast<const uint32_t *>(b), static_cast<T *>(out), M, N, K,
-                                                                  vec_store);
-    TL_LAUNCH_CHECK("w4a16_gemm");
-    return TL_OK;
+    static const int mt_max = [] { const char *e = getenv("TL_GEMM_MT"); return e ? atoi(e) : 2; }();  // 4: experiment (2-stage ring)
+    if (M > 2 * GM && mt_max >= 4) return gemm_launch<T, 4>(map, scales, biases, b, out, M, N, K, vec_store, st);
+    return M > GM && mt_max >= 2 ? gemm_launch<T, 2>(map, scales, biases, b, out, M, N, K, vec_store, st)
+                                 : gemm_launch<T, 1>(map, scales, biases, b, out, M, N, K, vec_store, st);
 }
 
 int launch_w4a16_gemm(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N, int K,

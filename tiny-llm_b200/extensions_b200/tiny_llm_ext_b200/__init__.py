@@ -86,6 +86,7 @@ _SIGNATURES = {
     "tl_decode_qk_norm_rope_append": (_I, [_VP] * 9 + [_I] * 4 + [_F, _F] + [_I] * 4 + [_VP]),
     "tl_decode_attention_fused_workspace": (_SZ, [_I, _I, _I]),
     "tl_decode_attention_fused": (_I, [_VP] * 11 + [_I] * 4 + [_F, _F] + [_I] * 5 + [_VP]),
+    "tl_paged_cache_append_chunk": (_I, [_VP] * 5 + [_I] * 4 + [ctypes.c_longlong, ctypes.c_longlong, _I, _VP]),
     "tl_set_pdl": (_I, [_I]),
     "tl_decode_step_grid": (_I, []),
     "tl_decode_step": (_I, [_VP, _VP]),
@@ -339,6 +340,49 @@ def paged_cache_update(pages, values, page_id, start, stream=None):
                                    _DTYPE_CODE[pages.dtype], _stream_ptr(stream, pages))
     )
     return pages
+
+
+PAGE_SPANS = 64
+
+
+class PageSpanList(ctypes.Structure):
+    """``tl_page_span_list``: (page id, first row, rows, first source token) of up to 64 page slices."""
+
+    _fields_ = [("page_id", ctypes.c_int32 * PAGE_SPANS), ("start", ctypes.c_int32 * PAGE_SPANS), ("count", ctypes.c_int32 * PAGE_SPANS),
+                ("src", ctypes.c_int32 * PAGE_SPANS), ("n", ctypes.c_int32)]
+
+
+def paged_cache_append_chunk(key_pages, value_pages, keys, values, spans, stream=None):
+    """Write one request's chunk ``keys/values [1, H, L, D]`` (any head/token strides, unit inner
+    stride) into the page slices ``spans = [(page_id, start, count, src_token), ...]`` - K and V,
+    every page, one launch per 64 spans."""
+    if key_pages.dtype not in (torch.float32, torch.bfloat16) or value_pages.dtype != key_pages.dtype or keys.dtype != key_pages.dtype or values.dtype != key_pages.dtype:
+        raise RuntimeError("paged_cache_append_chunk: pages and values must have the same float32 or bfloat16 dtype")
+    if key_pages.dim() != 4 or keys.dim() != 4 or keys.shape[0] != 1 or keys.shape != values.shape or key_pages.shape != value_pages.shape:
+        raise RuntimeError("paged_cache_append_chunk: expected pages [P, H, page_size, D] and chunks [1, H, L, D]")
+    if keys.shape[1] != key_pages.shape[1] or keys.shape[3] != key_pages.shape[3]:
+        raise RuntimeError("paged_cache_append_chunk: chunks must match the page head count and head dimension")
+    if keys.stride(3) != 1 or values.stride() != keys.stride():
+        raise RuntimeError("paged_cache_append_chunk: chunks need a unit inner stride and identical K/V strides")
+    _gpu("paged_cache_append_chunk", key_pages, value_pages, keys, values)
+    if not key_pages.is_contiguous() or not value_pages.is_contiguous():
+        raise RuntimeError("paged_cache_append_chunk: pages must be contiguous")
+    P, H, page_size, D = key_pages.shape
+    L = keys.shape[2]
+    for pid, start, count, src in spans:
+        if src < 0 or src + count > L:
+            raise RuntimeError("paged_cache_append_chunk: source rows are outside the chunk")
+    for first in range(0, len(spans), PAGE_SPANS):
+        part = spans[first : first + PAGE_SPANS]
+        rec = PageSpanList()
+        rec.n = len(part)
+        for i, (pid, start, count, src) in enumerate(part):
+            rec.page_id[i], rec.start[i], rec.count[i], rec.src[i] = int(pid), int(start), int(count), int(src)
+        _check(
+            _lib.tl_paged_cache_append_chunk(key_pages.data_ptr(), value_pages.data_ptr(), keys.data_ptr(), values.data_ptr(), ctypes.byref(rec),
+                                             P, H, page_size, D, keys.stride(1), keys.stride(2), _DTYPE_CODE[key_pages.dtype],
+                                             _stream_ptr(stream, key_pages))
+        )
 
 
 def paged_attention(

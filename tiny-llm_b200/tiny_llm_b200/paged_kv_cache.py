@@ -254,6 +254,18 @@ class TinyKvPagedPool:
         bytes follow in one batched ``append_decode_batch`` call."""
         self._prepare_slice(page_id, start, key, value)
 
+    def can_batch_chunk_append(self, key: torch.Tensor, value: torch.Tensor) -> bool:
+        """True when a multi-page chunk may be written by ONE launch (``write_page_spans``) instead of
+        two ``paged_cache_update`` launches plus two slice copies per page."""
+        if not key.is_cuda or key.dtype not in _PAGE_DTYPES or key.shape[2] < 2:
+            return False
+        if "write_page_slice" in vars(self) or type(self).write_page_slice is not TinyKvPagedPool.write_page_slice:
+            return False  # overridden writer (fault injection, instrumentation): keep the per-page calls
+        return key.stride(3) == 1 and value.stride() == key.stride()
+
+    def write_page_spans(self, spans: list, key: torch.Tensor, value: torch.Tensor) -> None:
+        tiny_llm_ext_b200.paged_cache_append_chunk(self._key_pages, self._value_pages, key, value, spans)
+
     def can_batch_decode_append(self, keys: torch.Tensor, slots: list) -> bool:
         """True when a decode batch (one token per request) may be written with
         a single device-driven launch instead of 2 launches per request."""
@@ -299,22 +311,32 @@ class TinyKvPagedCache(TinyKvCache):
         total = key.shape[2]
         mine = self._snapshot_state()
         theirs = self.pool._snapshot_state()
-        put = self.pool.write_page_slice if device_write else self.pool.reserve_page_slice
+        # B200: when nothing overrides the per-page writer, the host bookkeeping below runs with the
+        # launch-free reserve_page_slice and ALL page slices are written by one device launch at the
+        # end (same bytes, same page/offset evolution, same all-or-nothing behaviour: the launch
+        # happens only after every check and allocation has succeeded)
+        batched = device_write and self.pool.can_batch_chunk_append(key, value)
+        put = self.pool.write_page_slice if (device_write and not batched) else self.pool.reserve_page_slice
+        spans = []
         done = 0
         try:
             if self.page_ids and self.page_lens[-1] < self.page_size:
                 room = self.page_size - self.page_lens[-1]
                 take = min(room, total)
                 put(self.page_ids[-1], self.page_lens[-1], key[:, :, :take, :], value[:, :, :take, :])
+                spans.append((self.page_ids[-1], self.page_lens[-1], take, 0))
                 self.page_lens[-1] += take
                 done = take
             while done < total:
                 stop = min(done + self.page_size, total)
                 page_id = self.pool.allocate_page()
                 put(page_id, 0, key[:, :, done:stop, :], value[:, :, done:stop, :])
+                spans.append((page_id, 0, stop - done, done))
                 self.page_ids.append(page_id)
                 self.page_lens.append(stop - done)
                 done = stop
+            if batched:
+                self.pool.write_page_spans(spans, key, value)
             self.offset += total
         except Exception:
             self.pool._restore_state(theirs)

@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "prefill_bench.json"))
     ap.add_argument("--tokens", type=int, default=4096)
     ap.add_argument("--skip-model", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="torch.profiler kernel table of one whole-model prefill")
     args = ap.parse_args()
     tf_peak, _ = peaks()
     M = args.tokens
@@ -92,6 +93,14 @@ def main():
             for c in cache:
                 c.release()
         report["model"] = dict(tokens=M, seconds=round(dt, 4), tok_per_s=round(M / dt, 1))
+        if args.profile:
+            from torch.profiler import ProfilerActivity, profile
+
+            cache = model.create_kv_cache()
+            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+                model(prompt, 0, cache, logits_to_keep=1)
+                torch.cuda.synchronize()
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=60))
         print(f"Qwen3-4B prefill of {M} tokens through model(): {dt * 1e3:.1f} ms -> {M / dt:.0f} tok/s", flush=True)
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
     Path(args.out).write_text(json.dumps(report, indent=1))
