@@ -377,8 +377,11 @@ static int gemm_t(const void *scales, const void *biases, const void *a, const v
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TL_ECUDA, "quantized_matmul: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
     const int vec_store = (K % 8 == 0 && aligned16(out)) ? 1 : 0;
-    static const int mt_max = [] { const char *e = getenv("TL_GEMM_MT"); return e ? atoi(e) : 2; }();  // 4: experiment (2-stage ring)
-    if (M > 2 * GM && mt_max >= 4) return gemm_launch<T, 4>(map, scales, biases, b, out, M, N, K, vec_store, st);
+    // Four token tiles per CTA leave room for a 2-stage ring only: measured at M = 4096, that wins for the
+    // short reductions (N = 2560: q|k|v 641 -> 769 TF/s, gate|up 782 -> 882) and loses for the long ones
+    // (N = 9728: 706 -> 655), so it is used up to N = 3072.  TL_GEMM_MT caps the tile count (A/B runs).
+    static const int mt_max = [] { const char *e = getenv("TL_GEMM_MT"); return e ? atoi(e) : 4; }();
+    if (M > 2 * GM && mt_max >= 4 && N <= 3072) return gemm_launch<T, 4>(map, scales, biases, b, out, M, N, K, vec_store, st);
     return M > GM && mt_max >= 2 ? gemm_launch<T, 2>(map, scales, biases, b, out, M, N, K, vec_store, st)
                                  : gemm_launch<T, 1>(map, scales, biases, b, out, M, N, K, vec_store, st);
 }
