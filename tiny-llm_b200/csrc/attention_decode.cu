@@ -471,7 +471,7 @@ int launch_paged_gqa(const void *q, const void *kp, const void *vp, const int32_
     if (allow_split) {
         const long long target = 4LL * sm_count();
         long long want = ceil_div_ll(target, base_ctas);
-        const long long most = bound / 512 > 0 ? bound / 512 : 1;  // at least 512 tokens per split: a short context is one CTA per KV head
+        const long long most = bound / 128 > 0 ? bound / 128 : 1;  // at least 128 tokens per split (512 measured 3.6x slower at S = 1024: the per-step chain dominates)
         if (want > most) want = most;
         if (want > GQA_MAX_SPLITS) want = GQA_MAX_SPLITS;
         if (want < 1) want = 1;
@@ -529,10 +529,6 @@ int launch_paged_decode(const void *q, const void *kp, const void *vp, const int
                         int is_causal, int num_kv_heads, int num_heads, int dtype, void *ws, size_t ws_bytes,
                         cudaStream_t st) {
     const bool fast = dtype == TL_BF16 && D == GQA_D && aligned16(q) && aligned16(kp) && aligned16(vp);
-    static const bool fa_off = [] { const char *e = getenv("TL_PREFILL_FA"); return e != nullptr && e[0] == '0'; }();
-    if (fast && !fa_off && rows <= 65535)  // tensor-core flash kernel (attention_prefill.cu); TL_PREFILL_FA=0: CUDA-core control
-        return launch_paged_prefill_fa(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal, num_kv_heads,
-                                       num_heads, st);
     if (fast)
         return launch_paged_gqa(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal,
                                 num_kv_heads, num_heads, true, ws, ws_bytes, st);
@@ -540,9 +536,9 @@ int launch_paged_decode(const void *q, const void *kp, const void *vp, const int
                                 num_kv_heads, num_heads, dtype, st);
 }
 
-// Interim prefill path (L > 8) until the tcgen05 FlashAttention kernel lands:
-// bf16/D=128 reuses the GQA-grouped kernel over row groups (K/V shared by the
-// 4 rows of a group, causal early exit per group); everything else is row-wise.
+// Prefill path (L > 8): bf16 / D = 128 runs the tensor-core flash kernel (attention_prefill.cu);
+// TL_PREFILL_FA=0 selects the older CUDA-core GQA-grouped kernel as a control; everything else is
+// row-wise.
 int launch_paged_prefill(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out,
                          int rows, int L, int D, int num_pages, int page_size, int max_pages, float scale,
                          int is_causal, int num_kv_heads, int num_heads, int dtype, cudaStream_t st) {

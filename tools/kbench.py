@@ -112,6 +112,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--lib", default=None, help="alternative libtiny_llm_b200*.so (experiment builds)")
     ap.add_argument("--only", default=None, help="comma-separated matvec shape names; skips attention and small ops")
+    ap.add_argument("--attention-only", action="store_true")
     args = ap.parse_args()
     import os
 
@@ -125,6 +126,8 @@ def main():
     batches = [1, 8] if args.quick else [1, 2, 4, 8, 16, 32]
     if args.only:
         shapes = [s for s in shapes if s[0] in args.only.split(",")]
+    if args.attention_only:
+        shapes = []
     for name, N, K in shapes:
         copies = max(2, min(48, int(300e6 // (K * N // 2)) + 1))
         for M in batches:
