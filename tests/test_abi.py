@@ -96,3 +96,29 @@ def test_c_abi_reports_argument_errors_without_a_device():
     assert b"expected float32, float16, or bfloat16" in lib.tl_last_error()
     assert lib.tl_rms_norm(None, None, None, 4, 8, 1e-5, 2, None) == -1  # TL_EINVAL: null pointers
     assert lib.tl_rms_norm(None, None, None, 0, 8, 1e-5, 2, None) == 0  # empty input is a no-op
+
+
+def test_gate_up_interleave_layout_and_span_record():
+    """Host-side helpers of the B200 extensions: the row layout the SWIGLU_PAIRS epilogue expects,
+    and the by-value span record of tl_paged_cache_append_chunk (4 x 64 int32 + count)."""
+    import ctypes
+
+    import torch
+
+    from extensions_b200 import tiny_llm_ext_b200 as ext
+
+    gate = torch.arange(32 * 3, dtype=torch.int32).reshape(32, 3)
+    up = -gate - 1
+    both = ext.interleave_gate_up(gate, up)
+    assert both.shape == (64, 3)
+    for c in range(4):
+        assert torch.equal(both[16 * c : 16 * c + 8], gate[8 * c : 8 * c + 8])
+        assert torch.equal(both[16 * c + 8 : 16 * c + 16], up[8 * c : 8 * c + 8])
+    try:
+        ext.interleave_gate_up(gate[:30], up[:30])
+    except RuntimeError as exc:
+        assert "rows % 8" in str(exc)
+    else:
+        raise AssertionError("rows not divisible by 8 must be rejected")
+    assert ctypes.sizeof(ext.PageSpanList) == 4 * 64 * 4 + 4
+    assert ext.EPI_SWIGLU_PAIRS == 2 and ext.PAGE_SPANS == 64

@@ -5,25 +5,14 @@
 // a [M, N] (bf16|f16), b [K, N/8] packed u32 (code i of a word = (w >> 4i) & 15,
 // /root/reference/src/tiny_llm_ref/quantize.py:113-115), scales/biases [K, N/128].
 //
-// w4a16_stream_kernel is the decode kernel (reference: quantized_matvec_x4_fast,
-// /root/reference/src/extensions_ref/src/quantized_matmul.metal:441-538).  It is
-// HBM-bound: every packed weight byte is read exactly once with 128-bit
-// coalesced loads that bypass L1; activations (tiny, shared by every CTA) are
-// staged once per CTA in shared memory.  The per-weight ALU work would exceed
-// the HBM time on CUDA cores (~3 ops/weight), so the 16x128 code tile of each
-// warp is fed to the tensor cores as an exact small-integer bf16 operand:
-//
-//   * codes are turned into bf16 (128 + q) two at a time with ONE lop3
-//     ((w >> 4i) & 0x000F000F | 0x43004300): ~1 ALU op per weight;
-//   * mma.sync m16n8k16 (fp32 accumulate) forms D = sum_n (128 + q) * a exactly
-//     (products of an 8-bit and a 4-bit significand are exact in fp32);
-//   * once per 128-wide group: acc += scale * D + (bias - 128 * scale) * sum_n a,
-//     which equals sum_n (q*scale + bias) * a - the same "scale * qdot +
-//     bias * asum" factorisation the Metal kernel uses (:515-521), in fp32.
-//
-// The k-slot <-> n mapping of the MMA is a free permutation (the reduction is
-// commutative), chosen so that a lane's A fragment comes from ITS OWN 128-bit
-// weight load and the matching B fragment is one 128-bit shared-memory load.
+// w4a16_stream5_kernel is the decode kernel (reference: quantized_matvec_x4_fast,
+// /root/reference/src/extensions_ref/src/quantized_matmul.metal:441-538): every packed
+// weight byte is read exactly once with 128-bit loads that bypass L1; activations (tiny,
+// shared by every CTA) are staged once per CTA in shared memory.  The per-weight ALU work
+// would exceed the HBM time on CUDA cores (~3 ops/weight), so the 16 x 128 code tile of
+// each warp is fed to the tensor cores as an exact small-integer bf16 operand (details and
+// the instruction budget: w4a16_item.cuh), with the Metal kernel's "scale * qdot +
+// bias * asum" factorisation (:515-521) applied once per 128-wide group in fp32.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -33,292 +22,14 @@
 
 namespace tl {
 
-template <typename T>
-struct Mma;
-template <>
-struct Mma<__nv_bfloat16> {
-    static constexpr uint32_t MAGIC = 0x43004300u;  // bf16 128.0 in both halves
-    static constexpr float OFFSET = 128.f;
-    static __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                               uint32_t b0, uint32_t b1) {
-        asm volatile(
-            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-            : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-    }
-};
-template <>
-struct Mma<__half> {
-    static constexpr uint32_t MAGIC = 0x64006400u;  // fp16 1024.0 in both halves
-    static constexpr float OFFSET = 1024.f;
-    static __device__ __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                               uint32_t b0, uint32_t b1) {
-        asm volatile(
-            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-            : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-    }
-};
-
-constexpr int STREAM_TEAM_WARPS = 4;  // warps that split the reduction of one 16-row tile
-constexpr int STREAM_TEAM_THREADS = STREAM_TEAM_WARPS * 32;
-constexpr int STREAM_PREFETCH = 2;  // weight groups in flight per warp beyond the current one
-
-__device__ __forceinline__ void team_barrier(int team) {
-    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(STREAM_TEAM_THREADS) : "memory");
-}
-
-struct GroupLoad {
-    uint4 w0, w1;       // 32 codes of row g and of row g+8 for this lane
-    float s0, c0, s1, c1;  // scale and (bias - OFFSET*scale) of the two rows
-};
-
-// MT = number of 8-column activation tiles (rows of `a` handled per pass = 8*MT).
-template <typename T, int MT>
-__global__ void __launch_bounds__(512) w4a16_stream_kernel(const T *__restrict__ scales, const T *__restrict__ biases,
-                                                          const T *__restrict__ a_all, const uint32_t *__restrict__ b,
-                                                          T *__restrict__ out_all, int M, int N, int K,
-                                                          int rows_per_pass) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int pass = blockIdx.y;
-    const int Mp = min(rows_per_pass, M - pass * rows_per_pass);
-    const T *a = a_all + static_cast<size_t>(pass) * rows_per_pass * N;
-    T *out = out_all + static_cast<size_t>(pass) * rows_per_pass * K;
-
-    const int words = N / 8;   // packed words per weight row == 8-element activation chunks
-    const int G = N / 128;     // quantisation groups per row
-    const int teams = blockDim.x / STREAM_TEAM_THREADS;
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int team = warp / STREAM_TEAM_WARPS;
-    const int wit = warp % STREAM_TEAM_WARPS;  // warp in team
-    const int g = lane >> 2;                   // MMA group id: weight row / activation column
-    const int t = lane & 3;                    // MMA thread-in-group: k-slot owner
-
-    // shared: [words][Mp] 16-byte permuted activation chunks | asum [G][Mp] | red [teams][4][16][8*MT]
-    uint4 *act = reinterpret_cast<uint4 *>(smem_raw);
-    float *asum = reinterpret_cast<float *>(smem_raw + static_cast<size_t>(words) * Mp * 16);
-    float *red = asum + ((G * Mp + 3) & ~3);
-
-    // ---- stage activations once: chunk order [0,4,1,5,2,6,3,7] so that the B
-    // fragment registers {(e0,e4),(e1,e5),(e2,e6),(e3,e7)} are one LDS.128.
-    {
-        const int total = Mp * words;
-        for (int base = (threadIdx.x & ~31); base < total; base += blockDim.x) {
-            const int idx = base + lane;
-            float part = 0.f;
-            int m = 0, c = 0;
-            if (idx < total) {
-                m = idx / words;
-                c = idx - m * words;
-                const uint4 raw = *reinterpret_cast<const uint4 *>(a + static_cast<size_t>(m) * N + c * 8);
-                uint4 p;
-                p.x = __byte_perm(raw.x, raw.z, 0x5410);
-                p.y = __byte_perm(raw.x, raw.z, 0x7632);
-                p.z = __byte_perm(raw.y, raw.w, 0x5410);
-                p.w = __byte_perm(raw.y, raw.w, 0x7632);
-                // 4x4 transpose of the chunk order inside a group: the four lanes of an MMA
-                // group then read 64 contiguous bytes per sub-step (no bank conflicts).
-                const int pos = (c & ~15) | ((c & 3) << 2) | ((c >> 2) & 3);
-                act[static_cast<size_t>(pos) * Mp + m] = p;
-                const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
-                part = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
-            }
-            // 16 consecutive chunks (one group) live in 16 consecutive lanes.
-            part += __shfl_xor_sync(0xffffffffu, part, 8);
-            part += __shfl_xor_sync(0xffffffffu, part, 4);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            if (idx < total && (c & 15) == 0) asum[(c >> 4) * Mp + m] = part;
-        }
-    }
-    __syncthreads();
-
-    const int tiles = (K + 15) / 16;
-    float *my_red = red + static_cast<size_t>(team) * STREAM_TEAM_WARPS * 16 * 8 * MT;
-
-    for (int tile = blockIdx.x * teams + team; tile < tiles; tile += gridDim.x * teams) {
-        const int row0 = min(tile * 16 + g, K - 1);
-        const int row1 = min(tile * 16 + g + 8, K - 1);
-        const uint32_t *b0p = b + static_cast<size_t>(row0) * words + 4 * t;
-        const uint32_t *b1p = b + static_cast<size_t>(row1) * words + 4 * t;
-        const T *s0p = scales + static_cast<size_t>(row0) * G;
-        const T *s1p = scales + static_cast<size_t>(row1) * G;
-        const T *c0p = biases + static_cast<size_t>(row0) * G;
-        const T *c1p = biases + static_cast<size_t>(row1) * G;
-
-        auto load_group = [&](int u) -> GroupLoad {
-            GroupLoad r;
-            r.w0 = ldg_stream(b0p + 16 * u);
-            r.w1 = ldg_stream(b1p + 16 * u);
-            r.s0 = to_f(s0p[u]);
-            r.s1 = to_f(s1p[u]);
-            r.c0 = to_f(c0p[u]) - Mma<T>::OFFSET * r.s0;
-            r.c1 = to_f(c1p[u]) - Mma<T>::OFFSET * r.s1;
-            return r;
-        };
-
-        float acc[MT][4];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
-
-        GroupLoad buf[STREAM_PREFETCH + 1];
-#pragma unroll
-        for (int p = 0; p < STREAM_PREFETCH; ++p) {
-            const int u = wit + p * STREAM_TEAM_WARPS;
-            if (u < G) buf[p] = load_group(u);
-        }
-
-        for (int u = wit; u < G; u += STREAM_TEAM_WARPS) {
-            {
-                const int un = u + STREAM_PREFETCH * STREAM_TEAM_WARPS;
-                if (un < G) buf[STREAM_PREFETCH] = load_group(un);
-            }
-            const GroupLoad cur = buf[0];
-            float d[MT][4];
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) d[mt][0] = d[mt][1] = d[mt][2] = d[mt][3] = 0.f;
-
-            const uint32_t x0[4] = {cur.w0.x, cur.w0.y, cur.w0.z, cur.w0.w};
-            const uint32_t x1[4] = {cur.w1.x, cur.w1.y, cur.w1.z, cur.w1.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                constexpr uint32_t MASK = 0x000F000Fu;
-                const uint32_t p0 = (x0[j] & MASK) | Mma<T>::MAGIC;
-                const uint32_t p1 = ((x0[j] >> 4) & MASK) | Mma<T>::MAGIC;
-                const uint32_t p2 = ((x0[j] >> 8) & MASK) | Mma<T>::MAGIC;
-                const uint32_t p3 = ((x0[j] >> 12) & MASK) | Mma<T>::MAGIC;
-                const uint32_t q0 = (x1[j] & MASK) | Mma<T>::MAGIC;
-                const uint32_t q1 = ((x1[j] >> 4) & MASK) | Mma<T>::MAGIC;
-                const uint32_t q2 = ((x1[j] >> 8) & MASK) | Mma<T>::MAGIC;
-                const uint32_t q3 = ((x1[j] >> 12) & MASK) | Mma<T>::MAGIC;
-                const int chunk = 16 * u + 4 * j + t;  // staged position of chunk 16u + 4t + j
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const int col = mt * 8 + g;
-                    uint4 bf = make_uint4(0u, 0u, 0u, 0u);
-                    if (col < Mp) bf = act[static_cast<size_t>(chunk) * Mp + col];
-                    Mma<T>::mma(d[mt], p0, q0, p1, q1, bf.x, bf.y);
-                    Mma<T>::mma(d[mt], p2, q2, p3, q3, bf.z, bf.w);
-                }
-            }
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int m0 = mt * 8 + 2 * t;
-                const float as0 = m0 < Mp ? asum[u * Mp + m0] : 0.f;
-                const float as1 = m0 + 1 < Mp ? asum[u * Mp + m0 + 1] : 0.f;
-                acc[mt][0] += cur.s0 * d[mt][0] + cur.c0 * as0;
-                acc[mt][1] += cur.s0 * d[mt][1] + cur.c0 * as1;
-                acc[mt][2] += cur.s1 * d[mt][2] + cur.c1 * as0;
-                acc[mt][3] += cur.s1 * d[mt][3] + cur.c1 * as1;
-            }
-#pragma unroll
-            for (int p = 0; p < STREAM_PREFETCH; ++p) buf[p] = buf[p + 1];
-        }
-
-        // ---- reduce the 4 warps of the team, then 128 threads store 16 x (8*MT) outputs
-        float *wred = my_red + static_cast<size_t>(wit) * 16 * 8 * MT;
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            wred[g * 8 * MT + mt * 8 + 2 * t] = acc[mt][0];
-            wred[g * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][1];
-            wred[(g + 8) * 8 * MT + mt * 8 + 2 * t] = acc[mt][2];
-            wred[(g + 8) * 8 * MT + mt * 8 + 2 * t + 1] = acc[mt][3];
-        }
-        team_barrier(team);
-        const int tt = threadIdx.x % STREAM_TEAM_THREADS;
-#pragma unroll
-        for (int rep = 0; rep < MT; ++rep) {
-            const int o = rep * STREAM_TEAM_THREADS + tt;  // o = m * 16 + r
-            const int m = o >> 4;
-            const int r = o & 15;
-            const int k = tile * 16 + r;
-            if (m < Mp && k < K) {
-                float v = 0.f;
-#pragma unroll
-                for (int w = 0; w < STREAM_TEAM_WARPS; ++w) v += my_red[(w * 16 + r) * 8 * MT + m];
-                out[static_cast<size_t>(m) * K + k] = from_f<T>(v);
-            }
-        }
-        team_barrier(team);
-    }
-}
-
-static size_t stream_smem_bytes(int N, int Mp, int MT, int teams) {
-    const size_t act = static_cast<size_t>(N / 8) * Mp * 16;
-    const size_t asum = static_cast<size_t>(((N / 128) * Mp + 3) & ~3) * 4;
-    const size_t red = static_cast<size_t>(teams) * STREAM_TEAM_WARPS * 16 * 8 * MT * 4;
-    return act + asum + red;
-}
-
-template <typename T, int MT>
-static int stream_launch(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N,
-                         int K, int rows_per_pass, int teams, cudaStream_t st) {
-    static size_t configured = 0;
-    const size_t smem = stream_smem_bytes(N, rows_per_pass < M ? rows_per_pass : M, MT, teams);
-    if (smem > configured && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(w4a16_stream_kernel<T, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             200 * 1024);
-        if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
-        configured = 200 * 1024;
-    }
-    const int tiles = ceil_div(K, 16);
-    const int want = ceil_div(tiles, teams);
-    const int cap = sm_count() * 4;
-    dim3 grid(want < cap ? want : cap, ceil_div(M, rows_per_pass));
-    w4a16_stream_kernel<T, MT><<<grid, teams * STREAM_TEAM_THREADS, smem, st>>>(
-        static_cast<const T *>(scales), static_cast<const T *>(biases), static_cast<const T *>(a),
-        static_cast<const uint32_t *>(b), static_cast<T *>(out), M, N, K, rows_per_pass);
-    TL_LAUNCH_CHECK("w4a16_stream");
-    return TL_OK;
-}
-
-template <typename T>
-static int stream_t(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N,
-                    int K, cudaStream_t st) {
-    if (!aligned16(a) || !aligned16(b)) return fail(TL_EINVAL, "quantized_matmul: a and b must be 16-byte aligned");
-    // Rows per pass: as many as fit in shared memory next to the reduction scratch.
-    const size_t budget = 160 * 1024;
-    int rpp = 8;
-    if (M > 16 && static_cast<size_t>(N) * 32 * 2 <= budget)
-        rpp = 32;
-    else if (M > 8 && static_cast<size_t>(N) * 16 * 2 <= budget)
-        rpp = 16;
-    const int tiles = ceil_div(K, 16);
-    const int sms = sm_count();
-    int teams = 1;
-    if (tiles >= 8 * sms)
-        teams = 4;
-    else if (tiles >= 4 * sms)
-        teams = 2;
-    if (rpp == 32) return stream_launch<T, 4>(scales, biases, a, b, out, M, N, K, rpp, teams, st);
-    if (rpp == 16) return stream_launch<T, 2>(scales, biases, a, b, out, M, N, K, rpp, teams, st);
-    return stream_launch<T, 1>(scales, biases, a, b, out, M, N, K, rpp, teams, st);
-}
-
 int launch_w4a16_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *p1,
                        const void *residual, int M, int N, int K, int lda, int prologue, int epilogue, float eps, int dtype,
                        cudaStream_t st);
 
-static bool stream_v1_forced() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char *e = getenv("TL_STREAM_V1");
-        cached = (e != nullptr && e[0] == '1') ? 1 : 0;
-    }
-    return cached == 1;
-}
-
 int launch_w4a16_stream(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N,
                         int K, int dtype, cudaStream_t st) {
     if (M == 0 || K == 0) return TL_OK;
-    if (!stream_v1_forced())
-        return launch_w4a16_fused(scales, biases, b, out, a, nullptr, nullptr, M, N, K, N, 0, 0, 0.f, dtype, st);
-    switch (dtype) {
-        case TL_F16: return stream_t<__half>(scales, biases, a, b, out, M, N, K, st);
-        case TL_BF16: return stream_t<__nv_bfloat16>(scales, biases, a, b, out, M, N, K, st);
-    }
-    return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
+    return launch_w4a16_fused(scales, biases, b, out, a, nullptr, nullptr, M, N, K, N, 0, 0, 0.f, dtype, st);
 }
 
 // ---------------------------------------------------------------------------
