@@ -129,6 +129,61 @@ def test_fused_decode_attention_equals_the_operator_sequence(dev, contexts, page
     torch.testing.assert_close(got.float().view(B * Hq, D), want.float().view(B * Hq, D), rtol=2**-7, atol=4e-3)
 
 
+def test_fused_decode_attention_and_swiglu_epilogue_against_the_cpu_oracle(dev):
+    """The two fused decode launches against the CPU restatement of the reference operators
+    (oracle/ops.py), not against other GPU kernels: q/k rms_norm -> rope -> paged_cache_update ->
+    paged_attention, and quantized_matmul x2 -> swiglu."""
+    from oracle import ops as oracle
+
+    g = torch.Generator().manual_seed(11)
+    B, Hq, Hkv, D, page = 2, 8, 2, 128, 16
+    contexts = [37, 70]
+    max_pages = 6
+    P = B * max_pages
+    qkv = torch.randn(B, (Hq + 2 * Hkv) * D, generator=g).to(BF16)
+    qw = (1 + 0.1 * torch.randn(D, generator=g)).to(BF16)
+    kw = (1 + 0.1 * torch.randn(D, generator=g)).to(BF16)
+    ctx = torch.tensor(contexts, dtype=torch.int32)
+    offsets = ctx - 1
+    bt = torch.full((B, max_pages), -1, dtype=torch.int32)
+    perm = torch.randperm(P, generator=g)
+    for b, c in enumerate(contexts):
+        n = (c + page - 1) // page
+        bt[b, :n] = perm[b * max_pages : b * max_pages + n].to(torch.int32)
+    kp = torch.randn(P, Hkv, page, D, generator=g).to(BF16)
+    vp = torch.randn(P, Hkv, page, D, generator=g).to(BF16)
+    scale = D**-0.5
+    # oracle: the reference operator sequence, request by request
+    kp_ref, vp_ref = kp.clone(), vp.clone()
+    q_in = qkv[:, : Hq * D].reshape(B, 1, Hq, D)
+    k_in = qkv[:, Hq * D : (Hq + Hkv) * D].reshape(B, 1, Hkv, D)
+    v_in = qkv[:, (Hq + Hkv) * D :].reshape(B, 1, Hkv, D)
+    q_ref = oracle.rope(oracle.rms_norm(q_in, qw, 1e-6), offsets, D, 1e6)
+    k_ref = oracle.rope(oracle.rms_norm(k_in, kw, 1e-6), offsets, D, 1e6)
+    for b, c in enumerate(contexts):
+        tok = c - 1
+        pid = int(bt[b, tok // page])
+        oracle.paged_cache_update(kp_ref, k_ref[b : b + 1].transpose(1, 2).contiguous(), pid, tok % page)
+        oracle.paged_cache_update(vp_ref, v_in[b : b + 1].transpose(1, 2).contiguous(), pid, tok % page)
+    want = oracle.paged_attention(q_ref.transpose(1, 2).reshape(B * Hq, 1, D).contiguous(), kp_ref, vp_ref, bt, ctx, scale, True, Hkv, Hq)
+    kd, vd = kp.to(dev), vp.to(dev)
+    got = ext.decode_attention_fused(qkv.to(dev), qw.to(dev), kw.to(dev), offsets.to(dev), bt.to(dev), ctx.to(dev),
+                                     ext.rope_inv_freq_table(D, 1e6, dev), kd, vd, Hq, Hkv, 1e-6, scale, max(contexts))
+    torch.testing.assert_close(kd.cpu().float(), kp_ref.float(), rtol=2**-7, atol=4e-3)
+    assert torch.equal(vd.cpu(), vp_ref)
+    torch.testing.assert_close(got.cpu().float().view(B * Hq, D), want.float().view(B * Hq, D), rtol=2e-2, atol=5e-3)  # 2e-2: test_week_3_day_5.py:61
+
+    # gate|up projection with the SwiGLU epilogue
+    N, inter, M = 512, 256, 3
+    wg, sg, bg = packed(inter, N, g, torch.device("cpu"))
+    wu, su, bu = packed(inter, N, g, torch.device("cpu"))
+    x = (torch.randn(M, N, generator=g) * 2).to(BF16)
+    want = oracle.swiglu(oracle.quantized_matmul(sg, bg, 128, 4, x, wg, True), oracle.quantized_matmul(su, bu, 128, 4, x, wu, True))
+    w, s_, b_ = ext.interleave_gate_up(wg, wu), ext.interleave_gate_up(sg, su), ext.interleave_gate_up(bg, bu)
+    got = ext.quantized_matmul_fused(s_.to(dev), b_.to(dev), w.to(dev), x.to(dev), epilogue=ext.EPI_SWIGLU_PAIRS)
+    torch.testing.assert_close(got.cpu().float(), want.float(), rtol=2e-2, atol=2e-2 * float(want.float().abs().max()))
+
+
 @pytest.fixture(scope="module")
 def tiny_gpu(dev):
     return synthetic_qwen3("tiny-d128", seed=0, realistic=True, max_position_embeddings=512, device=dev)
