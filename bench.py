@@ -148,7 +148,7 @@ def run_ours(args) -> None:
 
     # ---- value: device-resident decode (graph replays, token feedback on device)
     offset = PROMPT_LEN
-    engine.decode_on_device([token], [offset], cache, warmup)
+    engine.decode_on_device([token], [offset], cache, min(warmup, engine.log_capacity))
     torch.cuda.synchronize()
     offset += warmup
     token = int(engine.next_tokens[0])
@@ -161,7 +161,13 @@ def run_ours(args) -> None:
     torch.cuda.synchronize()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    out_tokens = engine.decode_on_device([token], [offset], cache, steps)
+    done = 0
+    while done < steps:  # one call unless --steps exceeds the engine's on-device token log (4096)
+        take = min(steps - done, engine.log_capacity)
+        out_tokens = engine.decode_on_device([token], [offset + done], cache, take)
+        done += take
+        if done < steps:
+            token = int(out_tokens[-1, 0])
     end.record()
     torch.cuda.synchronize()
     barrier(device)
