@@ -15,9 +15,10 @@ Numbers on the JSON line:
             decode step with token feedback on the device (CUDA events, max over ranks)
   e2e       same metric through the public model call, per step: pinned-host token
             -> device copy, model(...), device -> host read of the sampled token
-  roofline  the W4A16 weight-streaming kernel: all 253 projections of one token
-            (2.137 GB of packed weights, > L2) replayed back to back from a CUDA
-            graph, CUDA-event timed; achieved = algorithmic bytes / time
+  roofline  the W4A16 weight-streaming kernel: the 145 projection launches of one token
+            exactly as the decode graph issues them (2.137 GB of packed weights, > L2),
+            replayed from a CUDA graph, CUDA-event timed; achieved = algorithmic
+            bytes / time, traffic = ncu DRAM bytes of the same launches
   cpu_baseline  the reference's CPU path (oracle.model: dense bf16 weights, readable
             operators) on the host cores, bounded sample
 """
