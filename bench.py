@@ -255,7 +255,7 @@ def run_ours(args) -> None:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the w4a16_stream5_kernel launches of one decode
-# token, averaged over its 145 launches (profiles/r01_launches_fused_v5_dram.csv; algorithmic: 14.76 MB).
+# token, averaged over its 145 launches (profiles/r01_launches_decode_final.csv; algorithmic: 14.76 MB).
 NCU_TRAFFIC_PER_LAUNCH = 14826718
 
 
