@@ -234,7 +234,7 @@ def run_ours(args) -> None:
                 "workload": "Qwen3-4B W4A16 single-request decode, batch=1 per GPU, paged-KV GQA + dequant matvec",
                 "prompt_len": PROMPT_LEN, "page_size": PAGE_SIZE, "requests_per_gpu": 1, "parallelism": f"dp{world}",
                 "l2_policy": "inputs larger than L2: each step streams 2.14 GB of packed weights (L2 = 126 MB)",
-                "decode_graph": "cuda-graph replay, fused=%s, pdl=%s, persistent=%s" % (engine.fused, int(pdl), int(engine.persistent)),
+                "decode_graph": "cuda-graph replay, fused=%s, pdl=%s" % (engine.fused, int(pdl)),
             },
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": 4 + engine._meta_len * 4,
                     "d2h_bytes_per_step": 4, "steps": e2e_steps},

@@ -186,51 +186,8 @@ int tl_decode_attention_fused(const void *qkv, const void *q_norm_weight, const 
                               float *workspace, int batch, int num_heads, int num_kv_heads, int head_dim, float eps,
                               float scale, int num_pages, int page_size, int max_pages, int max_context, int dtype,
                               void *stream);
-/* ---- whole-step persistent decode kernel -------------------------------------
- * One cooperative launch runs a complete decode step (L == 1, bf16, W4A16, paged
- * KV, batch 1..8, head_dim 128, <= 4 query heads per KV head) of the Week-3
- * model: the call sequence of qwen3_week3.py:320-338 at L == 1 plus the greedy
- * sampler of batch.py:8-13, with the same rounding points as the per-operator
- * launchers.  q|k|v are passed row-concatenated; gate|up interleaved in blocks of
- * 8 rows (the TL_EPI_SWIGLU_PAIRS layout), gu holds swiglu(gate, up) [B, I].
- * `layers` points to DEVICE memory holding n_layers tl_decode_layer records;
- * every other pointer is a device pointer too.  block tables are per layer. */
-typedef struct tl_decode_layer {
-    const void *w_qkv, *w_o, *w_gu, *w_down;        /* packed u32 [K, N/8] */
-    const void *s_qkv, *b_qkv, *s_o, *b_o, *s_gu, *b_gu, *s_down, *b_down; /* bf16 [K, N/128] */
-    const void *ln1, *ln2, *q_norm, *k_norm;        /* bf16 norm weights */
-    void *k_pages, *v_pages;                        /* bf16 [P, Hkv, page, D] */
-    const int32_t *table;                           /* int32 [B, max_pages], -1 padded */
-} tl_decode_layer;
-
-typedef struct tl_decode_args {
-    const tl_decode_layer *layers;
-    int n_layers;
-    const void *w_emb, *s_emb, *b_emb;              /* embedding table [V, H/8] */
-    const void *w_head, *s_head, *b_head, *final_norm; /* head (= embedding when tied) */
-    int B, H, Hq, Hkv, D, I, V;
-    float eps, rope_base, attn_scale;
-    int page_size, max_pages, num_pages;
-    int32_t *tokens, *offsets, *context_lens;       /* [B]: ids in, RoPE positions, post-append lengths */
-    int32_t *next_tokens, *out_log, *step_counter;  /* sampled ids [B]; log [log_capacity, B]; counter [1] */
-    int log_capacity, advance;                      /* advance != 0: feed tokens back, positions += 1, log */
-    void *xa, *xb, *qkv, *y, *gu, *logits;          /* bf16 scratch [B,H] [B,H] [B,(Hq+2Hkv)D] [B,HqD] [B,2I] [B,V] */
-    float *attn_ws;                                 /* [B*Hq*nsplit*(D+2)] when nsplit > 1 */
-    float *amax_val;                                /* [grid * B] */
-    int *amax_idx;                                  /* [grid * B] */
-    unsigned *sync_counter, *exit_counter;          /* zero-initialised, self-cleaning */
-    int nsplit, tokens_per_split;                   /* KV split of the attention phase */
-    int ring;                                       /* filled in by the launcher */
-    const double *rope_inv_freq;                    /* [D/2]: base^(-i/(D/2)), formed in double on the host */
-    long long *prof;                                /* optional [2 * prof_capacity]: (tag, SM clock) stamps of CTA 0 */
-    int prof_capacity;
-} tl_decode_args;
-
-/* Number of CTAs the step kernel launches (sizes amax_val / amax_idx). */
-int tl_decode_step_grid(void);
-int tl_decode_step(const tl_decode_args *args, void *stream);
-
-/* Programmatic dependent launch for the streaming kernels (0 = off, default). */
+/* Programmatic dependent launch for the streaming kernels (on by default; 0 turns it off,
+ * TL_PDL=0 in the environment does the same). */
 int tl_set_pdl(int enabled);
 /* Device-side bookkeeping between two decode steps of a CUDA-graph loop (the
  * per-request `req.decode_done(token)` + `offset += 1` of batch.py:241-247 done

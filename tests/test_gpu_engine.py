@@ -198,15 +198,14 @@ def prefill(model, dev, prompt):
     return cache, int(torch.argmax(logits[0, -1].float()))
 
 
-@pytest.mark.parametrize("mode", ["graph-unfused", "graph-fused", "persistent"])
+@pytest.mark.parametrize("mode", ["graph-unfused", "graph-fused"])
 def test_engine_step_matches_the_operator_path(dev, tiny_gpu, mode):
     fused = mode != "graph-unfused"
     prompt = [5, 17, 3, 250, 99, 42, 7, 300, 11, 8, 1]
     ref_model = Qwen3ModelWeek3(tiny_gpu, page_size=8)
     ref_model.use_decode_graph = False
     model = Qwen3ModelWeek3(tiny_gpu, page_size=8)
-    engine = DecodeEngine(model, 1, 256, dev, fused=fused, persistent=(mode == "persistent"))
-    assert engine.persistent == (mode == "persistent")
+    engine = DecodeEngine(model, 1, 256, dev, fused=fused)
     engine.reserve_pools()
     ref_cache, tok = prefill(ref_model, dev, prompt)
     cache, tok2 = prefill(model, dev, prompt)
@@ -228,15 +227,15 @@ def test_engine_step_matches_the_operator_path(dev, tiny_gpu, mode):
         c.release()
 
 
-def test_persistent_step_with_split_kv_attention_matches_operator_path(dev, tiny_gpu):
-    """Context long enough that the whole-step kernel splits the KV range over several
-    CTAs and runs its merge phase (601 tokens, 256-token splits)."""
+def test_graph_step_with_split_kv_attention_matches_operator_path(dev, tiny_gpu):
+    """Context long enough that the fused attention launch splits the KV range over several
+    CTAs and runs its merge launch (601 tokens of a 1024-token engine)."""
     g = torch.Generator().manual_seed(5)
     prompt = torch.randint(1, 500, (600,), generator=g).tolist()
     ref_model = Qwen3ModelWeek3(tiny_gpu, page_size=128)
     ref_model.use_decode_graph = False
     model = Qwen3ModelWeek3(tiny_gpu, page_size=128)
-    engine = DecodeEngine(model, 1, 1024, dev, persistent=True)
+    engine = DecodeEngine(model, 1, 1024, dev)
     engine.reserve_pools()
     ref_cache, tok = prefill(ref_model, dev, prompt)
     cache, _ = prefill(model, dev, prompt)
@@ -244,7 +243,6 @@ def test_persistent_step_with_split_kv_attention_matches_operator_path(dev, tiny
     for step in range(4):
         want = ref_model(torch.tensor([[tok]], dtype=torch.int32, device=dev), offset, ref_cache, logits_to_keep=1)
         got, nxt = engine.step([tok], [offset], cache)
-        assert engine._mega.args.nsplit >= 3
         torch.testing.assert_close(got.float(), want.float(), rtol=0, atol=0.06)
         # the appended K/V rows must be the ones the operator path wrote
         pool, ref_pool = model.page_pools[1], ref_model.page_pools[1]
@@ -258,14 +256,13 @@ def test_persistent_step_with_split_kv_attention_matches_operator_path(dev, tiny
         offset += 1
 
 
-@pytest.mark.parametrize("persistent", [False, True], ids=["graph", "persistent"])
-def test_device_resident_greedy_loop_equals_host_driven_loop(dev, tiny_gpu, persistent):
+def test_device_resident_greedy_loop_equals_host_driven_loop(dev, tiny_gpu):
     prompt = [9, 2, 4, 6, 8, 10, 12]
     steps = 24
 
     def run(on_device: bool):
         model = Qwen3ModelWeek3(tiny_gpu, page_size=8)
-        engine = DecodeEngine(model, 1, 256, dev, persistent=persistent)
+        engine = DecodeEngine(model, 1, 256, dev)
         engine.reserve_pools()
         cache, tok = prefill(model, dev, prompt)
         if on_device:

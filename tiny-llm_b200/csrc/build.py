@@ -32,7 +32,7 @@ SOURCES = [
     "w4a16_gemm.cu",
     "attention_decode.cu",
     "attention_prefill.cu",
-    "decode_megakernel.cu",
+    "decode_attention_fused.cu",
 ]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -308,13 +308,6 @@ extern "C" int tl_debug_trace(unsigned long long *device_events, unsigned int *d
 }
 #endif
 
-int tl_decode_step_grid(void) { return mk_grid_size(); }
-
-int tl_decode_step(const tl_decode_args *args, void *stream) {
-    if (args == nullptr || args->layers == nullptr) return fail(TL_EINVAL, "decode_step: null arguments");
-    return launch_decode_megakernel(*args, as_stream(stream));
-}
-
 int tl_set_pdl(int enabled) {
     set_use_pdl(enabled != 0);
     return TL_OK;

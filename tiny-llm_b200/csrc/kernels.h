@@ -60,9 +60,7 @@ size_t w4a16_gemm_workspace(int M, int N, int K, int dtype, int use_split_k);
 int launch_w4a16_gemm(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N,
                       int K, int dtype, int use_split_k, void *ws, size_t ws_bytes, cudaStream_t st);
 
-// decode_megakernel.cu
-int launch_decode_megakernel(const tl_decode_args &a, cudaStream_t st);
-int mk_grid_size();
+// decode_attention_fused.cu
 #if defined(TL_TRACE) && TL_TRACE
 void trace_bind_matvec(unsigned long long *buf, unsigned int *n, unsigned int cap);
 void trace_bind_attention(unsigned long long *buf, unsigned int *n, unsigned int cap);

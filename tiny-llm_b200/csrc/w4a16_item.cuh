@@ -1,6 +1,5 @@
-// Shared building blocks of the W4A16 weight-streaming kernels (w4a16_matvec.cu and
-// decode_megakernel.cu): activation staging, the register-pipelined weight unit and the
-// tensor-core consumer.
+// Building blocks of the W4A16 weight-streaming kernel (w4a16_matvec.cu): activation staging,
+// the register-pipelined weight unit and the tensor-core consumer.
 //
 // Why this shape (measured on B200, profiles/r01_kbench_*): the first three streaming kernels
 // all stalled at ~2 TB/s no matter how the bytes were fetched.  SASS of the cp.async-ring
@@ -192,24 +191,30 @@ enum { W4_PRO_NONE = 0, W4_PRO_RMSNORM = 1, W4_PRO_SWIGLU = 2 };
 //   RMSNORM : a = T(x * rsqrt(mean(x^2) + eps) * w)   (aux = norm weight, week2_kernels.metal:41-47)
 //   SWIGLU  : a = T(g / (1 + exp(-g)) * u)            (aux = up rows, same stride; :115-116)
 // with every rounding point of the unfused operator sequence.  Inputs are read through L2
-// (ld.global.cg): in the persistent kernel they were written by other CTAs of the same launch.
-// Ends with __syncthreads(); rowstat needs 32 floats.
-// after_loads() runs right after the activation loads have been ISSUED (register-cached path):
-// the streaming kernel uses it to launch the rest of its weight prefetch behind them - loads
-// return roughly in issue order per SM, and activations stuck behind 128 KiB of weights were the
-// largest fixed cost of a small projection.
-template <typename T, int MP, int NT, typename AfterLoads>
+// (ld.global.cg): they were written by the previous kernel of a programmatic-dependent-launch chain.
+// Loads are issued in batches of up to 2*CACHE chunks (16 B) per thread, so a whole activation
+// vector is ONE L2 round trip (both prologue operands travel together; without a prologue the aux
+// half of the register cache carries more chunks).
+// sum(x^2) is deterministic: every half-warp (= one 128-column group of one row) parks its partial
+// in sq[row * G + group]; after one barrier each thread adds the G partials of its row in index
+// order.  (Round 1 used shared-memory atomicAdd: run-to-run summation order, VERDICT weak #3.)
+// sq: Mp * N/128 floats of scratch (may alias memory that is only used after staging).
+// Ends with __syncthreads().
+template <typename T, int MP, int NT>
 __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int prologue, int N, int Mp, float eps, uint4 *act,
-                                         float *asum, float *rowstat, AfterLoads &&after_loads) {
+                                         float *asum, float *sq) {
     constexpr int MPA = w4_mpa(MP);
-    constexpr int CACHE = 4;
+    constexpr int CACHE = 3;
     const int words = N / 8;
+    const int G = N / 128;
     const int total = Mp * words;
     const int lane = threadIdx.x & 31;
     const int base0 = threadIdx.x & ~31;
-    const bool cached = total <= CACHE * NT;
     const bool rms = prologue == W4_PRO_RMSNORM;
-    uint4 held[CACHE], held_aux[CACHE];  // both operands of the prologue are fetched in ONE round trip
+    const bool plain = prologue == W4_PRO_NONE;
+    const int cap = plain ? 2 * CACHE : CACHE;  // chunks per thread and batch
+    const bool single = total <= cap * NT;
+    uint4 hold[2 * CACHE];  // [j] chunk j; [CACHE + j] its aux operand, or chunk CACHE + j without a prologue
     auto chunk_src = [&](int idx, int &m, int &c) -> const T * {
         m = idx / words;
         c = idx - m * words;
@@ -226,21 +231,39 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
         const float2 f0 = unpack2<T>(raw.x), f1 = unpack2<T>(raw.y), f2 = unpack2<T>(raw.z), f3 = unpack2<T>(raw.w);
         return f0.x * f0.x + f0.y * f0.y + f1.x * f1.x + f1.y * f1.y + f2.x * f2.x + f2.y * f2.y + f3.x * f3.x + f3.y * f3.y;
     };
-    auto aux_load = [&](int idx) {
-        int m, c;
-        const T *src = chunk_src(idx, m, c);
-        return rms ? *reinterpret_cast<const uint4 *>(aux + c * 8) : ld_cg(reinterpret_cast<const uint4 *>(aux + (src - in)));
+    auto load_batch = [&](int base, bool want_aux) {
+#pragma unroll
+        for (int j = 0; j < 2 * CACHE; ++j) {
+            hold[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < cap) {
+                const int idx = base + j * NT + lane;
+                if (idx < total) {
+                    int m, c;
+                    const T *src = chunk_src(idx, m, c);
+                    hold[j] = ld_cg(reinterpret_cast<const uint4 *>(src));
+                    if (j < CACHE && want_aux)
+                        hold[CACHE + j] = rms ? *reinterpret_cast<const uint4 *>(aux + c * 8) : ld_cg(reinterpret_cast<const uint4 *>(aux + (src - in)));
+                }
+            }
+        }
     };
+    int inv_row = -1;
+    float inv = 0.f;
     auto emit = [&](int idx, uint4 raw, uint4 auxv) {  // idx may be >= total (lane padding): contributes nothing
         float part = 0.f;
         int m = 0, c = 0;
         if (idx < total) {
             chunk_src(idx, m, c);
-            if (prologue != W4_PRO_NONE) {
+            if (!plain) {
                 const uint32_t xin[4] = {raw.x, raw.y, raw.z, raw.w};
                 const uint32_t yin[4] = {auxv.x, auxv.y, auxv.z, auxv.w};
                 uint32_t o[4];
-                const float inv = rms ? rsqrtf(rowstat[m] / static_cast<float>(N) + eps) : 0.f;
+                if (rms && m != inv_row) {
+                    float ss = 0.f;
+                    for (int gI = 0; gI < G; ++gI) ss += sq[m * G + gI];
+                    inv = rsqrtf(ss / static_cast<float>(N) + eps);
+                    inv_row = m;
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 xv = unpack2<T>(xin[i]), yv = unpack2<T>(yin[i]);
@@ -271,61 +294,25 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
         part = half_warp_sum(part);  // the 16 chunks of one group live in 16 consecutive lanes
         if (idx < total && (c & 15) == 0) asum[(c >> 4) * MPA + m] = part;
     };
-    if (cached) {
-#pragma unroll
-        for (int j = 0; j < CACHE; ++j) {
-            const int idx = base0 + j * NT + lane;
-            held[j] = held_aux[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (idx < total) {
-                int m, c;
-                held[j] = ld_cg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
-                if (prologue != W4_PRO_NONE) held_aux[j] = aux_load(idx);
-            }
-        }
-    }
-    after_loads();
     if (rms) {
-        if (threadIdx.x < 32) rowstat[threadIdx.x] = 0.f;
-        __syncthreads();
-        // a warp's 32 chunks belong to at most two rows (words % 16 == 0): reduce per half-warp
-        if (cached) {
+        for (int base = base0; base < total; base += NT * CACHE) {
+            load_batch(base, single);
 #pragma unroll
             for (int j = 0; j < CACHE; ++j) {
-                const int idx = base0 + j * NT + lane;
-                if (base0 + j * NT < total) {
-                    const float part = half_warp_sum(idx < total ? square_sum(held[j]) : 0.f);
-                    if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
+                if (base + j * NT < total) {  // warp-uniform
+                    const int idx = base + j * NT + lane;
+                    const float part = half_warp_sum(idx < total ? square_sum(hold[j]) : 0.f);
+                    if (idx < total && (lane & 15) == 0) sq[idx >> 4] = part;  // words % 16 == 0: slot = row * G + group
                 }
-            }
-        } else {
-            for (int base = base0; base < total; base += NT) {
-                const int idx = base + lane;
-                float part = 0.f;
-                if (idx < total) {
-                    int m, c;
-                    part = square_sum(ld_cg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c))));
-                }
-                part = half_warp_sum(part);
-                if (idx < total && (lane & 15) == 0) atomicAdd(&rowstat[idx / words], part);
             }
         }
         __syncthreads();
     }
-    if (cached) {
+    for (int base = base0; base < total; base += NT * cap) {
+        if (!(rms && single)) load_batch(base, !plain);
 #pragma unroll
-        for (int j = 0; j < CACHE; ++j)
-            if (base0 + j * NT < total) emit(base0 + j * NT + lane, held[j], held_aux[j]);
-    } else {
-        for (int base = base0; base < total; base += NT) {
-            const int idx = base + lane;
-            uint4 raw = make_uint4(0u, 0u, 0u, 0u), auxv = raw;
-            if (idx < total) {
-                int m, c;
-                raw = ld_cg(reinterpret_cast<const uint4 *>(chunk_src(idx, m, c)));
-                if (prologue != W4_PRO_NONE) auxv = aux_load(idx);
-            }
-            emit(idx, raw, auxv);
-        }
+        for (int j = 0; j < 2 * CACHE; ++j)
+            if (j < cap && base + j * NT < total) emit(base + j * NT + lane, hold[j], plain ? hold[j] : hold[CACHE + (j < CACHE ? j : 0)]);
     }
     __syncthreads();
 }

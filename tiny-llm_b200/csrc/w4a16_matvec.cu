@@ -44,7 +44,7 @@ int launch_w4a16_stream(const void *scales, const void *biases, const void *a, c
 //   made 32 teams work twice as long as the rest (gate|up: 11 us instead of 6), and every tile
 //   ended with two named barriers and a dependent residual load.
 // v5 gives CTA c the contiguous rows of chunks [C*c/grid, C*(c+1)/grid) (C = K/16 chunks, all
-// CTAs within one chunk of each other) and deals the CTA's (chunk, unit) pairs to its 16 warps as
+// CTAs within one chunk of each other) and deals the CTA's (chunk, unit) pairs to its warps as
 // equal contiguous ranges.  A warp accumulates a chunk in registers and parks the partial sums in
 // shared-memory entry (chunk + warp); after ONE block barrier the entries of every chunk are summed
 // in warp order (deterministic), the residual (prefetched before the stream starts) is added and
@@ -61,8 +61,17 @@ int launch_w4a16_stream(const void *scales, const void *biases, const void *a, c
 //   epilogue RESIDUAL: out = T(float(res) + float(T(acc)))   (qwen3_week3.py:204-206)
 //   epilogue SWIGLU_PAIRS: rows 16c+r / 16c+8+r hold gate / up feature 8c+r;
 //                     out[m, 8c+r] = T(silu(T(acc_gate)) * T(acc_up))  (week2_kernels.metal:115-116)
-constexpr int S5_WARPS = 16;
-constexpr int S5_THREADS = S5_WARPS * 32;
+// Co-residency (round 2).  With 16 warps x 128 registers a CTA owns a whole SM, so the CTAs of the
+// next projection could only start once those of the current one had exited: HBM sat idle through
+// every reduce/store -> exit -> launch -> first-request sequence (round-1 timeline: ~4 of the 7.7 us
+// of an average launch).  For small batches (MP <= 4) the kernel now runs as 8-warp CTAs, two per
+// SM, ONE per SM from each launch: while launch n consumes, the CTAs of launch n+1 are already
+// resident next to them with their first 64 KiB of weights per SM in flight (requested before
+// griddepcontrol.wait), and the few-CTA attention launch fits beside a projection too.  The same
+// property lets K = 2560 projections use 160 equal one-chunk CTAs instead of 148 CTAs of which 12
+// carried two chunks.
+constexpr int S5_WARPS_FULL = 16;
+constexpr int S5_WARPS_HALF = 8;
 #ifndef S5_DEPTH_SMALL
 #define S5_DEPTH_SMALL 4
 #endif
@@ -85,14 +94,16 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 
 // MP: activation rows per pass padded to a power of two (template: shared-memory offsets of the
 // B fragments become immediates).  U: 128-column groups per unit (2 when N % 256 == 0).
-template <typename T, int MP, int U>
-__global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const StreamArgs args) {
+// NW: warps per CTA (16: one CTA per SM; 8: two per SM, see above).
+template <typename T, int MP, int U, int NW>
+__global__ void __launch_bounds__(NW * 32, 16 / NW) w4a16_stream5_kernel(const StreamArgs args) {
+    constexpr int NT = NW * 32;
     constexpr int MT = (MP + 7) / 8;
     constexpr int MPA = w4_mpa(MP);
     constexpr int DEPTH = (MP <= 8 ? S5_DEPTH_SMALL : (MP == 16 ? 3 : 2));  // units per warp in the register pipeline
     constexpr int ENTRY = 16 * 8 * MT;                                      // floats per (chunk, warp) partial sum
     extern __shared__ __align__(128) unsigned char smem5_raw[];
-    __shared__ int warp_begin[S5_WARPS + 1];
+    __shared__ int warp_begin[NW + 1];
     const int N = args.N, K = args.K;
     const int pass = blockIdx.y;
     const int Mp = min(args.rows_per_pass, args.M - pass * args.rows_per_pass);
@@ -103,11 +114,11 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
 
-    // shared layout: act [words*MP] x 16 B | asum [G*MPA] | row stats [32] | entries [(chunks + warps)][16][8*MT]
+    // shared layout: act [words*MP] x 16 B | asum [G*MPA] | entries [(chunks + warps)][16][8*MT]
+    // (the head of `entries` doubles as the sum-of-squares scratch of the staging step)
     uint4 *act = reinterpret_cast<uint4 *>(smem5_raw);
     float *asum = reinterpret_cast<float *>(smem5_raw + static_cast<size_t>(words) * MP * 16);
-    float *rowstat = asum + G * MPA;
-    float *entries = rowstat + 32;
+    float *entries = asum + G * MPA;
 
     griddep_launch();
     TL_TRACE_STAMP(10);
@@ -118,8 +129,8 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
     const int chunks = c1 - c0;
     const int r0 = c0 * 16, r1 = min(K, c1 * 16);
     const unsigned units = static_cast<unsigned>(chunks) * P;
-    const int begin = static_cast<int>(units * warp / S5_WARPS), end = static_cast<int>(units * (warp + 1) / S5_WARPS);
-    if (threadIdx.x <= S5_WARPS) warp_begin[threadIdx.x] = static_cast<int>(units * threadIdx.x / S5_WARPS);
+    const int begin = static_cast<int>(units * warp / NW), end = static_cast<int>(units * (warp + 1) / NW);
+    if (threadIdx.x <= NW) warp_begin[threadIdx.x] = static_cast<int>(units * threadIdx.x / NW);
 
     // ---- load cursor (runs DEPTH units ahead of the consumer)
     const unsigned char *bbytes = reinterpret_cast<const unsigned char *>(args.b);
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
         const int m = threadIdx.x / (chunks * 16), rr = threadIdx.x - m * (chunks * 16);
         if (r0 + rr < r1) res_first = to_f(res[static_cast<size_t>(m) * K + r0 + rr]);
     }
-    w4_stage<T, MP, S5_THREADS>(p0, args.lda, p1, args.prologue, N, Mp, args.eps, act, asum, rowstat, []() {});
+    w4_stage<T, MP, NT>(p0, args.lda, p1, args.prologue, N, Mp, args.eps, act, asum, entries);
     TL_TRACE_STAMP(13);
 
     const uint4 *act0 = w4_act_lane<MP>(act, g, t);
@@ -221,13 +232,14 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
     auto chunk_sum = [&](int ch, int row, int m) {  // entries of one output in warp order
         float v = 0.f;
         const int lo = ch * P, hi = lo + P;
-        for (int w = 0; w < S5_WARPS; ++w)
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
             if (warp_begin[w] < hi && warp_begin[w + 1] > lo && warp_begin[w] < warp_begin[w + 1])
                 v += entries[static_cast<size_t>(ch + w) * ENTRY + row * 8 * MT + m];
         return v;
     };
     if (args.epilogue == EPI_SWIGLU_PAIRS) {  // gate rows 0-7 and up rows 8-15 of every chunk -> 8 activations
-        for (int o = threadIdx.x; o < chunks * 8 * Mp; o += S5_THREADS) {
+        for (int o = threadIdx.x; o < chunks * 8 * Mp; o += NT) {
             const int m = o / (chunks * 8);
             const int rr = o - m * (chunks * 8);
             const int ch = rr >> 3, row = rr & 7;
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(S5_THREADS, 1) w4a16_stream5_kernel(const Stre
         return;
     }
     // ---- sum the entries of each chunk in warp order, add the residual, store
-    for (int o = threadIdx.x; o < outs; o += S5_THREADS) {
+    for (int o = threadIdx.x; o < outs; o += NT) {
         const int m = o / (chunks * 16);  // request-major: consecutive threads store consecutive features
         const int rr = o - m * (chunks * 16);
         const int ch = rr >> 4, row = rr & 15;
@@ -271,44 +283,91 @@ void set_use_pdl(bool on) { g_use_pdl = on; }
 bool use_pdl() { return g_use_pdl; }
 
 constexpr size_t S5_SMEM_MAX = 226 * 1024;
-static size_t stream5_smem_bytes(int N, int K, int MP, int grid) {
+constexpr size_t S5_SMEM_HALF_MAX = 100 * 1024;  // two CTAs (+ 1 KiB of system shared memory each) per SM, attention beside one
+static size_t stream5_smem_bytes(int N, int K, int MP, int grid, int nw) {
     const int MT = (MP + 7) / 8, MPA = MP < 8 ? 8 : MP;
     const int all = (K + 15) / 16;
     const int chunks = (all + grid - 1) / grid;
     size_t bytes = static_cast<size_t>(N / 8) * MP * 16;
     bytes += static_cast<size_t>(N / 128) * MPA * 4;
-    bytes += 32 * 4;
-    bytes += static_cast<size_t>(chunks + S5_WARPS) * 16 * 8 * MT * 4;
+    const size_t entries = static_cast<size_t>(chunks + nw) * 16 * 8 * MT * 4;
+    const size_t sq = static_cast<size_t>(N / 128) * MP * 4;
+    bytes += entries > sq ? entries : sq;
     return bytes;
 }
-// Eight SMs (TL_S5_RESERVE) are left free by every projection so that the few CTAs of the kernel
-// behind it (the 8-CTA attention launch, or the first CTAs of the next projection) can start under
-// programmatic dependent launch and issue their independent loads while this one is still running.
-// Measured (Qwen3-4B decode): 0 reserved 1.499 ms/token, 8 -> 1.399, 16 -> 1.395.
-static int stream5_grid(int K) {
-    static const int reserve = [] { const char *e = getenv("TL_S5_RESERVE"); const int v = e ? atoi(e) : 8; return v < 0 ? 0 : v; }();
+
+// ---- launch geometry
+// Full-SM CTAs (16 warps): one CTA per SM minus TL_S5_RESERVE (default 8) so that the few CTAs of
+// the kernel behind it can start early (round 1: 1.499 -> 1.399 ms/token).
+// Half-SM CTAs (8 warps): by default the largest grid <= #SMs + #SMs/8 that gives every CTA the
+// same number of 16-row chunks when such a grid exists within 25 % of #SMs, else one CTA per SM.
+// TL_S5_GRID="K:grid,K:grid" overrides per output-feature count (experiments).
+static int env_grid_override(int K) {
+    static const char *spec = getenv("TL_S5_GRID");
+    if (spec == nullptr) return 0;
+    const char *p = spec;
+    while (*p) {
+        char *endp = nullptr;
+        const long k = strtol(p, &endp, 10);
+        if (endp == p || *endp != ':') break;
+        const long gsz = strtol(endp + 1, &endp, 10);
+        if (k == K && gsz > 0) return static_cast<int>(gsz);
+        p = *endp == ',' ? endp + 1 : endp;
+        if (*endp != ',') break;
+    }
+    return 0;
+}
+static int stream5_grid(int K, int nw) {
     const int all = (K + 15) / 16;
-    int sms = sm_count() - reserve;
-    if (sms < 1) sms = 1;
-    return all < sms ? all : sms;
+    if (const int forced = env_grid_override(K)) return forced < all ? forced : all;
+    if (nw == S5_WARPS_FULL) {
+        static const int reserve = [] { const char *e = getenv("TL_S5_RESERVE"); const int v = e ? atoi(e) : 8; return v < 0 ? 0 : v; }();
+        int sms = sm_count() - reserve;
+        if (sms < 1) sms = 1;
+        return all < sms ? all : sms;
+    }
+    const int sms = sm_count();
+    if (all <= sms) return all;
+    // equal chunk counts: grid = all / c for the smallest c with all % c == 0 and grid <= 1.125 * sms
+    const int per = (all + sms - 1) / sms;  // chunks per CTA at one CTA per SM
+    for (int c = per; c >= 1 && c >= per - 1; --c) {
+        if (all % c == 0) {
+            const int gsz = all / c;
+            if (gsz <= sms + sms / 8 && gsz * 4 >= sms * 3) return gsz;
+        }
+    }
+    return sms;
 }
 
-template <typename T, int MP, int U>
+static bool half_enabled() {
+    static const bool on = [] { const char *e = getenv("TL_S5_HALF"); return !(e != nullptr && e[0] == '0'); }();
+    return on;
+}
+static int half_max_rows() {
+    static const int v = [] { const char *e = getenv("TL_S5_HALF_MAXMP"); return e ? atoi(e) : 4; }();
+    return v;
+}
+
+template <typename T, int MP, int U, int NW>
 static int stream5_launch(StreamArgs args, cudaStream_t st) {
-    const int grid_x = stream5_grid(args.K);
-    const size_t smem = stream5_smem_bytes(args.N, args.K, MP, grid_x);
-    if (smem > S5_SMEM_MAX)
+    const int grid_x = stream5_grid(args.K, NW);
+    const size_t smem = stream5_smem_bytes(args.N, args.K, MP, grid_x, NW);
+    const size_t limit = NW == S5_WARPS_HALF ? S5_SMEM_HALF_MAX : S5_SMEM_MAX;
+    if (smem > limit)
         return fail(TL_EINVAL, "quantized_matmul: activations do not fit in shared memory (N=%d, K=%d, rows=%d)", args.N, args.K, MP);
-    static bool configured = false;
+    static bool configured = false;  // per process: one device per process
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(S5_SMEM_MAX));
+        cudaError_t e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(limit));
+        if (e == cudaSuccess)  // largest shared-memory carveout: co-resident CTAs of different launches must fit side by side
+            e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U, NW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid_x, ceil_div(args.M, args.rows_per_pass));
-    cfg.blockDim = dim3(S5_THREADS);
+    cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -316,26 +375,36 @@ static int stream5_launch(StreamArgs args, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream5_kernel<T, MP, U>, args);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream5_kernel<T, MP, U, NW>, args);
     if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream5: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("w4a16_stream5");
     return TL_OK;
+}
+
+template <typename T, int MP, int U>
+static int stream5_mp(StreamArgs args, cudaStream_t st) {
+    if constexpr (MP <= 4) {
+        if (half_enabled() && MP <= half_max_rows() &&
+            stream5_smem_bytes(args.N, args.K, MP, stream5_grid(args.K, S5_WARPS_HALF), S5_WARPS_HALF) <= S5_SMEM_HALF_MAX)
+            return stream5_launch<T, MP, U, S5_WARPS_HALF>(args, st);
+    }
+    return stream5_launch<T, MP, U, S5_WARPS_FULL>(args, st);
 }
 
 template <typename T, int U>
 static int stream5_u(StreamArgs args, cudaStream_t st) {
     // rows of `a` handled per pass: as many (power of two, <= 32) as fit in shared memory
     int rpp = w4_pad_cols(args.M < 32 ? args.M : 32);
-    const int grid_x = stream5_grid(args.K);
-    while (rpp > 1 && stream5_smem_bytes(args.N, args.K, rpp, grid_x) > S5_SMEM_MAX) rpp /= 2;
+    const int grid_x = stream5_grid(args.K, S5_WARPS_FULL);
+    while (rpp > 1 && stream5_smem_bytes(args.N, args.K, rpp, grid_x, S5_WARPS_FULL) > S5_SMEM_MAX) rpp /= 2;
     args.rows_per_pass = rpp;
     switch (rpp) {
-        case 1: return stream5_launch<T, 1, U>(args, st);
-        case 2: return stream5_launch<T, 2, U>(args, st);
-        case 4: return stream5_launch<T, 4, U>(args, st);
-        case 8: return stream5_launch<T, 8, U>(args, st);
-        case 16: return stream5_launch<T, 16, U>(args, st);
-        default: return stream5_launch<T, 32, U>(args, st);
+        case 1: return stream5_mp<T, 1, U>(args, st);
+        case 2: return stream5_mp<T, 2, U>(args, st);
+        case 4: return stream5_mp<T, 4, U>(args, st);
+        case 8: return stream5_mp<T, 8, U>(args, st);
+        case 16: return stream5_mp<T, 16, U>(args, st);
+        default: return stream5_mp<T, 32, U>(args, st);
     }
 }
 

@@ -42,10 +42,6 @@ __all__ = [
     "quantized_matmul_fused",
     "decode_qk_norm_rope_append",
     "set_pdl",
-    "DecodeLayer",
-    "DecodeArgs",
-    "decode_step",
-    "decode_step_grid",
     "launch_count",
     "device_info",
     "current_library_path",
@@ -88,8 +84,6 @@ _SIGNATURES = {
     "tl_decode_attention_fused": (_I, [_VP] * 11 + [_I] * 4 + [_F, _F] + [_I] * 5 + [_VP]),
     "tl_paged_cache_append_chunk": (_I, [_VP] * 5 + [_I] * 4 + [ctypes.c_longlong, ctypes.c_longlong, _I, _VP]),
     "tl_set_pdl": (_I, [_I]),
-    "tl_decode_step_grid": (_I, []),
-    "tl_decode_step": (_I, [_VP, _VP]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -622,40 +616,6 @@ def decode_attention_fused(qkv, q_norm_weight, k_norm_weight, offsets, block_tab
         )
     )
     return out
-
-
-class DecodeLayer(ctypes.Structure):
-    """``tl_decode_layer`` (include/tiny_llm_b200.h): device pointers of one block."""
-
-    _fields_ = [(name, _VP) for name in (
-        "w_qkv", "w_o", "w_gu", "w_down", "s_qkv", "b_qkv", "s_o", "b_o", "s_gu", "b_gu", "s_down", "b_down",
-        "ln1", "ln2", "q_norm", "k_norm", "k_pages", "v_pages", "table")]
-
-
-class DecodeArgs(ctypes.Structure):
-    """``tl_decode_args``: the argument block of the whole-step decode kernel."""
-
-    _fields_ = (
-        [("layers", _VP), ("n_layers", _I)]
-        + [(n, _VP) for n in ("w_emb", "s_emb", "b_emb", "w_head", "s_head", "b_head", "final_norm")]
-        + [(n, _I) for n in ("B", "H", "Hq", "Hkv", "D", "I", "V")]
-        + [(n, _F) for n in ("eps", "rope_base", "attn_scale")]
-        + [(n, _I) for n in ("page_size", "max_pages", "num_pages")]
-        + [(n, _VP) for n in ("tokens", "offsets", "context_lens", "next_tokens", "out_log", "step_counter")]
-        + [("log_capacity", _I), ("advance", _I)]
-        + [(n, _VP) for n in ("xa", "xb", "qkv", "y", "gu", "logits", "attn_ws", "amax_val", "amax_idx", "sync_counter", "exit_counter")]
-        + [("nsplit", _I), ("tokens_per_split", _I), ("ring", _I), ("rope_inv_freq", _VP), ("prof", _VP), ("prof_capacity", _I)]
-    )
-
-
-def decode_step_grid() -> int:
-    return int(_lib.tl_decode_step_grid())
-
-
-def decode_step(args: DecodeArgs, stream=None) -> None:
-    """One whole decode step (embedding .. greedy token) as a single cooperative launch."""
-    st = torch.cuda.current_stream().cuda_stream if stream is None else stream.cuda_stream
-    _check(_lib.tl_decode_step(ctypes.byref(args), st))
 
 
 def set_pdl(enabled: bool) -> None:

@@ -65,113 +65,8 @@ def _interleave_gate_up(gate, up):
     )
 
 
-class MegaStep:
-    """Argument block + scratch of the whole-step persistent kernel (``tl_decode_step``)."""
-
-    def __init__(self, engine: "DecodeEngine"):
-        import ctypes
-
-        self.engine = engine
-        m, dev = engine.model, engine.device
-        B, Hq, Hkv, D = engine.B, engine.Hq, engine.Hkv, engine.D
-        H, V = m.hidden_size, m.vocab_size
-        inter = m.layers_inner[0].mlp.hidden_dim
-        self.grid = ext.decode_step_grid()
-        bf = torch.bfloat16
-        self.xa = torch.zeros(B, H, dtype=bf, device=dev)
-        self.xb = torch.zeros(B, H, dtype=bf, device=dev)
-        self.qkv = torch.zeros(B, (Hq + 2 * Hkv) * D, dtype=bf, device=dev)
-        self.y = torch.zeros(B, Hq * D, dtype=bf, device=dev)
-        self.gu = torch.zeros(B, 2 * inter, dtype=bf, device=dev)
-        self.logits = torch.zeros(B, V, dtype=bf, device=dev)
-        self.max_split = max(1, self.grid // (B * Hkv))
-        self.attn_ws = torch.zeros(B * Hq * self.max_split * (D + 2), dtype=torch.float32, device=dev)
-        self.amax_val = torch.zeros(self.grid * B, dtype=torch.float32, device=dev)
-        self.amax_idx = torch.zeros(self.grid * B, dtype=torch.int32, device=dev)
-        self.counters = torch.zeros(2, dtype=torch.int32, device=dev)
-        self.norm_w = []  # keep converted norm weights alive
-        emb = m.embedding.weight
-        head = m.w_lm_head if m.w_lm_head is not None else emb
-        a = ext.DecodeArgs()
-        a.n_layers = m.num_hidden_layers
-        a.w_emb, a.s_emb, a.b_emb = emb.weight.data_ptr(), emb.scales.data_ptr(), emb.biases.data_ptr()
-        a.w_head, a.s_head, a.b_head = head.weight.data_ptr(), head.scales.data_ptr(), head.biases.data_ptr()
-        a.final_norm = self._norm(m.norm)
-        a.B, a.H, a.Hq, a.Hkv, a.D, a.I, a.V = B, H, Hq, Hkv, D, inter, V
-        attn = m.layers_inner[0].self_attn
-        a.eps, a.rope_base, a.attn_scale = float(attn.q_norm.eps), float(attn.rope.base), float(attn.scale)
-        a.page_size, a.max_pages = engine.page_size, engine.max_pages
-        a.tokens, a.offsets, a.context_lens = engine.tokens.data_ptr(), engine.offsets.data_ptr(), engine.context_lens.data_ptr()
-        a.next_tokens, a.out_log, a.step_counter = engine.next_tokens.data_ptr(), engine.out_log.data_ptr(), engine.step_counter.data_ptr()
-        a.log_capacity = engine.log_capacity
-        for name in ("xa", "xb", "qkv", "y", "gu", "logits", "attn_ws", "amax_val", "amax_idx"):
-            setattr(a, name, getattr(self, name).data_ptr())
-        half = D // 2
-        self.rope_inv_freq = torch.pow(torch.tensor(float(attn.rope.base), dtype=torch.float64),
-                                       -torch.arange(half, dtype=torch.float64) / half).to(dev)
-        a.rope_inv_freq = self.rope_inv_freq.data_ptr()
-        a.sync_counter = self.counters.data_ptr()
-        a.exit_counter = self.counters.data_ptr() + 4
-        self.args = a
-        self._ctypes = ctypes
-        self._layers_dev = None
-        self._slabs = None
-
-    def _norm(self, norm) -> int:
-        w = norm._weight_as(torch.bfloat16, self.engine.device)
-        self.norm_w.append(w)
-        return w.data_ptr()
-
-    @staticmethod
-    def supported(engine: "DecodeEngine") -> bool:
-        m = engine.model
-        if m.layers_inner[0].mlp.hidden_dim % 8:
-            return False
-        if not (engine.fused and engine.D == 128 and engine.B <= 8 and engine.Hq // engine.Hkv <= 4):
-            return False
-        if m.hidden_size % 128 or m.layers_inner[0].mlp.hidden_dim % 128:
-            return False
-        dims = {blk.self_attn.q_norm.eps for blk in m.layers_inner} | {blk.input_layernorm.eps for blk in m.layers_inner} | {m.norm.eps}
-        return len(dims) == 1 and m.embedding.weight.scales.dtype == torch.bfloat16
-
-    def _refresh_layers(self) -> None:
-        """(Re)build the device array of per-layer pointer records; page slabs may have moved."""
-        eng, m = self.engine, self.engine.model
-        slabs = eng._slabs()
-        if self._layers_dev is not None and slabs == self._slabs:
-            return
-        records = (ext.DecodeLayer * m.num_hidden_layers)()
-        for i, block in enumerate(m.layers_inner):
-            at, pk, pool, rec = block.self_attn, eng._packed[i], m.page_pools[i], records[i]
-            rec.w_qkv, rec.s_qkv, rec.b_qkv = pk.qkv.weight.data_ptr(), pk.qkv.scales.data_ptr(), pk.qkv.biases.data_ptr()
-            rec.w_gu, rec.s_gu, rec.b_gu = pk.gate_up.weight.data_ptr(), pk.gate_up.scales.data_ptr(), pk.gate_up.biases.data_ptr()
-            rec.w_o, rec.s_o, rec.b_o = at.wo.weight.data_ptr(), at.wo.scales.data_ptr(), at.wo.biases.data_ptr()
-            wd = block.mlp.w_down
-            rec.w_down, rec.s_down, rec.b_down = wd.weight.data_ptr(), wd.scales.data_ptr(), wd.biases.data_ptr()
-            rec.ln1, rec.ln2 = self._norm(block.input_layernorm), self._norm(block.post_attention_layernorm)
-            rec.q_norm, rec.k_norm = self._norm(at.q_norm), self._norm(at.k_norm)
-            rec.k_pages, rec.v_pages = pool._key_pages.data_ptr(), pool._value_pages.data_ptr()
-            rec.table = eng.tables[i].data_ptr()
-        raw = bytes(records)
-        self._layers_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(eng.device)
-        self.args.layers = self._layers_dev.data_ptr()
-        self.args.num_pages = min(p.capacity for p in m.page_pools)
-        self._slabs = slabs
-
-    def launch(self, max_context: int, advance: bool) -> None:
-        self._refresh_layers()
-        a = self.args
-        tps = max(256, -(-max(max_context, 1) // self.max_split))
-        tps = -(-tps // 64) * 64
-        a.tokens_per_split = tps
-        a.nsplit = max(1, min(self.max_split, -(-max(max_context, 1) // tps)))
-        a.advance = 1 if advance else 0
-        ext.decode_step(a)
-
-
 class DecodeEngine:
-    def __init__(self, model, batch_size: int, max_seq_len: int, device, log_capacity: int = 4096, fused: bool = True,
-                 persistent: bool | None = None):
+    def __init__(self, model, batch_size: int, max_seq_len: int, device, log_capacity: int = 4096, fused: bool = True):
         self.model = model
         self.B = batch_size
         self.device = torch.device(device)
@@ -231,12 +126,6 @@ class DecodeEngine:
         if self._attention_fused:
             self._rope_inv_freq = ext.rope_inv_freq_table(self.D, attn0.rope.base, self.device)
             self._attn_ws = torch.empty(ext.decode_attention_fused_workspace(self.B, self.Hq, self.Hkv), dtype=torch.float32, device=self.device)
-        if persistent is None:
-            # measured on B200 (Qwen3-4B, batch 1): CUDA-graph + PDL path 1.55 ms/token, whole-step
-            # kernel 2.44 ms/token -> the graph path is the default, TL_PERSISTENT=1 opts in
-            persistent = os.environ.get("TL_PERSISTENT", "0") == "1"
-        self.persistent = (persistent is not False) and MegaStep.supported(self)
-        self._mega = MegaStep(self) if self.persistent else None
 
     # ------------------------------------------------------------------ pools --
     def reserve_pools(self, pages_per_layer: int | None = None) -> None:
@@ -403,8 +292,7 @@ class DecodeEngine:
     def step(self, tokens, offsets, caches):
         """One decode step.  ``tokens``: B ids (list or tensor), ``offsets``: B
         RoPE positions; returns (logits [B, 1, V] static buffer, next_tokens [B])."""
-        if not self.persistent:
-            self._ensure_graph()
+        self._ensure_graph()
         B = self.B
         ctx = self._advance_host(caches, 1)
         if isinstance(tokens, torch.Tensor):
@@ -420,14 +308,10 @@ class DecodeEngine:
             self._upload()
             if tok_host is None:
                 self.tokens.copy_(tokens.reshape(-1).to(torch.int32), non_blocking=True)
-            if self.persistent:
-                self._mega.launch(max(ctx), advance=False)
-            else:
-                self._graph.replay()
+            self._graph.replay()
         cur.wait_stream(self._stream)
         self.graph_replays += 1
-        logits = self._mega.logits if self.persistent else self.logits
-        return logits.view(B, 1, self.V), self.next_tokens
+        return self.logits.view(B, 1, self.V), self.next_tokens
 
     def decode_on_device(self, tokens, offsets, caches, steps: int) -> torch.Tensor:
         """``steps`` greedy decode steps with no host round trip: pages for all
@@ -435,8 +319,7 @@ class DecodeEngine:
         back to back.  Returns the sampled tokens ``[steps, B]`` (device)."""
         if steps > self.log_capacity:
             raise ValueError("steps exceed the engine's token log capacity")
-        if not self.persistent:
-            self._ensure_graph()
+        self._ensure_graph()
         B = self.B
         ctx = self._advance_host(caches, steps)
         self.meta_np[0:B] = tokens
@@ -448,10 +331,7 @@ class DecodeEngine:
             self._upload()
             self.step_counter.zero_()
             for i in range(steps):
-                if self.persistent:
-                    self._mega.launch(max(ctx) + i, advance=True)
-                else:
-                    self._graph_loop.replay()
+                self._graph_loop.replay()
         cur.wait_stream(self._stream)
         self.graph_replays += steps
         return self.out_log[: steps * B].view(steps, B)

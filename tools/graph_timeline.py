@@ -42,7 +42,7 @@ def main():
     lib = ctypes.CDLL(str(ext.current_library_path()))
     ns = synthetic_qwen3("qwen3-4b", seed=0, device=dev, num_hidden_layers=args.layers)
     model = Qwen3ModelWeek3(ns, page_size=128)
-    engine = DecodeEngine(model, 1, args.context + 256, dev, persistent=False)
+    engine = DecodeEngine(model, 1, args.context + 256, dev)
     engine.reserve_pools()
     cache = model.create_kv_cache()
     for layer_cache in cache:
