@@ -41,6 +41,7 @@ struct MkArgs {
     float *attn_ws;                         // [B*Hq*nsplit*(D+2)] when nsplit > 1
     int nsplit, tokens_per_split;
     const double *rope_inv_freq;            // [D/2]
+    ChainLink link;                         // data hand-off from the q|k|v projection / to the o projection
 };
 
 __device__ __forceinline__ float mk_bf(bf16 v) { return __bfloat162float(v); }
@@ -175,7 +176,7 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         prof.stamp(50003);
         if (DEPWAIT && rb == begin) {
             TL_TRACE_STAMP(21);
-            asm volatile("griddepcontrol.wait;" ::: "memory");  // the qkv row of this step exists now
+            chain_wait(a.link);  // the qkv row of this step exists now
             TL_TRACE_STAMP(22);
             load_q();
         }
@@ -353,14 +354,16 @@ __global__ void __launch_bounds__(MK_THREADS, 2) decode_attention_fused_kernel(c
     Prof prof;
     mk_attention<true>(a, l, att_smem_raw, prof);
     TL_TRACE_STAMP(29);
+    chain_signal(a.link);
 }
 #if TL_TRACE
 void trace_bind_attention(unsigned long long *buf, unsigned int *n, unsigned int cap) { trace_bind(buf, n, cap); }
 #endif
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_attention_merge_kernel(const MkArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    chain_wait(a.link);
     mk_attention_merge(a);
+    chain_signal(a.link);
 }
 
 static int attention_max_split(int batch, int num_kv_heads) {
@@ -413,6 +416,7 @@ int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, co
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl() ? 1 : 0;  // without the attribute griddepcontrol.wait returns at once
+    a.link = use_pdl() ? chain_link(static_cast<int>(cfg.gridDim.x)) : ChainLink{nullptr, 0, nullptr};
     cudaError_t e = cudaLaunchKernelEx(&cfg, decode_attention_fused_kernel, a, l);
     if (e != cudaSuccess) return fail(TL_ECUDA, "decode_attention_fused: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("decode_attention_fused");
@@ -420,6 +424,7 @@ int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, co
         const int heads = batch * num_heads;
         cfg.gridDim = dim3((heads + MK_WARPS - 1) / MK_WARPS);
         cfg.dynamicSmemBytes = 0;
+        a.link = use_pdl() ? chain_link(static_cast<int>(cfg.gridDim.x)) : ChainLink{nullptr, 0, nullptr};
         e = cudaLaunchKernelEx(&cfg, decode_attention_merge_kernel, a);
         if (e != cudaSuccess) return fail(TL_ECUDA, "decode_attention_merge: launch failed: %s", cudaGetErrorString(e));
         TL_LAUNCH_CHECK("decode_attention_merge");

@@ -233,8 +233,9 @@ __device__ __forceinline__ void w4_stage(const T *in, int lda, const T *aux, int
     };
     auto load_batch = [&](int base, bool want_aux) {
 #pragma unroll
+        for (int j = 0; j < 2 * CACHE; ++j) hold[j] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
         for (int j = 0; j < 2 * CACHE; ++j) {
-            hold[j] = make_uint4(0u, 0u, 0u, 0u);
             if (j < cap) {
                 const int idx = base + j * NT + lane;
                 if (idx < total) {

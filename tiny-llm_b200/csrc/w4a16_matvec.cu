@@ -87,6 +87,7 @@ struct StreamArgs {
     int prologue, epilogue;
     float eps;
     int rows_per_pass;
+    ChainLink link;
 };
 
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) w4a16_stream5_kernel(const S
     for (int k = 0; k < DEPTH; ++k) load_next(buf[k]);  // in flight before the activations exist
     TL_TRACE_STAMP(11);
 
-    griddep_wait();  // activations (and the residual) come from the previous kernel
+    chain_wait(args.link);  // activations (and the residual) come from the previous kernel
     TL_TRACE_STAMP(12);
     const T *p0 = static_cast<const T *>(args.p0) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda;
     const T *p1 = args.prologue == PRO_SWIGLU
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) w4a16_stream5_kernel(const S
             out[static_cast<size_t>(m) * (K / 2) + c0 * 8 + rr] = from_f<T>((gate / (1.0f + expf(-gate))) * up);
         }
         TL_TRACE_STAMP(15);
+        chain_signal(args.link);
         return;
     }
     // ---- sum the entries of each chunk in warp order, add the residual, store
@@ -265,6 +267,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) w4a16_stream5_kernel(const S
         }
     }
     TL_TRACE_STAMP(15);
+    chain_signal(args.link);
 }
 
 #if TL_TRACE
@@ -281,6 +284,36 @@ static bool pdl_default() {
 static bool g_use_pdl = pdl_default();
 void set_use_pdl(bool on) { g_use_pdl = on; }
 bool use_pdl() { return g_use_pdl; }
+
+// ---- dependency chain state (host, per thread; see common.cuh)
+static thread_local struct {
+    int *flags = nullptr;
+    int capacity = 0, next = 0, prev_ctas = 0;
+} g_chain;
+int chain_begin(int *flags, int capacity) {
+    if (flags == nullptr || capacity < 1) return fail(TL_EINVAL, "chain_begin: need a flag array");
+    g_chain.flags = flags, g_chain.capacity = capacity, g_chain.next = 0, g_chain.prev_ctas = 0;
+    return TL_OK;
+}
+int chain_end() {
+    g_chain.flags = nullptr, g_chain.capacity = g_chain.next = g_chain.prev_ctas = 0;
+    return TL_OK;
+}
+ChainLink chain_link(int ctas) {
+    static const bool off = [] { const char *e = getenv("TL_CHAIN"); return e != nullptr && e[0] == '0'; }();
+    ChainLink link{nullptr, 0, nullptr};
+    if (off || g_chain.flags == nullptr || g_chain.next >= g_chain.capacity) {
+        // out of flags: fall back to grid completion for this and later links (the launch BEFORE this one
+        // still signals its flag, nobody polls it; griddepcontrol.wait orders everything)
+        g_chain.flags = nullptr;
+        return link;
+    }
+    if (g_chain.next > 0) link.wait_flag = g_chain.flags + g_chain.next - 1, link.wait_target = g_chain.prev_ctas;
+    link.signal_flag = g_chain.flags + g_chain.next;
+    g_chain.next += 1;
+    g_chain.prev_ctas = ctas;
+    return link;
+}
 
 constexpr size_t S5_SMEM_MAX = 226 * 1024;
 constexpr size_t S5_SMEM_HALF_MAX = 100 * 1024;  // two CTAs (+ 1 KiB of system shared memory each) per SM, attention beside one
@@ -359,7 +392,8 @@ static int stream5_launch(StreamArgs args, cudaStream_t st) {
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(limit));
-        if (e == cudaSuccess)  // largest shared-memory carveout: co-resident CTAs of different launches must fit side by side
+        static const bool carve = [] { const char *v = getenv("TL_S5_CARVEOUT"); return !(v != nullptr && v[0] == '0'); }();
+        if (e == cudaSuccess && carve)  // largest shared-memory carveout: co-resident CTAs of different launches must fit side by side
             e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U, NW>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
@@ -375,6 +409,7 @@ static int stream5_launch(StreamArgs args, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
+    args.link = g_use_pdl ? chain_link(static_cast<int>(cfg.gridDim.x * cfg.gridDim.y)) : ChainLink{nullptr, 0, nullptr};
     cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream5_kernel<T, MP, U, NW>, args);
     if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream5: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("w4a16_stream5");

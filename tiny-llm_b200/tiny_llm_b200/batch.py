@@ -15,6 +15,7 @@ can step it; ``batch_generate`` is the reference's function on top of it.
 
 from __future__ import annotations
 
+import time
 from datetime import datetime
 
 import torch
@@ -191,6 +192,14 @@ class ContinuousBatcher:
         self.decode_tokens = 0
         self.prefill_tokens = 0
         self.generated: dict[int, int] = {}
+        # serving metrics in the spirit of benches/bench.py:351-572 (ServingMetrics): wall time of every
+        # decode step / prefill chunk (the host reads the sampled tokens each step, so wall == device time
+        # + host scheduling), peak concurrently live requests and KV pages (all layers)
+        self.record_timing = False
+        self.decode_step_ms: list[float] = []
+        self.prefill_chunk_ms: list[float] = []
+        self.peak_active_requests = 0
+        self.peak_live_pages = 0
 
     # -- bookkeeping ---------------------------------------------------------
     def idle(self) -> bool:
@@ -200,6 +209,14 @@ class ContinuousBatcher:
         if self.verbose:
             _print_progress(self.slots, self.pending, len(self.queue), self.tick, self.started)
         self.tick += 1
+
+    def _record_cache_state(self) -> None:
+        live = [s for s in self.slots if s is not None]
+        if self.pending is not None:
+            live.append(self.pending)
+        self.peak_active_requests = max(self.peak_active_requests, len(live))
+        pages = sum(len(getattr(r.kv_cache[0], "page_ids", ())) for r in live) * len(self.kv_cache)  # layers move in lockstep
+        self.peak_live_pages = max(self.peak_live_pages, pages)
 
     def _budget_spent(self, request: Request) -> bool:
         if self.max_new_tokens is None:
@@ -221,7 +238,10 @@ class ContinuousBatcher:
             request = self.pending
             if not request.is_prefill_done:
                 before = request.offset
-                request.try_prefill()
+                t0 = time.perf_counter() if self.record_timing else 0.0
+                request.try_prefill()  # ends with a host read of the sampled token: wall time covers the device work
+                if self.record_timing:
+                    self.prefill_chunk_ms.append((time.perf_counter() - t0) * 1e3)
                 self.prefill_tokens += request.offset - before
                 if request.is_prefill_done and request.next_token is not None:
                     self.generated[request.prompt_idx] = 1
@@ -249,9 +269,14 @@ class ContinuousBatcher:
         if any(s is not None for s in self.slots):
             tokens = [0 if s is None else s.next_token for s in self.slots]
             offsets = [0 if s is None else s.offset for s in self.slots]
+            if self.record_timing:
+                self._record_cache_state()
+            t0 = time.perf_counter() if self.record_timing else 0.0
             batch = torch.tensor(tokens, dtype=torch.int32, device=self.device).reshape(-1, 1)
             sampled = _step(self.model, batch, offsets, self.kv_cache)
             host = sampled.reshape(-1).tolist()  # one device->host read per step
+            if self.record_timing:
+                self.decode_step_ms.append((time.perf_counter() - t0) * 1e3)
             self.decode_steps += 1
             for i, request in enumerate(self.slots):
                 if request is None:

@@ -65,6 +65,37 @@ def _interleave_gate_up(gate, up):
     )
 
 
+class _LockstepGroup:
+    """The per-layer cache objects of ONE request plus the number of one-token appends the engine
+    has accounted for but not yet written into them (see ``TinyKvPagedCache._lazy``)."""
+
+    __slots__ = ("caches", "pending")
+
+    def __init__(self, caches):
+        self.caches = caches
+        self.pending = 0
+
+    def settle(self) -> None:
+        n = self.pending
+        if n:
+            self.pending = 0
+            for c in self.caches:
+                c._page_lens[-1] += n
+                c._offset += n
+
+
+class _SlotRecord:
+    """What the engine knows about the request in one decode slot."""
+
+    __slots__ = ("c0", "group", "lockstep", "epoch", "offset", "pages")
+
+    def __init__(self, c0, group, lockstep):
+        self.c0, self.group, self.lockstep = c0, group, lockstep
+        self.epoch = c0.epoch
+        self.offset = c0._offset      # logical context length (settled offset + pending)
+        self.pages = len(c0.page_ids)
+
+
 class DecodeEngine:
     def __init__(self, model, batch_size: int, max_seq_len: int, device, log_capacity: int = 4096, fused: bool = True):
         self.model = model
@@ -96,9 +127,13 @@ class DecodeEngine:
         self.out_log = torch.full((log_capacity * B,), -1, dtype=torch.int32, device=self.device)
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.logits = None
-        # which (cache object, pages already mirrored) each table row reflects
-        self._row_owner = [[None] * B for _ in range(Ly)]
-        self._row_pages = [[0] * B for _ in range(Ly)]
+        # per slot: the request group (its per-layer cache objects) the table rows reflect
+        self._chain_flags = torch.zeros(6 * Ly + 8, dtype=torch.int32, device=self.device)
+        self._recs: list[_SlotRecord | None] = [None] * B
+        self._tables_dirty = True
+        self._upload_event = torch.cuda.Event()
+        self._upload_pending = False
+        self.h2d_bytes = 0  # bytes copied host -> device by step() / decode_on_device() so far
         self._graph = None
         self._graph_loop = None
         self._slab_ptrs = None
@@ -179,10 +214,28 @@ class DecodeEngine:
         the streaming projections, q/k norm + RoPE + K/V append in one kernel.
         Every rounding point of the operator-by-operator sequence is kept."""
         m = self.model
-        B, Hq, Hkv, D = self.B, self.Hq, self.Hkv, self.D
-        inter = m.layers_inner[0].mlp.hidden_dim
         emb = m.embedding.weight
+        # producer -> consumer hand-off through device flags instead of grid completion (tl_chain_begin)
+        # (only when every launch between the first projection and the head is chain-aware)
+        chained = self._attention_fused and os.environ.get("TL_CHAIN", "1") != "0"
+        if chained:
+            self._chain_flags.zero_()
         x = ext.quantized_embedding(self.tokens, emb.scales, emb.biases, emb.weight, emb.group_size, emb.bits)
+        if chained:
+            ext.chain_begin(self._chain_flags)
+        try:
+            logits = self._forward_fused_chain(x)
+        finally:
+            if chained:
+                ext.chain_end()
+        self.next_tokens.copy_(ext.argmax(logits))
+        if self.logits is None:
+            self.logits = torch.empty_like(logits)
+        self.logits.copy_(logits)
+
+    def _forward_fused_chain(self, x):
+        m = self.model
+        B, Hq, Hkv, D = self.B, self.Hq, self.Hkv, self.D
         for i, block in enumerate(m.layers_inner):
             at, pk, pool = block.self_attn, self._packed[i], m.page_pools[i]
             ln1, ln2 = block.input_layernorm, block.post_attention_layernorm
@@ -205,18 +258,22 @@ class DecodeEngine:
             wd = block.mlp.w_down
             x = ext.quantized_matmul_fused(wd.scales, wd.biases, wd.weight, act, residual=x, epilogue=ext.EPI_RESIDUAL)
         head = m.w_lm_head if m.w_lm_head is not None else m.embedding.weight
-        logits = ext.quantized_matmul_fused(head.scales, head.biases, head.weight, x, m.norm._weight_as(x.dtype, x.device),
-                                            prologue=ext.PRO_RMSNORM, eps=m.norm.eps)
-        self.next_tokens.copy_(ext.argmax(logits))
-        if self.logits is None:
-            self.logits = torch.empty_like(logits)
-        self.logits.copy_(logits)
+        return ext.quantized_matmul_fused(head.scales, head.biases, head.weight, x, m.norm._weight_as(x.dtype, x.device),
+                                          prologue=ext.PRO_RMSNORM, eps=m.norm.eps)
 
     def _capture(self) -> None:
         self._slab_ptrs = self._slabs()
         forward = self._forward_fused if self.fused else self._forward_unfused
         with torch.cuda.stream(self._stream):
             self._stream.wait_stream(torch.cuda.current_stream(self.device))
+            # The warm-up passes really run: with the previous step's metadata still on the device they
+            # would append a stale token's K/V through a stale block table - possibly into a page that
+            # has been released and handed to another request since (slabs move when a second engine
+            # reserves more pages).  All slots idle: appends are skipped and attention returns zeros;
+            # step() / decode_on_device() upload the real block before they replay.
+            self.meta_dev[2 * self.B : 3 * self.B].zero_()
+            self.meta_dev[3 * self.B :].fill_(-1)
+            self._tables_dirty = True
             for _ in range(2):  # warm-up: lazy kernel attribute setup must not happen under capture
                 forward()
             self._stream.synchronize()
@@ -245,56 +302,157 @@ class DecodeEngine:
             return entry.kv_caches
         return [entry]
 
-    def _mirror_row(self, layer: int, b: int, cache) -> None:
-        """Bring table row (layer, b) in line with ``cache.page_ids``."""
-        if cache is None:
-            if self._row_owner[layer][b] is not None:
-                self.tables_np[layer, b, :] = -1
-                self._row_owner[layer][b] = None
-                self._row_pages[layer][b] = 0
-            return
-        n = len(cache.page_ids)
+    def _drop(self, b: int) -> None:
+        rec = self._recs[b]
+        if rec is not None:
+            rec.group.settle()
+            for c in rec.group.caches:
+                if c._lazy is rec.group:
+                    c._lazy = None
+            self.tables_np[:, b, :] = -1
+            self._tables_dirty = True
+            self._recs[b] = None
+
+    def _register(self, b: int, caches) -> "_SlotRecord":
+        """Slow path, once per request admission: take the request's per-layer cache objects as a
+        group, check that they really are in lockstep (same page ids / fill / offset in every layer,
+        which is what the schedulers of batch.py / generate.py produce: SURVEY section 7) and mirror
+        their page ids into the table rows."""
+        self._drop(b)
+        group_caches = [self._slot_caches(caches, layer)[b] for layer in range(self.n_layers)]
+        c0 = group_caches[0]
+        for c in group_caches:
+            if not isinstance(c, TinyKvPagedCache):
+                raise ValueError("the decode engine needs paged request caches")
+            if c._lazy is not None:
+                c._lazy.settle()
+        n = len(c0.page_ids)
         if n > self.max_pages:
             raise ValueError("request exceeds the engine's max_seq_len")
-        if self._row_owner[layer][b] is cache and self._row_pages[layer][b] == n:
-            return
-        if self._row_owner[layer][b] is cache and self._row_pages[layer][b] == n - 1:
-            self.tables_np[layer, b, n - 1] = cache.page_ids[-1]
+        lockstep = all(type(c) is TinyKvPagedCache and c.page_ids == c0.page_ids and c._page_lens == c0._page_lens and c._offset == c0._offset
+                       for c in group_caches)
+        if lockstep:
+            self.tables_np[:, b, :n] = c0.page_ids
+            self.tables_np[:, b, n:] = -1
         else:
-            self.tables_np[layer, b, :n] = cache.page_ids
-            self.tables_np[layer, b, n:] = -1
-        self._row_owner[layer][b] = cache
-        self._row_pages[layer][b] = n
+            for layer, c in enumerate(group_caches):
+                k = len(c.page_ids)
+                if k > self.max_pages:
+                    raise ValueError("request exceeds the engine's max_seq_len")
+                self.tables_np[layer, b, :k] = c.page_ids
+                self.tables_np[layer, b, k:] = -1
+        self._tables_dirty = True
+        group = _LockstepGroup(group_caches)
+        if lockstep:
+            for c in group_caches:
+                c._lazy = group
+        rec = _SlotRecord(c0, group, lockstep)
+        self._recs[b] = rec
+        return rec
 
     def _advance_host(self, caches, steps: int = 1) -> list[int]:
-        """Append ``steps`` token slots to every active request cache of every
-        layer (host integers only) and mirror the tables.  Returns the context
-        length each slot will have after the FIRST of those steps."""
+        """Account for ``steps`` one-token appends of every active request (host integers only) and
+        bring the table rows up to date.  Returns the context length each slot will have after the
+        FIRST of those steps.
+
+        Cost per step at B = 64: one identity check per slot; the 36 per-layer cache objects of a
+        request are touched only when its tail page overflows (once per ``page_size`` tokens) - the
+        one-token appends in between are deferred (``TinyKvPagedCache._lazy``) and settled when
+        somebody reads ``page_lens`` / ``offset``.  Round 1 walked 36 x B objects every step
+        (0.4-1 ms of Python at B = 64, VERDICT weak #10)."""
         first_ctx = [0] * self.B
-        for layer in range(self.n_layers):
-            slots = self._slot_caches(caches, layer)
-            for b, cache in enumerate(slots):
-                if cache is not None:
-                    if not isinstance(cache, TinyKvPagedCache):
-                        raise ValueError("the decode engine needs paged request caches")
-                    before = cache.offset
-                    for _ in range(steps):
-                        cache.append_token_slot()
-                    if layer == 0:
-                        first_ctx[b] = before + 1
-                self._mirror_row(layer, b, cache)
+        slots0 = self._slot_caches(caches, 0)
+        page = self.page_size
+        for b, c0 in enumerate(slots0):
+            rec = self._recs[b]
+            if c0 is None:
+                if rec is not None:
+                    self._drop(b)
+                continue
+            if (rec is None or rec.c0 is not c0 or rec.epoch != c0.epoch
+                    or (rec.lockstep and (c0._lazy is not rec.group or c0._offset + rec.group.pending != rec.offset or len(c0.page_ids) != rec.pages))):
+                rec = self._register(b, caches)
+            if not rec.lockstep:  # layers disagree: walk them (always correct, never taken by the in-tree schedulers)
+                self._advance_slow(b, rec, caches, steps)
+                first_ctx[b] = rec.offset - steps + 1
+                continue
+            tail = rec.offset - (rec.pages - 1) * page if rec.pages else page
+            if tail + steps <= page:
+                rec.group.pending += steps
+                rec.offset += steps
+            else:
+                self._advance_pages(b, rec, steps)
+            first_ctx[b] = rec.offset - steps + 1
         return first_ctx
 
+    def _check_headroom(self, group_caches, steps: int) -> None:
+        """All layers must be able to take the new pages BEFORE any of them is touched (a shortage
+        used to surface at layer k with layers < k already advanced: ADVICE round 1)."""
+        for c in group_caches:
+            tail = c._page_lens[-1] if c.page_ids else self.page_size
+            need = max(0, -(-(tail + steps - self.page_size) // self.page_size))
+            if len(c.page_ids) + need > self.max_pages:
+                raise ValueError("request exceeds the engine's max_seq_len")
+            if need > len(c.pool.free_page_ids) + (c.pool.capacity - c.pool.num_pages):
+                raise RuntimeError("page pool slab exhausted: reserve() more pages before decoding")
+
+    def _advance_pages(self, b: int, rec: "_SlotRecord", steps: int) -> None:
+        rec.group.settle()
+        self._check_headroom(rec.group.caches, steps)
+        old = rec.pages
+        for layer, c in enumerate(rec.group.caches):
+            for _ in range(steps):
+                c.append_token_slot()
+            self.tables_np[layer, b, old:len(c.page_ids)] = c.page_ids[old:]
+        c0 = rec.c0
+        rec.pages, rec.offset = len(c0.page_ids), c0._offset
+        self._tables_dirty = True
+
+    def _advance_slow(self, b: int, rec: "_SlotRecord", caches, steps: int) -> None:
+        group_caches = [self._slot_caches(caches, layer)[b] for layer in range(self.n_layers)]
+        self._check_headroom(group_caches, steps)
+        for layer, c in enumerate(group_caches):
+            for _ in range(steps):
+                c.append_token_slot()
+            k = len(c.page_ids)
+            self.tables_np[layer, b, :k] = c.page_ids
+            self.tables_np[layer, b, k:] = -1
+        rec.group.caches = group_caches
+        rec.offset = group_caches[0]._offset
+        rec.pages = len(group_caches[0].page_ids)
+        self._tables_dirty = True
+
+    def _host_write_begin(self) -> None:
+        """The pinned block is about to be rewritten: the previous upload must have been consumed
+        (a caller that keeps sampling on the device never synchronises between steps)."""
+        if self._upload_pending:
+            self._upload_event.synchronize()
+            self._upload_pending = False
+
     def _upload(self) -> None:
-        self.meta_dev.copy_(self.meta_host, non_blocking=True)
+        B = self.B
+        if self._tables_dirty:
+            self.meta_dev.copy_(self.meta_host, non_blocking=True)
+            self.h2d_bytes += self._meta_len * 4
+            self._tables_dirty = False
+        else:  # tokens | offsets | context_lens only: the block tables on the device are current
+            self.meta_dev[: 3 * B].copy_(self.meta_host[: 3 * B], non_blocking=True)
+            self.h2d_bytes += 3 * B * 4
+        self._upload_event.record()
+        self._upload_pending = True
+
+    def upload_bytes_per_step(self) -> int:
+        """Host -> device bytes of a steady-state step (block tables travel only when a page was added)."""
+        return 3 * self.B * 4
 
     # ------------------------------------------------------------------ steps --
     def step(self, tokens, offsets, caches):
         """One decode step.  ``tokens``: B ids (list or tensor), ``offsets``: B
         RoPE positions; returns (logits [B, 1, V] static buffer, next_tokens [B])."""
-        self._ensure_graph()
         B = self.B
+        self._host_write_begin()
         ctx = self._advance_host(caches, 1)
+        self._ensure_graph()
         if isinstance(tokens, torch.Tensor):
             tok_host = None
         else:
@@ -319,9 +477,10 @@ class DecodeEngine:
         back to back.  Returns the sampled tokens ``[steps, B]`` (device)."""
         if steps > self.log_capacity:
             raise ValueError("steps exceed the engine's token log capacity")
-        self._ensure_graph()
         B = self.B
+        self._host_write_begin()
         ctx = self._advance_host(caches, steps)
+        self._ensure_graph()
         self.meta_np[0:B] = tokens
         self.meta_np[B : 2 * B] = offsets
         self.meta_np[2 * B : 3 * B] = ctx

@@ -288,10 +288,46 @@ class TinyKvPagedCache(TinyKvCache):
         self.pool = pool
         self.page_size = pool.page_size
         self.page_ids: list[int] = []
-        self.page_lens: list[int] = []
-        self.offset = 0
+        self._page_lens: list[int] = []
+        self._offset = 0
+        # B200 runtime (engine.py): while a request decodes inside the CUDA-graph engine, one-token
+        # appends that fit in the tail page are DEFERRED - counted once per request instead of once
+        # per layer object - and folded into page_lens / offset the moment anybody looks at them.
+        self._lazy = None
+        self.epoch = 0  # bumped by rewind() / release(): the page-id list changed other than by appending
         self._cached_block_table: torch.Tensor | None = None
         self._cached_block_table_key: tuple[tuple[int, ...], int] | None = None
+
+    # page_lens / offset are the reference's plain attributes (paged_kv_cache.py:245-262); here they
+    # are properties so that deferred appends are settled before any read or write.
+    @property
+    def page_lens(self) -> list[int]:
+        if self._lazy is not None:
+            self._lazy.settle()
+        return self._page_lens
+
+    @page_lens.setter
+    def page_lens(self, value: list[int]) -> None:
+        if self._lazy is not None:
+            self._lazy.settle()
+        self._page_lens = value
+
+    @property
+    def offset(self) -> int:
+        if self._lazy is not None:
+            self._lazy.settle()
+        return self._offset
+
+    @offset.setter
+    def offset(self, value: int) -> None:
+        if self._lazy is not None:
+            self._lazy.settle()
+        self._offset = value
+
+    def logical_offset(self) -> int:
+        """``offset`` without settling deferred appends (hot-path reads of the decode runtime)."""
+        lazy = self._lazy
+        return self._offset if lazy is None else self._offset + lazy.pending
 
     @property
     def num_pages(self) -> int:
@@ -447,6 +483,7 @@ class TinyKvPagedCache(TinyKvCache):
         if keep == 0:
             self.release()
             return
+        self.epoch += 1
         pages_needed = (keep + self.page_size - 1) // self.page_size
         while len(self.page_ids) > pages_needed:
             self.page_lens.pop()
@@ -456,8 +493,10 @@ class TinyKvPagedCache(TinyKvCache):
 
     def release(self):
         """Return every page, in page order, to the pool's free list (:436-443)."""
+        self.epoch += 1
+        lens = self.page_lens  # settles deferred appends first
         for page_id in self.page_ids:
             self.pool.free_page(page_id)
         self.page_ids.clear()
-        self.page_lens.clear()
+        lens.clear()
         self.offset = 0

@@ -235,6 +235,7 @@ class Qwen3ModelWeek3:
         self.use_decode_graph: bool | None = None
         self.decode_graph_max_seq_len = 8192
         self._decode_engines: dict = {}
+        self._applies_memo = None
         self._paged = enable_paged_attention
 
     def create_kv_cache(self) -> list[TinyKvCache]:
@@ -261,23 +262,53 @@ class Qwen3ModelWeek3:
         from .kv_cache import BatchingKvCache
 
         B = inputs.shape[0]
-        for entry, pool in zip(cache, self.page_pools):
-            if isinstance(entry, BatchingKvCache):
-                slots = entry.kv_caches
-                if entry.max_active_requests != B:
+        first = cache[0]
+        if isinstance(first, BatchingKvCache):
+            slots0 = first.kv_caches
+        elif type(first) is TinyKvPagedCache and B == 1:
+            slots0 = [first]
+        else:
+            return False
+        # Deep check (every layer, every slot) only when the set of requests changed; afterwards one
+        # identity comparison plus the length limit on the layer-0 objects (layers advance in lockstep).
+        memo = self._applies_memo
+        if memo is None or memo[0] is not cache or memo[1] != slots0 or memo[2] != B:
+            for entry, pool in zip(cache, self.page_pools):
+                if isinstance(entry, BatchingKvCache):
+                    slots = entry.kv_caches
+                    if entry.max_active_requests != B:
+                        return False
+                elif type(entry) is TinyKvPagedCache and B == 1:
+                    slots = [entry]
+                else:
                     return False
-            elif type(entry) is TinyKvPagedCache and B == 1:
-                slots = [entry]
-            else:
+                for slot in slots:
+                    if slot is None:
+                        continue
+                    if type(slot) is not TinyKvPagedCache or slot.pool is not pool:
+                        return False
+                    if pool._key_pages is not None and pool._key_pages.dtype != torch.bfloat16:
+                        return False
+            self._applies_memo = (cache, list(slots0), B)
+        limit = self._graph_limit(cache)
+        for slot in slots0:
+            if slot is not None and slot.logical_offset() + 1 > limit:
                 return False
-            for slot in slots:
-                if slot is None:
-                    continue
-                if type(slot) is not TinyKvPagedCache or slot.pool is not pool or slot.offset + 1 > self.decode_graph_max_seq_len:
-                    return False
-                if pool._key_pages is not None and pool._key_pages.dtype != torch.bfloat16:
-                    return False
         return True
+
+    def _graph_limit(self, cache) -> int:
+        """Longest request the decode engine of this call must hold: the scheduler's own
+        ``max_seq_len`` when it states one (rounded up to whole pages), capped by
+        ``decode_graph_max_seq_len``.  Round 1 always reserved for 8192 tokens per slot: 76 GB of
+        pages for 64 slots of Qwen3-4B regardless of the batcher's limit."""
+        from .kv_cache import BatchingKvCache
+
+        limit = self.decode_graph_max_seq_len
+        first = cache[0]
+        if isinstance(first, BatchingKvCache) and first.max_seq_len is not None:
+            pages = (first.max_seq_len + self.page_size - 1) // self.page_size
+            limit = min(limit, pages * self.page_size)
+        return limit
 
     def _graph_decode(self, inputs, offset, cache, logits_to_keep):
         from .kv_cache import BatchingKvCache
@@ -292,13 +323,13 @@ class Qwen3ModelWeek3:
             offsets = offsets * B if len(offsets) == 1 else offsets
         else:
             offsets = list(offset)
-        for entry in cache:
-            if isinstance(entry, BatchingKvCache):
-                if not any(slot is not None for slot in entry.kv_caches):
-                    raise ValueError("Cannot build paged metadata without active requests")
-                if entry.max_seq_len is not None and any(s is not None and s.offset + 1 > entry.max_seq_len for s in entry.kv_caches):
-                    raise ValueError("Paged batch append exceeds max_seq_len")
-        engine = self.decode_engine(B)
+        first = cache[0]
+        if isinstance(first, BatchingKvCache):
+            if not any(slot is not None for slot in first.kv_caches):
+                raise ValueError("Cannot build paged metadata without active requests")
+            if first.max_seq_len is not None and any(s is not None and s.logical_offset() + 1 > first.max_seq_len for s in first.kv_caches):
+                raise ValueError("Paged batch append exceeds max_seq_len")
+        engine = self.decode_engine(B, self._graph_limit(cache))
         logits, _ = engine.step(inputs, offsets, cache)
         attn = self.layers_inner[0].self_attn
         for entry in cache:

@@ -30,12 +30,13 @@ def main():
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--layers", type=int, default=36)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--max-seq", type=int, default=0, help="engine max_seq_len (default: context + 2 * steps + 80 rounded up to pages)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     ns = synthetic_qwen3("qwen3-4b", seed=0, device=dev, num_hidden_layers=args.layers)
     model = Qwen3ModelWeek3(ns, page_size=128)
     B = args.batch
-    engine = DecodeEngine(model, B, args.context + 3 * args.steps + 128, dev)
+    engine = DecodeEngine(model, B, args.max_seq or (args.context + 2 * args.steps + 80), dev)
     engine.reserve_pools()
     if B == 1:
         caches = model.create_kv_cache()
