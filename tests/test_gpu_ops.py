@@ -322,7 +322,12 @@ PAGED_CASES = [
     (BF16, 128, 128, 32, 8, 1, [1000, 0, 17, 4097]), (BF16, 128, 128, 32, 8, 4, [900, 4]), (BF16, 128, 128, 32, 8, 8, [300]),
     (BF16, 128, 128, 16, 8, 1, [2500]), (BF16, 128, 16, 8, 8, 2, [77, 130]), (BF16, 128, 128, 32, 8, 128, [128]),
     (BF16, 128, 128, 32, 8, 40, [300]), (BF16, 128, 16, 8, 2, 70, [70, 200]), (BF16, 128, 128, 32, 8, 257, [600]),
-    (BF16, 128, 64, 8, 8, 64, [64, 0, 500]), (BF16, 128, 32, 4, 1, 100, [40, 100]), (BF16, 64, 16, 4, 2, 1, [50]), (BF16, 64, 16, 4, 2, 5, [50]), (F32, 128, 8, 2, 1, 12, [40]),
+    (BF16, 128, 64, 8, 8, 64, [64, 0, 500]), (BF16, 128, 32, 4, 1, 100, [40, 100]),
+    # tcgen05 flash prefill (page % 64 == 0, Hq/Hkv divides 128): head ratios 1/2/4/8, chunk continuation (ctx > L),
+    # L not a multiple of the 128/G-row query block, several requests, a 64-slot page
+    (BF16, 128, 128, 16, 8, 200, [200]), (BF16, 128, 128, 16, 2, 130, [130, 400]), (BF16, 128, 64, 6, 6, 90, [90, 1000]),
+    (BF16, 128, 128, 32, 8, 128, [4224]), (BF16, 128, 128, 32, 8, 33, [1025, 33]), (BF16, 128, 256, 8, 2, 300, [777]),
+    (BF16, 128, 128, 32, 8, 1000, [1000]), (BF16, 64, 16, 4, 2, 1, [50]), (BF16, 64, 16, 4, 2, 5, [50]), (F32, 128, 8, 2, 1, 12, [40]),
 ]
 
 
@@ -330,8 +335,8 @@ PAGED_CASES = [
 @pytest.mark.parametrize("causal", [True, False], ids=["causal", "full"])
 def test_paged_attention_matches_oracle(dev, case, causal):
     dtype, D, page, Hq, Hkv, L, lens = case
-    if not causal and L > 8:
-        pytest.skip("non-causal prefill is never issued by the models")
+    if not causal and L > 8 and not (dtype == BF16 and D == 128 and page % 64 == 0):
+        pytest.skip("non-causal prefill is never issued by the models (only the tcgen05 kernel takes it)")
     g = gen(D * 1000 + page + L + sum(lens))
     kp, vp, bt, cl = build_paged(g, lens, page, Hkv, D, dtype)
     B = len(lens)
@@ -368,6 +373,51 @@ def test_full_size_prefill_attention_properties(dev):
     dense = vp2[bt[0].long()].permute(1, 0, 2, 3).reshape(Hkv, S, D).float()
     running = dense.cumsum(dim=1) / torch.arange(1, S + 1, device=dev, dtype=torch.float32)[None, :, None]
     assert_close(out2, running.repeat_interleave(Hq // Hkv, dim=0), rtol=2e-2, atol=4e-3, msg="causal running mean of V")
+
+
+def test_full_size_prefill_attention_matches_oracle_on_sampled_rows(dev):
+    """Config-3 size through the tcgen05 flash kernel, compared with the ORACLE: query row l of a causal
+    chunk is exactly a decode query over the first ctx - L + l + 1 keys (bottom-right alignment,
+    paged_attention.metal:158-160 / :411), so sampled rows are checked with the oracle's L == 1 path.
+    Two shapes: the whole 4096-token prompt in one chunk, and a 512-token chunk that continues a
+    3584-token context."""
+    g = gen(47)
+    page, Hq, Hkv, D = 128, 32, 8, 128
+    for L, ctx in ((4096, 4096), (512, 4096)):
+        pages = ctx // page
+        bt = torch.randperm(pages, generator=g).reshape(1, pages).to(torch.int32)
+        cl = torch.tensor([ctx], dtype=torch.int32)
+        q = torch.randn(Hq, L, D, generator=g).to(BF16)
+        kp = torch.randn(pages, Hkv, page, D, generator=g).to(BF16)
+        vp = torch.randn(pages, Hkv, page, D, generator=g).to(BF16)
+        out = ext.paged_attention(q.to(dev), kp.to(dev), vp.to(dev), bt.to(dev), cl.to(dev), D**-0.5, is_causal=True,
+                                  num_kv_heads=Hkv, num_heads=Hq).cpu()
+        for l in (0, 1, 31, 32, 63, 64, 127, 128, L // 2 - 1, L // 2, L - 65, L - 2, L - 1):
+            seen = torch.tensor([ctx - L + l + 1], dtype=torch.int32)
+            want = oracle.paged_attention(q[:, l : l + 1].contiguous(), kp, vp, bt, seen, D**-0.5, True, Hkv, Hq)
+            assert_close(out[:, l : l + 1], want, rtol=2e-2, atol=5e-3, msg=f"L={L} ctx={ctx} row {l}")
+
+
+def test_prefill_attention_ignores_pages_outside_the_block_table(dev):
+    """Invalid page ids (-1 padding inside the visible range cannot occur after validation, attention.py:131-146,
+    but the C ABI must not read through them): an id beyond the physical pages masks that page's keys."""
+    g = gen(48)
+    page, Hq, Hkv, D, L = 64, 8, 2, 128, 128
+    kp = torch.randn(4, Hkv, page, D, generator=g).to(BF16)
+    vp = torch.randn(4, Hkv, page, D, generator=g).to(BF16)
+    q = torch.randn(Hq, L, D, generator=g).to(BF16)
+    cl = torch.tensor([128], dtype=torch.int32)
+    good = torch.tensor([[2, 1]], dtype=torch.int32)
+    want = oracle.paged_attention(q, kp, vp, good, cl, D**-0.5, True, Hkv, Hq)
+    got = ext.paged_attention(q.to(dev), kp.to(dev), vp.to(dev), good.to(dev), cl.to(dev), D**-0.5, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
+    assert_close(got, want, rtol=2e-2, atol=5e-3)
+    # second page id out of range: queries 64.. see only their first 64 keys; launcher-level call (the Python layer rejects this table)
+    bad = torch.tensor([[2, 99]], dtype=torch.int32)
+    got_bad = ext.paged_attention(q.to(dev), kp.to(dev), vp.to(dev), bad.to(dev), cl.to(dev), D**-0.5, is_causal=True, num_kv_heads=Hkv, num_heads=Hq).cpu()
+    first = oracle.paged_attention(q[:, :64].contiguous(), kp, vp, good[:, :1], torch.tensor([64], dtype=torch.int32), D**-0.5, True, Hkv, Hq)
+    assert_close(got_bad[:, :64], first, rtol=2e-2, atol=5e-3)
+    full_first_page = oracle.paged_attention(q[:, 64:].contiguous(), kp, vp, good[:, :1], torch.tensor([64], dtype=torch.int32), D**-0.5, False, Hkv, Hq)
+    assert_close(got_bad[:, 64:], full_first_page, rtol=2e-2, atol=5e-3)
 
 
 def test_full_size_decode_attention_properties(dev):

@@ -536,14 +536,18 @@ int launch_paged_decode(const void *q, const void *kp, const void *vp, const int
                                 num_kv_heads, num_heads, dtype, st);
 }
 
-// Prefill path (L > 8): bf16 / D = 128 runs the tensor-core flash kernel (attention_prefill.cu);
-// TL_PREFILL_FA=0 selects the older CUDA-core GQA-grouped kernel as a control; everything else is
-// row-wise.
+// Prefill path (L > 8): bf16 / D = 128 runs the tcgen05 + TMA flash kernel (attention_prefill_tc.cu)
+// when the page size is a multiple of 64 and Hq/Hkv divides 128 (TL_PREFILL_TC=0 turns it off), else
+// the mma.sync flash kernel (attention_prefill.cu); TL_PREFILL_FA=0 selects the older CUDA-core
+// GQA-grouped kernel as a control; everything else is row-wise.
 int launch_paged_prefill(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out,
                          int rows, int L, int D, int num_pages, int page_size, int max_pages, float scale,
                          int is_causal, int num_kv_heads, int num_heads, int dtype, cudaStream_t st) {
     const bool fast = dtype == TL_BF16 && D == GQA_D && aligned16(q) && aligned16(kp) && aligned16(vp);
     static const bool fa_off = [] { const char *e = getenv("TL_PREFILL_FA"); return e != nullptr && e[0] == '0'; }();
+    if (fast && !fa_off && aligned16(out) && rows % num_heads == 0 && paged_prefill_tc_supported(L, num_pages, page_size, num_kv_heads, num_heads))
+        return launch_paged_prefill_tc(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal, num_kv_heads,
+                                       num_heads, st);
     if (fast && !fa_off && rows <= 65535)  // tensor-core flash kernel (attention_prefill.cu); TL_PREFILL_FA=0: CUDA-core control
         return launch_paged_prefill_fa(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal, num_kv_heads,
                                        num_heads, st);

@@ -1,0 +1,398 @@
+// Paged causal FlashAttention prefill on the 5th-generation tensor cores (tcgen05 + TMEM + TMA),
+// bf16, head_dim 128, L > 8.
+//
+// Replaces paged_attention_mma_bf16_d128 (/root/reference/src/extensions_ref/src/
+// paged_attention.metal:250-506): same arithmetic - fp32 scores in base 2 (:414 scale_log2),
+// bottom-right causal limit key <= row + (context - L) (:411), fp32 running max / sum, the
+// probabilities rounded to bf16 before P V (:439-444), output = O / sum (0 when nothing is visible).
+//
+// One CTA = one (request, KV head, block of RH query positions): its 128 MMA rows are the G = Hq/Hkv
+// query heads of the KV head x RH = 128/G consecutive query positions, so every K/V tile the CTA
+// fetches is shared by all the query heads that need it, and the causal frontier is almost the same
+// for every row (RH <= 128 positions apart).  Per 64-key tile:
+//
+//   warp 4 (one lane)  TMA producer: Q once (3-D map [D, L, B*Hq], box 64 x RH x G, 128-byte
+//                      swizzle = the K-major UMMA layout), then K and V tiles - a (page, kv head)
+//                      slab is one contiguous [page x 128] bf16 block, fetched as 4-D boxes
+//                      [64 d x 64 keys] keyed by block_table (invalid page ids land outside the
+//                      tensor and are zero-filled by the TMA unit) - through a 2-stage ring;
+//   warp 5 (one lane)  MMA issuer: S = Q K^T  (tcgen05.mma kind::f16, M128 N64 K16 x 8, K tile =
+//                      K-major B operand), then O += P V (M128 N128 K16 x 4, V tile = MN-major B
+//                      operand straight from the page layout), accumulators S and O in TMEM;
+//   warps 0-3          softmax: thread = MMA row = TMEM lane.  tcgen05.ld the 64 scores of its row,
+//                      scale, mask, running max (no shuffles: a thread owns the row), exp2, row sum,
+//                      bf16 probabilities -> shared memory in the swizzled K-major layout (A operand
+//                      of P V).  O is rescaled IN TMEM (tcgen05.ld / st) only when a row's maximum
+//                      grows by more than 2^8 since the last rescale: P and the row sum always use
+//                      the same (possibly stale) maximum, so the result is exact.
+//                      Epilogue: O / sum -> bf16 -> global.
+//
+// 256 TMEM columns and 112 KB of shared memory per CTA: two CTAs per SM, so one CTA's softmax
+// overlaps the other's MMAs without an intra-CTA ping-pong.
+#include <stdlib.h>
+#include <math_constants.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc05.cuh"
+
+namespace tl {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int TC_D = 128;         // head dim
+constexpr int TC_BM = 128;        // MMA rows per CTA (G heads x RH query positions)
+constexpr int TC_BN = 64;         // keys per tile
+constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 6 * 32;
+constexpr int TC_SOFTMAX_THREADS = 128;
+constexpr int TC_Q_BYTES = TC_BM * TC_D * 2;        // 32 KiB: two 64-column halves of [128 rows x 128 B]
+constexpr int TC_KV_TILE = TC_BN * TC_D * 2;        // 16 KiB: two 64-column halves of [64 rows x 128 B]
+constexpr int TC_P_BYTES = TC_BM * TC_BN * 2;       // 16 KiB: [128 rows x 128 B]
+constexpr int TC_Q_OFF = 0;
+constexpr int TC_P_OFF = TC_Q_OFF + TC_Q_BYTES;
+constexpr int TC_K_OFF = TC_P_OFF + TC_P_BYTES;
+constexpr int TC_V_OFF = TC_K_OFF + TC_STAGES * TC_KV_TILE;
+constexpr int TC_BAR_OFF = TC_V_OFF + TC_STAGES * TC_KV_TILE;
+constexpr int TC_SMEM_BYTES = TC_BAR_OFF + 256;
+constexpr int TC_TMEM_COLS = 256;  // S: columns [0, 64), O: columns [128, 256)
+constexpr int TC_TMEM_O = 128;
+constexpr float TC_LOG2E = 1.44269504089f;
+constexpr float TC_RESCALE_THRESHOLD = 8.0f;  // log2: rescale O when a row maximum grew by more than 2^8
+
+// kind::f16 instruction descriptor: bf16 x bf16 -> f32, A K-major; b_mn: B operand MN-major.
+__host__ __device__ constexpr uint32_t tc_instr_desc(int n, bool b_mn) {
+    return (1u << 4)                                // c_format = f32
+           | (1u << 7)                              // a_format = bf16
+           | (1u << 10)                             // b_format = bf16
+           | (0u << 15)                             // a_major = K
+           | ((b_mn ? 1u : 0u) << 16)               // b_major
+           | (static_cast<uint32_t>(n >> 3) << 17)  // n_dim
+           | (static_cast<uint32_t>(TC_BM >> 4) << 24);
+}
+
+struct TcArgs {
+    const int32_t *block_table, *context_lens;
+    bf16 *out;
+    int L, Hq, Hkv, G, RH;       // RH = query positions per CTA = 128 / G
+    int page_size, max_pages, num_pages;
+    int tiles_per_page;          // page_size / 64
+    float scale_log2;
+    int is_causal;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const TcArgs a) {
+    extern __shared__ __align__(1024) unsigned char tsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);  // long (late) query blocks first
+    const int kvh = blockIdx.y, b = blockIdx.z;
+    const int q0 = qb * a.RH;
+    const int ctx = min(a.context_lens[b], a.max_pages * a.page_size);
+    // keys any row of this CTA may see: [0, key_end)
+    const int last_row = min(q0 + a.RH, a.L) - 1;
+    const int key_end = ctx <= 0 ? 0 : (a.is_causal ? min(ctx, max(ctx - a.L + last_row + 1, 0)) : ctx);
+    const int n_tiles = (key_end + TC_BN - 1) / TC_BN;
+
+    const uint32_t q_base = g_smem_u32(tsm + TC_Q_OFF), p_base = g_smem_u32(tsm + TC_P_OFF);
+    const uint32_t k_base = g_smem_u32(tsm + TC_K_OFF), v_base = g_smem_u32(tsm + TC_V_OFF);
+    const uint32_t bar = g_smem_u32(tsm + TC_BAR_OFF);
+    const uint32_t q_full = bar, s_full = bar + 8, p_full = bar + 16, o_full = bar + 24;
+    const uint32_t k_full = bar + 32, k_empty = bar + 32 + 8 * TC_STAGES, v_full = bar + 32 + 16 * TC_STAGES, v_empty = bar + 32 + 24 * TC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tsm + TC_BAR_OFF + 32 + 32 * TC_STAGES);
+
+    if (warp == 4 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
+    }
+    if (warp == 5 && lane == 0) {
+        g_mbar_init(q_full, 1);
+        g_mbar_init(s_full, 1);
+        g_mbar_init(p_full, TC_SOFTMAX_THREADS);
+        g_mbar_init(o_full, 1);
+        for (int i = 0; i < TC_STAGES; ++i) {
+            g_mbar_init(k_full + 8 * i, 1);
+            g_mbar_init(k_empty + 8 * i, 1);
+            g_mbar_init(v_full + 8 * i, 1);
+            g_mbar_init(v_empty + 8 * i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    g_tc_fence_before();
+    __syncthreads();
+    g_tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0 && n_tiles > 0) {
+            g_mbar_expect_tx(q_full, TC_Q_BYTES);
+            const int head0 = b * a.Hq + kvh * a.G;
+            g_tma_load_3d(q_base, &tmap_q, 0, q0, head0, q_full);
+            g_tma_load_3d(q_base + TC_Q_BYTES / 2, &tmap_q, 64, q0, head0, q_full);
+            const int32_t *table = a.block_table + static_cast<size_t>(b) * a.max_pages;
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % TC_STAGES;
+                const uint32_t ph = (j / TC_STAGES) & 1;
+                const int lp = j / a.tiles_per_page;
+                int pid = table[lp];
+                if (pid < 0 || pid >= a.num_pages) pid = a.num_pages;  // outside the tensor: the TMA unit writes zeros
+                const int slot0 = (j - lp * a.tiles_per_page) * TC_BN;
+                g_mbar_wait(k_empty + 8 * s, ph ^ 1);
+                g_mbar_expect_tx(k_full + 8 * s, TC_KV_TILE);
+                g_tma_load_4d(k_base + s * TC_KV_TILE, &tmap_k, 0, slot0, kvh, pid, k_full + 8 * s);
+                g_tma_load_4d(k_base + s * TC_KV_TILE + TC_KV_TILE / 2, &tmap_k, 64, slot0, kvh, pid, k_full + 8 * s);
+                g_mbar_wait(v_empty + 8 * s, ph ^ 1);
+                g_mbar_expect_tx(v_full + 8 * s, TC_KV_TILE);
+                g_tma_load_4d(v_base + s * TC_KV_TILE, &tmap_v, 0, slot0, kvh, pid, v_full + 8 * s);
+                g_tma_load_4d(v_base + s * TC_KV_TILE + TC_KV_TILE / 2, &tmap_v, 64, slot0, kvh, pid, v_full + 8 * s);
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0 && n_tiles > 0) {
+            constexpr uint32_t idesc_s = tc_instr_desc(TC_BN, false);
+            constexpr uint32_t idesc_o = tc_instr_desc(TC_D, true);
+            g_mbar_wait(q_full, 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % TC_STAGES;
+                const uint32_t ph = (j / TC_STAGES) & 1;
+                // ---- S = Q K^T: both operands K-major, two 64-wide halves of the head dimension
+                g_mbar_wait(k_full + 8 * s, ph);
+                g_tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < TC_D / 16; ++k) {
+                    const uint32_t half = (k >> 2), kk = (k & 3);
+                    const uint64_t adesc = g_smem_desc_sw128(q_base + half * (TC_Q_BYTES / 2), 0, 1024) + 2 * kk;
+                    const uint64_t bdesc = g_smem_desc_sw128(k_base + s * TC_KV_TILE + half * (TC_KV_TILE / 2), 0, 1024) + 2 * kk;
+                    g_tc_mma(tmem, adesc, bdesc, idesc_s, k > 0 ? 1u : 0u);
+                }
+                g_tc_commit(k_empty + 8 * s);  // K stage reusable once these MMAs have read it
+                g_tc_commit(s_full);           // ... and the scores are complete (also: every earlier MMA, i.e. P V of tile j-1)
+                // ---- O += P V: P K-major [128 x 64 keys], V MN-major [64 keys x 128 d] as loaded from the page
+                g_mbar_wait(p_full, j & 1);
+                g_mbar_wait(v_full + 8 * s, ph);
+                g_tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < TC_BN / 16; ++k) {
+                    const uint64_t adesc = g_smem_desc_sw128(p_base, 0, 1024) + 2 * k;
+                    // 16 keys = 2 groups of 8 rows (SBO 1024 B); the two 64-wide d blocks are TC_KV_TILE/2 apart (LBO)
+                    const uint64_t bdesc = g_smem_desc_sw128(v_base + s * TC_KV_TILE + k * 2048, TC_KV_TILE / 2, 1024);
+                    g_tc_mma(tmem + TC_TMEM_O, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                }
+                g_tc_commit(v_empty + 8 * s);
+            }
+            g_tc_commit(o_full);
+        }
+    } else {
+        // ------------------------------------------------------------ softmax warps (thread = row = TMEM lane)
+        const int r = threadIdx.x;                 // 0..127
+        const int g = r / a.RH, lq = r - g * a.RH;  // query head of the KV group, position inside the block
+        const int l = q0 + lq;
+        const bool row_valid = l < a.L && ctx > 0;
+        // last key this row may see (bottom-right causal alignment, paged_attention.metal:411)
+        const int limit = !row_valid ? -1 : (a.is_causal ? min(ctx - 1, l + (ctx - a.L)) : ctx - 1);
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        float m_used = -CUDART_INF_F, l_sum = 0.f;
+        const int32_t *table = a.block_table + static_cast<size_t>(b) * a.max_pages;
+        for (int j = 0; j < n_tiles; ++j) {
+            const int lp = j / a.tiles_per_page;
+            const int pid = table[lp];
+            const bool page_ok = pid >= 0 && pid < a.num_pages;
+            g_mbar_wait(s_full, j & 1);
+            g_tc_fence_after();
+            uint32_t sv[2][32];
+            g_tmem_ld32_nowait(tmem + lane_base, sv[0]);
+            g_tmem_ld32_nowait(tmem + lane_base + 32, sv[1]);
+            g_tmem_ld_wait();
+            const int key0 = j * TC_BN;
+            const int visible = page_ok ? min(limit - key0 + 1, TC_BN) : 0;  // keys [0, visible) of the tile
+            float tile_max = -CUDART_INF_F;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float sc = (h * 32 + c) < visible ? __uint_as_float(sv[h][c]) * a.scale_log2 : -CUDART_INF_F;
+                    sv[h][c] = __float_as_uint(sc);
+                    tile_max = fmaxf(tile_max, sc);
+                }
+            // lazy rescale: keep the stale maximum unless this tile exceeds it by more than 2^8
+            const bool grow = tile_max > m_used + TC_RESCALE_THRESHOLD || (m_used == -CUDART_INF_F && tile_max != -CUDART_INF_F);
+            if (__any_sync(0xffffffffu, grow) && j > 0) {
+                const float m_new = grow ? tile_max : m_used;
+                const float alpha = (grow && m_used != -CUDART_INF_F) ? exp2f(m_used - m_new) : (grow ? 0.f : 1.f);
+                l_sum *= alpha;
+#pragma unroll
+                for (int cb = 0; cb < TC_D / 32; ++cb) {  // s_full of tile j implies P V of tile j-1 has completed: O is stable
+                    uint32_t ov[32];
+                    g_tmem_ld32(tmem + lane_base + TC_TMEM_O + cb * 32, ov);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
+                    g_tmem_st32(tmem + lane_base + TC_TMEM_O + cb * 32, ov);
+                }
+                g_tmem_st_wait();
+                m_used = m_new;
+            } else if (grow) {
+                m_used = tile_max;  // first tile: nothing accumulated yet
+            }
+            const float m_eff = m_used == -CUDART_INF_F ? 0.f : m_used;
+            float tile_sum = 0.f;
+            uint32_t pk[32];  // 64 bf16 probabilities
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float p0 = exp2f(__uint_as_float(sv[h][c]) - m_eff), p1 = exp2f(__uint_as_float(sv[h][c + 1]) - m_eff);
+                    tile_sum += p0 + p1;
+                    pk[h * 16 + c / 2] = pack2<bf16>(p0, p1);
+                }
+            l_sum += tile_sum;
+            // P row r: 128 bytes = 8 chunks of 16 B, chunk c at (c ^ (r & 7)) - the 128-byte swizzle of a K-major tile
+            unsigned char *prow = tsm + TC_P_OFF + r * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4 *>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            g_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+            g_tc_fence_before();    // orders this thread's tcgen05.ld / st before the MMAs released by the arrive
+            g_mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / sum -> bf16 -> out[(b*Hq + head) * L + l, :]
+        if (n_tiles > 0) {
+            g_mbar_wait(o_full, 0);
+            g_tc_fence_after();
+        }
+        const float inv = (l_sum == 0.f || !row_valid) ? 0.f : 1.0f / l_sum;
+        bf16 *dst = a.out + (static_cast<size_t>(b * a.Hq + kvh * a.G + g) * a.L + l) * TC_D;
+#pragma unroll
+        for (int cb = 0; cb < TC_D / 32; ++cb) {
+            uint32_t ov[32];
+            if (n_tiles > 0) {
+                g_tmem_ld32(tmem + lane_base + TC_TMEM_O + cb * 32, ov);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) ov[c] = 0u;
+            }
+            if (l < a.L) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 o;
+                    o.x = pack2<bf16>(__uint_as_float(ov[c]) * inv, __uint_as_float(ov[c + 1]) * inv);
+                    o.y = pack2<bf16>(__uint_as_float(ov[c + 2]) * inv, __uint_as_float(ov[c + 3]) * inv);
+                    o.z = pack2<bf16>(__uint_as_float(ov[c + 4]) * inv, __uint_as_float(ov[c + 5]) * inv);
+                    o.w = pack2<bf16>(__uint_as_float(ov[c + 6]) * inv, __uint_as_float(ov[c + 7]) * inv);
+                    *reinterpret_cast<uint4 *>(dst + cb * 32 + c) = o;
+                }
+            }
+        }
+    }
+    g_tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        g_tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side --
+// Tensor maps are cached per (base pointer, shape): a prefill of 36 layers x N chunks re-uses a
+// handful of distinct operands, and cuTensorMapEncodeTiled costs microseconds per call.
+struct MapKey {
+    const void *ptr;
+    unsigned long long d0, d1, d2, d3;
+    unsigned b1, b2;
+    bool operator==(const MapKey &o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && b1 == o.b1 && b2 == o.b2; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey &k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        for (unsigned long long v : {k.d0, k.d1, k.d2, k.d3, static_cast<unsigned long long>(k.b1), static_cast<unsigned long long>(k.b2)})
+            h = h * 1000003u ^ static_cast<size_t>(v);
+        return h;
+    }
+};
+static int cached_map(CUtensorMap *out, const void *ptr, int rank, const cuuint64_t *dims, const cuuint32_t *box) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    MapKey key{ptr, dims[0], dims[1], dims[2], rank > 3 ? dims[3] : 0, box[1], box[2]};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return TL_OK;
+    }
+    PFN_cuTensorMapEncodeTiled_v12000 encode = tensor_map_encoder();
+    if (encode == nullptr) return fail(TL_ECUDA, "paged_attention: cuTensorMapEncodeTiled is unavailable");
+    cuuint64_t strides[3];
+    cuuint64_t acc = 2;
+    for (int i = 0; i + 1 < rank; ++i) {
+        acc *= dims[i];
+        strides[i] = acc;
+    }
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap map;
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void *>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TL_ECUDA, "paged_attention: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, map);
+    *out = map;
+    return TL_OK;
+}
+
+bool paged_prefill_tc_supported(int L, int num_pages, int page_size, int num_kv_heads, int num_heads) {
+    static const bool off = [] { const char *e = getenv("TL_PREFILL_TC"); return e != nullptr && e[0] == '0'; }();
+    if (off || num_kv_heads < 1 || num_heads % num_kv_heads != 0) return false;
+    const int G = num_heads / num_kv_heads;
+    if (G < 1 || G > TC_BM || (TC_BM % G) != 0) return false;
+    return L > 0 && num_pages > 0 && page_size >= TC_BN && page_size % TC_BN == 0;
+}
+
+int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out, int rows,
+                            int L, int num_pages, int page_size, int max_pages, float scale, int is_causal, int num_kv_heads,
+                            int num_heads, cudaStream_t st) {
+    const int G = num_heads / num_kv_heads;
+    const int B = rows / num_heads;
+    TcArgs a{};
+    a.block_table = bt, a.context_lens = cl, a.out = static_cast<bf16 *>(out);
+    a.L = L, a.Hq = num_heads, a.Hkv = num_kv_heads, a.G = G, a.RH = TC_BM / G;
+    a.page_size = page_size, a.max_pages = max_pages, a.num_pages = num_pages;
+    a.tiles_per_page = page_size / TC_BN;
+    a.scale_log2 = scale * TC_LOG2E;
+    a.is_causal = is_causal;
+    CUtensorMap mq, mk, mv;
+    {
+        const cuuint64_t dims[3] = {TC_D, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(rows)};
+        const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(a.RH), static_cast<cuuint32_t>(G)};
+        if (int e = cached_map(&mq, q, 3, dims, box)) return e;
+    }
+    {
+        const cuuint64_t dims[4] = {TC_D, static_cast<cuuint64_t>(page_size), static_cast<cuuint64_t>(num_kv_heads), static_cast<cuuint64_t>(num_pages)};
+        const cuuint32_t box[4] = {64, TC_BN, 1, 1};
+        if (int e = cached_map(&mk, kp, 4, dims, box)) return e;
+        if (int e = cached_map(&mv, vp, 4, dims, box)) return e;
+    }
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(paged_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(paged_prefill_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+            return fail(TL_ECUDA, "paged_attention: cannot raise shared memory limit");
+        configured = true;
+    }
+    dim3 grid((L + a.RH - 1) / a.RH, num_kv_heads, B);
+    if (grid.y > 65535 || grid.z > 65535) return fail(TL_EINVAL, "paged_attention: too many heads / requests for one launch");
+    paged_prefill_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mk, mv, a);
+    TL_LAUNCH_CHECK("paged_prefill_tc");
+    return TL_OK;
+}
+
+}  // namespace tl

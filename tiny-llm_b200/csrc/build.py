@@ -32,6 +32,7 @@ SOURCES = [
     "w4a16_gemm.cu",
     "attention_decode.cu",
     "attention_prefill.cu",
+    "attention_prefill_tc.cu",
     "decode_attention_fused.cu",
 ]
 

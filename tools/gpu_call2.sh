@@ -1,8 +1,10 @@
 #!/bin/bash
 # round-2 call 2: full GPU tests, decode hand-off A/B (flag chain x half CTAs), timelines, first runs of the new bench workloads
 mkdir -p gpurun_out; rm -f gpurun_out/decode_ab.jsonl
-timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/c2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/c2_pytest.log
+timeout 1200 python -m pytest tests -m gpu -q -x -k "not (paged_attention_matches_oracle or prefill)" > gpurun_out/c2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/c2_pytest.log
 tail -4 gpurun_out/c2_pytest.log
+timeout 900 python -m pytest tests -m gpu -q -k "paged_attention_matches_oracle or prefill" > gpurun_out/c2_pytest_tc.log 2>&1; echo "pytest tc rc=$?" >> gpurun_out/c2_pytest_tc.log
+tail -25 gpurun_out/c2_pytest_tc.log | cut -c1-300
 ab() { tag=$1; shift; env "$@" timeout 300 python tools/decode_ab.py --tag "$tag" --steps 96 2>&1 | tail -1; }
 ab full_nochain TL_S5_HALF=0 TL_CHAIN=0
 ab full_nochain_nocarve TL_S5_HALF=0 TL_CHAIN=0 TL_S5_CARVEOUT=0
