@@ -65,7 +65,31 @@ def tiny_model_trace():
     )
 
 
+def qwen3_0p6b_trace():
+    """BASELINE config 1: Qwen3-0.6B-shaped random W4 weights (the benchmark's direct
+    code/scale draw, seed 0), 16-token prompt, 128 greedy tokens through the reference's CPU path
+    (oracle.model = Qwen3ModelWeek2(checkpoint="kv-cache") + simple_generate_with_kv_cache,
+    generate.py:49-81).  Stored: the tokens and, per step, the ids and log-probabilities of the four
+    most likely tokens (full 151,936-wide rows would be 78 MB)."""
+    import random
+
+    from tiny_llm_b200.synthetic import synthetic_qwen3
+
+    model_ns = synthetic_qwen3("qwen3-0.6b", seed=0)
+    model = ReferenceCpuModel(model_ns)
+    rng = random.Random(16)
+    prompt = [rng.randint(256, model.args.vocab_size - 1) for _ in range(16)]
+    tokens, logprobs = greedy_decode(model, prompt, 128, return_logprobs=True)
+    top = [[int(i) for i in torch.topk(lp, 4).indices] for lp in logprobs]
+    vals = [[round(float(x), 4) for x in torch.topk(lp, 4).values] for lp in logprobs]
+    (HERE / "qwen3_0p6b_greedy_trace.json").write_text(
+        json.dumps({"config": "qwen3-0.6b", "seed": 0, "realistic": False, "prompt": prompt, "tokens": tokens, "top4_ids": top, "top4_logprobs": vals})
+    )
+
+
 if __name__ == "__main__":
     decode_attention_checksums()
     tiny_model_trace()
+    if "--config1" in sys.argv:  # ~5 minutes of CPU time
+        qwen3_0p6b_trace()
     print("golden fixtures written to", HERE)

@@ -270,3 +270,97 @@ def test_paged_cache_update_writes_one_slice_in_place():
         ops.paged_cache_update(pages, vals, 1, 3)
     with pytest.raises(RuntimeError, match="outside page storage"):
         ops.paged_cache_update(pages, vals, 3, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# fp64 referee: the float operators of the oracle are fp32 restatements of
+# the Metal kernels; MLX cannot run here, so their only other witness was a second restatement.
+# Each operator is evaluated once more in float64 straight from its mathematical definition (no
+# shared code with oracle/ops.py beyond the nibble unpacking spec of quantize.py:113-115) - an
+# arithmetic-free third opinion: the oracle's bf16 result must be the correctly rounded fp64 value
+# up to one output ulp: |err| <= 2^-8 |x| is half an ulp at the bottom of a bf16 binade, a full ulp is
+# allowed where fp32 accumulation noise can flip a rounding.
+def _ulp_close(got, want64, ulps=2.0, floor=1e-6):
+    want = want64.to(torch.float64)
+    err = (got.to(torch.float64) - want).abs()
+    bound = ulps * 2.0**-8 * want.abs() + floor
+    assert bool((err <= bound).all()), f"max excess {float((err - bound).max()):.3e}"
+
+
+def _codes64(words, N):
+    w = words.to(torch.int64) & 0xFFFFFFFF
+    shifts = torch.arange(0, 32, 4, dtype=torch.int64)
+    return ((w[..., None] >> shifts) & 0xF).reshape(words.shape[0], N).to(torch.float64)
+
+
+def test_fp64_referee_quantized_matmul_and_embedding():
+    g = torch.Generator().manual_seed(64)
+    K, N, M = 48, 512, 5
+    words = torch.randint(-(2**31), 2**31, (K, N // 8), dtype=torch.int64, generator=g).to(torch.int32)
+    scales = (torch.randn(K, N // 128, generator=g) * 0.02).to(torch.bfloat16)
+    biases = (-7.5 * scales.float() + torch.randn(K, N // 128, generator=g) * 0.02).to(torch.bfloat16)
+    a = torch.randn(M, N, generator=g).to(torch.bfloat16)
+    w64 = _codes64(words, N) * scales.double().repeat_interleave(128, dim=1) + biases.double().repeat_interleave(128, dim=1)
+    got = ops.quantized_matmul(scales, biases, 128, 4, a, words, True, use_simdgroup=False)
+    _ulp_close(got, a.double() @ w64.T, ulps=2.0, floor=2e-3 * float((a.double() @ w64.T).abs().max()) * 2.0**-8)
+    idx = torch.tensor([[3, 47, 0]], dtype=torch.int32)
+    emb = ops.quantized_embedding(idx, scales, biases, words, 128, 4)
+    _ulp_close(emb[0], w64[idx[0].long()], ulps=1.01)
+
+
+def test_fp64_referee_rms_norm_rope_swiglu():
+    g = torch.Generator().manual_seed(65)
+    x = (torch.randn(3, 7, 256, generator=g) * 3).to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(256, generator=g)).to(torch.bfloat16)
+    want = x.double() * torch.rsqrt((x.double() ** 2).mean(dim=-1, keepdim=True) + 1e-6) * w.double()
+    _ulp_close(ops.rms_norm(x, w, 1e-6), want, ulps=1.01)
+    gate = (torch.randn(4, 96, generator=g) * 4).to(torch.bfloat16)
+    up = torch.randn(4, 96, generator=g).to(torch.bfloat16)
+    want = gate.double() / (1 + torch.exp(-gate.double())) * up.double()
+    _ulp_close(ops.swiglu(gate, up), want, ulps=1.01)
+    B, L, H, D = 2, 5, 3, 64
+    q = torch.randn(B, L, H, D, generator=g).to(torch.bfloat16)
+    offsets = torch.tensor([0, 37], dtype=torch.int32)
+    half = D // 2
+    freq = 10000.0 ** (-torch.arange(half, dtype=torch.float64) / half)
+    pos = offsets.double()[:, None] + torch.arange(L, dtype=torch.float64)[None, :]
+    ang = pos[:, :, None, None] * freq[None, None, None, :]
+    re, im = q.double()[..., :half], q.double()[..., half:]
+    want = torch.cat([re * torch.cos(ang) - im * torch.sin(ang), im * torch.cos(ang) + re * torch.sin(ang)], dim=-1)
+    # the reference forms the angle in fp32 (week2_kernels.metal:78-104): ~1e-6 relative angle noise at these positions
+    _ulp_close(ops.rope(q, offsets, D, 10000.0), want, ulps=2.0, floor=2e-5)
+
+
+def test_fp64_referee_attention_paged_and_dense():
+    g = torch.Generator().manual_seed(66)
+    Hq, Hkv, D, page = 4, 2, 32, 8
+    lens = [19, 8]
+    L = 3
+    q = torch.randn(len(lens) * Hq, L, D, generator=g).to(torch.bfloat16)
+    total_pages = 6
+    kp = torch.randn(total_pages, Hkv, page, D, generator=g).to(torch.bfloat16)
+    vp = torch.randn(total_pages, Hkv, page, D, generator=g).to(torch.bfloat16)
+    bt = torch.tensor([[4, 1, 5], [2, -1, -1]], dtype=torch.int32)
+    cl = torch.tensor(lens, dtype=torch.int32)
+    scale = D**-0.5
+    got = ops.paged_attention(q, kp, vp, bt, cl, scale, True, Hkv, Hq)
+    for b, ctx in enumerate(lens):
+        ids = bt[b, : (ctx + page - 1) // page].long()
+        k = kp[ids].permute(1, 0, 2, 3).reshape(Hkv, -1, D)[:, :ctx].double()
+        v = vp[ids].permute(1, 0, 2, 3).reshape(Hkv, -1, D)[:, :ctx].double()
+        for h in range(Hq):
+            for l in range(L):
+                seen = ctx - L + l + 1  # bottom-right causal alignment (attention.py:24-27)
+                s = (q[b * Hq + h, l].double() @ k[h // (Hq // Hkv), :seen].T) * scale
+                p = torch.softmax(s, dim=-1)
+                _ulp_close(got[b * Hq + h, l], p @ v[h // (Hq // Hkv), :seen], ulps=2.0, floor=1e-4)
+    # dense decode attention with an explicit additive mask (week2_kernels.metal:119-235)
+    S = 11
+    kd = torch.randn(Hkv, S, D, generator=g).to(torch.bfloat16)
+    vd = torch.randn(Hkv, S, D, generator=g).to(torch.bfloat16)
+    qd = torch.randn(Hq, 2, D, generator=g).to(torch.bfloat16)
+    mask = torch.where(torch.arange(S) % 3 == 0, -1.5, 0.0).reshape(1, 1, S).expand(Hq, 2, S).contiguous()
+    got = ops.decode_attention(qd, kd, vd, mask, scale, False, True, Hq, Hkv)
+    for h in range(Hq):
+        s = (qd[h].double() @ kd[h // 2].double().T) * scale + mask[h].double()
+        _ulp_close(got[h], torch.softmax(s, dim=-1) @ vd[h // 2].double(), ulps=2.0, floor=1e-4)
