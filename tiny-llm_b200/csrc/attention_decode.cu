@@ -451,6 +451,12 @@ __global__ void __launch_bounds__(GQA_THREADS) paged_gqa_merge_kernel(const floa
     out[qi * GQA_D + d] = __float2bfloat16_rn(gl == 0.f ? 0.f : o / gl);
 }
 
+int launch_paged_gqa_merge(const float *ws_o, const float *ws_m, const float *ws_l, void *out, int rows_total, int splits, cudaStream_t st) {
+    paged_gqa_merge_kernel<<<static_cast<unsigned>(rows_total), GQA_THREADS, 0, st>>>(ws_o, ws_m, ws_l, static_cast<__nv_bfloat16 *>(out), splits);
+    TL_LAUNCH_CHECK("paged_gqa_merge");
+    return TL_OK;
+}
+
 size_t paged_decode_workspace(int rows, int L, int D, int num_kv_heads, int num_heads, int dtype) {
     if (dtype != TL_BF16 || D != GQA_D) return 0;
     return static_cast<size_t>(rows) * L * GQA_MAX_SPLITS * (GQA_D + 2) * sizeof(float);
@@ -529,6 +535,17 @@ int launch_paged_decode(const void *q, const void *kp, const void *vp, const int
                         int is_causal, int num_kv_heads, int num_heads, int dtype, void *ws, size_t ws_bytes,
                         cudaStream_t st) {
     const bool fast = dtype == TL_BF16 && D == GQA_D && aligned16(q) && aligned16(kp) && aligned16(vp);
+    // Long contexts stream K/V through the TMA + tcgen05 kernel (attention_prefill_tc.cu; the G x L query rows ride
+    // in a 128-row MMA tile - the tensor-core time is far below the HBM time of the tile even at 4 live rows); short
+    // ones stay on the cp.async kernel, whose fixed cost per CTA is lower.  TL_DECODE_TC: 0 never, 1 always (when supported).
+    static const int tc_mode = [] { const char *e = getenv("TL_DECODE_TC"); return e == nullptr ? -1 : atoi(e); }();
+    static const long long tc_min_keys = [] { const char *e = getenv("TL_DECODE_TC_MIN"); return e == nullptr ? 1024LL : atoll(e); }();
+    const int group = num_kv_heads > 0 ? num_heads / num_kv_heads : 0;
+    if (fast && tc_mode != 0 && aligned16(out) && rows % num_heads == 0 && group > 0 && L <= 128 / group &&
+        paged_prefill_tc_supported(L, num_pages, page_size, num_kv_heads, num_heads) &&
+        (tc_mode == 1 || static_cast<long long>(max_pages) * page_size >= tc_min_keys))
+        return launch_paged_prefill_tc(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal, num_kv_heads,
+                                       num_heads, true, ws, ws_bytes, st);
     if (fast)
         return launch_paged_gqa(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal,
                                 num_kv_heads, num_heads, true, ws, ws_bytes, st);
@@ -547,7 +564,7 @@ int launch_paged_prefill(const void *q, const void *kp, const void *vp, const in
     static const bool fa_off = [] { const char *e = getenv("TL_PREFILL_FA"); return e != nullptr && e[0] == '0'; }();
     if (fast && !fa_off && aligned16(out) && rows % num_heads == 0 && paged_prefill_tc_supported(L, num_pages, page_size, num_kv_heads, num_heads))
         return launch_paged_prefill_tc(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal, num_kv_heads,
-                                       num_heads, st);
+                                       num_heads, false, nullptr, 0, st);
     if (fast && !fa_off && rows <= 65535)  // tensor-core flash kernel (attention_prefill.cu); TL_PREFILL_FA=0: CUDA-core control
         return launch_paged_prefill_fa(q, kp, vp, bt, cl, out, rows, L, num_pages, page_size, max_pages, scale, is_causal, num_kv_heads,
                                        num_heads, st);

@@ -82,6 +82,10 @@ struct TcArgs {
     int tiles_per_page;          // page_size / 64
     float scale_log2;
     int is_causal;
+    // split-KV (decode, L <= 8): CTA (query block, split) covers key tiles [split * tiles_per_split, ...) and
+    // leaves an unnormalised partial (O fp32, running max in log2 units, sum) for paged_gqa_merge_kernel
+    int splits, tiles_per_split;
+    float *ws_o, *ws_m, *ws_l;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -89,14 +93,17 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                         const __grid_constant__ CUtensorMap tmap_v, const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char tsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qb = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);  // long (late) query blocks first
+    const int split = static_cast<int>(blockIdx.x) % a.splits;
+    const int qb = static_cast<int>(gridDim.x) / a.splits - 1 - static_cast<int>(blockIdx.x) / a.splits;  // long (late) query blocks first
     const int kvh = blockIdx.y, b = blockIdx.z;
     const int q0 = qb * a.RH;
     const int ctx = min(a.context_lens[b], a.max_pages * a.page_size);
     // keys any row of this CTA may see: [0, key_end)
     const int last_row = min(q0 + a.RH, a.L) - 1;
     const int key_end = ctx <= 0 ? 0 : (a.is_causal ? min(ctx, max(ctx - a.L + last_row + 1, 0)) : ctx);
-    const int n_tiles = (key_end + TC_BN - 1) / TC_BN;
+    const int all_tiles = (key_end + TC_BN - 1) / TC_BN;
+    const int t0 = min(split * a.tiles_per_split, all_tiles);
+    const int n_tiles = min(a.tiles_per_split, all_tiles - t0);  // this CTA: global tiles t0 .. t0 + n_tiles - 1
 
     const uint32_t q_base = g_smem_u32(tsm + TC_Q_OFF), p_base = g_smem_u32(tsm + TC_P_OFF);
     const uint32_t k_base = g_smem_u32(tsm + TC_K_OFF), v_base = g_smem_u32(tsm + TC_V_OFF);
@@ -143,10 +150,10 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j % TC_STAGES;
                 const uint32_t ph = (j / TC_STAGES) & 1;
-                const int lp = j / a.tiles_per_page;
+                const int lp = (t0 + j) / a.tiles_per_page;
                 int pid = table[lp];
                 if (pid < 0 || pid >= a.num_pages) pid = a.num_pages;  // outside the tensor: the TMA unit writes zeros
-                const int slot0 = (j - lp * a.tiles_per_page) * TC_BN;
+                const int slot0 = (t0 + j - lp * a.tiles_per_page) * TC_BN;
                 g_mbar_wait(k_empty + 8 * s, ph ^ 1);
                 g_mbar_expect_tx(k_full + 8 * s, TC_KV_TILE);
                 g_tma_load_4d(k_base + s * TC_KV_TILE, &tmap_k, 0, slot0, kvh, pid, k_full + 8 * s);
@@ -205,7 +212,7 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         float m_used = -CUDART_INF_F, l_sum = 0.f;
         const int32_t *table = a.block_table + static_cast<size_t>(b) * a.max_pages;
         for (int j = 0; j < n_tiles; ++j) {
-            const int lp = j / a.tiles_per_page;
+            const int lp = (t0 + j) / a.tiles_per_page;
             const int pid = table[lp];
             const bool page_ok = pid >= 0 && pid < a.num_pages;
             g_mbar_wait(s_full, j & 1);
@@ -214,7 +221,7 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             g_tmem_ld32_nowait(tmem + lane_base, sv[0]);
             g_tmem_ld32_nowait(tmem + lane_base + 32, sv[1]);
             g_tmem_ld_wait();
-            const int key0 = j * TC_BN;
+            const int key0 = (t0 + j) * TC_BN;
             const int visible = page_ok ? min(limit - key0 + 1, TC_BN) : 0;  // keys [0, visible) of the tile
             float tile_max = -CUDART_INF_F;
 #pragma unroll
@@ -270,8 +277,32 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             g_mbar_wait(o_full, 0);
             g_tc_fence_after();
         }
+        const size_t out_row = static_cast<size_t>(b * a.Hq + kvh * a.G + g) * a.L + l;
+        if (a.splits > 1) {  // unnormalised partial for the merge kernel (attention_decode.cu: paged_gqa_merge_kernel)
+            const size_t slot = out_row * a.splits + split;
+            float *po = a.ws_o + slot * TC_D;
+#pragma unroll
+            for (int cb = 0; cb < TC_D / 32; ++cb) {
+                uint32_t ov[32];
+                if (n_tiles > 0) {  // warp-uniform: tcgen05.ld is warp-collective, rows beyond L take part too
+                    g_tmem_ld32(tmem + lane_base + TC_TMEM_O + cb * 32, ov);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) ov[c] = 0u;
+                }
+                if (l < a.L) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<uint4 *>(po + cb * 32 + c) = make_uint4(ov[c], ov[c + 1], ov[c + 2], ov[c + 3]);
+                }
+            }
+            if (l < a.L) {
+                a.ws_m[slot] = (m_used == -CUDART_INF_F || !row_valid) ? -1e30f : m_used;
+                a.ws_l[slot] = row_valid ? l_sum : 0.f;
+            }
+        } else {
         const float inv = (l_sum == 0.f || !row_valid) ? 0.f : 1.0f / l_sum;
-        bf16 *dst = a.out + (static_cast<size_t>(b * a.Hq + kvh * a.G + g) * a.L + l) * TC_D;
+        bf16 *dst = a.out + out_row * TC_D;
 #pragma unroll
         for (int cb = 0; cb < TC_D / 32; ++cb) {
             uint32_t ov[32];
@@ -292,6 +323,7 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     *reinterpret_cast<uint4 *>(dst + cb * 32 + c) = o;
                 }
             }
+        }
         }
     }
     g_tc_fence_before();
@@ -357,9 +389,12 @@ bool paged_prefill_tc_supported(int L, int num_pages, int page_size, int num_kv_
     return L > 0 && num_pages > 0 && page_size >= TC_BN && page_size % TC_BN == 0;
 }
 
+// allow_split (decode, L <= 8): the key range of every (request, KV head) is cut into up to GQA_MAX_SPLITS (32, the
+// size paged_decode_workspace() budgets for) pieces of >= 4 tiles so that a small batch still fills the GPU; the
+// partials are combined by paged_gqa_merge_kernel.
 int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out, int rows,
                             int L, int num_pages, int page_size, int max_pages, float scale, int is_causal, int num_kv_heads,
-                            int num_heads, cudaStream_t st) {
+                            int num_heads, bool allow_split, void *ws, size_t ws_bytes, cudaStream_t st) {
     const int G = num_heads / num_kv_heads;
     const int B = rows / num_heads;
     TcArgs a{};
@@ -388,10 +423,33 @@ int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const
             return fail(TL_ECUDA, "paged_attention: cannot raise shared memory limit");
         configured = true;
     }
-    dim3 grid((L + a.RH - 1) / a.RH, num_kv_heads, B);
+    const int q_blocks = (L + a.RH - 1) / a.RH;
+    const long long max_tiles = (static_cast<long long>(max_pages) * page_size + TC_BN - 1) / TC_BN;
+    a.splits = 1;
+    a.tiles_per_split = static_cast<int>(max_tiles < 1 ? 1 : max_tiles);
+    if (allow_split && ws != nullptr) {
+        const long long base = static_cast<long long>(q_blocks) * num_kv_heads * B;
+        long long want = (4LL * sm_count() + base - 1) / base;
+        const long long most = max_tiles / 4 > 0 ? max_tiles / 4 : 1;
+        if (want > most) want = most;
+        if (want > 32) want = 32;
+        if (want > 1) {
+            const long long tps = (max_tiles + want - 1) / want;
+            const long long splits = (max_tiles + tps - 1) / tps;
+            const size_t rows_total = static_cast<size_t>(rows) * L;
+            if (splits > 1 && ws_bytes >= rows_total * splits * (TC_D + 2) * sizeof(float)) {
+                a.splits = static_cast<int>(splits), a.tiles_per_split = static_cast<int>(tps);
+                a.ws_o = static_cast<float *>(ws);
+                a.ws_m = a.ws_o + rows_total * splits * TC_D;
+                a.ws_l = a.ws_m + rows_total * splits;
+            }
+        }
+    }
+    dim3 grid(q_blocks * a.splits, num_kv_heads, B);
     if (grid.y > 65535 || grid.z > 65535) return fail(TL_EINVAL, "paged_attention: too many heads / requests for one launch");
     paged_prefill_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mk, mv, a);
     TL_LAUNCH_CHECK("paged_prefill_tc");
+    if (a.splits > 1) return launch_paged_gqa_merge(a.ws_o, a.ws_m, a.ws_l, out, rows * L, a.splits, st);
     return TL_OK;
 }
 

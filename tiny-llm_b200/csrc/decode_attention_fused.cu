@@ -347,7 +347,10 @@ __device__ void mk_attention_merge(const MkArgs &a) {
 // ---- the attention phase as a kernel of its own (CUDA-graph decode path) ----
 // 2 blocks/SM in the launch bounds caps the kernel at 64 registers (62 used, no spills): 512 threads x 64 = half the
 // register file, so a CTA of this launch fits on an SM NEXT to an 8-warp CTA of the projection before or after it.
-__global__ void __launch_bounds__(MK_THREADS, 2) decode_attention_fused_kernel(const MkArgs a, const MkLayer l) {
+#ifndef MK_ATT_MINBLOCKS
+#define MK_ATT_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(MK_THREADS, MK_ATT_MINBLOCKS) decode_attention_fused_kernel(const MkArgs a, const MkLayer l) {
     extern __shared__ __align__(128) unsigned char att_smem_raw[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the o_proj stream may prefetch its weights now
     TL_TRACE_STAMP(20);
@@ -401,8 +404,9 @@ int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, co
     l.k_pages = key_pages, l.v_pages = value_pages;
     static bool configured = false;
     if (!configured) {
+        static const bool carve = [] { const char *v = getenv("TL_S5_CARVEOUT"); return !(v != nullptr && v[0] == '0'); }();
         if (cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MK_ATT_BYTES + 64)) != cudaSuccess ||
-            cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+            (carve && cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess))
             return fail(TL_ECUDA, "decode_attention_fused: cannot raise shared memory limit");
         configured = true;
     }

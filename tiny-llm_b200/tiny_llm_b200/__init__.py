@@ -6,6 +6,7 @@ from .attention import *  # noqa: F401,F403
 from .attention import paged_attention, scaled_dot_product_attention_grouped, scaled_dot_product_attention_simple, causal_mask
 from .basics import linear, silu, softmax
 from .batch import ContinuousBatcher, Request, batch_generate
+from .checkpoint import load_checkpoint, load_tokenizer, save_checkpoint
 from .embedding import Embedding, QuantizedEmbedding
 from .generate import greedy_generate_ids, simple_generate_with_kv_cache
 from .kv_cache import BatchingKvCache, TinyKvCache, TinyKvFullCache
@@ -13,6 +14,7 @@ from .layer_norm import RMSNorm
 from .models import dispatch_model, shortcut_name_to_full_name
 from .paged_kv_cache import PagedKvMetadata, TinyKvPagedCache, TinyKvPagedPool
 from .positional_encoding import RoPE
+from .sampler import make_sampler
 from .quantize import (
     QuantizedWeights,
     dequantize_linear,

@@ -154,10 +154,16 @@ class DecodeEngine:
             ]
         # one-launch attention (q/k norm + rope + append + paged GQA) when the head layout allows it
         attn0 = model.layers_inner[0].self_attn
+        # The one-launch attention is a latency design (few CTAs, K/V rows staged per lane): it wins while the
+        # step is launch-bound.  With many slots or long contexts the K/V stream dominates and the step uses
+        # q/k norm + rope + append as one small launch followed by tl_paged_attention, whose long-context path
+        # is the TMA + tcgen05 streaming kernel (attention_prefill_tc.cu).  TL_ATTENTION_FUSED=0/1 forces either.
+        fused_env = os.environ.get("TL_ATTENTION_FUSED")
+        fused_pays = self.B * self.max_seq_len <= int(os.environ.get("TL_ATTENTION_FUSED_MAX_TOKENS", "16384"))
         self._attention_fused = (self.fused and self.D == 128 and self.Hq // self.Hkv <= 4
                                  and model.embedding.weight.scales.dtype == torch.bfloat16
                                  and not getattr(attn0.rope, "traditional", False)
-                                 and os.environ.get("TL_ATTENTION_FUSED", "1") != "0")
+                                 and (fused_env == "1" or (fused_env != "0" and fused_pays)))
         if self._attention_fused:
             self._rope_inv_freq = ext.rope_inv_freq_table(self.D, attn0.rope.base, self.device)
             self._attn_ws = torch.empty(ext.decode_attention_fused_workspace(self.B, self.Hq, self.Hkv), dtype=torch.float32, device=self.device)

@@ -14,10 +14,12 @@ def _release_kv_cache(kv_cache) -> None:
             layer_cache.release()
 
 
-def greedy_generate_ids(model, prompt_ids, max_new_tokens: int, eos_token_id: int | None = None, device=None, on_token=None):
+def greedy_generate_ids(model, prompt_ids, max_new_tokens: int, eos_token_id: int | None = None, device=None, on_token=None, sampler=None):
     """The loop of ``simple_generate_with_kv_cache`` on token ids: the whole
     prompt is prefilled at offset 0 (its last-row logits give the first token),
-    then one token per step at a growing offset.  Returns the generated ids."""
+    then one token per step at a growing offset.  Returns the generated ids.
+    ``sampler`` (``make_sampler``; B200 extension - the reference's cached loop is greedy only) draws
+    from ``logits - logsumexp`` instead of taking the arg-max."""
     kv_cache = model.create_kv_cache()
     produced: list[int] = []
     try:
@@ -25,7 +27,11 @@ def greedy_generate_ids(model, prompt_ids, max_new_tokens: int, eos_token_id: in
         offset = 0
         while len(produced) < max_new_tokens:
             logits = model(tokens[None], offset, kv_cache, logits_to_keep=1)
-            token = greedy_tokens(logits[:, -1, :])
+            if sampler is None:
+                token = greedy_tokens(logits[:, -1, :])
+            else:
+                row = logits[:, -1, :].to(torch.float32)
+                token = sampler(row - torch.logsumexp(row, dim=-1, keepdim=True))
             value = int(token.reshape(-1)[0])  # device->host read, one per step (mx.eval + .item())
             if eos_token_id is not None and value == eos_token_id:
                 break
