@@ -58,16 +58,25 @@ long long tl_launch_count(void);
  * Replaces quantized_matmul (tiny_llm_ext.h:12-21, quantized_matmul.cpp:14-80,
  * eval_gpu :111-240).  scales/biases [K, N/128] (f16|bf16), a [M, N],
  * b [K, N/8] u32, out [M, K].  Kernel selection:
- *   use_simdgroup && M <= TL_MATVEC_MAX_ROWS : weight-streaming tensor-core
- *       matvec, weights kept fp32-exact (reference: M <= 8 matvec);
- *   use_simdgroup                            : tiled GEMM, weights rounded to
+ *   use_simdgroup && M <= TL_MATVEC_REF_ROWS : weight-streaming tensor-core
+ *       matvec, weights kept fp32-exact (reference: M <= 8 matvec, quantize.py:162-163);
+ *   use_simdgroup && M <= 128                : swap-AB tcgen05 GEMM with the reduction split over
+ *       CTAs (reference: quantized_matmul_splitk, quantized_matmul.metal:251-293), weights rounded to
+ *       the activation dtype before the MMA, fp32 partial planes added in split order;
+ *   use_simdgroup                            : 128 x 128-tile tcgen05 GEMM, weights rounded to
  *       the activation dtype before the MMA (reference: simdgroup tile);
  *   !use_simdgroup                           : scalar control kernel.
- * use_split_k only requests a split of the reduction; when the policy keeps
- * split == 1 the very same kernel runs (bit-identical results,
- * tests_refsol/test_week_2_day_7.py:80-109).  workspace is needed only when
- * tl_quantized_matmul_workspace() reports a non-zero size. */
+ * (Shapes a tensor-core kernel cannot take - odd alignments - fall back to the streaming kernel, which
+ * handles up to TL_MATVEC_MAX_ROWS rows per pass.)
+ * The split of the reduction is a scheduling decision of this backend (SURVEY 8a' item 12): it depends only on
+ * (N, K), never on use_split_k, so a split request and a plain request run the very same kernel with
+ * bit-identical results (tests_refsol/test_week_2_day_7.py:80-109).
+ * workspace: tl_quantized_matmul_workspace() bytes (0 = none).  When it is non-zero its first
+ * TL_QMM_TICKET_BYTES are int32 arrival tickets that must be ZERO on entry; the kernel leaves them zero,
+ * so one zero-initialised buffer can be reused by successive launches on a stream. */
+#define TL_MATVEC_REF_ROWS 8
 #define TL_MATVEC_MAX_ROWS 32
+#define TL_QMM_TICKET_BYTES 8192
 size_t tl_quantized_matmul_workspace(int M, int N, int K, int dtype, int use_simdgroup, int use_split_k);
 int tl_quantized_matmul(const void *scales, const void *biases, const void *a, const void *b, void *out, int M,
                         int N, int K, int dtype, int use_simdgroup, int use_split_k, void *workspace,
@@ -142,12 +151,16 @@ size_t tl_argmax_workspace(int rows, int vocab);
  *                             MLP activation leaves the gate|up projection already combined
  *                             (week2_kernels.metal:115-116 applied to the rounded projection outputs)
  * lda is the row stride (elements) of p0 (and of p1 for SWIGLU), so gate/up may
- * be the two halves of one [M, 2N] buffer. */
+ * be the two halves of one [M, 2N] buffer.
+ * With 9 <= M <= 128, no prologue and lda == N the launch goes to the swap-AB tcgen05 kernel (same
+ * epilogues; weights rounded to the activation dtype like every tensor-core path) and needs
+ * tl_quantized_matmul_fused_workspace() bytes of workspace (ticket convention as above). */
 enum { TL_PRO_NONE = 0, TL_PRO_RMSNORM = 1, TL_PRO_SWIGLU = 2 };
 enum { TL_EPI_NONE = 0, TL_EPI_RESIDUAL = 1, TL_EPI_SWIGLU_PAIRS = 2 };
+size_t tl_quantized_matmul_fused_workspace(int M, int N, int K, int lda, int prologue, int dtype);
 int tl_quantized_matmul_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0,
                               const void *p1, const void *residual, int M, int N, int K, int lda, int prologue,
-                              int epilogue, float eps, int dtype, void *stream);
+                              int epilogue, float eps, int dtype, void *workspace, size_t workspace_bytes, void *stream);
 /* Decode step, L == 1: per-head q/k RMSNorm + RoPE + K/V append in one launch.
  * qkv [B, (Hq + 2*Hkv) * D] (q heads | k heads | v heads); q_out [B, Hq, D];
  * K/V rows land in the page slot of token context_lens[b]-1 (rows with context

@@ -48,10 +48,13 @@ def test_fused_projection_equals_the_unfused_operator_sequence(dev, M, N, K):
     gu = (torch.randn(M, 2 * N, generator=g) * 2).to(BF16).to(dev)
     want = ext.quantized_matmul(s, b, 128, 4, ext.swiglu(gu[:, :N].contiguous(), gu[:, N:].contiguous()), w, True)
     got = ext.quantized_matmul_fused(s, b, w, gu[:, :N], gu[:, N:], residual=res, prologue=ext.PRO_SWIGLU, epilogue=ext.EPI_RESIDUAL)
-    assert torch.equal(got, ext.add(res, want))
+    if M <= 8:
+        assert torch.equal(got, ext.add(res, want))
+    else:  # more than 8 rows: the unfused product runs on the tensor-core kernel (weights rounded to bf16), the prologue form on the streaming kernel
+        torch.testing.assert_close(got.float(), ext.add(res, want).float(), rtol=2**-7, atol=2e-3 * float(want.float().abs().max()) + 2**-7)
 
 
-@pytest.mark.parametrize("M", [1, 5, 8, 16])
+@pytest.mark.parametrize("M", [1, 5, 8, 16, 64])
 @pytest.mark.parametrize("N,inter", [(2560, 9728), (256, 384), (1024, 40)])
 def test_swiglu_pairs_epilogue_equals_projection_then_swiglu(dev, M, N, inter):
     """gate|up rows interleaved in blocks of 8: the projection emits swiglu(gate, up) itself."""

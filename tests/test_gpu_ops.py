@@ -48,6 +48,9 @@ QMM_SHAPES = [
     # beyond the reference matvec limit: small decode batches and ragged tiles
     (9, 2560, 1024), (16, 2560, 1024), (17, 2560, 1032), (32, 2560, 1024), (10, 256, 96), (33, 256, 96),
     (64, 9728, 2560), (128, 256, 96), (40, 4096, 2560), (129, 2560, 1024), (300, 1024, 520), (512, 2560, 4096),
+    # swap-AB split-reduction kernel: every token-column width (16/32/64/128), ragged feature tiles, split and unsplit reductions
+    (12, 128, 40), (16, 4096, 2560), (24, 2560, 6144), (48, 2560, 19456), (64, 2560, 6144), (100, 9728, 2560), (128, 4096, 2560),
+    (128, 2560, 1000), (77, 1024, 3072),
 ]
 
 
@@ -59,8 +62,8 @@ def test_quantized_matmul_matches_oracle(dev, shape, dtype):
     words, scales, biases = rand_packed(K, N, g, dtype)
     a = torch.randn(M, N, generator=g).to(dtype)
     want = oracle.quantized_matmul(scales, biases, 128, 4, a, words, True, use_simdgroup=False)  # fp32-exact weights
-    # tensor-core GEMM (M > 32): weights rounded to the activation dtype before the MMA, like the
-    # reference's tiled kernel (quantized_matmul.metal:183-194)
+    # tensor-core GEMMs (M > 8: swap-AB split-reduction kernel up to 128 rows, 128 x 128 tiles above): weights
+    # rounded to the activation dtype before the MMA, like the reference's tiled kernel (quantized_matmul.metal:183-194)
     w_rounded = oracle.dequantize_weights(words, scales, biases, 128, 4).float()
     want_tiled = (a.float() @ w_rounded.T).to(dtype)
     args = (scales.to(dev), biases.to(dev), 128, 4, a.to(dev), words.to(dev), True)
@@ -69,7 +72,7 @@ def test_quantized_matmul_matches_oracle(dev, shape, dtype):
     tol = dict(rtol=2 * ULP[dtype], atol=2e-3 * scale_ref)
     got = ext.quantized_matmul(*args)  # extension default: use_simdgroup=True
     assert got.dtype == dtype and tuple(got.shape) == (M, K)
-    assert_close(got, want if M <= 32 else want_tiled, **tol, msg=f"stream/gemm {shape}")
+    assert_close(got, want if M <= 8 else want_tiled, **tol, msg=f"stream/gemm {shape}")
     vanilla = ext.quantized_matmul(*args, use_simdgroup=False)
     assert_close(vanilla, want, **tol, msg=f"vanilla {shape}")
     split = ext.quantized_matmul(*args, use_simdgroup=True, use_split_k=True)

@@ -74,12 +74,21 @@ int tl_device_info(int *sms, int *major, int *minor) {
 }
 
 // ------------------------------------------------------------ W4A16 ------
+// Dispatch by activation rows (use_simdgroup): M <= 8 weight-streaming matvec (the reference's matvec limit,
+// quantize.py:162-163); 9..128 swap-AB tcgen05 GEMM with split reduction (w4a16_skinny.cu); above that the
+// 128 x 128-tile tcgen05 GEMM.  The streaming kernel also takes what the tensor-core kernels cannot.
+static bool use_skinny_kernel(int M, int N, int K, int dtype, int use_simdgroup) {
+    return use_simdgroup && M > TL_MATVEC_REF_ROWS && w4a16_skinny_supported(M, N, K, dtype);
+}
 static bool use_stream_kernel(int M, int N, int K, int dtype, int use_simdgroup) {
-    return use_simdgroup && (M <= TL_MATVEC_MAX_ROWS || !w4a16_gemm_supported(M, N, K, dtype));
+    return use_simdgroup && !use_skinny_kernel(M, N, K, dtype, use_simdgroup) &&
+           (M <= TL_MATVEC_MAX_ROWS || !w4a16_gemm_supported(M, N, K, dtype));
 }
 
 size_t tl_quantized_matmul_workspace(int M, int N, int K, int dtype, int use_simdgroup, int use_split_k) {
-    if (!use_simdgroup || use_stream_kernel(M, N, K, dtype, use_simdgroup)) return 0;
+    if (!use_simdgroup) return 0;
+    if (use_skinny_kernel(M, N, K, dtype, use_simdgroup)) return w4a16_skinny_workspace(M, N, K);
+    if (use_stream_kernel(M, N, K, dtype, use_simdgroup)) return 0;
     return w4a16_gemm_workspace(M, N, K, dtype, use_split_k);
 }
 
@@ -95,6 +104,8 @@ int tl_quantized_matmul(const void *scales, const void *biases, const void *a, c
     }
     cudaStream_t st = as_stream(stream);
     if (!use_simdgroup) return launch_w4a16_vanilla(scales, biases, a, b, out, M, N, K, dtype, st);
+    if (M > 0 && K > 0 && use_skinny_kernel(M, N, K, dtype, use_simdgroup))
+        return launch_w4a16_skinny(scales, biases, a, b, out, nullptr, M, N, K, TL_EPI_NONE, dtype, workspace, workspace_bytes, st);
     if (use_stream_kernel(M, N, K, dtype, use_simdgroup))
         return launch_w4a16_stream(scales, biases, a, b, out, M, N, K, dtype, st);
     return launch_w4a16_gemm(scales, biases, a, b, out, M, N, K, dtype, use_split_k, workspace, workspace_bytes, st);
@@ -246,9 +257,14 @@ int tl_argmax(const void *logits, int32_t *out_tokens, int rows, int vocab, int 
     return launch_argmax(logits, out_tokens, rows, vocab, dtype, workspace, workspace_bytes, as_stream(stream));
 }
 
+size_t tl_quantized_matmul_fused_workspace(int M, int N, int K, int lda, int prologue, int dtype) {
+    if (prologue == TL_PRO_NONE && lda == N && use_skinny_kernel(M, N, K, dtype, 1)) return w4a16_skinny_workspace(M, N, K);
+    return 0;
+}
+
 int tl_quantized_matmul_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0,
                               const void *p1, const void *residual, int M, int N, int K, int lda, int prologue,
-                              int epilogue, float eps, int dtype, void *stream) {
+                              int epilogue, float eps, int dtype, void *workspace, size_t workspace_bytes, void *stream) {
     if (dtype != TL_F16 && dtype != TL_BF16) return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
     if (M < 0 || N <= 0 || K < 0 || lda < N) return fail(TL_EINVAL, "quantized_matmul_fused: bad shape");
     if (N % 128 != 0) return fail(TL_EINVAL, "quantized_matmul: N must be divisible by group_size");
@@ -259,6 +275,8 @@ int tl_quantized_matmul_fused(const void *scales, const void *biases, const void
     if (M == 0 || K == 0) return TL_OK;
     if (!scales || !biases || !b || !out || !p0 || (prologue != TL_PRO_NONE && !p1) || (epilogue == TL_EPI_RESIDUAL && !residual))
         return fail(TL_EINVAL, "quantized_matmul_fused: null pointer");
+    if (prologue == TL_PRO_NONE && lda == N && use_skinny_kernel(M, N, K, dtype, 1) && workspace != nullptr)
+        return launch_w4a16_skinny(scales, biases, p0, b, out, residual, M, N, K, epilogue, dtype, workspace, workspace_bytes, as_stream(stream));
     return launch_w4a16_fused(scales, biases, b, out, p0, p1, residual, M, N, K, lda, prologue, epilogue, eps, dtype,
                               as_stream(stream));
 }

@@ -53,6 +53,13 @@ bool use_pdl();
 int launch_w4a16_vanilla(const void *scales, const void *biases, const void *a, const void *b, void *out, int M,
                          int N, int K, int dtype, cudaStream_t st);
 
+// w4a16_skinny.cu (swap-AB tcgen05 GEMM with split reduction, 9 <= M <= 128)
+bool w4a16_skinny_supported(int M, int N, int K, int dtype);
+int w4a16_skinny_splits(int N, int K);
+size_t w4a16_skinny_workspace(int M, int N, int K);
+int launch_w4a16_skinny(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N,
+                        int K, int epilogue, int dtype, void *ws, size_t ws_bytes, cudaStream_t st);
+
 // w4a16_gemm.cu (tcgen05 prefill GEMM)
 bool w4a16_gemm_supported(int M, int N, int K, int dtype);
 int w4a16_gemm_split(int M, int N, int K, int use_split_k);

@@ -1,0 +1,447 @@
+// W4A16 "skinny" GEMM for 9 <= M <= 128 activation rows (batched decode steps, 128-token prefill
+// chunks): swap-AB tcgen05 with split reduction, so that EVERY SM streams weights.
+//
+//   out[m, n] = sum_k a[m, k] * T(code[n, k] * scale[n, k/128] + bias[n, k/128])       (m = token, n = feature)
+//
+// Why (round-1 VERDICT, missing #5 / row N4): with M <= 128 the 128 x 128-tile GEMM has K_out/128
+// CTAs (20 for the o / down projections of Qwen3-4B) and the streaming kernel re-reads the weights
+// once per 32 rows; a 64-slot decode step took 16 ms where the weights are worth 0.33 ms of HBM time.
+// Reference's answer on its hardware: quantized_matmul_splitk (quantized_matmul.metal:251-293, policy
+// quantized_matmul.cpp:136-150).  Here:
+//
+//   * the WEIGHTS are the 128-row M operand of the MMA (one CTA tile = 128 output features), the tokens
+//     are the N operand (16..128 columns): D[feature, token] lives in TMEM, lane = feature;
+//   * the reduction is split over `splits` CTAs per feature tile so that tiles x splits ~ #SMs; partial
+//     sums go to a workspace in fp32 and the LAST CTA of a tile (atomic ticket) adds them in split order
+//     (deterministic) and runs the epilogue (plain / + residual / SwiGLU of interleaved gate|up rows);
+//   * packed weights arrive by TMA (one 128 rows x 32 B box per 64-wide reduction block, 8-deep ring:
+//     32 KiB in flight per CTA without a register), 256 dequantiser threads turn them into the K-major
+//     128B-swizzled bf16 tile (LOP3 magic -> exact code -> one HFMA2, the rounding point of the
+//     reference's tiled kernel, quantized_matmul.metal:183-194), activations arrive by TMA (tokens beyond M
+//     zero-filled), one thread issues tcgen05.mma M128 N{16..128} K16.
+// Two CTAs fit per SM (<= 112 KB of shared memory, <= 128 TMEM columns each).
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc05.cuh"
+
+namespace tl {
+
+constexpr int SK_FEAT = 128;      // features per CTA tile (UMMA M)
+constexpr int SK_KB = 64;         // reduction elements per stage (one 128-byte swizzle atom)
+constexpr int SK_PSTAGES = 8;     // packed-weight ring (4 KiB per stage)
+constexpr int SK_PACKED_BYTES = SK_FEAT * SK_KB / 2;  // 4096
+constexpr int SK_A_BYTES = SK_FEAT * SK_KB * 2;       // 16 KiB dequantised tile
+constexpr int SK_DEQ_THREADS = 256;
+constexpr int SK_THREADS = 128 + SK_DEQ_THREADS;
+constexpr int SK_COUNTER_BYTES = 8192;                // zeroed int32 tickets at the head of the workspace (2048 feature tiles)
+enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
+
+template <int NT>
+struct SkSmem {
+    static constexpr int STAGES = NT >= 64 ? 2 : 3;  // <= 112 KB with the 32 KiB packed ring: two CTAs per SM
+    static constexpr int B_BYTES = NT * SK_KB * 2;
+    static constexpr int A_OFF = 0;
+    static constexpr int B_OFF = A_OFF + STAGES * SK_A_BYTES;
+    static constexpr int P_OFF = B_OFF + STAGES * B_BYTES;
+    static constexpr int BAR_OFF = P_OFF + SK_PSTAGES * SK_PACKED_BYTES;
+    static constexpr int SB_OFF = BAR_OFF + 512;  // scale|bias pairs [groups][128 rows] u32 follow
+    static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+};
+
+struct SkArgs {
+    const void *scales, *biases, *residual;
+    void *out;
+    float *partials;   // [splits][M][K] fp32 (splits > 1)
+    int *tickets;      // [tiles], zero on entry, left zero
+    int M, N, K;       // tokens, reduction, features
+    int splits, kb_per_split;
+    int epilogue;
+};
+
+template <typename T>
+struct SkNum;
+template <>
+struct SkNum<__nv_bfloat16> {
+    using V2 = __nv_bfloat162;
+    static constexpr uint32_t MAGIC = 0x43004300u;
+    static constexpr uint32_t FMT = 1u;
+};
+template <>
+struct SkNum<__half> {
+    using V2 = __half2;
+    static constexpr uint32_t MAGIC = 0x64006400u;
+    static constexpr uint32_t FMT = 0u;
+};
+
+template <typename T, int NT>
+__host__ __device__ constexpr uint32_t sk_instr_desc() {
+    return (1u << 4) | (SkNum<T>::FMT << 7) | (SkNum<T>::FMT << 10) | (0u << 15) | (0u << 16) | (static_cast<uint32_t>(NT >> 3) << 17) |
+           (static_cast<uint32_t>(SK_FEAT >> 4) << 24);
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(SK_THREADS, 2)
+w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const SkArgs args) {
+    using Smem = SkSmem<NT>;
+    constexpr int STAGES = Smem::STAGES;
+    extern __shared__ __align__(1024) unsigned char ssm[];
+    __shared__ int s_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x / args.splits, split = blockIdx.x - tile * args.splits;
+    const int num_kb = args.N / SK_KB;
+    const int kb0 = min(split * args.kb_per_split, num_kb), kb1 = min(kb0 + args.kb_per_split, num_kb);
+    const int n_kb = kb1 - kb0;
+    const int G = args.N / 128;
+    const int g0 = kb0 >> 1, g_cnt = n_kb > 0 ? ((kb1 - 1) >> 1) - g0 + 1 : 0;
+
+    const uint32_t a_base = g_smem_u32(ssm + Smem::A_OFF), b_base = g_smem_u32(ssm + Smem::B_OFF), p_base = g_smem_u32(ssm + Smem::P_OFF);
+    const uint32_t bar = g_smem_u32(ssm + Smem::BAR_OFF);
+    const uint32_t full_a = bar, full_b = bar + 8 * STAGES, empty = bar + 16 * STAGES;
+    const uint32_t p_full = bar + 24 * STAGES, p_empty = p_full + 8 * SK_PSTAGES, tmem_full = p_empty + 8 * SK_PSTAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ssm + Smem::BAR_OFF + 24 * STAGES + 16 * SK_PSTAGES + 8);
+    uint32_t *sb = reinterpret_cast<uint32_t *>(ssm + Smem::SB_OFF);  // [g_cnt][128]: (scale, bias) of the tile's rows
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            g_mbar_init(full_a + 8 * i, SK_DEQ_THREADS);
+            g_mbar_init(full_b + 8 * i, 1);
+            g_mbar_init(empty + 8 * i, 1);
+        }
+        for (int i = 0; i < SK_PSTAGES; ++i) {
+            g_mbar_init(p_full + 8 * i, 1);
+            g_mbar_init(p_empty + 8 * i, SK_DEQ_THREADS);
+        }
+        g_mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "n"(Smem::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // scale | bias pairs of this tile's rows for the groups of this split (tiny; plain loads)
+    for (int i = threadIdx.x; i < g_cnt * SK_FEAT; i += SK_THREADS) {
+        const int g = i / SK_FEAT, r = i - g * SK_FEAT;
+        const int row = min(tile * SK_FEAT + r, args.K - 1);
+        const size_t at = static_cast<size_t>(row) * G + g0 + g;
+        const uint32_t s = reinterpret_cast<const unsigned short *>(args.scales)[at], bb = reinterpret_cast<const unsigned short *>(args.biases)[at];
+        sb[i] = s | (bb << 16);
+    }
+    g_tc_fence_before();
+    __syncthreads();
+    g_tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer: packed weights, 8 blocks ahead
+        if (lane == 0) {
+            for (int i = 0; i < n_kb; ++i) {
+                const int ps = i % SK_PSTAGES;
+                g_mbar_wait(p_empty + 8 * ps, ((i / SK_PSTAGES) & 1) ^ 1);
+                g_mbar_expect_tx(p_full + 8 * ps, SK_PACKED_BYTES);
+                g_tma_load_2d(p_base + ps * SK_PACKED_BYTES, &tmap_w, (kb0 + i) * (SK_KB / 2), tile * SK_FEAT, p_full + 8 * ps);
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------ TMA producer: activations
+        if (lane == 0) {
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % STAGES;
+                g_mbar_wait(empty + 8 * s, ((i / STAGES) & 1) ^ 1);
+                g_mbar_expect_tx(full_b + 8 * s, Smem::B_BYTES);
+                g_tma_load_2d(b_base + s * Smem::B_BYTES, &tmap_a, (kb0 + i) * SK_KB, 0, full_b + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer: D[feature, token] += W_tile . A_tile^T
+        if (lane == 0) {
+            constexpr uint32_t idesc = sk_instr_desc<T, NT>();
+            for (int i = 0; i < n_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                g_mbar_wait(full_a + 8 * s, ph);
+                g_mbar_wait(full_b + 8 * s, ph);
+                g_tc_fence_after();
+                const uint64_t adesc = g_smem_desc_sw128(a_base + s * SK_A_BYTES, 0, 1024);
+                const uint64_t bdesc = g_smem_desc_sw128(b_base + s * Smem::B_BYTES, 0, 1024);
+#pragma unroll
+                for (int k = 0; k < SK_KB / 16; ++k) g_tc_mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                g_tc_commit(empty + 8 * s);
+            }
+            g_tc_commit(tmem_full);
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------ dequantisers: thread = (row, 32-element half of the 64-wide block)
+        const int dt = threadIdx.x - 128;
+        const int row = dt >> 1, half = dt & 1;  // the two halves of a row sit in adjacent lanes: one 32-byte shared-memory segment
+        using V2 = typename SkNum<T>::V2;
+        const uint32_t magic = SkNum<T>::MAGIC;
+        const V2 offset2 = *reinterpret_cast<const V2 *>(&magic);
+        for (int i = 0; i < n_kb; ++i) {
+            const int ps = i % SK_PSTAGES, s = i % STAGES;
+            g_mbar_wait(p_full + 8 * ps, (i / SK_PSTAGES) & 1);
+            const uint4 cur = *reinterpret_cast<const uint4 *>(ssm + Smem::P_OFF + ps * SK_PACKED_BYTES + row * 32 + half * 16);
+            g_mbar_arrive(p_empty + 8 * ps);  // the 16 bytes are in registers
+            const uint32_t pair = sb[(((kb0 + i) >> 1) - g0) * SK_FEAT + row];
+            const unsigned short s16 = static_cast<unsigned short>(pair & 0xffffu), b16 = static_cast<unsigned short>(pair >> 16);
+            V2 s2, b2;
+            s2.x = s2.y = *reinterpret_cast<const T *>(&s16);
+            b2.x = b2.y = *reinterpret_cast<const T *>(&b16);
+            uint32_t outw[16];
+            const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t p[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t bits = ((wv[j] >> (4 * q)) & 0x000F000Fu) | magic;  // (128 + code_q, 128 + code_{q+4})
+                    V2 code = __hsub2(*reinterpret_cast<V2 *>(&bits), offset2);
+                    V2 v = __hfma2(code, s2, b2);                                   // code * scale + bias, one rounding
+                    p[q] = *reinterpret_cast<uint32_t *>(&v);
+                }
+                outw[4 * j + 0] = __byte_perm(p[0], p[1], 0x5410);
+                outw[4 * j + 1] = __byte_perm(p[2], p[3], 0x5410);
+                outw[4 * j + 2] = __byte_perm(p[0], p[1], 0x7632);
+                outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);
+            }
+            g_mbar_wait(empty + 8 * s, ((i / STAGES) & 1) ^ 1);
+            unsigned char *dst = ssm + Smem::A_OFF + s * SK_A_BYTES + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int chunk = half * 4 + j;
+                *reinterpret_cast<uint4 *>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
+            }
+            g_fence_proxy_async();
+            g_mbar_arrive(full_a + 8 * s);
+        }
+        // ------------------------------------------------ epilogue: TMEM lane = feature; warps 4-7 take token columns [0, NT/2), 8-11 the rest
+        if (n_kb > 0) {
+            g_mbar_wait(tmem_full, 0);
+            g_tc_fence_after();
+        }
+        const int q = warp & 3;
+        const int f = q * 32 + lane;            // feature row inside the tile
+        const int n = tile * SK_FEAT + f;       // global feature
+        constexpr int HALF_COLS = NT >= 64 ? NT / 2 : NT;   // with fewer than 64 tokens warps 8-11 have nothing to read
+        const int col0 = ((warp - 4) >> 2) * HALF_COLS;
+        const bool reader = NT >= 64 || warp < 8;
+        constexpr int CH = HALF_COLS < 32 ? HALF_COLS : 32;  // columns per tcgen05.ld (x16 or x32)
+        float *part = args.partials;
+        const size_t plane = static_cast<size_t>(args.M) * args.K;
+        // ---- pass 1 (splits > 1): park the partial tile, take a ticket
+        if (args.splits > 1) {
+            if (reader) {
+#pragma unroll
+                for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+                    uint32_t v[32];
+                    if (n_kb > 0) {
+                        g_tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + col0 + c0, v);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = 0u;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int m = col0 + c0 + c;
+                        if (c < CH && m < args.M && n < args.K) part[split * plane + static_cast<size_t>(m) * args.K + n] = __uint_as_float(v[c]);
+                    }
+                }
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(SK_DEQ_THREADS) : "memory");
+            if (threadIdx.x == 128) s_last = (atomicAdd(args.tickets + tile, 1) == args.splits - 1) ? 1 : 0;
+            asm volatile("bar.sync 1, %0;" ::"n"(SK_DEQ_THREADS) : "memory");
+            if (s_last) {
+                __threadfence();
+                if (threadIdx.x == 128) args.tickets[tile] = 0;  // leave the ticket clean for the next launch
+            }
+        }
+        const bool finisher = args.splits == 1 || s_last;
+        if (finisher && reader) {
+            T *out = static_cast<T *>(args.out);
+            const T *res = static_cast<const T *>(args.residual);
+#pragma unroll
+            for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+                float acc[32];
+                if (args.splits == 1) {
+                    uint32_t v[32];
+                    if (n_kb > 0) {
+                        g_tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + col0 + c0, v);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = 0u;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) acc[c] = __uint_as_float(v[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int m = col0 + c0 + c;
+                        float sum = 0.f;
+                        if (c < CH && m < args.M && n < args.K)
+                            for (int sp = 0; sp < args.splits; ++sp) sum += ld_cg(part + sp * plane + static_cast<size_t>(m) * args.K + n);  // split order: deterministic
+                        acc[c] = sum;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int m = col0 + c0 + c;
+                    const bool live = c < CH && m < args.M;  // warp-uniform in m; the shuffle below needs every lane
+                    if (args.epilogue == SK_EPI_SWIGLU_PAIRS) {
+                        // rows 16j + r (gate) and 16j + 8 + r (up) of the interleaved weight -> activation 8j + r
+                        const float mine = to_f(from_f<T>(acc[c]));
+                        const float other = __shfl_xor_sync(0xffffffffu, mine, 8);
+                        if (live && (f & 8) == 0 && n < args.K) {
+                            const int feat = (n >> 4) * 8 + (n & 7);
+                            out[static_cast<size_t>(m) * (args.K / 2) + feat] = from_f<T>((mine / (1.0f + expf(-mine))) * other);
+                        }
+                    } else if (live && n < args.K) {
+                        T vb = from_f<T>(acc[c]);
+                        if (args.epilogue == SK_EPI_RESIDUAL) vb = from_f<T>(to_f(res[static_cast<size_t>(m) * args.K + n]) + to_f(vb));
+                        out[static_cast<size_t>(m) * args.K + n] = vb;
+                    }
+                }
+            }
+        }
+    }
+    g_tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        g_tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(Smem::TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side --
+bool w4a16_skinny_supported(int M, int N, int K, int dtype) {
+    static const bool off = [] { const char *e = getenv("TL_SKINNY"); return e != nullptr && e[0] == '0'; }();
+    static const int min_rows = [] { const char *e = getenv("TL_SKINNY_MIN_ROWS"); return e ? atoi(e) : 9; }();
+    if (off) return false;
+    return (dtype == TL_BF16 || dtype == TL_F16) && M >= min_rows && M <= 128 && K > 0 && N % 128 == 0 && (K + SK_FEAT - 1) / SK_FEAT <= SK_COUNTER_BYTES / 4;
+}
+
+// Split policy (ours; the reference's constants are M4-Pro tuning, quantized_matmul.cpp:138-150): as many CTAs as
+// the GPU holds at one per SM, at least 4 reduction blocks per CTA.
+int w4a16_skinny_splits(int N, int K) {
+    const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
+    const int num_kb = N / SK_KB;
+    int splits = (sm_count() + tiles / 2) / tiles;
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    if (splits < 1) splits = 1;
+    const int kbps = (num_kb + splits - 1) / splits;
+    return (num_kb + kbps - 1) / kbps;
+}
+
+size_t w4a16_skinny_workspace(int M, int N, int K) {
+    const int splits = w4a16_skinny_splits(N, K);
+    return SK_COUNTER_BYTES + (splits > 1 ? static_cast<size_t>(splits) * M * K * sizeof(float) : 0);
+}
+
+struct SkMapKey {
+    const void *ptr;
+    unsigned long long d0, d1;
+    unsigned b0, b1;
+    int kind;
+    bool operator==(const SkMapKey &o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && b0 == o.b0 && b1 == o.b1 && kind == o.kind; }
+};
+struct SkMapKeyHash {
+    size_t operator()(const SkMapKey &k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        for (unsigned long long v : {k.d0, k.d1, static_cast<unsigned long long>(k.b0), static_cast<unsigned long long>(k.b1), static_cast<unsigned long long>(k.kind)})
+            h = h * 1000003u ^ static_cast<size_t>(v);
+        return h;
+    }
+};
+// 2-D tensor maps cached per (pointer, shape): kind 0 = 16-bit activations [rows, cols] with the 128-byte swizzle,
+// kind 1 = packed weights as bytes [rows, cols/2], no swizzle.
+static int sk_cached_map(CUtensorMap *out, const void *ptr, int kind, cuuint64_t cols, cuuint64_t rows, cuuint32_t box_cols, cuuint32_t box_rows,
+                         CUtensorMapDataType dt, size_t elem) {
+    static std::mutex mu;
+    static std::unordered_map<SkMapKey, CUtensorMap, SkMapKeyHash> cache;
+    SkMapKey key{ptr, cols, rows, box_cols, box_rows, kind * 4 + static_cast<int>(dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT16)};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return TL_OK;
+    }
+    PFN_cuTensorMapEncodeTiled_v12000 encode = tensor_map_encoder();
+    if (encode == nullptr) return fail(TL_ECUDA, "quantized_matmul: cuTensorMapEncodeTiled is unavailable");
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * elem};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap map;
+    CUresult r = encode(&map, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        kind == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TL_ECUDA, "quantized_matmul: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, map);
+    *out = map;
+    return TL_OK;
+}
+
+template <typename T, int NT>
+static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkArgs &args, int grid, size_t smem, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+            return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit");
+        configured = true;
+    }
+    w4a16_skinny_kernel<T, NT><<<grid, SK_THREADS, smem, st>>>(ma, mw, args);
+    TL_LAUNCH_CHECK("w4a16_skinny");
+    return TL_OK;
+}
+
+template <typename T>
+static int skinny_t(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N, int K,
+                    int epilogue, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!aligned16(a) || !aligned16(b)) return fail(TL_EINVAL, "quantized_matmul: a and b must be 16-byte aligned");
+    const int NT = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
+    const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
+    const int num_kb = N / SK_KB;
+    SkArgs args{};
+    args.scales = scales, args.biases = biases, args.residual = residual, args.out = out;
+    args.M = M, args.N = N, args.K = K, args.epilogue = epilogue;
+    args.splits = w4a16_skinny_splits(N, K);
+    args.kb_per_split = (num_kb + args.splits - 1) / args.splits;
+    if (ws == nullptr || ws_bytes < w4a16_skinny_workspace(M, N, K))
+        return fail(TL_EWORKSPACE, "quantized_matmul: workspace too small (%zu < %zu)", ws_bytes, w4a16_skinny_workspace(M, N, K));
+    args.tickets = static_cast<int *>(ws);
+    args.partials = reinterpret_cast<float *>(static_cast<unsigned char *>(ws) + SK_COUNTER_BYTES);
+    CUtensorMap ma, mw;
+    const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    if (int e = sk_cached_map(&ma, a, 0, N, M, SK_KB, NT, dt, 2)) return e;
+    if (int e = sk_cached_map(&mw, b, 1, static_cast<cuuint64_t>(N) / 2, K, SK_KB / 2, SK_FEAT, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1)) return e;
+    const int groups = (args.kb_per_split + 1) / 2 + 1;
+    const int grid = tiles * args.splits;
+    auto smem_for = [&](int stages, int b_bytes) { return static_cast<size_t>(stages) * (SK_A_BYTES + b_bytes) + SK_PSTAGES * SK_PACKED_BYTES + 512 + static_cast<size_t>(groups) * SK_FEAT * 4; };
+    switch (NT) {
+        case 16: return skinny_launch<T, 16>(ma, mw, args, grid, smem_for(SkSmem<16>::STAGES, SkSmem<16>::B_BYTES), st);
+        case 32: return skinny_launch<T, 32>(ma, mw, args, grid, smem_for(SkSmem<32>::STAGES, SkSmem<32>::B_BYTES), st);
+        case 64: return skinny_launch<T, 64>(ma, mw, args, grid, smem_for(SkSmem<64>::STAGES, SkSmem<64>::B_BYTES), st);
+        default: return skinny_launch<T, 128>(ma, mw, args, grid, smem_for(SkSmem<128>::STAGES, SkSmem<128>::B_BYTES), st);
+    }
+}
+
+int launch_w4a16_skinny(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N,
+                        int K, int epilogue, int dtype, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (M == 0 || K == 0) return TL_OK;
+    if (epilogue == SK_EPI_SWIGLU_PAIRS && K % 16 != 0) return fail(TL_EINVAL, "quantized_matmul: interleaved gate|up rows need K %% 16 == 0");
+    if (dtype == TL_BF16) return skinny_t<__nv_bfloat16>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, st);
+    if (dtype == TL_F16) return skinny_t<__half>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, st);
+    return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
+}
+
+}  // namespace tl

@@ -80,7 +80,8 @@ _SIGNATURES = {
     "tl_argmax_workspace": (_SZ, [_I, _I]),
     "tl_argmax": (_I, [_VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "tl_decode_advance": (_I, [_VP] * 6 + [_I, _I, _VP]),
-    "tl_quantized_matmul_fused": (_I, [_VP] * 7 + [_I] * 6 + [_F, _I, _VP]),
+    "tl_quantized_matmul_fused_workspace": (_SZ, [_I] * 6),
+    "tl_quantized_matmul_fused": (_I, [_VP] * 7 + [_I] * 6 + [_F, _I, _VP, _SZ, _VP]),
     "tl_decode_qk_norm_rope_append": (_I, [_VP] * 9 + [_I] * 4 + [_F, _F] + [_I] * 4 + [_VP]),
     "tl_decode_attention_fused_workspace": (_SZ, [_I, _I, _I]),
     "tl_decode_attention_fused": (_I, [_VP] * 11 + [_I] * 4 + [_F, _F] + [_I] * 5 + [_VP]),
@@ -153,6 +154,26 @@ def _workspace(nbytes: int, device) -> torch.Tensor | None:
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
+_ZERO_WS: dict = {}
+_ZERO_WS_KEEP: list = []  # outgrown buffers may still be referenced by captured CUDA graphs
+
+
+def _zero_workspace(nbytes: int, device) -> torch.Tensor | None:
+    """Persistent zero-initialised workspace per device for the split-reduction GEMM: its head holds
+    arrival tickets that must be zero on entry and are left zero by the kernel
+    (``TL_QMM_TICKET_BYTES``), so one buffer serves every launch issued in stream order."""
+    if nbytes == 0:
+        return None
+    key = torch.device(device)
+    buf = _ZERO_WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ZERO_WS_KEEP.append(buf)
+        buf = torch.zeros(max(nbytes, 16 << 20), dtype=torch.uint8, device=device)
+        _ZERO_WS[key] = buf
+    return buf
+
+
 # --------------------------------------------------------------------------
 def quantized_matmul(
     scales,
@@ -202,7 +223,7 @@ def quantized_matmul(
     out = torch.empty((M, K), dtype=a.dtype, device=a.device)
     code = _DTYPE_CODE[a.dtype]
     ws_bytes = _lib.tl_quantized_matmul_workspace(M, N, K, code, int(use_simdgroup), int(use_split_k))
-    ws = _workspace(ws_bytes, a.device)
+    ws = _zero_workspace(ws_bytes, a.device)
     _check(
         _lib.tl_quantized_matmul(
             scales.data_ptr(), biases.data_ptr(), a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, code,
@@ -532,11 +553,15 @@ def quantized_matmul_fused(scales, biases, b, p0, p1=None, residual=None, prolog
         raise RuntimeError("quantized_matmul_fused: interleaved gate|up rows need K % 16 == 0")
     if out is None:
         out = torch.empty((M, K // 2 if epilogue == EPI_SWIGLU_PAIRS else K), dtype=p0.dtype, device=p0.device)
+    code = _DTYPE_CODE[p0.dtype]
+    ws_bytes = _lib.tl_quantized_matmul_fused_workspace(M, N, K, lda, int(prologue), code)
+    ws = _zero_workspace(ws_bytes, p0.device)
     _check(
         _lib.tl_quantized_matmul_fused(
             scales.data_ptr(), biases.data_ptr(), b.data_ptr(), out.data_ptr(), p0.data_ptr(),
             None if p1 is None else p1.data_ptr(), None if residual is None else residual.data_ptr(), M, N, K, lda,
-            int(prologue), int(epilogue), float(eps), _DTYPE_CODE[p0.dtype], _stream_ptr(stream, p0),
+            int(prologue), int(epilogue), float(eps), code, None if ws is None else ws.data_ptr(), ws_bytes,
+            _stream_ptr(stream, p0),
         )
     )
     return out

@@ -223,7 +223,7 @@ class DecodeEngine:
         emb = m.embedding.weight
         # producer -> consumer hand-off through device flags instead of grid completion (tl_chain_begin)
         # (only when every launch between the first projection and the head is chain-aware)
-        chained = self._attention_fused and os.environ.get("TL_CHAIN", "1") != "0"
+        chained = self._attention_fused and self.B <= 8 and os.environ.get("TL_CHAIN", "1") != "0"
         if chained:
             self._chain_flags.zero_()
         x = ext.quantized_embedding(self.tokens, emb.scales, emb.biases, emb.weight, emb.group_size, emb.bits)
@@ -242,11 +242,21 @@ class DecodeEngine:
     def _forward_fused_chain(self, x):
         m = self.model
         B, Hq, Hkv, D = self.B, self.Hq, self.Hkv, self.D
+        # More than 8 rows: the projections run on the swap-AB tcgen05 kernel (w4a16_skinny.cu: weights streamed once
+        # for all rows), which has no prologue, so RMSNorm is its own (tiny) launch; the rounding points are the same.
+        wide = B > 8
+
+        def normed(h, norm):
+            return ext.rms_norm(h, norm._weight_as(h.dtype, h.device), norm.eps)
+
         for i, block in enumerate(m.layers_inner):
             at, pk, pool = block.self_attn, self._packed[i], m.page_pools[i]
             ln1, ln2 = block.input_layernorm, block.post_attention_layernorm
-            qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, x, ln1._weight_as(x.dtype, x.device),
-                                             prologue=ext.PRO_RMSNORM, eps=ln1.eps)
+            if wide:
+                qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, normed(x, ln1))
+            else:
+                qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, x, ln1._weight_as(x.dtype, x.device),
+                                                 prologue=ext.PRO_RMSNORM, eps=ln1.eps)
             if self._attention_fused:
                 y = ext.decode_attention_fused(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
                                                self.offsets, self.tables[i], self.context_lens, self._rope_inv_freq,
@@ -259,11 +269,17 @@ class DecodeEngine:
                 y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i], self.context_lens,
                                         at.scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
             x = ext.quantized_matmul_fused(at.wo.scales, at.wo.biases, at.wo.weight, y.view(B, Hq * D), residual=x, epilogue=ext.EPI_RESIDUAL)
-            act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, x, ln2._weight_as(x.dtype, x.device),
-                                             prologue=ext.PRO_RMSNORM, eps=ln2.eps, epilogue=ext.EPI_SWIGLU_PAIRS)  # [B, inter]
+            if wide:
+                act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, normed(x, ln2),
+                                                 epilogue=ext.EPI_SWIGLU_PAIRS)
+            else:
+                act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, x, ln2._weight_as(x.dtype, x.device),
+                                                 prologue=ext.PRO_RMSNORM, eps=ln2.eps, epilogue=ext.EPI_SWIGLU_PAIRS)  # [B, inter]
             wd = block.mlp.w_down
             x = ext.quantized_matmul_fused(wd.scales, wd.biases, wd.weight, act, residual=x, epilogue=ext.EPI_RESIDUAL)
         head = m.w_lm_head if m.w_lm_head is not None else m.embedding.weight
+        if wide:
+            return ext.quantized_matmul_fused(head.scales, head.biases, head.weight, normed(x, m.norm))
         return ext.quantized_matmul_fused(head.scales, head.biases, head.weight, x, m.norm._weight_as(x.dtype, x.device),
                                           prologue=ext.PRO_RMSNORM, eps=m.norm.eps)
 
