@@ -404,9 +404,9 @@ int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, co
     l.k_pages = key_pages, l.v_pages = value_pages;
     static bool configured = false;
     if (!configured) {
-        static const bool carve = [] { const char *v = getenv("TL_S5_CARVEOUT"); return !(v != nullptr && v[0] == '0'); }();
+        static const int carve = [] { const char *v = getenv("TL_S5_CARVEOUT"); return v != nullptr ? atoi(v) : -1; }();  // see w4a16_matvec.cu
         if (cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MK_ATT_BYTES + 64)) != cudaSuccess ||
-            (carve && cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess))
+            (carve > 0 && cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve) != cudaSuccess))
             return fail(TL_ECUDA, "decode_attention_fused: cannot raise shared memory limit");
         configured = true;
     }

@@ -392,10 +392,13 @@ static int stream5_launch(StreamArgs args, cudaStream_t st) {
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(limit));
-        static const bool carve = [] { const char *v = getenv("TL_S5_CARVEOUT"); return !(v != nullptr && v[0] == '0'); }();
-        if (e == cudaSuccess && carve)  // largest shared-memory carveout: co-resident CTAs of different launches must fit side by side
-            e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U, NW>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared);
+        // NO shared-memory carveout preference by default: the register pipeline keeps up to 128 KiB of weight loads in
+        // flight per SM and those loads are staged in L1 lines even with L1::no_allocate; forcing the largest shared-memory
+        // carveout (tried in round 2 for co-residency) left ~1 KiB of L1 and cost 1.75x on every projection
+        // (lm_head 49 -> 86 us, whole token 1.42 -> 1.95 ms).  TL_S5_CARVEOUT=<percent> sets one for experiments.
+        static const int carve = [] { const char *v = getenv("TL_S5_CARVEOUT"); return v != nullptr ? atoi(v) : -1; }();
+        if (e == cudaSuccess && carve > 0)
+            e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
         configured = true;
     }

@@ -113,6 +113,7 @@ def main():
     ap.add_argument("--lib", default=None, help="alternative libtiny_llm_b200*.so (experiment builds)")
     ap.add_argument("--only", default=None, help="comma-separated matvec shape names; skips attention and small ops")
     ap.add_argument("--attention-only", action="store_true")
+    ap.add_argument("--batches", default=None, help="comma-separated activation row counts for the projection sweep")
     args = ap.parse_args()
     import os
 
@@ -124,6 +125,8 @@ def main():
     report = {"hbm_peak_gbs": peak, "gpu": torch.cuda.get_device_name(0), "matvec": [], "attention": [], "small_ops_us": {}}
     shapes = [("q", 2560, 4096), ("kv", 2560, 1024), ("o", 4096, 2560), ("gate_up", 2560, 9728), ("down", 9728, 2560), ("lm_head", 2560, 151936)]
     batches = [1, 8] if args.quick else [1, 2, 4, 8, 16, 32]
+    if args.batches:
+        batches = [int(b) for b in args.batches.split(",")]
     if args.only:
         shapes = [s for s in shapes if s[0] in args.only.split(",")]
     if args.attention_only:
@@ -135,7 +138,7 @@ def main():
             gbs = nbytes / us / 1e3
             report["matvec"].append(dict(name=name, M=M, N=N, K=K, us=round(us, 2), gbs=round(gbs, 1), frac=round(gbs / peak, 3)))
             print(f"matvec {name:8s} M={M:2d} {N}->{K}: {us:8.2f} us  {gbs:7.1f} GB/s  {gbs / peak:5.1%}", flush=True)
-    for B, S in [] if args.only else ([(1, 1024), (1, 8192)] if args.quick else [(1, 128), (1, 1024), (1, 4096), (1, 8192), (8, 4096), (32, 2048), (64, 8192)]):
+    for B, S in [] if args.only else ([(1, 1024), (1, 8192)] if args.quick else [(1, 128), (1, 1024), (1, 4096), (1, 8192), (8, 4096), (32, 2048), (64, 1024), (64, 8192)]):
         try:
             us, nbytes = attention_case(B, S)
         except torch.OutOfMemoryError:
