@@ -58,7 +58,7 @@ constexpr int TC_K_OFF = TC_P_OFF + TC_P_BYTES;
 constexpr int TC_V_OFF = TC_K_OFF + TC_STAGES * TC_KV_TILE;
 constexpr int TC_BAR_OFF = TC_V_OFF + TC_STAGES * TC_KV_TILE;
 constexpr int TC_SMEM_BYTES = TC_BAR_OFF + 256;
-constexpr int TC_TMEM_COLS = 256;  // S: columns [0, 64), O: columns [128, 256)
+constexpr int TC_TMEM_COLS = 256;  // S (two buffers): columns [0, 64) and [64, 128), O: columns [128, 256)
 constexpr int TC_TMEM_O = 128;
 constexpr float TC_LOG2E = 1.44269504089f;
 constexpr float TC_RESCALE_THRESHOLD = 8.0f;  // log2: rescale O when a row maximum grew by more than 2^8
@@ -108,9 +108,9 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const uint32_t q_base = g_smem_u32(tsm + TC_Q_OFF), p_base = g_smem_u32(tsm + TC_P_OFF);
     const uint32_t k_base = g_smem_u32(tsm + TC_K_OFF), v_base = g_smem_u32(tsm + TC_V_OFF);
     const uint32_t bar = g_smem_u32(tsm + TC_BAR_OFF);
-    const uint32_t q_full = bar, s_full = bar + 8, p_full = bar + 16, o_full = bar + 24;
-    const uint32_t k_full = bar + 32, k_empty = bar + 32 + 8 * TC_STAGES, v_full = bar + 32 + 16 * TC_STAGES, v_empty = bar + 32 + 24 * TC_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tsm + TC_BAR_OFF + 32 + 32 * TC_STAGES);
+    const uint32_t q_full = bar, s_full = bar + 8 /* two: one per S buffer */, p_full = bar + 24, pv_done = bar + 32;
+    const uint32_t k_full = bar + 40, k_empty = k_full + 8 * TC_STAGES, v_full = k_full + 16 * TC_STAGES, v_empty = k_full + 24 * TC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tsm + TC_BAR_OFF + 40 + 32 * TC_STAGES);
 
     if (warp == 4 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
@@ -120,8 +120,9 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     if (warp == 5 && lane == 0) {
         g_mbar_init(q_full, 1);
         g_mbar_init(s_full, 1);
+        g_mbar_init(s_full + 8, 1);
         g_mbar_init(p_full, TC_SOFTMAX_THREADS);
-        g_mbar_init(o_full, 1);
+        g_mbar_init(pv_done, 1);
         for (int i = 0; i < TC_STAGES; ++i) {
             g_mbar_init(k_full + 8 * i, 1);
             g_mbar_init(k_empty + 8 * i, 1);
@@ -166,28 +167,34 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
     } else if (warp == 5) {
         // ------------------------------------------------------------ MMA issuer
+        // Order: S_0, then per tile j: S_{j+1} (second score buffer) | wait P_j | O += P_j V_j.  The tensor core works
+        // on the next tile's scores while the softmax warps are busy with this tile's.
         if (lane == 0 && n_tiles > 0) {
             constexpr uint32_t idesc_s = tc_instr_desc(TC_BN, false);
             constexpr uint32_t idesc_o = tc_instr_desc(TC_D, true);
             g_mbar_wait(q_full, 0);
-            for (int j = 0; j < n_tiles; ++j) {
+            auto issue_scores = [&](int j) {  // S_j = Q K_j^T: both operands K-major, two 64-wide halves of the head dimension
                 const int s = j % TC_STAGES;
-                const uint32_t ph = (j / TC_STAGES) & 1;
-                // ---- S = Q K^T: both operands K-major, two 64-wide halves of the head dimension
-                g_mbar_wait(k_full + 8 * s, ph);
+                g_mbar_wait(k_full + 8 * s, (j / TC_STAGES) & 1);
                 g_tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < TC_D / 16; ++k) {
                     const uint32_t half = (k >> 2), kk = (k & 3);
                     const uint64_t adesc = g_smem_desc_sw128(q_base + half * (TC_Q_BYTES / 2), 0, 1024) + 2 * kk;
                     const uint64_t bdesc = g_smem_desc_sw128(k_base + s * TC_KV_TILE + half * (TC_KV_TILE / 2), 0, 1024) + 2 * kk;
-                    g_tc_mma(tmem, adesc, bdesc, idesc_s, k > 0 ? 1u : 0u);
+                    g_tc_mma(tmem + (j & 1) * TC_BN, adesc, bdesc, idesc_s, k > 0 ? 1u : 0u);
                 }
-                g_tc_commit(k_empty + 8 * s);  // K stage reusable once these MMAs have read it
-                g_tc_commit(s_full);           // ... and the scores are complete (also: every earlier MMA, i.e. P V of tile j-1)
+                g_tc_commit(k_empty + 8 * s);        // K stage reusable once these MMAs have read it
+                g_tc_commit(s_full + 8 * (j & 1));   // ... and the scores of tile j are complete
+            };
+            issue_scores(0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % TC_STAGES;
+                // score buffer (j+1)&1 was last read for tile j-1, whose P has been waited for below
+                if (j + 1 < n_tiles) issue_scores(j + 1);
                 // ---- O += P V: P K-major [128 x 64 keys], V MN-major [64 keys x 128 d] as loaded from the page
                 g_mbar_wait(p_full, j & 1);
-                g_mbar_wait(v_full + 8 * s, ph);
+                g_mbar_wait(v_full + 8 * s, (j / TC_STAGES) & 1);
                 g_tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < TC_BN / 16; ++k) {
@@ -197,8 +204,8 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     g_tc_mma(tmem + TC_TMEM_O, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                 }
                 g_tc_commit(v_empty + 8 * s);
+                g_tc_commit(pv_done);  // O holds tiles 0..j and the P buffer is free again
             }
-            g_tc_commit(o_full);
         }
     } else {
         // ------------------------------------------------------------ softmax warps (thread = row = TMEM lane)
@@ -215,31 +222,41 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             const int lp = (t0 + j) / a.tiles_per_page;
             const int pid = table[lp];
             const bool page_ok = pid >= 0 && pid < a.num_pages;
-            g_mbar_wait(s_full, j & 1);
+            g_mbar_wait(s_full + 8 * (j & 1), (j >> 1) & 1);
             g_tc_fence_after();
             uint32_t sv[2][32];
-            g_tmem_ld32_nowait(tmem + lane_base, sv[0]);
-            g_tmem_ld32_nowait(tmem + lane_base + 32, sv[1]);
+            g_tmem_ld32_nowait(tmem + lane_base + (j & 1) * TC_BN, sv[0]);
+            g_tmem_ld32_nowait(tmem + lane_base + (j & 1) * TC_BN + 32, sv[1]);
             g_tmem_ld_wait();
             const int key0 = (t0 + j) * TC_BN;
             const int visible = page_ok ? min(limit - key0 + 1, TC_BN) : 0;  // keys [0, visible) of the tile
-            float tile_max = -CUDART_INF_F;
+            // raw maximum (the scale is positive, so it commutes with max); masking only on boundary tiles
+            float raw_max = -CUDART_INF_F;
+            if (visible >= TC_BN) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float sc = (h * 32 + c) < visible ? __uint_as_float(sv[h][c]) * a.scale_log2 : -CUDART_INF_F;
-                    sv[h][c] = __float_as_uint(sc);
-                    tile_max = fmaxf(tile_max, sc);
-                }
+                    for (int c = 0; c < 32; ++c) raw_max = fmaxf(raw_max, __uint_as_float(sv[h][c]));
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if ((h * 32 + c) >= visible) sv[h][c] = 0xff800000u;  // -inf: exp2 gives exactly 0
+                        raw_max = fmaxf(raw_max, __uint_as_float(sv[h][c]));
+                    }
+            }
+            const float tile_max = raw_max * a.scale_log2;  // -inf stays -inf
+            if (j > 0) g_mbar_wait(pv_done, (j - 1) & 1);   // P V of tile j-1 complete: O is stable, the P buffer is free
             // lazy rescale: keep the stale maximum unless this tile exceeds it by more than 2^8
             const bool grow = tile_max > m_used + TC_RESCALE_THRESHOLD || (m_used == -CUDART_INF_F && tile_max != -CUDART_INF_F);
             if (__any_sync(0xffffffffu, grow) && j > 0) {
+                g_tc_fence_after();
                 const float m_new = grow ? tile_max : m_used;
                 const float alpha = (grow && m_used != -CUDART_INF_F) ? exp2f(m_used - m_new) : (grow ? 0.f : 1.f);
                 l_sum *= alpha;
 #pragma unroll
-                for (int cb = 0; cb < TC_D / 32; ++cb) {  // s_full of tile j implies P V of tile j-1 has completed: O is stable
+                for (int cb = 0; cb < TC_D / 32; ++cb) {
                     uint32_t ov[32];
                     g_tmem_ld32(tmem + lane_base + TC_TMEM_O + cb * 32, ov);
 #pragma unroll
@@ -258,7 +275,8 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
-                    const float p0 = exp2f(__uint_as_float(sv[h][c]) - m_eff), p1 = exp2f(__uint_as_float(sv[h][c + 1]) - m_eff);
+                    const float p0 = exp2f(fmaf(__uint_as_float(sv[h][c]), a.scale_log2, -m_eff));
+                    const float p1 = exp2f(fmaf(__uint_as_float(sv[h][c + 1]), a.scale_log2, -m_eff));
                     tile_sum += p0 + p1;
                     pk[h * 16 + c / 2] = pack2<bf16>(p0, p1);
                 }
@@ -274,7 +292,7 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         // ---- epilogue: O / sum -> bf16 -> out[(b*Hq + head) * L + l, :]
         if (n_tiles > 0) {
-            g_mbar_wait(o_full, 0);
+            g_mbar_wait(pv_done, (n_tiles - 1) & 1);
             g_tc_fence_after();
         }
         const size_t out_row = static_cast<size_t>(b * a.Hq + kvh * a.G + g) * a.L + l;

@@ -14,8 +14,8 @@
 //   * the reduction is split over `splits` CTAs per feature tile so that tiles x splits ~ #SMs; partial
 //     sums go to a workspace in fp32 and the LAST CTA of a tile (atomic ticket) adds them in split order
 //     (deterministic) and runs the epilogue (plain / + residual / SwiGLU of interleaved gate|up rows);
-//   * packed weights arrive by TMA (one 128 rows x 32 B box per 64-wide reduction block, 8-deep ring:
-//     32 KiB in flight per CTA without a register), 256 dequantiser threads turn them into the K-major
+//   * packed weights arrive by TMA (one 128-row x 128-byte box = four 64-wide reduction blocks per copy, 2-3 boxes
+//     in flight: 32-48 KiB per CTA without a register), 256 dequantiser threads turn them into the K-major
 //     128B-swizzled bf16 tile (LOP3 magic -> exact code -> one HFMA2, the rounding point of the
 //     reference's tiled kernel, quantized_matmul.metal:183-194), activations arrive by TMA (tokens beyond M
 //     zero-filled), one thread issues tcgen05.mma M128 N{16..128} K16.
@@ -33,8 +33,8 @@ namespace tl {
 
 constexpr int SK_FEAT = 128;      // features per CTA tile (UMMA M)
 constexpr int SK_KB = 64;         // reduction elements per stage (one 128-byte swizzle atom)
-constexpr int SK_PSTAGES = 8;     // packed-weight ring (4 KiB per stage)
-constexpr int SK_PACKED_BYTES = SK_FEAT * SK_KB / 2;  // 4096
+constexpr int SK_PK = 4;          // reduction blocks per packed-weight TMA box: 128 rows x 128 B (a 32-byte-wide box cost ~3 us per block)
+constexpr int SK_PACKED_BYTES = SK_PK * SK_FEAT * SK_KB / 2;  // 16 KiB per box, 128-byte swizzle
 constexpr int SK_A_BYTES = SK_FEAT * SK_KB * 2;       // 16 KiB dequantised tile
 constexpr int SK_DEQ_THREADS = 256;
 constexpr int SK_THREADS = 128 + SK_DEQ_THREADS;
@@ -43,12 +43,13 @@ enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
 
 template <int NT>
 struct SkSmem {
-    static constexpr int STAGES = NT >= 64 ? 2 : 3;  // <= 112 KB with the 32 KiB packed ring: two CTAs per SM
+    static constexpr int STAGES = NT >= 64 ? 2 : 3;
+    static constexpr int PSTAGES = NT >= 128 ? 2 : 3;  // packed ring: 32 / 48 KiB in flight; total <= 112 KB: two CTAs per SM
     static constexpr int B_BYTES = NT * SK_KB * 2;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = A_OFF + STAGES * SK_A_BYTES;
     static constexpr int P_OFF = B_OFF + STAGES * B_BYTES;
-    static constexpr int BAR_OFF = P_OFF + SK_PSTAGES * SK_PACKED_BYTES;
+    static constexpr int BAR_OFF = P_OFF + PSTAGES * SK_PACKED_BYTES;
     static constexpr int SB_OFF = BAR_OFF + 512;  // scale|bias pairs [groups][128 rows] u32 follow
     static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
 };
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(SK_THREADS, 2)
 w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const SkArgs args) {
     using Smem = SkSmem<NT>;
     constexpr int STAGES = Smem::STAGES;
+    constexpr int PSTAGES = Smem::PSTAGES;
     extern __shared__ __align__(1024) unsigned char ssm[];
     __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,8 +104,8 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t a_base = g_smem_u32(ssm + Smem::A_OFF), b_base = g_smem_u32(ssm + Smem::B_OFF), p_base = g_smem_u32(ssm + Smem::P_OFF);
     const uint32_t bar = g_smem_u32(ssm + Smem::BAR_OFF);
     const uint32_t full_a = bar, full_b = bar + 8 * STAGES, empty = bar + 16 * STAGES;
-    const uint32_t p_full = bar + 24 * STAGES, p_empty = p_full + 8 * SK_PSTAGES, tmem_full = p_empty + 8 * SK_PSTAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ssm + Smem::BAR_OFF + 24 * STAGES + 16 * SK_PSTAGES + 8);
+    const uint32_t p_full = bar + 24 * STAGES, p_empty = p_full + 8 * PSTAGES, tmem_full = p_empty + 8 * PSTAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ssm + Smem::BAR_OFF + 24 * STAGES + 16 * PSTAGES + 8);
     uint32_t *sb = reinterpret_cast<uint32_t *>(ssm + Smem::SB_OFF);  // [g_cnt][128]: (scale, bias) of the tile's rows
 
     if (warp == 0 && lane == 0) {
@@ -116,7 +118,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             g_mbar_init(full_b + 8 * i, 1);
             g_mbar_init(empty + 8 * i, 1);
         }
-        for (int i = 0; i < SK_PSTAGES; ++i) {
+        for (int i = 0; i < PSTAGES; ++i) {
             g_mbar_init(p_full + 8 * i, 1);
             g_mbar_init(p_empty + 8 * i, SK_DEQ_THREADS);
         }
@@ -141,13 +143,14 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------ TMA producer: packed weights, 8 blocks ahead
+        // ------------------------------------------------ TMA producer: packed weights, one 128-row x 128-byte box per 4 blocks
         if (lane == 0) {
-            for (int i = 0; i < n_kb; ++i) {
-                const int ps = i % SK_PSTAGES;
-                g_mbar_wait(p_empty + 8 * ps, ((i / SK_PSTAGES) & 1) ^ 1);
-                g_mbar_expect_tx(p_full + 8 * ps, SK_PACKED_BYTES);
-                g_tma_load_2d(p_base + ps * SK_PACKED_BYTES, &tmap_w, (kb0 + i) * (SK_KB / 2), tile * SK_FEAT, p_full + 8 * ps);
+            const int n_box = (n_kb + SK_PK - 1) / SK_PK;
+            for (int i = 0; i < n_box; ++i) {
+                const int ps = i % PSTAGES;
+                g_mbar_wait(p_empty + 8 * ps, ((i / PSTAGES) & 1) ^ 1);
+                g_mbar_expect_tx(p_full + 8 * ps, SK_PACKED_BYTES);  // columns past the row end are zero-filled and still counted
+                g_tma_load_2d(p_base + ps * SK_PACKED_BYTES, &tmap_w, (kb0 + i * SK_PK) * (SK_KB / 2), tile * SK_FEAT, p_full + 8 * ps);
             }
         }
     } else if (warp == 3) {
@@ -186,10 +189,13 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t magic = SkNum<T>::MAGIC;
         const V2 offset2 = *reinterpret_cast<const V2 *>(&magic);
         for (int i = 0; i < n_kb; ++i) {
-            const int ps = i % SK_PSTAGES, s = i % STAGES;
-            g_mbar_wait(p_full + 8 * ps, (i / SK_PSTAGES) & 1);
-            const uint4 cur = *reinterpret_cast<const uint4 *>(ssm + Smem::P_OFF + ps * SK_PACKED_BYTES + row * 32 + half * 16);
-            g_mbar_arrive(p_empty + 8 * ps);  // the 16 bytes are in registers
+            const int box = i / SK_PK, sub = i - box * SK_PK;
+            const int ps = box % PSTAGES, s = i % STAGES;
+            if (sub == 0) g_mbar_wait(p_full + 8 * ps, (box / PSTAGES) & 1);
+            // row `row` of the box: 128 bytes = 8 chunks of 16 B, chunk c stored at (c ^ (row & 7)) by the TMA swizzle
+            const int chunk = sub * 2 + half;
+            const uint4 cur = *reinterpret_cast<const uint4 *>(ssm + Smem::P_OFF + ps * SK_PACKED_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4));
+            if (sub == SK_PK - 1 || i == n_kb - 1) g_mbar_arrive(p_empty + 8 * ps);  // this thread is done with the box
             const uint32_t pair = sb[(((kb0 + i) >> 1) - g0) * SK_FEAT + row];
             const unsigned short s16 = static_cast<unsigned short>(pair & 0xffffu), b16 = static_cast<unsigned short>(pair >> 16);
             V2 s2, b2;
@@ -257,12 +263,14 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             __threadfence();
             asm volatile("bar.sync 1, %0;" ::"n"(SK_DEQ_THREADS) : "memory");
-            if (threadIdx.x == 128) s_last = (atomicAdd(args.tickets + tile, 1) == args.splits - 1) ? 1 : 0;
-            asm volatile("bar.sync 1, %0;" ::"n"(SK_DEQ_THREADS) : "memory");
-            if (s_last) {
-                __threadfence();
-                if (threadIdx.x == 128) args.tickets[tile] = 0;  // leave the ticket clean for the next launch
+            if (threadIdx.x == 128) {
+                int prev;  // release: this CTA's partial plane precedes the ticket; acquire: the other planes precede the reads below
+                asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(prev) : "l"(args.tickets + tile) : "memory");
+                s_last = prev == args.splits - 1 ? 1 : 0;
+                if (s_last) args.tickets[tile] = 0;  // leave the ticket clean for the next launch
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(SK_DEQ_THREADS) : "memory");
+            if (s_last) __threadfence();
         }
         const bool finisher = args.splits == 1 || s_last;
         if (finisher && reader) {
@@ -361,7 +369,7 @@ struct SkMapKeyHash {
     }
 };
 // 2-D tensor maps cached per (pointer, shape): kind 0 = 16-bit activations [rows, cols] with the 128-byte swizzle,
-// kind 1 = packed weights as bytes [rows, cols/2], no swizzle.
+// kind 1 = packed weights as bytes [rows, cols/2], 128-byte boxes with the 128-byte swizzle.
 static int sk_cached_map(CUtensorMap *out, const void *ptr, int kind, cuuint64_t cols, cuuint64_t rows, cuuint32_t box_cols, cuuint32_t box_rows,
                          CUtensorMapDataType dt, size_t elem) {
     static std::mutex mu;
@@ -381,7 +389,7 @@ static int sk_cached_map(CUtensorMap *out, const void *ptr, int kind, cuuint64_t
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMap map;
     CUresult r = encode(&map, dt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        kind == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TL_ECUDA, "quantized_matmul: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
     if (cache.size() > 8192) cache.clear();
@@ -423,15 +431,15 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
     CUtensorMap ma, mw;
     const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (int e = sk_cached_map(&ma, a, 0, N, M, SK_KB, NT, dt, 2)) return e;
-    if (int e = sk_cached_map(&mw, b, 1, static_cast<cuuint64_t>(N) / 2, K, SK_KB / 2, SK_FEAT, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1)) return e;
+    if (int e = sk_cached_map(&mw, b, 1, static_cast<cuuint64_t>(N) / 2, K, SK_PK * SK_KB / 2, SK_FEAT, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1)) return e;
     const int groups = (args.kb_per_split + 1) / 2 + 1;
     const int grid = tiles * args.splits;
-    auto smem_for = [&](int stages, int b_bytes) { return static_cast<size_t>(stages) * (SK_A_BYTES + b_bytes) + SK_PSTAGES * SK_PACKED_BYTES + 512 + static_cast<size_t>(groups) * SK_FEAT * 4; };
+    const size_t sb_bytes = static_cast<size_t>(groups) * SK_FEAT * 4;
     switch (NT) {
-        case 16: return skinny_launch<T, 16>(ma, mw, args, grid, smem_for(SkSmem<16>::STAGES, SkSmem<16>::B_BYTES), st);
-        case 32: return skinny_launch<T, 32>(ma, mw, args, grid, smem_for(SkSmem<32>::STAGES, SkSmem<32>::B_BYTES), st);
-        case 64: return skinny_launch<T, 64>(ma, mw, args, grid, smem_for(SkSmem<64>::STAGES, SkSmem<64>::B_BYTES), st);
-        default: return skinny_launch<T, 128>(ma, mw, args, grid, smem_for(SkSmem<128>::STAGES, SkSmem<128>::B_BYTES), st);
+        case 16: return skinny_launch<T, 16>(ma, mw, args, grid, SkSmem<16>::SB_OFF + sb_bytes, st);
+        case 32: return skinny_launch<T, 32>(ma, mw, args, grid, SkSmem<32>::SB_OFF + sb_bytes, st);
+        case 64: return skinny_launch<T, 64>(ma, mw, args, grid, SkSmem<64>::SB_OFF + sb_bytes, st);
+        default: return skinny_launch<T, 128>(ma, mw, args, grid, SkSmem<128>::SB_OFF + sb_bytes, st);
     }
 }
 
