@@ -314,17 +314,7 @@ def matvec_roofline(model, engine, ext, device) -> dict:
     head = model.w_lm_head if model.w_lm_head is not None else model.embedding.weight
     launches = 4 * len(model.layers_inner) + 1
 
-    flags = torch.zeros(launches + 1, dtype=torch.int32, device=device)
-
     def body():
-        flags.zero_()
-        ext.chain_begin(flags)  # the engine's hand-off between dependent launches (tl_chain_begin)
-        try:
-            chain()
-        finally:
-            ext.chain_end()
-
-    def chain():
         for block, pk in zip(model.layers_inner, engine._packed):
             wo, wd = block.self_attn.wo, block.mlp.w_down
             ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, x, norm_w, prologue=ext.PRO_RMSNORM, eps=1e-6)

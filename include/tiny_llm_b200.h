@@ -199,19 +199,6 @@ int tl_decode_attention_fused(const void *qkv, const void *q_norm_weight, const 
                               float *workspace, int batch, int num_heads, int num_kv_heads, int head_dim, float eps,
                               float scale, int num_pages, int page_size, int max_pages, int max_context, int dtype,
                               void *stream);
-/* Dependency chain of one decode step (B200 runtime; no reference counterpart: the reference orders
- * its ~500 operator calls per token through the MLX graph, quantized_matmul.cpp:74-79).
- * Between tl_chain_begin and tl_chain_end every launch of tl_quantized_matmul_fused and
- * tl_decode_attention_fused on the calling thread takes the next flag of `flags`: it waits until
- * all CTAs of the previous chain launch have release-incremented that launch's flag (instead of
- * waiting for the whole grid to complete and flush, ~4 us on B200) and increments its own flag
- * after its last store.  Requirements: programmatic dependent launch on (tl_set_pdl), the launches
- * form a linear producer -> consumer sequence on one stream, `flags` holds `capacity` zeroed int32
- * (zero them in stream order before the first launch of every run, e.g. a memset node of the same
- * graph).  Launches beyond `capacity` fall back to grid completion. */
-int tl_chain_begin(int32_t *flags, int capacity);
-int tl_chain_end(void);
-
 /* Programmatic dependent launch for the streaming kernels (on by default; 0 turns it off,
  * TL_PDL=0 in the environment does the same). */
 int tl_set_pdl(int enabled);

@@ -326,9 +326,6 @@ extern "C" int tl_debug_trace(unsigned long long *device_events, unsigned int *d
 }
 #endif
 
-int tl_chain_begin(int32_t *flags, int capacity) { return chain_begin(flags, capacity); }
-int tl_chain_end(void) { return chain_end(); }
-
 int tl_set_pdl(int enabled) {
     set_use_pdl(enabled != 0);
     return TL_OK;

@@ -16,17 +16,6 @@ int check_launch(const char *what);        // cudaPeekAtLastError -> TL_ECUDA
 void count_launch(int n = 1);
 int sm_count();
 
-// ---- dependency chain (w4a16_matvec.cu): between tl_chain_begin() and tl_chain_end() every chain-aware
-// launch waits for its predecessor's data through a device flag instead of griddepcontrol.wait.
-struct ChainLink {
-    const int *wait_flag;  // nullptr: first link (or no chain) -> griddepcontrol.wait
-    int wait_target;       // CTAs of the predecessor
-    int *signal_flag;      // nullptr: no chain
-};
-ChainLink chain_link(int ctas);
-int chain_begin(int *flags, int capacity);
-int chain_end();
-
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -129,33 +118,6 @@ __device__ __forceinline__ __nv_bfloat16 ld_cg(const __nv_bfloat16 *p) {
     asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");
     return __ushort_as_bfloat16(r);
 }
-// Data hand-off between two launches of a dependency chain without waiting for the producer grid to
-// COMPLETE (griddepcontrol.wait = all CTAs exited + memory flush, measured ~4 us on B200): every
-// producer CTA release-increments the flag after its last store, the consumer's thread 0
-// acquire-polls until all producer CTAs have arrived, then a block barrier publishes the observation.
-__device__ __forceinline__ void chain_wait(const ChainLink &link) {
-    if (link.wait_flag == nullptr) {
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        return;
-    }
-    if (threadIdx.x == 0) {
-        unsigned spins = 0;
-        while (true) {
-            int seen;
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(link.wait_flag) : "memory");
-            if (seen >= link.wait_target) break;
-            if (++spins > (1u << 24)) __trap();  // seconds: a lost producer must not hang the GPU
-        }
-    }
-    __syncthreads();
-}
-// Call with ALL threads after the CTA's last global store.
-__device__ __forceinline__ void chain_signal(const ChainLink &link) {
-    if (link.signal_flag == nullptr) return;
-    __syncthreads();
-    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(link.signal_flag) : "memory");
-}
-
 __device__ __forceinline__ __half ld_cg(const __half *p) {
     unsigned short r;
     asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p) : "memory");

@@ -41,7 +41,6 @@ struct MkArgs {
     float *attn_ws;                         // [B*Hq*nsplit*(D+2)] when nsplit > 1
     int nsplit, tokens_per_split;
     const double *rope_inv_freq;            // [D/2]
-    ChainLink link;                         // data hand-off from the q|k|v projection / to the o projection
 };
 
 __device__ __forceinline__ float mk_bf(bf16 v) { return __bfloat162float(v); }
@@ -176,7 +175,7 @@ __device__ void mk_attention(const MkArgs &a, const MkLayer &l, unsigned char *d
         prof.stamp(50003);
         if (DEPWAIT && rb == begin) {
             TL_TRACE_STAMP(21);
-            chain_wait(a.link);  // the qkv row of this step exists now
+            asm volatile("griddepcontrol.wait;" ::: "memory");  // the qkv row of this step exists now
             TL_TRACE_STAMP(22);
             load_q();
         }
@@ -345,28 +344,21 @@ __device__ void mk_attention_merge(const MkArgs &a) {
 }
 
 // ---- the attention phase as a kernel of its own (CUDA-graph decode path) ----
-// 2 blocks/SM in the launch bounds caps the kernel at 64 registers (62 used, no spills): 512 threads x 64 = half the
-// register file, so a CTA of this launch fits on an SM NEXT to an 8-warp CTA of the projection before or after it.
-#ifndef MK_ATT_MINBLOCKS
-#define MK_ATT_MINBLOCKS 2
-#endif
-__global__ void __launch_bounds__(MK_THREADS, MK_ATT_MINBLOCKS) decode_attention_fused_kernel(const MkArgs a, const MkLayer l) {
+__global__ void __launch_bounds__(MK_THREADS, 1) decode_attention_fused_kernel(const MkArgs a, const MkLayer l) {
     extern __shared__ __align__(128) unsigned char att_smem_raw[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the o_proj stream may prefetch its weights now
     TL_TRACE_STAMP(20);
     Prof prof;
     mk_attention<true>(a, l, att_smem_raw, prof);
     TL_TRACE_STAMP(29);
-    chain_signal(a.link);
 }
 #if TL_TRACE
 void trace_bind_attention(unsigned long long *buf, unsigned int *n, unsigned int cap) { trace_bind(buf, n, cap); }
 #endif
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_attention_merge_kernel(const MkArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    chain_wait(a.link);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     mk_attention_merge(a);
-    chain_signal(a.link);
 }
 
 static int attention_max_split(int batch, int num_kv_heads) {
@@ -404,9 +396,7 @@ int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, co
     l.k_pages = key_pages, l.v_pages = value_pages;
     static bool configured = false;
     if (!configured) {
-        static const int carve = [] { const char *v = getenv("TL_S5_CARVEOUT"); return v != nullptr ? atoi(v) : -1; }();  // see w4a16_matvec.cu
-        if (cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MK_ATT_BYTES + 64)) != cudaSuccess ||
-            (carve > 0 && cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve) != cudaSuccess))
+        if (cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MK_ATT_BYTES + 64)) != cudaSuccess)
             return fail(TL_ECUDA, "decode_attention_fused: cannot raise shared memory limit");
         configured = true;
     }
@@ -420,7 +410,6 @@ int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, co
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl() ? 1 : 0;  // without the attribute griddepcontrol.wait returns at once
-    a.link = use_pdl() ? chain_link(static_cast<int>(cfg.gridDim.x)) : ChainLink{nullptr, 0, nullptr};
     cudaError_t e = cudaLaunchKernelEx(&cfg, decode_attention_fused_kernel, a, l);
     if (e != cudaSuccess) return fail(TL_ECUDA, "decode_attention_fused: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("decode_attention_fused");
@@ -428,7 +417,6 @@ int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, co
         const int heads = batch * num_heads;
         cfg.gridDim = dim3((heads + MK_WARPS - 1) / MK_WARPS);
         cfg.dynamicSmemBytes = 0;
-        a.link = use_pdl() ? chain_link(static_cast<int>(cfg.gridDim.x)) : ChainLink{nullptr, 0, nullptr};
         e = cudaLaunchKernelEx(&cfg, decode_attention_merge_kernel, a);
         if (e != cudaSuccess) return fail(TL_ECUDA, "decode_attention_merge: launch failed: %s", cudaGetErrorString(e));
         TL_LAUNCH_CHECK("decode_attention_merge");

@@ -61,17 +61,16 @@ int launch_w4a16_stream(const void *scales, const void *biases, const void *a, c
 //   epilogue RESIDUAL: out = T(float(res) + float(T(acc)))   (qwen3_week3.py:204-206)
 //   epilogue SWIGLU_PAIRS: rows 16c+r / 16c+8+r hold gate / up feature 8c+r;
 //                     out[m, 8c+r] = T(silu(T(acc_gate)) * T(acc_up))  (week2_kernels.metal:115-116)
-// Co-residency (round 2).  With 16 warps x 128 registers a CTA owns a whole SM, so the CTAs of the
-// next projection could only start once those of the current one had exited: HBM sat idle through
-// every reduce/store -> exit -> launch -> first-request sequence (round-1 timeline: ~4 of the 7.7 us
-// of an average launch).  For small batches (MP <= 4) the kernel now runs as 8-warp CTAs, two per
-// SM, ONE per SM from each launch: while launch n consumes, the CTAs of launch n+1 are already
-// resident next to them with their first 64 KiB of weights per SM in flight (requested before
-// griddepcontrol.wait), and the few-CTA attention launch fits beside a projection too.  The same
-// property lets K = 2560 projections use 160 equal one-chunk CTAs instead of 148 CTAs of which 12
-// carried two chunks.
-constexpr int S5_WARPS_FULL = 16;
-constexpr int S5_WARPS_HALF = 8;
+// Round-2 experiments that did NOT pay and were removed again (numbers: DESIGN.md section 4, profiles/r02_decode_ab.jsonl):
+//   * 8-warp CTAs, two per SM, one from each of two consecutive launches (so that launch n+1 prefetches while launch n
+//     consumes): the consume phase is issue-bound, half the warps per launch doubled it (gate|up 5.4 -> 11.9 us) and the
+//     token went 1.44 -> 1.75 ms;
+//   * a device-flag hand-off between dependent launches instead of griddepcontrol.wait: 1.44 -> 1.55 ms (the CTAs of the
+//     consumer cannot start before the producer's CTAs exit anyway, the flag traffic only adds);
+//   * forcing the largest shared-memory carveout: the register pipeline keeps up to 128 KiB of weight loads in flight per
+//     SM and those loads are staged in L1 lines even with L1::no_allocate - with ~1 KiB of L1 left every projection was
+//     1.75x slower (lm_head 49 -> 86 us, token 1.42 -> 1.95 ms).  No carveout preference is set here.
+constexpr int S5_WARPS = 16;
 #ifndef S5_DEPTH_SMALL
 #define S5_DEPTH_SMALL 4
 #endif
@@ -87,7 +86,6 @@ struct StreamArgs {
     int prologue, epilogue;
     float eps;
     int rows_per_pass;
-    ChainLink link;
 };
 
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -95,9 +93,9 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 
 // MP: activation rows per pass padded to a power of two (template: shared-memory offsets of the
 // B fragments become immediates).  U: 128-column groups per unit (2 when N % 256 == 0).
-// NW: warps per CTA (16: one CTA per SM; 8: two per SM, see above).
-template <typename T, int MP, int U, int NW>
-__global__ void __launch_bounds__(NW * 32, 16 / NW) w4a16_stream5_kernel(const StreamArgs args) {
+template <typename T, int MP, int U>
+__global__ void __launch_bounds__(S5_WARPS * 32, 1) w4a16_stream5_kernel(const StreamArgs args) {
+    constexpr int NW = S5_WARPS;
     constexpr int NT = NW * 32;
     constexpr int MT = (MP + 7) / 8;
     constexpr int MPA = w4_mpa(MP);
@@ -168,7 +166,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) w4a16_stream5_kernel(const S
     for (int k = 0; k < DEPTH; ++k) load_next(buf[k]);  // in flight before the activations exist
     TL_TRACE_STAMP(11);
 
-    chain_wait(args.link);  // activations (and the residual) come from the previous kernel
+    griddep_wait();  // activations (and the residual) come from the previous kernel
     TL_TRACE_STAMP(12);
     const T *p0 = static_cast<const T *>(args.p0) + static_cast<size_t>(pass) * args.rows_per_pass * args.lda;
     const T *p1 = args.prologue == PRO_SWIGLU
@@ -248,7 +246,6 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) w4a16_stream5_kernel(const S
             out[static_cast<size_t>(m) * (K / 2) + c0 * 8 + rr] = from_f<T>((gate / (1.0f + expf(-gate))) * up);
         }
         TL_TRACE_STAMP(15);
-        chain_signal(args.link);
         return;
     }
     // ---- sum the entries of each chunk in warp order, add the residual, store
@@ -267,7 +264,6 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) w4a16_stream5_kernel(const S
         }
     }
     TL_TRACE_STAMP(15);
-    chain_signal(args.link);
 }
 
 #if TL_TRACE
@@ -285,39 +281,9 @@ static bool g_use_pdl = pdl_default();
 void set_use_pdl(bool on) { g_use_pdl = on; }
 bool use_pdl() { return g_use_pdl; }
 
-// ---- dependency chain state (host, per thread; see common.cuh)
-static thread_local struct {
-    int *flags = nullptr;
-    int capacity = 0, next = 0, prev_ctas = 0;
-} g_chain;
-int chain_begin(int *flags, int capacity) {
-    if (flags == nullptr || capacity < 1) return fail(TL_EINVAL, "chain_begin: need a flag array");
-    g_chain.flags = flags, g_chain.capacity = capacity, g_chain.next = 0, g_chain.prev_ctas = 0;
-    return TL_OK;
-}
-int chain_end() {
-    g_chain.flags = nullptr, g_chain.capacity = g_chain.next = g_chain.prev_ctas = 0;
-    return TL_OK;
-}
-ChainLink chain_link(int ctas) {
-    static const bool off = [] { const char *e = getenv("TL_CHAIN"); return e != nullptr && e[0] == '0'; }();
-    ChainLink link{nullptr, 0, nullptr};
-    if (off || g_chain.flags == nullptr || g_chain.next >= g_chain.capacity) {
-        // out of flags: fall back to grid completion for this and later links (the launch BEFORE this one
-        // still signals its flag, nobody polls it; griddepcontrol.wait orders everything)
-        g_chain.flags = nullptr;
-        return link;
-    }
-    if (g_chain.next > 0) link.wait_flag = g_chain.flags + g_chain.next - 1, link.wait_target = g_chain.prev_ctas;
-    link.signal_flag = g_chain.flags + g_chain.next;
-    g_chain.next += 1;
-    g_chain.prev_ctas = ctas;
-    return link;
-}
-
 constexpr size_t S5_SMEM_MAX = 226 * 1024;
-constexpr size_t S5_SMEM_HALF_MAX = 100 * 1024;  // two CTAs (+ 1 KiB of system shared memory each) per SM, attention beside one
-static size_t stream5_smem_bytes(int N, int K, int MP, int grid, int nw) {
+static size_t stream5_smem_bytes(int N, int K, int MP, int grid) {
+    const int nw = S5_WARPS;
     const int MT = (MP + 7) / 8, MPA = MP < 8 ? 8 : MP;
     const int all = (K + 15) / 16;
     const int chunks = (all + grid - 1) / grid;
@@ -330,81 +296,34 @@ static size_t stream5_smem_bytes(int N, int K, int MP, int grid, int nw) {
 }
 
 // ---- launch geometry
-// Full-SM CTAs (16 warps): one CTA per SM minus TL_S5_RESERVE (default 8) so that the few CTAs of
-// the kernel behind it can start early (round 1: 1.499 -> 1.399 ms/token).
-// Half-SM CTAs (8 warps): by default the largest grid <= #SMs + #SMs/8 that gives every CTA the
-// same number of 16-row chunks when such a grid exists within 25 % of #SMs, else one CTA per SM.
-// TL_S5_GRID="K:grid,K:grid" overrides per output-feature count (experiments).
-static int env_grid_override(int K) {
-    static const char *spec = getenv("TL_S5_GRID");
-    if (spec == nullptr) return 0;
-    const char *p = spec;
-    while (*p) {
-        char *endp = nullptr;
-        const long k = strtol(p, &endp, 10);
-        if (endp == p || *endp != ':') break;
-        const long gsz = strtol(endp + 1, &endp, 10);
-        if (k == K && gsz > 0) return static_cast<int>(gsz);
-        p = *endp == ',' ? endp + 1 : endp;
-        if (*endp != ',') break;
-    }
-    return 0;
-}
-static int stream5_grid(int K, int nw) {
+// One CTA per SM minus TL_S5_RESERVE (default 8): the few CTAs of the kernel behind it (the 8-CTA attention launch, the
+// first CTAs of the next projection) then start early under programmatic dependent launch and issue their independent
+// loads while this one is still running (round 1: 1.499 -> 1.399 ms/token; 16 reserved: no further gain).
+static int stream5_grid(int K) {
+    static const int reserve = [] { const char *e = getenv("TL_S5_RESERVE"); const int v = e ? atoi(e) : 8; return v < 0 ? 0 : v; }();
     const int all = (K + 15) / 16;
-    if (const int forced = env_grid_override(K)) return forced < all ? forced : all;
-    if (nw == S5_WARPS_FULL) {
-        static const int reserve = [] { const char *e = getenv("TL_S5_RESERVE"); const int v = e ? atoi(e) : 8; return v < 0 ? 0 : v; }();
-        int sms = sm_count() - reserve;
-        if (sms < 1) sms = 1;
-        return all < sms ? all : sms;
-    }
-    const int sms = sm_count();
-    if (all <= sms) return all;
-    // equal chunk counts: grid = all / c for the smallest c with all % c == 0 and grid <= 1.125 * sms
-    const int per = (all + sms - 1) / sms;  // chunks per CTA at one CTA per SM
-    for (int c = per; c >= 1 && c >= per - 1; --c) {
-        if (all % c == 0) {
-            const int gsz = all / c;
-            if (gsz <= sms + sms / 8 && gsz * 4 >= sms * 3) return gsz;
-        }
-    }
-    return sms;
+    int sms = sm_count() - reserve;
+    if (sms < 1) sms = 1;
+    return all < sms ? all : sms;
 }
 
-static bool half_enabled() {
-    static const bool on = [] { const char *e = getenv("TL_S5_HALF"); return !(e != nullptr && e[0] == '0'); }();
-    return on;
-}
-static int half_max_rows() {
-    static const int v = [] { const char *e = getenv("TL_S5_HALF_MAXMP"); return e ? atoi(e) : 4; }();
-    return v;
-}
-
-template <typename T, int MP, int U, int NW>
+template <typename T, int MP, int U>
 static int stream5_launch(StreamArgs args, cudaStream_t st) {
-    const int grid_x = stream5_grid(args.K, NW);
-    const size_t smem = stream5_smem_bytes(args.N, args.K, MP, grid_x, NW);
-    const size_t limit = NW == S5_WARPS_HALF ? S5_SMEM_HALF_MAX : S5_SMEM_MAX;
+    const int grid_x = stream5_grid(args.K);
+    const size_t smem = stream5_smem_bytes(args.N, args.K, MP, grid_x);
+    const size_t limit = S5_SMEM_MAX;
     if (smem > limit)
         return fail(TL_EINVAL, "quantized_matmul: activations do not fit in shared memory (N=%d, K=%d, rows=%d)", args.N, args.K, MP);
     static bool configured = false;  // per process: one device per process
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(limit));
-        // NO shared-memory carveout preference by default: the register pipeline keeps up to 128 KiB of weight loads in
-        // flight per SM and those loads are staged in L1 lines even with L1::no_allocate; forcing the largest shared-memory
-        // carveout (tried in round 2 for co-residency) left ~1 KiB of L1 and cost 1.75x on every projection
-        // (lm_head 49 -> 86 us, whole token 1.42 -> 1.95 ms).  TL_S5_CARVEOUT=<percent> sets one for experiments.
-        static const int carve = [] { const char *v = getenv("TL_S5_CARVEOUT"); return v != nullptr ? atoi(v) : -1; }();
-        if (e == cudaSuccess && carve > 0)
-            e = cudaFuncSetAttribute(w4a16_stream5_kernel<T, MP, U, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit: %s", cudaGetErrorString(e));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid_x, ceil_div(args.M, args.rows_per_pass));
-    cfg.blockDim = dim3(NW * 32);
+    cfg.blockDim = dim3(S5_WARPS * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -412,37 +331,26 @@ static int stream5_launch(StreamArgs args, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 1 : 0;
-    args.link = g_use_pdl ? chain_link(static_cast<int>(cfg.gridDim.x * cfg.gridDim.y)) : ChainLink{nullptr, 0, nullptr};
-    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream5_kernel<T, MP, U, NW>, args);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, w4a16_stream5_kernel<T, MP, U>, args);
     if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_stream5: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("w4a16_stream5");
     return TL_OK;
-}
-
-template <typename T, int MP, int U>
-static int stream5_mp(StreamArgs args, cudaStream_t st) {
-    if constexpr (MP <= 4) {
-        if (half_enabled() && MP <= half_max_rows() &&
-            stream5_smem_bytes(args.N, args.K, MP, stream5_grid(args.K, S5_WARPS_HALF), S5_WARPS_HALF) <= S5_SMEM_HALF_MAX)
-            return stream5_launch<T, MP, U, S5_WARPS_HALF>(args, st);
-    }
-    return stream5_launch<T, MP, U, S5_WARPS_FULL>(args, st);
 }
 
 template <typename T, int U>
 static int stream5_u(StreamArgs args, cudaStream_t st) {
     // rows of `a` handled per pass: as many (power of two, <= 32) as fit in shared memory
     int rpp = w4_pad_cols(args.M < 32 ? args.M : 32);
-    const int grid_x = stream5_grid(args.K, S5_WARPS_FULL);
-    while (rpp > 1 && stream5_smem_bytes(args.N, args.K, rpp, grid_x, S5_WARPS_FULL) > S5_SMEM_MAX) rpp /= 2;
+    const int grid_x = stream5_grid(args.K);
+    while (rpp > 1 && stream5_smem_bytes(args.N, args.K, rpp, grid_x) > S5_SMEM_MAX) rpp /= 2;
     args.rows_per_pass = rpp;
     switch (rpp) {
-        case 1: return stream5_mp<T, 1, U>(args, st);
-        case 2: return stream5_mp<T, 2, U>(args, st);
-        case 4: return stream5_mp<T, 4, U>(args, st);
-        case 8: return stream5_mp<T, 8, U>(args, st);
-        case 16: return stream5_mp<T, 16, U>(args, st);
-        default: return stream5_mp<T, 32, U>(args, st);
+        case 1: return stream5_launch<T, 1, U>(args, st);
+        case 2: return stream5_launch<T, 2, U>(args, st);
+        case 4: return stream5_launch<T, 4, U>(args, st);
+        case 8: return stream5_launch<T, 8, U>(args, st);
+        case 16: return stream5_launch<T, 16, U>(args, st);
+        default: return stream5_launch<T, 32, U>(args, st);
     }
 }
 

@@ -42,8 +42,6 @@ __all__ = [
     "quantized_matmul_fused",
     "decode_qk_norm_rope_append",
     "set_pdl",
-    "chain_begin",
-    "chain_end",
     "launch_count",
     "device_info",
     "current_library_path",
@@ -87,8 +85,6 @@ _SIGNATURES = {
     "tl_decode_attention_fused": (_I, [_VP] * 11 + [_I] * 4 + [_F, _F] + [_I] * 5 + [_VP]),
     "tl_paged_cache_append_chunk": (_I, [_VP] * 5 + [_I] * 4 + [ctypes.c_longlong, ctypes.c_longlong, _I, _VP]),
     "tl_set_pdl": (_I, [_I]),
-    "tl_chain_begin": (_I, [_VP, _I]),
-    "tl_chain_end": (_I, []),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -645,18 +641,6 @@ def decode_attention_fused(qkv, q_norm_weight, k_norm_weight, offsets, block_tab
         )
     )
     return out
-
-
-def chain_begin(flags: torch.Tensor) -> None:
-    """Start a dependency chain (``tl_chain_begin``): ``flags`` is a zeroed int32 CUDA tensor with one
-    entry per chain-aware launch that follows (``quantized_matmul_fused``, ``decode_attention_fused``)."""
-    if not flags.is_cuda or flags.dtype != torch.int32 or not flags.is_contiguous():
-        raise RuntimeError("chain_begin: flags must be a contiguous int32 CUDA tensor")
-    _check(_lib.tl_chain_begin(flags.data_ptr(), int(flags.numel())))
-
-
-def chain_end() -> None:
-    _check(_lib.tl_chain_end())
 
 
 def set_pdl(enabled: bool) -> None:

@@ -128,7 +128,6 @@ class DecodeEngine:
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.logits = None
         # per slot: the request group (its per-layer cache objects) the table rows reflect
-        self._chain_flags = torch.zeros(6 * Ly + 8, dtype=torch.int32, device=self.device)
         self._recs: list[_SlotRecord | None] = [None] * B
         self._tables_dirty = True
         self._upload_event = torch.cuda.Event()
@@ -221,25 +220,14 @@ class DecodeEngine:
         Every rounding point of the operator-by-operator sequence is kept."""
         m = self.model
         emb = m.embedding.weight
-        # producer -> consumer hand-off through device flags instead of grid completion (tl_chain_begin)
-        # (only when every launch between the first projection and the head is chain-aware)
-        chained = self._attention_fused and self.B <= 8 and os.environ.get("TL_CHAIN", "1") != "0"
-        if chained:
-            self._chain_flags.zero_()
         x = ext.quantized_embedding(self.tokens, emb.scales, emb.biases, emb.weight, emb.group_size, emb.bits)
-        if chained:
-            ext.chain_begin(self._chain_flags)
-        try:
-            logits = self._forward_fused_chain(x)
-        finally:
-            if chained:
-                ext.chain_end()
+        logits = self._forward_fused_layers(x)
         self.next_tokens.copy_(ext.argmax(logits))
         if self.logits is None:
             self.logits = torch.empty_like(logits)
         self.logits.copy_(logits)
 
-    def _forward_fused_chain(self, x):
+    def _forward_fused_layers(self, x):
         m = self.model
         B, Hq, Hkv, D = self.B, self.Hq, self.Hkv, self.D
         # More than 8 rows: the projections run on the swap-AB tcgen05 kernel (w4a16_skinny.cu: weights streamed once
