@@ -170,6 +170,16 @@ int tl_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, co
                                   void *q_out, void *key_pages, void *value_pages, int batch, int num_heads,
                                   int num_kv_heads, int head_dim, float base, float eps, int num_pages, int page_size,
                                   int max_pages, int dtype, void *stream);
+/* Prefill-chunk form of the same kernel: the rows of qkv [tokens, (Hq + 2*Hkv) * D] are consecutive tokens of ONE
+ * request (one shared block-table row, int32 [max_pages]); offsets[t] is the RoPE position and context_lens[t]
+ * the post-append length of token t (0 = padding row: nothing is appended), all DEVICE data, so a captured
+ * chunk replays for any position.  q_out is [Hq, tokens, D] - the layout tl_paged_attention takes.  Replaces,
+ * for one chunk, rms_norm x2 + rope x2 + the paged_cache_update calls of qwen3_week3.py:62-84. */
+int tl_chunk_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, const void *k_norm_weight,
+                                 const int32_t *offsets, const int32_t *block_table_row, const int32_t *context_lens,
+                                 void *q_out, void *key_pages, void *value_pages, int tokens, int num_heads,
+                                 int num_kv_heads, int head_dim, float base, float eps, int num_pages, int page_size,
+                                 int max_pages, int dtype, void *stream);
 /* Chunk append (B200 extension of paged_cache_update, paged_attention.cpp:14-31): the rows of ONE
  * request's key/value chunk [1, H, L, D] (element strides src_head_stride / src_token_stride, unit
  * inner stride) are written into up to TL_PAGE_SPANS page slices in one launch:

@@ -268,3 +268,41 @@ def test_config1_golden_trace_qwen3_0p6b_shape(dev):
     for c in cache:
         c.release()
     print(f"config-1 trace: worst top-4 log-prob deviation {worst:.4f} nat over {len(golden['tokens'])} steps")
+
+
+# ------------------------------------------------------------------ chunked-prefill graph engine --
+def test_prefill_chunk_graph_equals_the_operator_path(dev):
+    """engine.PrefillEngine (one captured chunk, right-aligned tail chunks, device-driven K/V append) against the
+    operator-by-operator path of the same model: logits of every chunk's last token, the pages written and the
+    integer bookkeeping (page ids / page lens / offset, bit-exact), then a decode step on top of both caches."""
+    ns = to_device(synthetic_qwen3("tiny-d128", seed=5, realistic=True, max_position_embeddings=512), dev)
+    eager = Qwen3ModelWeek3(ns, page_size=64)
+    eager.prefill_graph_len = 0
+    graph = Qwen3ModelWeek3(ns, page_size=64)
+    graph.prefill_graph_len = 32
+    graph.decode_graph_max_seq_len = 256
+    graph.prefill_engine(32).reserve_pools(16)
+    for pool in eager.page_pools:
+        pool.reserve(16, 2, 128, dtype=torch.bfloat16, device=dev)
+    g = gen(77)
+    prompt = torch.randint(1, 500, (77,), generator=g).tolist()  # chunks of 32, 32, 13 (the tail is right-aligned in 32 rows)
+    ce, cg = eager.create_kv_cache(), graph.create_kv_cache()
+    offset = 0
+    while offset < len(prompt):
+        ids = torch.tensor([prompt[offset : offset + 32]], dtype=torch.int32, device=dev)
+        want = eager(ids, [offset], ce, logits_to_keep=1)
+        got = graph(ids, [offset], cg, logits_to_keep=1)
+        assert got.shape == want.shape
+        torch.testing.assert_close(got.float(), want.float(), rtol=0, atol=0.08, msg=lambda m: f"chunk at {offset}: {m}")
+        offset += ids.shape[1]
+        for a, b in zip(ce, cg):
+            assert a.page_ids == b.page_ids and a.page_lens == b.page_lens and a.offset == b.offset == offset
+    assert graph.prefill_engine(32).replays == 3
+    for layer, (pe, pg) in enumerate(zip(eager.page_pools, graph.page_pools)):
+        for pid, fill in zip(ce[layer].page_ids, ce[layer].page_lens):
+            torch.testing.assert_close(pg._key_pages[pid, :, :fill].float(), pe._key_pages[pid, :, :fill].float(), rtol=2**-6, atol=6e-2)
+            torch.testing.assert_close(pg._value_pages[pid, :, :fill].float(), pe._value_pages[pid, :, :fill].float(), rtol=2**-6, atol=6e-2)
+    tok = torch.tensor([[7]], dtype=torch.int32, device=dev)
+    torch.testing.assert_close(graph(tok, len(prompt), cg, logits_to_keep=1).float(), eager(tok, len(prompt), ce, logits_to_keep=1).float(), rtol=0, atol=0.08)
+    for c in (*ce, *cg):
+        c.release()

@@ -298,6 +298,22 @@ int tl_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, co
                                              num_pages, page_size, max_pages, dtype, as_stream(stream));
 }
 
+int tl_chunk_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, const void *k_norm_weight, const int32_t *offsets,
+                                 const int32_t *block_table_row, const int32_t *context_lens, void *q_out, void *key_pages,
+                                 void *value_pages, int tokens, int num_heads, int num_kv_heads, int head_dim, float base, float eps,
+                                 int num_pages, int page_size, int max_pages, int dtype, void *stream) {
+    if (dtype != TL_F32 && dtype != TL_BF16) return fail(TL_EDTYPE, "chunk_qk_norm_rope_append: bfloat16 or float32 required");
+    if (tokens < 0 || num_heads <= 0 || num_kv_heads <= 0 || head_dim <= 0 || head_dim % 2 != 0 || head_dim > 512 || num_pages <= 0 ||
+        page_size <= 0 || max_pages <= 0)
+        return fail(TL_EINVAL, "chunk_qk_norm_rope_append: bad shape");
+    if (tokens == 0) return TL_OK;
+    if (!qkv || !q_norm_weight || !k_norm_weight || !offsets || !block_table_row || !context_lens || !q_out || !key_pages || !value_pages)
+        return fail(TL_EINVAL, "chunk_qk_norm_rope_append: null pointer");
+    return launch_decode_qk_norm_rope_append(qkv, q_norm_weight, k_norm_weight, offsets, block_table_row, context_lens, q_out, key_pages,
+                                             value_pages, tokens, num_heads, num_kv_heads, head_dim, base, eps, num_pages, page_size,
+                                             max_pages, dtype, as_stream(stream), true);
+}
+
 size_t tl_decode_attention_fused_workspace(int batch, int num_heads, int num_kv_heads) {
     if (batch < 1 || num_heads < 1 || num_kv_heads < 1) return 0;
     return decode_attention_fused_workspace(batch, num_heads, num_kv_heads);

@@ -618,7 +618,9 @@ __global__ void decode_qk_norm_rope_append_kernel(const T *__restrict__ qkv, con
                                                   const int32_t *__restrict__ bt, const int32_t *__restrict__ cl,
                                                   T *__restrict__ q_out, T *__restrict__ kp, T *__restrict__ vp, int Hq,
                                                   int Hkv, int D, float base, float eps, int num_pages, int page_size,
-                                                  int max_pages) {
+                                                  int max_pages, int bt_stride, long long q_row_stride, long long q_head_stride) {
+    // bt_stride: block-table elements between rows (max_pages: one request per row; 0: every row is a token of ONE
+    // request - a prefill chunk).  q_out element (row b, head h) starts at b * q_row_stride + h * q_head_stride.
     __shared__ float warp_part[8];
     const int head = blockIdx.x;  // 0..Hq-1 q | Hq..Hq+Hkv-1 k | rest v
     const int b = blockIdx.y;
@@ -658,7 +660,7 @@ __global__ void decode_qk_norm_rope_append_kernel(const T *__restrict__ qkv, con
     }
     if (i >= half) return;
     if (is_q) {
-        T *dst = q_out + (static_cast<size_t>(b) * Hq + head) * D;
+        T *dst = q_out + static_cast<size_t>(b) * q_row_stride + static_cast<size_t>(head) * q_head_stride;
         dst[i] = out_re, dst[i + half] = out_im;
         return;
     }
@@ -667,7 +669,7 @@ __global__ void decode_qk_norm_rope_append_kernel(const T *__restrict__ qkv, con
     const int tok = ctx - 1;
     const int lp = tok / page_size;
     if (lp >= max_pages) return;
-    const int pid = bt[static_cast<size_t>(b) * max_pages + lp];
+    const int pid = bt[static_cast<size_t>(b) * bt_stride + lp];
     if (pid < 0 || pid >= num_pages) return;
     T *dst = (is_k ? kp : vp) + ((static_cast<size_t>(pid) * Hkv + kvh) * page_size + (tok - lp * page_size)) * D;
     dst[i] = out_re, dst[i + half] = out_im;
@@ -676,15 +678,20 @@ __global__ void decode_qk_norm_rope_append_kernel(const T *__restrict__ qkv, con
 int launch_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_w, const void *k_norm_w, const int32_t *offsets,
                                       const int32_t *block_table, const int32_t *context_lens, void *q_out, void *key_pages,
                                       void *value_pages, int batch, int Hq, int Hkv, int D, float base, float eps,
-                                      int num_pages, int page_size, int max_pages, int dtype, cudaStream_t st) {
+                                      int num_pages, int page_size, int max_pages, int dtype, cudaStream_t st, bool chunk) {
     if (batch == 0) return TL_OK;
+    // chunk: the rows are the tokens of one request (shared block-table row); q_out is [Hq, rows, D], the layout
+    // paged_attention takes; otherwise one request per row and q_out [rows, Hq, D]
+    const int bt_stride = chunk ? 0 : max_pages;
+    const long long q_row_stride = chunk ? D : static_cast<long long>(Hq) * D;
+    const long long q_head_stride = chunk ? static_cast<long long>(batch) * D : D;
     const int threads = ((D / 2 + 31) / 32) * 32;
     dim3 grid(Hq + 2 * Hkv, batch);
 #define TL_QKN(T)                                                                                                      \
     decode_qk_norm_rope_append_kernel<T><<<grid, threads, 0, st>>>(                                                    \
         static_cast<const T *>(qkv), static_cast<const T *>(q_norm_w), static_cast<const T *>(k_norm_w), offsets,     \
         block_table, context_lens, static_cast<T *>(q_out), static_cast<T *>(key_pages), static_cast<T *>(value_pages), \
-        Hq, Hkv, D, base, eps, num_pages, page_size, max_pages)
+        Hq, Hkv, D, base, eps, num_pages, page_size, max_pages, bt_stride, q_row_stride, q_head_stride)
     if (dtype == TL_BF16)
         TL_QKN(__nv_bfloat16);
     else if (dtype == TL_F32)

@@ -36,7 +36,7 @@ int launch_decode_advance(int32_t *tokens, const int32_t *next_tokens, int32_t *
 int launch_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_w, const void *k_norm_w, const int32_t *offsets,
                                       const int32_t *block_table, const int32_t *context_lens, void *q_out, void *key_pages,
                                       void *value_pages, int batch, int Hq, int Hkv, int D, float base, float eps,
-                                      int num_pages, int page_size, int max_pages, int dtype, cudaStream_t st);
+                                      int num_pages, int page_size, int max_pages, int dtype, cudaStream_t st, bool chunk = false);
 
 // w4a16_matvec.cu
 // Weight-streaming tensor-core kernel for M <= 32 rows per pass (larger M is
@@ -55,7 +55,7 @@ int launch_w4a16_vanilla(const void *scales, const void *biases, const void *a, 
 
 // w4a16_skinny.cu (swap-AB tcgen05 GEMM with split reduction, 9 <= M <= 128)
 bool w4a16_skinny_supported(int M, int N, int K, int dtype);
-int w4a16_skinny_splits(int N, int K);
+int w4a16_skinny_splits(int M, int N, int K);
 size_t w4a16_skinny_workspace(int M, int N, int K);
 int launch_w4a16_skinny(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N,
                         int K, int epilogue, int dtype, void *ws, size_t ws_bytes, cudaStream_t st);

@@ -14,8 +14,8 @@
 //   * the reduction is split over `splits` CTAs per feature tile so that tiles x splits ~ #SMs; partial
 //     sums go to a workspace in fp32 and the LAST CTA of a tile (atomic ticket) adds them in split order
 //     (deterministic) and runs the epilogue (plain / + residual / SwiGLU of interleaved gate|up rows);
-//   * packed weights arrive by TMA (one 128-row x 128-byte box = four 64-wide reduction blocks per copy, 2-3 boxes
-//     in flight: 32-48 KiB per CTA without a register), 256 dequantiser threads turn them into the K-major
+//   * packed weights arrive by TMA (one 128-row x 128-byte box = four 64-wide reduction blocks per copy, two boxes
+//     in flight: 32 KiB per CTA without a register), 256 dequantiser threads turn them into the K-major
 //     128B-swizzled bf16 tile (LOP3 magic -> exact code -> one HFMA2, the rounding point of the
 //     reference's tiled kernel, quantized_matmul.metal:183-194), activations arrive by TMA (tokens beyond M
 //     zero-filled), one thread issues tcgen05.mma M128 N{16..128} K16.
@@ -43,12 +43,15 @@ enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
 
 template <int NT>
 struct SkSmem {
-    static constexpr int STAGES = NT >= 64 ? 2 : 3;
-    static constexpr int PSTAGES = NT >= 128 ? 2 : 3;  // packed ring: 32 / 48 KiB in flight; total <= 112 KB: two CTAs per SM
+    static constexpr int STAGES = 2;                    // dequantised weight tiles (16 KiB each)
+    static constexpr int PSTAGES = 2;                   // packed boxes: 8 reduction blocks ahead
     static constexpr int B_BYTES = NT * SK_KB * 2;
+    // activation tiles: their own ring, deep enough to cover an L2 round trip (~1 us) at ~0.15 us per block; the first
+    // version shared the 2-3 weight-tile slots and paid that latency every other block (0.9 us per block measured)
+    static constexpr int BSTAGES = NT >= 64 ? 4 : 8;  // NT = 64: 96 KB + scales -> two CTAs per SM; NT = 128: 128 KB, one
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = A_OFF + STAGES * SK_A_BYTES;
-    static constexpr int P_OFF = B_OFF + STAGES * B_BYTES;
+    static constexpr int P_OFF = B_OFF + BSTAGES * B_BYTES;
     static constexpr int BAR_OFF = P_OFF + PSTAGES * SK_PACKED_BYTES;
     static constexpr int SB_OFF = BAR_OFF + 512;  // scale|bias pairs [groups][128 rows] u32 follow
     static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
@@ -91,6 +94,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     using Smem = SkSmem<NT>;
     constexpr int STAGES = Smem::STAGES;
     constexpr int PSTAGES = Smem::PSTAGES;
+    constexpr int BSTAGES = Smem::BSTAGES;
     extern __shared__ __align__(1024) unsigned char ssm[];
     __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,9 +107,9 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const uint32_t a_base = g_smem_u32(ssm + Smem::A_OFF), b_base = g_smem_u32(ssm + Smem::B_OFF), p_base = g_smem_u32(ssm + Smem::P_OFF);
     const uint32_t bar = g_smem_u32(ssm + Smem::BAR_OFF);
-    const uint32_t full_a = bar, full_b = bar + 8 * STAGES, empty = bar + 16 * STAGES;
-    const uint32_t p_full = bar + 24 * STAGES, p_empty = p_full + 8 * PSTAGES, tmem_full = p_empty + 8 * PSTAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ssm + Smem::BAR_OFF + 24 * STAGES + 16 * PSTAGES + 8);
+    const uint32_t full_a = bar, empty = bar + 8 * STAGES, p_full = bar + 16 * STAGES, p_empty = p_full + 8 * PSTAGES;
+    const uint32_t full_b = p_empty + 8 * PSTAGES, b_empty = full_b + 8 * BSTAGES, tmem_full = b_empty + 8 * BSTAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ssm + Smem::BAR_OFF + 16 * STAGES + 16 * PSTAGES + 16 * BSTAGES + 8);
     uint32_t *sb = reinterpret_cast<uint32_t *>(ssm + Smem::SB_OFF);  // [g_cnt][128]: (scale, bias) of the tile's rows
 
     if (warp == 0 && lane == 0) {
@@ -115,8 +119,11 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             g_mbar_init(full_a + 8 * i, SK_DEQ_THREADS);
-            g_mbar_init(full_b + 8 * i, 1);
             g_mbar_init(empty + 8 * i, 1);
+        }
+        for (int i = 0; i < BSTAGES; ++i) {
+            g_mbar_init(full_b + 8 * i, 1);
+            g_mbar_init(b_empty + 8 * i, 1);
         }
         for (int i = 0; i < PSTAGES; ++i) {
             g_mbar_init(p_full + 8 * i, 1);
@@ -157,8 +164,8 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ------------------------------------------------ TMA producer: activations
         if (lane == 0) {
             for (int i = 0; i < n_kb; ++i) {
-                const int s = i % STAGES;
-                g_mbar_wait(empty + 8 * s, ((i / STAGES) & 1) ^ 1);
+                const int s = i % BSTAGES;
+                g_mbar_wait(b_empty + 8 * s, ((i / BSTAGES) & 1) ^ 1);
                 g_mbar_expect_tx(full_b + 8 * s, Smem::B_BYTES);
                 g_tma_load_2d(b_base + s * Smem::B_BYTES, &tmap_a, (kb0 + i) * SK_KB, 0, full_b + 8 * s);
             }
@@ -168,16 +175,16 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             constexpr uint32_t idesc = sk_instr_desc<T, NT>();
             for (int i = 0; i < n_kb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                g_mbar_wait(full_a + 8 * s, ph);
-                g_mbar_wait(full_b + 8 * s, ph);
+                const int s = i % STAGES, bs = i % BSTAGES;
+                g_mbar_wait(full_a + 8 * s, (i / STAGES) & 1);
+                g_mbar_wait(full_b + 8 * bs, (i / BSTAGES) & 1);
                 g_tc_fence_after();
                 const uint64_t adesc = g_smem_desc_sw128(a_base + s * SK_A_BYTES, 0, 1024);
-                const uint64_t bdesc = g_smem_desc_sw128(b_base + s * Smem::B_BYTES, 0, 1024);
+                const uint64_t bdesc = g_smem_desc_sw128(b_base + bs * Smem::B_BYTES, 0, 1024);
 #pragma unroll
                 for (int k = 0; k < SK_KB / 16; ++k) g_tc_mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 g_tc_commit(empty + 8 * s);
+                g_tc_commit(b_empty + 8 * bs);
             }
             g_tc_commit(tmem_full);
         }
@@ -195,7 +202,6 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // row `row` of the box: 128 bytes = 8 chunks of 16 B, chunk c stored at (c ^ (row & 7)) by the TMA swizzle
             const int chunk = sub * 2 + half;
             const uint4 cur = *reinterpret_cast<const uint4 *>(ssm + Smem::P_OFF + ps * SK_PACKED_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4));
-            if (sub == SK_PK - 1 || i == n_kb - 1) g_mbar_arrive(p_empty + 8 * ps);  // this thread is done with the box
             const uint32_t pair = sb[(((kb0 + i) >> 1) - g0) * SK_FEAT + row];
             const unsigned short s16 = static_cast<unsigned short>(pair & 0xffffu), b16 = static_cast<unsigned short>(pair >> 16);
             V2 s2, b2;
@@ -218,6 +224,10 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 outw[4 * j + 2] = __byte_perm(p[0], p[1], 0x7632);
                 outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);
             }
+            // Release the packed box only now: `outw` depends on `cur`, so the shared-memory read has COMPLETED.  (Arriving
+            // right after issuing the load let the TMA refill the box under a load still in flight: single feature rows
+            // came out wrong in ~1 of 100 launches - mbarrier arrive is a SYNCS op, not ordered behind the LSU.)
+            if (sub == SK_PK - 1 || i == n_kb - 1) g_mbar_arrive(p_empty + 8 * ps);
             g_mbar_wait(empty + 8 * s, ((i / STAGES) & 1) ^ 1);
             unsigned char *dst = ssm + Smem::A_OFF + s * SK_A_BYTES + row * 128;
 #pragma unroll
@@ -291,12 +301,18 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int c = 0; c < 32; ++c) acc[c] = __uint_as_float(v[c]);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int m = col0 + c0 + c;
-                        float sum = 0.f;
-                        if (c < CH && m < args.M && n < args.K)
-                            for (int sp = 0; sp < args.splits; ++sp) sum += ld_cg(part + sp * plane + static_cast<size_t>(m) * args.K + n);  // split order: deterministic
-                        acc[c] = sum;
+                    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+                    // split order (deterministic); the 32 loads of one plane are issued back to back (ld_cg is volatile:
+                    // interleaving the adds serialised 32 x splits L2 round trips - 40 us per launch in the first version)
+                    for (int sp = 0; sp < args.splits; ++sp) {
+                        float v[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int m = col0 + c0 + c;
+                            v[c] = (c < CH && m < args.M && n < args.K) ? ld_cg(part + sp * plane + static_cast<size_t>(m) * args.K + n) : 0.f;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) acc[c] += v[c];
                     }
                 }
 #pragma unroll
@@ -336,20 +352,28 @@ bool w4a16_skinny_supported(int M, int N, int K, int dtype) {
     return (dtype == TL_BF16 || dtype == TL_F16) && M >= min_rows && M <= 128 && K > 0 && N % 128 == 0 && (K + SK_FEAT - 1) / SK_FEAT <= SK_COUNTER_BYTES / 4;
 }
 
-// Split policy (ours; the reference's constants are M4-Pro tuning, quantized_matmul.cpp:138-150): as many CTAs as
-// the GPU holds at one per SM, at least 4 reduction blocks per CTA.
-int w4a16_skinny_splits(int N, int K) {
+// Split policy (ours; the reference's constants are M4-Pro tuning, quantized_matmul.cpp:138-150): the split count that
+// minimises waves x (reduction blocks per CTA + fixed cost), with `slots` CTAs resident at once (two per SM up to 64
+// token columns, one for 128) and a fixed cost worth ~6 blocks (TMEM allocation, pipeline fill, epilogue).
+static int skinny_slots(int M) { return (M <= 64 ? 2 : 1) * sm_count(); }
+int w4a16_skinny_splits(int M, int N, int K) {
     const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
     const int num_kb = N / SK_KB;
-    int splits = (sm_count() + tiles / 2) / tiles;
-    if (splits > num_kb / 4) splits = num_kb / 4;
-    if (splits < 1) splits = 1;
-    const int kbps = (num_kb + splits - 1) / splits;
-    return (num_kb + kbps - 1) / kbps;
+    const int slots = skinny_slots(M);
+    int best = 1;
+    long long best_cost = -1;
+    for (int s = 1; s <= 16 && s <= num_kb / 4 + (num_kb < 4); ++s) {
+        const int kbps = (num_kb + s - 1) / s;
+        const int real = (num_kb + kbps - 1) / kbps;  // splits that actually get blocks
+        const long long waves = (static_cast<long long>(tiles) * real + slots - 1) / slots;
+        const long long cost = waves * (kbps + 6 + (real > 1 ? 2 : 0));
+        if (best_cost < 0 || cost < best_cost) best_cost = cost, best = real;
+    }
+    return best;
 }
 
 size_t w4a16_skinny_workspace(int M, int N, int K) {
-    const int splits = w4a16_skinny_splits(N, K);
+    const int splits = w4a16_skinny_splits(M, N, K);
     return SK_COUNTER_BYTES + (splits > 1 ? static_cast<size_t>(splits) * M * K * sizeof(float) : 0);
 }
 
@@ -422,7 +446,7 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
     SkArgs args{};
     args.scales = scales, args.biases = biases, args.residual = residual, args.out = out;
     args.M = M, args.N = N, args.K = K, args.epilogue = epilogue;
-    args.splits = w4a16_skinny_splits(N, K);
+    args.splits = w4a16_skinny_splits(M, N, K);
     args.kb_per_split = (num_kb + args.splits - 1) / args.splits;
     if (ws == nullptr || ws_bytes < w4a16_skinny_workspace(M, N, K))
         return fail(TL_EWORKSPACE, "quantized_matmul: workspace too small (%zu < %zu)", ws_bytes, w4a16_skinny_workspace(M, N, K));
@@ -434,7 +458,7 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
     if (int e = sk_cached_map(&mw, b, 1, static_cast<cuuint64_t>(N) / 2, K, SK_PK * SK_KB / 2, SK_FEAT, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1)) return e;
     const int groups = (args.kb_per_split + 1) / 2 + 1;
     const int grid = tiles * args.splits;
-    const size_t sb_bytes = static_cast<size_t>(groups) * SK_FEAT * 4;
+    const size_t sb_bytes = static_cast<size_t>(groups) * SK_FEAT * 4;  // + rings: <= ~120 KB, one or two CTAs per SM
     switch (NT) {
         case 16: return skinny_launch<T, 16>(ma, mw, args, grid, SkSmem<16>::SB_OFF + sb_bytes, st);
         case 32: return skinny_launch<T, 32>(ma, mw, args, grid, SkSmem<32>::SB_OFF + sb_bytes, st);

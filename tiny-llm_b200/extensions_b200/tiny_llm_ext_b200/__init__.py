@@ -41,6 +41,7 @@ __all__ = [
     "decode_advance",
     "quantized_matmul_fused",
     "decode_qk_norm_rope_append",
+    "chunk_qk_norm_rope_append",
     "set_pdl",
     "launch_count",
     "device_info",
@@ -81,6 +82,7 @@ _SIGNATURES = {
     "tl_quantized_matmul_fused_workspace": (_SZ, [_I] * 6),
     "tl_quantized_matmul_fused": (_I, [_VP] * 7 + [_I] * 6 + [_F, _I, _VP, _SZ, _VP]),
     "tl_decode_qk_norm_rope_append": (_I, [_VP] * 9 + [_I] * 4 + [_F, _F] + [_I] * 4 + [_VP]),
+    "tl_chunk_qk_norm_rope_append": (_I, [_VP] * 9 + [_I] * 4 + [_F, _F] + [_I] * 4 + [_VP]),
     "tl_decode_attention_fused_workspace": (_SZ, [_I, _I, _I]),
     "tl_decode_attention_fused": (_I, [_VP] * 11 + [_I] * 4 + [_F, _F] + [_I] * 5 + [_VP]),
     "tl_paged_cache_append_chunk": (_I, [_VP] * 5 + [_I] * 4 + [ctypes.c_longlong, ctypes.c_longlong, _I, _VP]),
@@ -561,6 +563,33 @@ def quantized_matmul_fused(scales, biases, b, p0, p1=None, residual=None, prolog
         )
     )
     return out
+
+
+def chunk_qk_norm_rope_append(qkv, q_norm_weight, k_norm_weight, offsets, block_table_row, context_lens, key_pages, value_pages,
+                              num_heads, num_kv_heads, base, eps, stream=None):
+    """Prefill-chunk form of ``decode_qk_norm_rope_append``: the rows of ``qkv`` are consecutive tokens of one
+    request; returns the rotated queries ``[Hq, tokens, D]`` (the layout ``paged_attention`` takes)."""
+    T = qkv.shape[0]
+    P, Hkv, page_size, D = key_pages.shape
+    if qkv.dim() != 2 or qkv.shape[1] != (num_heads + 2 * num_kv_heads) * D or Hkv != num_kv_heads:
+        raise RuntimeError("chunk_qk_norm_rope_append: qkv must be [tokens, (Hq + 2*Hkv) * D]")
+    if qkv.dtype != key_pages.dtype or value_pages.dtype != key_pages.dtype or q_norm_weight.dtype != qkv.dtype:
+        raise RuntimeError("chunk_qk_norm_rope_append: dtype mismatch")
+    if block_table_row.dim() != 1 or offsets.numel() != T or context_lens.numel() != T:
+        raise RuntimeError("chunk_qk_norm_rope_append: one block-table row, one offset and one context length per token")
+    _gpu("chunk_qk_norm_rope_append", qkv, q_norm_weight, k_norm_weight, offsets, block_table_row, context_lens, key_pages, value_pages)
+    _contig("chunk_qk_norm_rope_append", qkv=qkv, offsets=offsets, block_table_row=block_table_row, context_lens=context_lens,
+            key_pages=key_pages, value_pages=value_pages)
+    q_out = torch.empty((num_heads, T, D), dtype=qkv.dtype, device=qkv.device)
+    _check(
+        _lib.tl_chunk_qk_norm_rope_append(
+            qkv.data_ptr(), q_norm_weight.data_ptr(), k_norm_weight.data_ptr(), offsets.data_ptr(), block_table_row.data_ptr(),
+            context_lens.data_ptr(), q_out.data_ptr(), key_pages.data_ptr(), value_pages.data_ptr(), T, int(num_heads),
+            int(num_kv_heads), D, float(base), float(eps), P, page_size, block_table_row.shape[0], _DTYPE_CODE[qkv.dtype],
+            _stream_ptr(stream, qkv),
+        )
+    )
+    return q_out
 
 
 def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:

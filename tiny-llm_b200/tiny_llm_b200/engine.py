@@ -504,3 +504,182 @@ class DecodeEngine:
         cur.wait_stream(self._stream)
         self.graph_replays += steps
         return self.out_log[: steps * B].view(steps, B)
+
+
+class PrefillEngine:
+    """CUDA-graph replay of ONE chunked-prefill step (``Request.try_prefill``: B = 1, up to ``chunk`` prompt tokens,
+    ``/root/reference/src/tiny_llm_ref/batch.py:48-76``) for the Week-3 paged model.
+
+    The reference (and the operator path of this backend) issues ~20 operator calls per layer per chunk from
+    Python: ~700 launches, 10-25 ms of host time for a 128-token chunk whose GPU work is ~1.5 ms.  Here the
+    chunk's whole forward pass is captured once over static buffers; what changes between chunks is DATA in one
+    pinned block: the token ids, per-token RoPE positions and post-append lengths, the request's block-table
+    row per layer and the final context length.  A short (tail) chunk is RIGHT-aligned in the ``chunk`` rows:
+    the padding rows in front carry context length 0 (nothing is appended for them) and the bottom-right causal
+    rule of paged attention (``key <= row + ctx - L``) then gives every real row exactly its own prefix.
+
+    Per layer: rms_norm -> q|k|v projection (one launch) -> q/k norm + RoPE + K/V append for all rows (one
+    launch, ``tl_chunk_qk_norm_rope_append``) -> paged FlashAttention (tcgen05) -> o projection + residual ->
+    rms_norm -> gate|up (+ SwiGLU) -> down + residual.  Rounding points are those of the operator sequence.
+    Integer page bookkeeping stays in the request's ``TinyKvPagedCache`` objects (``append_slots``)."""
+
+    def __init__(self, model, chunk: int, max_seq_len: int, device):
+        self.model, self.L, self.device = model, int(chunk), torch.device(device)
+        self.page_size = model.page_size
+        self.max_pages = (max_seq_len + self.page_size - 1) // self.page_size
+        self.max_seq_len = self.max_pages * self.page_size
+        attn = model.layers_inner[0].self_attn
+        self.Hq, self.Hkv, self.D = attn.num_heads, attn.num_kv_heads, attn.head_dim
+        self.n_layers = model.num_hidden_layers
+        L, Ly, MP = self.L, self.n_layers, self.max_pages
+        # one int32 block: tokens [L] | offsets [L] | context_lens [L] | ctx_after [1] | tables [Ly, MP]
+        self._meta_len = 3 * L + 1 + Ly * MP
+        self.meta_host = torch.empty(self._meta_len, dtype=torch.int32, pin_memory=True)
+        self.meta_np = self.meta_host.numpy()
+        self.meta_np[:] = 0
+        self.meta_np[3 * L + 1:] = -1
+        self.meta_dev = torch.zeros(self._meta_len, dtype=torch.int32, device=self.device)
+        self.meta_dev[3 * L + 1:] = -1
+        self.tokens = self.meta_dev[0:L].view(1, L)
+        self.offsets = self.meta_dev[L:2 * L]
+        self.ctxs = self.meta_dev[2 * L:3 * L]
+        self.ctx_after = self.meta_dev[3 * L:3 * L + 1]
+        self.tables = self.meta_dev[3 * L + 1:].view(Ly, MP)
+        self.tables_np = self.meta_np[3 * L + 1:].reshape(Ly, MP)
+        self.logits = None
+        self.next_token = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._graph = None
+        self._slab_ptrs = None
+        self._stream = torch.cuda.Stream(device=self.device)
+        self._upload_event = torch.cuda.Event()
+        self._upload_pending = False
+        self.replays = 0
+        self.kernels_per_chunk = 0
+        self._packed = [
+            SimpleNamespace(qkv=_concat_weights([b.self_attn.wq, b.self_attn.wk, b.self_attn.wv]),
+                            gate_up=_interleave_gate_up(b.mlp.w_gate, b.mlp.w_up))
+            for b in model.layers_inner
+        ]
+
+    @staticmethod
+    def supported(model, device) -> bool:
+        attn = model.layers_inner[0].self_attn
+        rope = attn.rope
+        return (torch.device(device).type == "cuda" and attn.head_dim == 128 and not rope.traditional and rope.dims == attn.head_dim
+                and model.embedding.weight.scales.dtype == torch.bfloat16 and model.page_size % 64 == 0
+                and 128 % (attn.num_heads // attn.num_kv_heads) == 0)
+
+    def _slabs(self):
+        return tuple((p._key_pages.data_ptr(), p._value_pages.data_ptr(), p.capacity) for p in self.model.page_pools)
+
+    def _forward(self) -> None:
+        m, L = self.model, self.L
+        Hq, Hkv, D = self.Hq, self.Hkv, self.D
+        emb = m.embedding.weight
+        x = ext.quantized_embedding(self.tokens, emb.scales, emb.biases, emb.weight, emb.group_size, emb.bits).view(L, -1)
+        skinny = L <= 128  # the fused epilogues live in the <= 128-row tensor-core kernel; longer chunks use the 128 x 128-tile GEMM
+
+        def normed(h, norm):
+            return ext.rms_norm(h, norm._weight_as(h.dtype, h.device), norm.eps)
+
+        def proj(h, w):
+            return ext.quantized_matmul(w.scales, w.biases, w.group_size, w.bits, h, w.weight, True)
+
+        for i, block in enumerate(m.layers_inner):
+            at, pk, pool = block.self_attn, self._packed[i], m.page_pools[i]
+            h = normed(x, block.input_layernorm)
+            qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, h) if skinny else proj(h, pk.qkv)
+            q = ext.chunk_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
+                                              self.offsets, self.tables[i], self.ctxs, pool._key_pages, pool._value_pages,
+                                              Hq, Hkv, at.rope.base, at.q_norm.eps)  # [Hq, L, D]
+            y = ext.paged_attention(q, pool._key_pages, pool._value_pages, self.tables[i:i + 1], self.ctx_after, at.scale,
+                                    is_causal=True, num_kv_heads=Hkv, num_heads=Hq)  # [Hq, L, D]
+            y = y.transpose(0, 1).reshape(L, Hq * D)  # one 2-byte-per-element copy per layer
+            if skinny:
+                x = ext.quantized_matmul_fused(at.wo.scales, at.wo.biases, at.wo.weight, y, residual=x, epilogue=ext.EPI_RESIDUAL)
+                act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, normed(x, block.post_attention_layernorm),
+                                                 epilogue=ext.EPI_SWIGLU_PAIRS)
+                wd = block.mlp.w_down
+                x = ext.quantized_matmul_fused(wd.scales, wd.biases, wd.weight, act, residual=x, epilogue=ext.EPI_RESIDUAL)
+            else:
+                x = ext.add(x, proj(y, at.wo))
+                h = normed(x, block.post_attention_layernorm)
+                x = ext.add(x, proj(ext.swiglu(proj(h, block.mlp.w_gate), proj(h, block.mlp.w_up)), block.mlp.w_down))
+        last = normed(x[L - 1:L], m.norm)  # logits_to_keep = 1: the hidden state is sliced before the final norm (qwen3_week3.py:330-338)
+        head = m.w_lm_head if m.w_lm_head is not None else m.embedding.weight
+        logits = proj(last, head)
+        self.next_token.copy_(ext.argmax(logits))
+        if self.logits is None:
+            self.logits = torch.empty_like(logits)
+        self.logits.copy_(logits)
+
+    def _capture(self) -> None:
+        self._slab_ptrs = self._slabs()
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_stream(torch.cuda.current_stream(self.device))
+            # warm-up passes run for real: all rows padding (context 0 -> no append), no visible keys
+            self.meta_dev[2 * self.L:3 * self.L + 1].zero_()
+            self.meta_dev[3 * self.L + 1:].fill_(-1)
+            for _ in range(2):
+                self._forward()
+            self._stream.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            launched = ext.launch_count()
+            with torch.cuda.graph(self._graph, stream=self._stream):
+                self._forward()
+            self.kernels_per_chunk = ext.launch_count() - launched
+        torch.cuda.current_stream(self.device).wait_stream(self._stream)
+
+    def reserve_pools(self, pages_per_layer: int) -> None:
+        for pool in self.model.page_pools:
+            pool.reserve(pages_per_layer, self.Hkv, self.D, dtype=torch.bfloat16, device=self.device)
+
+    def applies(self, tokens: int, offset: int, cache) -> bool:
+        if not (0 < tokens <= self.L) or offset + tokens > self.max_seq_len:
+            return False
+        for layer_cache, pool in zip(cache, self.model.page_pools):
+            if type(layer_cache) is not TinyKvPagedCache or layer_cache.pool is not pool or layer_cache.offset != offset:
+                return False
+            if pool._key_pages is None or pool._key_pages.dtype != torch.bfloat16:
+                return False
+            fresh = -(-(offset + tokens) // self.page_size) - len(layer_cache.page_ids)
+            if fresh > len(pool.free_page_ids) + (pool.capacity - pool.num_pages):
+                return False
+        return True
+
+    def prefill_chunk(self, token_ids, offset: int, cache):
+        """Append ``token_ids`` (1..chunk ids at positions offset.., a list or an int32 device tensor) to the request's
+        caches and return (logits [1, 1, V] of the last token - a static buffer -, greedy next token [1])."""
+        on_device = isinstance(token_ids, torch.Tensor)
+        r, L = (int(token_ids.numel()) if on_device else len(token_ids)), self.L
+        if self._upload_pending:
+            self._upload_event.synchronize()
+            self._upload_pending = False
+        for layer, layer_cache in enumerate(cache):
+            layer_cache.append_slots(r)
+            n = len(layer_cache.page_ids)
+            self.tables_np[layer, :n] = layer_cache.page_ids
+            self.tables_np[layer, n:] = -1
+        if self._graph is None or self._slab_ptrs != self._slabs():
+            self._capture()
+        pad = L - r
+        meta = self.meta_np
+        meta[0:L] = 0
+        if not on_device:
+            meta[pad:L] = token_ids
+        pos = np.arange(L, dtype=np.int32) - pad + offset
+        meta[L:2 * L] = pos
+        meta[2 * L:3 * L] = np.where(np.arange(L) >= pad, pos + 1, 0)
+        meta[3 * L] = offset + r
+        cur = torch.cuda.current_stream(self.device)
+        self._stream.wait_stream(cur)
+        with torch.cuda.stream(self._stream):
+            self.meta_dev.copy_(self.meta_host, non_blocking=True)
+            self._upload_event.record()
+            self._upload_pending = True
+            if on_device:  # ids stay on the device: no host round trip for the prompt
+                self.meta_dev[pad:L].copy_(token_ids.reshape(-1).to(torch.int32), non_blocking=True)
+            self._graph.replay()
+        cur.wait_stream(self._stream)
+        self.replays += 1
+        return self.logits.view(1, 1, -1), self.next_token

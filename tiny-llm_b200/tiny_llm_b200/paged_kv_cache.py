@@ -379,6 +379,27 @@ class TinyKvPagedCache(TinyKvCache):
             self._restore_state(mine)
             raise
 
+    def append_slots(self, count: int) -> None:
+        """Host bookkeeping of a ``count``-token append whose bytes are written by a device-driven kernel
+        (prefill-chunk engine): the page / offset evolution of ``_append_chunk`` (fill the tail page, then
+        take fresh pages), all-or-nothing, no launch.  The pool slab must cover the pages (``pool.reserve``)."""
+        if count <= 0:
+            return
+        tail_room = self.page_size - self.page_lens[-1] if self.page_ids else 0
+        fresh = max(0, -(-(count - tail_room) // self.page_size))
+        if fresh > len(self.pool.free_page_ids) + (self.pool.capacity - self.pool.num_pages):
+            raise RuntimeError("page pool slab exhausted: reserve() more pages before prefilling")
+        take = min(tail_room, count)
+        if take:
+            self.page_lens[-1] += take
+        left = count - take
+        while left > 0:
+            n = min(self.page_size, left)
+            self.page_ids.append(self.pool.allocate_page())
+            self.page_lens.append(n)
+            left -= n
+        self.offset += count
+
     def append_token_slot(self) -> tuple[int, int]:
         """Host bookkeeping of a ONE-token append whose bytes are written by a
         device-driven kernel (decode engine): same page/offset evolution as

@@ -236,6 +236,11 @@ class Qwen3ModelWeek3:
         self.decode_graph_max_seq_len = 8192
         self._decode_engines: dict = {}
         self._applies_memo = None
+        # B200 runtime: chunked-prefill steps (B == 1, 8 < L <= prefill_graph_len) of CUDA-resident paged requests
+        # replay a captured chunk graph too (engine.PrefillEngine).  0 disables; None = automatic (128, the scheduler's
+        # default prefill_step) once a decode engine exists, i.e. once the page slabs have been reserved.
+        self.prefill_graph_len: int | None = None
+        self._prefill_engines: dict = {}
         self._paged = enable_paged_attention
 
     def create_kv_cache(self) -> list[TinyKvCache]:
@@ -338,9 +343,51 @@ class Qwen3ModelWeek3:
                 entry.last_batch_bytes = 0
         return logits.clone()
 
+    def prefill_engine(self, chunk: int, max_seq_len: int | None = None, device=None):
+        from .engine import PrefillEngine
+
+        limit = max_seq_len or self.decode_graph_max_seq_len
+        key = (chunk, limit)
+        if key not in self._prefill_engines:
+            dev = device if device is not None else self.embedding.weight.scales.device
+            self._prefill_engines[key] = PrefillEngine(self, chunk, limit, dev)
+        return self._prefill_engines[key]
+
+    def _graph_prefill(self, inputs, offset, cache, logits_to_keep):
+        """Route a B == 1 prefill chunk through the captured chunk graph when it applies; None otherwise."""
+        from .engine import PrefillEngine
+
+        chunk = self.prefill_graph_len
+        if chunk == 0 or self.use_decode_graph is False or not self._paged or logits_to_keep != 1:
+            return None
+        if inputs.dim() != 2 or inputs.shape[0] != 1 or not inputs.is_cuda:
+            return None
+        if chunk is None:
+            if not self._decode_engines:
+                return None
+            chunk = 128
+        L = inputs.shape[1]
+        if not (8 < L <= chunk) or not PrefillEngine.supported(self, inputs.device):
+            return None
+        if isinstance(offset, torch.Tensor):
+            off = int(offset.reshape(-1)[0])
+        elif isinstance(offset, int):
+            off = offset
+        else:
+            off = int(list(offset)[0])
+        engine = self.prefill_engine(chunk)
+        if not engine.applies(L, off, cache):
+            return None
+        logits, _ = engine.prefill_chunk(inputs.reshape(-1), off, cache)
+        return logits.clone()
+
     def __call__(self, inputs, offset, cache: list[TinyKvCache], logits_to_keep: int | None = None):
         if self._graph_decode_applies(inputs, cache):
             return self._graph_decode(inputs, offset, cache, logits_to_keep)
+        if inputs.dim() == 2 and inputs.shape[1] > 8 and inputs.is_cuda:
+            out = self._graph_prefill(inputs, offset, cache, logits_to_keep)
+            if out is not None:
+                return out
         h = self.embedding(inputs)
         for block, layer_cache in zip(self.layers_inner, cache):
             h = block(h, offset, layer_cache, mask="causal")
