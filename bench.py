@@ -616,6 +616,7 @@ def run_serve(args, long_context: bool) -> None:
         workload = f"Qwen3-4B continuous batching, {slots} concurrent requests per GPU, {total} requests, chunked prefill + paged KV"
     mine = shard(all_reqs, rank, world)
     model.decode_graph_max_seq_len = ((max_seq + PAGE_SIZE - 1) // PAGE_SIZE) * PAGE_SIZE
+    model.prefill_graph_len = int(os.environ.get("TL_PREFILL_GRAPH", str(prefill_step)))  # captured chunk graph (0: operator path)
 
     def serve(reqs, timing=True):
         batcher = ContinuousBatcher(model, None, [p for p, _ in reqs], max_seq_len=max_seq, batch_size=slots, prefill_step=prefill_step,

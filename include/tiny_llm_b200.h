@@ -71,12 +71,10 @@ long long tl_launch_count(void);
  * The split of the reduction is a scheduling decision of this backend (SURVEY 8a' item 12): it depends only on
  * (N, K), never on use_split_k, so a split request and a plain request run the very same kernel with
  * bit-identical results (tests_refsol/test_week_2_day_7.py:80-109).
- * workspace: tl_quantized_matmul_workspace() bytes (0 = none).  When it is non-zero its first
- * TL_QMM_TICKET_BYTES are int32 arrival tickets that must be ZERO on entry; the kernel leaves them zero,
- * so one zero-initialised buffer can be reused by successive launches on a stream. */
+ * workspace: tl_quantized_matmul_workspace() bytes (0 = none; fp32 partial planes of a split reduction,
+ * no initialisation needed). */
 #define TL_MATVEC_REF_ROWS 8
 #define TL_MATVEC_MAX_ROWS 32
-#define TL_QMM_TICKET_BYTES 8192
 size_t tl_quantized_matmul_workspace(int M, int N, int K, int dtype, int use_simdgroup, int use_split_k);
 int tl_quantized_matmul(const void *scales, const void *biases, const void *a, const void *b, void *out, int M,
                         int N, int K, int dtype, int use_simdgroup, int use_split_k, void *workspace,
@@ -154,7 +152,7 @@ size_t tl_argmax_workspace(int rows, int vocab);
  * be the two halves of one [M, 2N] buffer.
  * With 9 <= M <= 128, no prologue and lda == N the launch goes to the swap-AB tcgen05 kernel (same
  * epilogues; weights rounded to the activation dtype like every tensor-core path) and needs
- * tl_quantized_matmul_fused_workspace() bytes of workspace (ticket convention as above). */
+ * tl_quantized_matmul_fused_workspace() bytes of workspace. */
 enum { TL_PRO_NONE = 0, TL_PRO_RMSNORM = 1, TL_PRO_SWIGLU = 2 };
 enum { TL_EPI_NONE = 0, TL_EPI_RESIDUAL = 1, TL_EPI_SWIGLU_PAIRS = 2 };
 size_t tl_quantized_matmul_fused_workspace(int M, int N, int K, int lda, int prologue, int dtype);

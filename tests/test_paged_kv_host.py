@@ -293,3 +293,60 @@ def test_decode_batch_append_matches_per_request_writes(cpu_ext):
     assert torch.equal(new_pool.key_pages, ref_pool.key_pages) and torch.equal(new_pool.value_pages, ref_pool.value_pages)
     for a, b in zip(new_metas, ref_metas):
         assert a.block_table.tolist() == b.block_table.tolist() and a.context_lens.tolist() == b.context_lens.tolist()
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 runtime additions to the cache objects (engine.py): deferred one-token appends and bulk slot appends must be
+# indistinguishable from the reference's per-token bookkeeping (paged_kv_cache.py:279-306).
+def _pool_with_capacity(pages, page_size=4):
+    pool = TinyKvPagedPool(page_size=page_size)
+    pool.reserve(pages, 2, 8, dtype=torch.float32, device="cpu")
+    return pool
+
+
+def test_deferred_appends_settle_on_first_read_and_match_per_token_bookkeeping():
+    from tiny_llm_b200.engine import _LockstepGroup
+
+    pools = [_pool_with_capacity(8) for _ in range(3)]
+    lazy = [TinyKvPagedCache(p) for p in pools]
+    plain = [TinyKvPagedCache(_pool_with_capacity(8)) for _ in range(3)]
+    for c in (*lazy, *plain):
+        c.append_slots(5)  # pages [4, 1]
+    group = _LockstepGroup(lazy)
+    for c in lazy:
+        c._lazy = group
+    group.pending += 3  # three decode steps that fit in the tail page: nothing touched yet
+    assert lazy[1]._page_lens == [4, 1] and lazy[1]._offset == 5
+    assert lazy[0].logical_offset() == 8
+    for c in plain:
+        for _ in range(3):
+            c.append_token_slot()
+    assert lazy[2].offset == 8  # first read settles the whole group
+    assert group.pending == 0
+    for a, b in zip(lazy, plain):
+        assert (a.page_ids, a.page_lens, a.offset) == (b.page_ids, b.page_lens, b.offset) == ([0, 1], [4, 4], 8)
+    group.pending += 0
+    lazy[0].rewind(3)
+    assert lazy[0].page_lens == [4, 1] and lazy[0].epoch == 1
+    group2 = _LockstepGroup(lazy[1:])
+    for c in lazy[1:]:
+        c._lazy = group2
+    for c in lazy[1:]:
+        c.append_token_slot()  # page boundary: [4, 4] -> new page, through the settled properties
+    group2.pending += 2
+    lazy[1].release()  # settles (both), frees the pages in page order, bumps the epoch
+    assert lazy[1].page_ids == [] and lazy[1].offset == 0 and pools[1].used_page_ids == set()
+    assert lazy[2].page_lens == [4, 4, 3] and lazy[2].offset == 11
+
+
+def test_append_slots_equals_repeated_token_slots_and_is_all_or_nothing():
+    a, b = TinyKvPagedCache(_pool_with_capacity(6)), TinyKvPagedCache(_pool_with_capacity(6))
+    for count in (1, 3, 4, 9):
+        a.append_slots(count)
+        for _ in range(count):
+            b.append_token_slot()
+        assert (a.page_ids, a.page_lens, a.offset) == (b.page_ids, b.page_lens, b.offset)
+    before = (list(a.page_ids), list(a.page_lens), a.offset, a.pool.num_pages)
+    with pytest.raises(RuntimeError, match="slab exhausted"):
+        a.append_slots(100)
+    assert (a.page_ids, a.page_lens, a.offset, a.pool.num_pages) == before

@@ -338,6 +338,7 @@ int tl_decode_attention_fused(const void *qkv, const void *q_norm_weight, const 
 extern "C" int tl_debug_trace(unsigned long long *device_events, unsigned int *device_count, unsigned int capacity) {
     trace_bind_matvec(device_events, device_count, capacity);
     trace_bind_attention(device_events, device_count, capacity);
+    trace_bind_skinny(device_events, device_count, capacity);
     return TL_OK;
 }
 #endif

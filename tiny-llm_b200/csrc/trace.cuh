@@ -14,8 +14,8 @@ namespace tl {
 static __device__ unsigned long long *g_trace_buf;
 static __device__ unsigned int *g_trace_n;
 static __device__ unsigned int g_trace_cap;
-__device__ __forceinline__ void trace_stamp(unsigned tag) {
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && g_trace_buf != nullptr) {
+__device__ __forceinline__ void trace_stamp(unsigned tag, unsigned thread = 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == thread && g_trace_buf != nullptr) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         const unsigned i = atomicAdd(g_trace_n, 1u);
@@ -29,6 +29,8 @@ static void trace_bind(unsigned long long *buf, unsigned int *n, unsigned int ca
 }
 }  // namespace tl
 #define TL_TRACE_STAMP(tag) ::tl::trace_stamp(tag)
+#define TL_TRACE_STAMP_T(tag, thread) ::tl::trace_stamp(tag, thread)
 #else
 #define TL_TRACE_STAMP(tag) do { } while (0)
+#define TL_TRACE_STAMP_T(tag, thread) do { } while (0)
 #endif

@@ -12,8 +12,8 @@
 //   * the WEIGHTS are the 128-row M operand of the MMA (one CTA tile = 128 output features), the tokens
 //     are the N operand (16..128 columns): D[feature, token] lives in TMEM, lane = feature;
 //   * the reduction is split over `splits` CTAs per feature tile so that tiles x splits ~ #SMs; partial
-//     sums go to a workspace in fp32 and the LAST CTA of a tile (atomic ticket) adds them in split order
-//     (deterministic) and runs the epilogue (plain / + residual / SwiGLU of interleaved gate|up rows);
+//     sums go to a workspace in fp32 and a small second launch adds the planes in split order (deterministic)
+//     and runs the epilogue (plain / + residual / SwiGLU of interleaved gate|up rows);
 //   * packed weights arrive by TMA (one 128-row x 128-byte box = four 64-wide reduction blocks per copy, two boxes
 //     in flight: 32 KiB per CTA without a register), 256 dequantiser threads turn them into the K-major
 //     128B-swizzled bf16 tile (LOP3 magic -> exact code -> one HFMA2, the rounding point of the
@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc05.cuh"
+#include "trace.cuh"
 
 namespace tl {
 
@@ -38,7 +39,6 @@ constexpr int SK_PACKED_BYTES = SK_PK * SK_FEAT * SK_KB / 2;  // 16 KiB per box,
 constexpr int SK_A_BYTES = SK_FEAT * SK_KB * 2;       // 16 KiB dequantised tile
 constexpr int SK_DEQ_THREADS = 256;
 constexpr int SK_THREADS = 128 + SK_DEQ_THREADS;
-constexpr int SK_COUNTER_BYTES = 8192;                // zeroed int32 tickets at the head of the workspace (2048 feature tiles)
 enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
 
 template <int NT>
@@ -61,7 +61,6 @@ struct SkArgs {
     const void *scales, *biases, *residual;
     void *out;
     float *partials;   // [splits][M][K] fp32 (splits > 1)
-    int *tickets;      // [tiles], zero on entry, left zero
     int M, N, K;       // tokens, reduction, features
     int splits, kb_per_split;
     int epilogue;
@@ -96,13 +95,13 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     constexpr int PSTAGES = Smem::PSTAGES;
     constexpr int BSTAGES = Smem::BSTAGES;
     extern __shared__ __align__(1024) unsigned char ssm[];
-    __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x / args.splits, split = blockIdx.x - tile * args.splits;
     const int num_kb = args.N / SK_KB;
     const int kb0 = min(split * args.kb_per_split, num_kb), kb1 = min(kb0 + args.kb_per_split, num_kb);
     const int n_kb = kb1 - kb0;
     const int G = args.N / 128;
+    TL_TRACE_STAMP(30);
     const int g0 = kb0 >> 1, g_cnt = n_kb > 0 ? ((kb1 - 1) >> 1) - g0 + 1 : 0;
 
     const uint32_t a_base = g_smem_u32(ssm + Smem::A_OFF), b_base = g_smem_u32(ssm + Smem::B_OFF), p_base = g_smem_u32(ssm + Smem::P_OFF);
@@ -148,6 +147,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     g_tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    TL_TRACE_STAMP(31);
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer: packed weights, one 128-row x 128-byte box per 4 blocks
@@ -200,6 +200,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int ps = box % PSTAGES, s = i % STAGES;
             if (sub == 0) g_mbar_wait(p_full + 8 * ps, (box / PSTAGES) & 1);
             // row `row` of the box: 128 bytes = 8 chunks of 16 B, chunk c stored at (c ^ (row & 7)) by the TMA swizzle
+            if (i == 0) TL_TRACE_STAMP_T(32, 128);  // first packed box has landed
             const int chunk = sub * 2 + half;
             const uint4 cur = *reinterpret_cast<const uint4 *>(ssm + Smem::P_OFF + ps * SK_PACKED_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4));
             const uint32_t pair = sb[(((kb0 + i) >> 1) - g0) * SK_FEAT + row];
@@ -224,10 +225,6 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 outw[4 * j + 2] = __byte_perm(p[0], p[1], 0x7632);
                 outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);
             }
-            // Release the packed box only now: `outw` depends on `cur`, so the shared-memory read has COMPLETED.  (Arriving
-            // right after issuing the load let the TMA refill the box under a load still in flight: single feature rows
-            // came out wrong in ~1 of 100 launches - mbarrier arrive is a SYNCS op, not ordered behind the LSU.)
-            if (sub == SK_PK - 1 || i == n_kb - 1) g_mbar_arrive(p_empty + 8 * ps);
             g_mbar_wait(empty + 8 * s, ((i / STAGES) & 1) ^ 1);
             unsigned char *dst = ssm + Smem::A_OFF + s * SK_A_BYTES + row * 128;
 #pragma unroll
@@ -237,12 +234,19 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             g_fence_proxy_async();
             g_mbar_arrive(full_a + 8 * s);
+            // Release the packed box only now: the stores above consumed `cur`, so this thread's shared-memory read of the
+            // box has COMPLETED (an arrive issued right behind the load let the TMA refill the box under a load still in
+            // flight - mbarrier ops are not ordered behind the load/store unit - and single feature rows came out wrong in
+            // ~1 of 600 CTA-loops of 40 blocks).
+            if (sub == SK_PK - 1 || i == n_kb - 1) g_mbar_arrive(p_empty + 8 * ps);
         }
         // ------------------------------------------------ epilogue: TMEM lane = feature; warps 4-7 take token columns [0, NT/2), 8-11 the rest
+        TL_TRACE_STAMP_T(33, 128);  // last weight tile handed to the MMA thread
         if (n_kb > 0) {
             g_mbar_wait(tmem_full, 0);
             g_tc_fence_after();
         }
+        TL_TRACE_STAMP_T(34, 128);  // accumulators complete
         const int q = warp & 3;
         const int f = q * 32 + lane;            // feature row inside the tile
         const int n = tile * SK_FEAT + f;       // global feature
@@ -252,7 +256,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         constexpr int CH = HALF_COLS < 32 ? HALF_COLS : 32;  // columns per tcgen05.ld (x16 or x32)
         float *part = args.partials;
         const size_t plane = static_cast<size_t>(args.M) * args.K;
-        // ---- pass 1 (splits > 1): park the partial tile, take a ticket
+        // ---- splits > 1: park the fp32 partial tile; w4a16_skinny_reduce_kernel adds the planes in split order
         if (args.splits > 1) {
             if (reader) {
 #pragma unroll
@@ -271,25 +275,14 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 }
             }
-            __threadfence();
-            asm volatile("bar.sync 1, %0;" ::"n"(SK_DEQ_THREADS) : "memory");
-            if (threadIdx.x == 128) {
-                int prev;  // release: this CTA's partial plane precedes the ticket; acquire: the other planes precede the reads below
-                asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(prev) : "l"(args.tickets + tile) : "memory");
-                s_last = prev == args.splits - 1 ? 1 : 0;
-                if (s_last) args.tickets[tile] = 0;  // leave the ticket clean for the next launch
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(SK_DEQ_THREADS) : "memory");
-            if (s_last) __threadfence();
         }
-        const bool finisher = args.splits == 1 || s_last;
-        if (finisher && reader) {
+        if (args.splits == 1 && reader) {
             T *out = static_cast<T *>(args.out);
             const T *res = static_cast<const T *>(args.residual);
 #pragma unroll
             for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
                 float acc[32];
-                if (args.splits == 1) {
+                {
                     uint32_t v[32];
                     if (n_kb > 0) {
                         g_tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + col0 + c0, v);
@@ -299,21 +292,6 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
 #pragma unroll
                     for (int c = 0; c < 32; ++c) acc[c] = __uint_as_float(v[c]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-                    // split order (deterministic); the 32 loads of one plane are issued back to back (ld_cg is volatile:
-                    // interleaving the adds serialised 32 x splits L2 round trips - 40 us per launch in the first version)
-                    for (int sp = 0; sp < args.splits; ++sp) {
-                        float v[32];
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const int m = col0 + c0 + c;
-                            v[c] = (c < CH && m < args.M && n < args.K) ? ld_cg(part + sp * plane + static_cast<size_t>(m) * args.K + n) : 0.f;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) acc[c] += v[c];
-                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -336,12 +314,49 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     }
+    TL_TRACE_STAMP_T(35, 128);  // epilogue stored
     g_tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         g_tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(Smem::TMEM_COLS) : "memory");
     }
+    TL_TRACE_STAMP(36);
+}
+
+#if TL_TRACE
+void trace_bind_skinny(unsigned long long *buf, unsigned int *n, unsigned int cap) { trace_bind(buf, n, cap); }
+#endif
+
+// Adds the fp32 partial planes of a split reduction in split order (deterministic: same bits on every run and for
+// every CTA schedule) and applies the epilogue; one thread per output.  All `splits` loads of a thread are independent
+// and in flight together (the first version let the last CTA of a tile do this with dependent round trips: 40 us).
+template <typename T>
+__global__ void __launch_bounds__(256) w4a16_skinny_reduce_kernel(const float *__restrict__ part, const T *__restrict__ res, T *__restrict__ out,
+                                                                  int M, int K, int splits, int epilogue) {
+    const size_t plane = static_cast<size_t>(M) * K;
+    if (epilogue == SK_EPI_SWIGLU_PAIRS) {
+        const int half = K / 2;
+        const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+        if (idx >= static_cast<size_t>(M) * half) return;
+        const int m = static_cast<int>(idx / half), feat = static_cast<int>(idx - static_cast<size_t>(m) * half);
+        const int n_gate = (feat >> 3) * 16 + (feat & 7);  // rows 16j + r (gate) and 16j + 8 + r (up) -> activation 8j + r
+        float g = 0.f, u = 0.f;
+        for (int sp = 0; sp < splits; ++sp) {
+            g += part[sp * plane + static_cast<size_t>(m) * K + n_gate];
+            u += part[sp * plane + static_cast<size_t>(m) * K + n_gate + 8];
+        }
+        const float gate = to_f(from_f<T>(g)), up = to_f(from_f<T>(u));
+        out[idx] = from_f<T>((gate / (1.0f + expf(-gate))) * up);
+        return;
+    }
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= plane) return;
+    float sum = 0.f;
+    for (int sp = 0; sp < splits; ++sp) sum += part[sp * plane + idx];
+    T vb = from_f<T>(sum);
+    if (epilogue == SK_EPI_RESIDUAL) vb = from_f<T>(to_f(res[idx]) + to_f(vb));
+    out[idx] = vb;
 }
 
 // ---------------------------------------------------------------- host side --
@@ -349,12 +364,13 @@ bool w4a16_skinny_supported(int M, int N, int K, int dtype) {
     static const bool off = [] { const char *e = getenv("TL_SKINNY"); return e != nullptr && e[0] == '0'; }();
     static const int min_rows = [] { const char *e = getenv("TL_SKINNY_MIN_ROWS"); return e ? atoi(e) : 9; }();
     if (off) return false;
-    return (dtype == TL_BF16 || dtype == TL_F16) && M >= min_rows && M <= 128 && K > 0 && N % 128 == 0 && (K + SK_FEAT - 1) / SK_FEAT <= SK_COUNTER_BYTES / 4;
+    return (dtype == TL_BF16 || dtype == TL_F16) && M >= min_rows && M <= 128 && K > 0 && N % 128 == 0;
 }
 
 // Split policy (ours; the reference's constants are M4-Pro tuning, quantized_matmul.cpp:138-150): the split count that
-// minimises waves x (reduction blocks per CTA + fixed cost), with `slots` CTAs resident at once (two per SM up to 64
-// token columns, one for 128) and a fixed cost worth ~6 blocks (TMEM allocation, pipeline fill, epilogue).
+// minimises waves x (reduction blocks per CTA + fixed cost) + reduce launch, with `slots` CTAs resident at once (two per
+// SM up to 64 token columns, one for 128), a fixed cost per CTA worth ~24 blocks (TMEM allocation, first TMA round
+// trips, epilogue: ~3.5 us measured) and ~20 blocks for the extra reduce launch.
 static int skinny_slots(int M) { return (M <= 64 ? 2 : 1) * sm_count(); }
 int w4a16_skinny_splits(int M, int N, int K) {
     const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
@@ -366,7 +382,7 @@ int w4a16_skinny_splits(int M, int N, int K) {
         const int kbps = (num_kb + s - 1) / s;
         const int real = (num_kb + kbps - 1) / kbps;  // splits that actually get blocks
         const long long waves = (static_cast<long long>(tiles) * real + slots - 1) / slots;
-        const long long cost = waves * (kbps + 6 + (real > 1 ? 2 : 0));
+        const long long cost = waves * (kbps + 24) + (real > 1 ? 20 : 0);  // in units of one reduction block (~0.15 us)
         if (best_cost < 0 || cost < best_cost) best_cost = cost, best = real;
     }
     return best;
@@ -374,7 +390,7 @@ int w4a16_skinny_splits(int M, int N, int K) {
 
 size_t w4a16_skinny_workspace(int M, int N, int K) {
     const int splits = w4a16_skinny_splits(M, N, K);
-    return SK_COUNTER_BYTES + (splits > 1 ? static_cast<size_t>(splits) * M * K * sizeof(float) : 0);
+    return splits > 1 ? static_cast<size_t>(splits) * M * K * sizeof(float) : 0;
 }
 
 struct SkMapKey {
@@ -448,10 +464,9 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
     args.M = M, args.N = N, args.K = K, args.epilogue = epilogue;
     args.splits = w4a16_skinny_splits(M, N, K);
     args.kb_per_split = (num_kb + args.splits - 1) / args.splits;
-    if (ws == nullptr || ws_bytes < w4a16_skinny_workspace(M, N, K))
+    if (args.splits > 1 && (ws == nullptr || ws_bytes < w4a16_skinny_workspace(M, N, K)))
         return fail(TL_EWORKSPACE, "quantized_matmul: workspace too small (%zu < %zu)", ws_bytes, w4a16_skinny_workspace(M, N, K));
-    args.tickets = static_cast<int *>(ws);
-    args.partials = reinterpret_cast<float *>(static_cast<unsigned char *>(ws) + SK_COUNTER_BYTES);
+    args.partials = static_cast<float *>(ws);
     CUtensorMap ma, mw;
     const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (int e = sk_cached_map(&ma, a, 0, N, M, SK_KB, NT, dt, 2)) return e;
@@ -459,12 +474,19 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
     const int groups = (args.kb_per_split + 1) / 2 + 1;
     const int grid = tiles * args.splits;
     const size_t sb_bytes = static_cast<size_t>(groups) * SK_FEAT * 4;  // + rings: <= ~120 KB, one or two CTAs per SM
+    int rc;
     switch (NT) {
-        case 16: return skinny_launch<T, 16>(ma, mw, args, grid, SkSmem<16>::SB_OFF + sb_bytes, st);
-        case 32: return skinny_launch<T, 32>(ma, mw, args, grid, SkSmem<32>::SB_OFF + sb_bytes, st);
-        case 64: return skinny_launch<T, 64>(ma, mw, args, grid, SkSmem<64>::SB_OFF + sb_bytes, st);
-        default: return skinny_launch<T, 128>(ma, mw, args, grid, SkSmem<128>::SB_OFF + sb_bytes, st);
+        case 16: rc = skinny_launch<T, 16>(ma, mw, args, grid, SkSmem<16>::SB_OFF + sb_bytes, st); break;
+        case 32: rc = skinny_launch<T, 32>(ma, mw, args, grid, SkSmem<32>::SB_OFF + sb_bytes, st); break;
+        case 64: rc = skinny_launch<T, 64>(ma, mw, args, grid, SkSmem<64>::SB_OFF + sb_bytes, st); break;
+        default: rc = skinny_launch<T, 128>(ma, mw, args, grid, SkSmem<128>::SB_OFF + sb_bytes, st); break;
     }
+    if (rc != TL_OK || args.splits == 1) return rc;
+    const size_t outputs = static_cast<size_t>(M) * (epilogue == SK_EPI_SWIGLU_PAIRS ? K / 2 : K);
+    w4a16_skinny_reduce_kernel<T><<<static_cast<unsigned>((outputs + 255) / 256), 256, 0, st>>>(
+        args.partials, static_cast<const T *>(residual), static_cast<T *>(out), M, K, args.splits, epilogue);
+    TL_LAUNCH_CHECK("w4a16_skinny_reduce");
+    return TL_OK;
 }
 
 int launch_w4a16_skinny(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N,

@@ -157,9 +157,8 @@ _ZERO_WS_KEEP: list = []  # outgrown buffers may still be referenced by captured
 
 
 def _zero_workspace(nbytes: int, device) -> torch.Tensor | None:
-    """Persistent zero-initialised workspace per device for the split-reduction GEMM: its head holds
-    arrival tickets that must be zero on entry and are left zero by the kernel
-    (``TL_QMM_TICKET_BYTES``), so one buffer serves every launch issued in stream order."""
+    """Persistent workspace per device for the split-reduction GEMM (fp32 partial planes): one buffer serves
+    every launch issued in stream order and captured graphs keep a stable pointer."""
     if nbytes == 0:
         return None
     key = torch.device(device)
