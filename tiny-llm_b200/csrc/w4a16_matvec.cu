@@ -368,6 +368,8 @@ int launch_w4a16_fused(const void *scales, const void *biases, const void *b, vo
                        const void *residual, int M, int N, int K, int lda, int prologue, int epilogue, float eps, int dtype,
                        cudaStream_t st) {
     if (M == 0 || K == 0) return TL_OK;
+    if (w4a16_stream6_supported(M, N, K, dtype))
+        return launch_w4a16_stream6(scales, biases, b, out, p0, p1, residual, M, N, K, lda, prologue, epilogue, eps, st);
     StreamArgs args{};
     args.scales = scales, args.biases = biases, args.b = static_cast<const uint32_t *>(b), args.out = out;
     args.p0 = p0, args.p1 = p1, args.residual = residual;

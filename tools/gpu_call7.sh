@@ -15,5 +15,5 @@ import json;d=json.load(open('gpurun_out/c7_bench_serve_pg$PG.json'));print(d['v
 done
 # ---- ncu: launch list + DRAM traffic of one decode token, then --set full of the round-2 kernels
 timeout 900 ncu --nvtx --nvtx-include "decode/" --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r02_launches_decode.csv python tools/profile_decode.py --layers 36 --steps 1 --pdl > gpurun_out/c7_ncu_decode.log 2>&1; echo "ncu decode rc=$?"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"paged_prefill_tc|w4a16_skinny_kernel|w4a16_stream5" -s 23 -c 7 -o gpurun_out/r02_kernels python tools/ncu_round2.py > gpurun_out/c7_ncu_kernels.log 2>&1; echo "ncu kernels rc=$?"; tail -3 gpurun_out/c7_ncu_kernels.log
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"paged_prefill_tc|w4a16_skinny_kernel|w4a16_stream5" -s 18 -c 6 -o gpurun_out/r02_kernels python tools/ncu_round2.py > gpurun_out/c7_ncu_kernels.log 2>&1; echo "ncu kernels rc=$?"; tail -3 gpurun_out/c7_ncu_kernels.log
 ls -la gpurun_out/*.ncu-rep
