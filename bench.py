@@ -645,10 +645,11 @@ def run_serve(args, long_context: bool) -> None:
     generated = sum(batcher.generated.values())
     total_generated = sum_over_ranks(generated, device)
     total_prefill = sum_over_ranks(batcher.prefill_tokens, device)
-    decode_ms = sum(batcher.decode_step_ms)
-    prefill_ms = sum(batcher.prefill_chunk_ms)
+    gpu_ms = batcher.gpu_phase_ms()  # device time per phase (CUDA events); the wall-time lists include queueing behind the other phase
+    decode_ms = sum(gpu_ms["decode"]) or sum(batcher.decode_step_ms)
+    prefill_ms = sum(gpu_ms["prefill"]) or sum(batcher.prefill_chunk_ms)
     gpu_launches = engine.kernels_per_step * (engine.graph_replays - replays0) + (ext.launch_count() - launches0)
-    steps_sorted = sorted(batcher.decode_step_ms)
+    steps_sorted = sorted(gpu_ms["decode"] or batcher.decode_step_ms)
     pct = lambda q: steps_sorted[min(len(steps_sorted) - 1, int(q * len(steps_sorted)))] if steps_sorted else None
     mine_stats = {
         "requests": len(mine), "wall_s": round(wall, 3), "generated_tokens": generated, "prefill_tokens": batcher.prefill_tokens,
@@ -657,6 +658,8 @@ def run_serve(args, long_context: bool) -> None:
         "decode_tok_s": round(batcher.decode_tokens / (decode_ms / 1e3), 1) if decode_ms else None,
         "decode_step_ms_p50": round(pct(0.5), 3) if steps_sorted else None, "decode_step_ms_p95": round(pct(0.95), 3) if steps_sorted else None,
         "time_in_decode_s": round(decode_ms / 1e3, 3), "time_in_prefill_s": round(prefill_ms / 1e3, 3),
+        "timing": "per-phase device time from CUDA events on the scheduler's stream; wall_s is host wall-clock of the whole run",
+        "prefill_chunk_ms_p50": round(sorted(gpu_ms["prefill"])[len(gpu_ms["prefill"]) // 2], 3) if gpu_ms["prefill"] else None,
         "peak_active_requests": batcher.peak_active_requests, "peak_live_pages": batcher.peak_live_pages,
         "peak_live_kv_gb": round(batcher.peak_live_pages * 2 * margs.num_key_value_heads * PAGE_SIZE * margs.head_dim * 2 / 1e9, 2),
     }

@@ -275,7 +275,7 @@ int tl_quantized_matmul_fused(const void *scales, const void *biases, const void
     if (M == 0 || K == 0) return TL_OK;
     if (!scales || !biases || !b || !out || !p0 || (prologue != TL_PRO_NONE && !p1) || (epilogue == TL_EPI_RESIDUAL && !residual))
         return fail(TL_EINVAL, "quantized_matmul_fused: null pointer");
-    if (prologue == TL_PRO_NONE && lda == N && use_skinny_kernel(M, N, K, dtype, 1) && workspace != nullptr)
+    if (prologue == TL_PRO_NONE && lda == N && use_skinny_kernel(M, N, K, dtype, 1))
         return launch_w4a16_skinny(scales, biases, p0, b, out, residual, M, N, K, epilogue, dtype, workspace, workspace_bytes, as_stream(stream));
     return launch_w4a16_fused(scales, biases, b, out, p0, p1, residual, M, N, K, lda, prologue, epilogue, eps, dtype,
                               as_stream(stream));

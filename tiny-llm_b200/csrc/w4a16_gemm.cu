@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < GSTAGES; ++i) {
             g_mbar_init(full_a + 8 * i, 1);
-            g_mbar_init(full_b + 8 * i, G_DEQ_WARPS * 32);
+            g_mbar_init(full_b + 8 * i, G_DEQ_WARPS);  // one arrival per dequantiser warp
             g_mbar_init(empty + 8 * i, 1);
         }
         g_mbar_init(tmem_full, 1);
@@ -217,7 +217,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
                     make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
             }
             g_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-            g_mbar_arrive(full_b + 8 * s);
+            __syncwarp();           // one arrival per warp instead of 256 serialised shared-memory atomics per stage
+            if (lane == 0) g_mbar_arrive(full_b + 8 * s);
         }
         // ---- epilogue: TMEM lane = token row; warps 4-7 take columns 0..63, warps 8-11 columns 64..127
         g_mbar_wait(tmem_full, 0);

@@ -117,7 +117,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            g_mbar_init(full_a + 8 * i, SK_DEQ_THREADS);
+            g_mbar_init(full_a + 8 * i, SK_DEQ_THREADS / 32);  // one arrival per dequantiser warp
             g_mbar_init(empty + 8 * i, 1);
         }
         for (int i = 0; i < BSTAGES; ++i) {
@@ -126,7 +126,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int i = 0; i < PSTAGES; ++i) {
             g_mbar_init(p_full + 8 * i, 1);
-            g_mbar_init(p_empty + 8 * i, SK_DEQ_THREADS);
+            g_mbar_init(p_empty + 8 * i, SK_DEQ_THREADS / 32);
         }
         g_mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -233,12 +233,15 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 *reinterpret_cast<uint4 *>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
             }
             g_fence_proxy_async();
-            g_mbar_arrive(full_a + 8 * s);
+            // one arrival per WARP (256 arrivals on one mbarrier are 256 serialised shared-memory atomics: ~0.4 us per block,
+            // the largest item of the first version's 0.6-1.4 us per block); __syncwarp orders the lanes' stores before it
+            __syncwarp();
+            if (lane == 0) g_mbar_arrive(full_a + 8 * s);
             // Release the packed box only now: the stores above consumed `cur`, so this thread's shared-memory read of the
             // box has COMPLETED (an arrive issued right behind the load let the TMA refill the box under a load still in
             // flight - mbarrier ops are not ordered behind the load/store unit - and single feature rows came out wrong in
             // ~1 of 600 CTA-loops of 40 blocks).
-            if (sub == SK_PK - 1 || i == n_kb - 1) g_mbar_arrive(p_empty + 8 * ps);
+            if ((sub == SK_PK - 1 || i == n_kb - 1) && lane == 0) g_mbar_arrive(p_empty + 8 * ps);
         }
         // ------------------------------------------------ epilogue: TMEM lane = feature; warps 4-7 take token columns [0, NT/2), 8-11 the rest
         TL_TRACE_STAMP_T(33, 128);  // last weight tile handed to the MMA thread

@@ -196,8 +196,9 @@ class ContinuousBatcher:
         # decode step / prefill chunk (the host reads the sampled tokens each step, so wall == device time
         # + host scheduling), peak concurrently live requests and KV pages (all layers)
         self.record_timing = False
-        self.decode_step_ms: list[float] = []
-        self.prefill_chunk_ms: list[float] = []
+        self.decode_step_ms: list[float] = []   # wall time per decode step (host reads the tokens: includes queued GPU work)
+        self.prefill_chunk_ms: list[float] = []  # wall time per prefill chunk (enqueue only unless it is a prompt's last chunk)
+        self._gpu_events: list[tuple[str, object, object]] = []  # (kind, start, end) CUDA events on the current stream
         self.peak_active_requests = 0
         self.peak_live_pages = 0
 
@@ -209,6 +210,25 @@ class ContinuousBatcher:
         if self.verbose:
             _print_progress(self.slots, self.pending, len(self.queue), self.tick, self.started)
         self.tick += 1
+
+    def _gpu_span(self, kind: str):
+        """CUDA events around one scheduler phase (device time without the host: an intermediate prefill chunk is not
+        synchronised by the scheduler, so its GPU work would otherwise be charged to the decode step behind it)."""
+        if not (self.record_timing and torch.cuda.is_available() and self.device is not None and torch.device(self.device).type == "cuda"):
+            return None
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        self._gpu_events.append((kind, start, end))
+        return end
+
+    def gpu_phase_ms(self) -> dict:
+        """Per-phase device times (ms) from the recorded CUDA events; call after the run (synchronises)."""
+        out: dict = {"prefill": [], "decode": []}
+        if self._gpu_events:
+            torch.cuda.synchronize()
+        for kind, start, end in self._gpu_events:
+            out[kind].append(start.elapsed_time(end))
+        return out
 
     def _record_cache_state(self) -> None:
         live = [s for s in self.slots if s is not None]
@@ -239,7 +259,10 @@ class ContinuousBatcher:
             if not request.is_prefill_done:
                 before = request.offset
                 t0 = time.perf_counter() if self.record_timing else 0.0
-                request.try_prefill()  # ends with a host read of the sampled token: wall time covers the device work
+                span = self._gpu_span("prefill")
+                request.try_prefill()
+                if span is not None:
+                    span.record()
                 if self.record_timing:
                     self.prefill_chunk_ms.append((time.perf_counter() - t0) * 1e3)
                 self.prefill_tokens += request.offset - before
@@ -272,8 +295,11 @@ class ContinuousBatcher:
             if self.record_timing:
                 self._record_cache_state()
             t0 = time.perf_counter() if self.record_timing else 0.0
+            span = self._gpu_span("decode")
             batch = torch.tensor(tokens, dtype=torch.int32, device=self.device).reshape(-1, 1)
             sampled = _step(self.model, batch, offsets, self.kv_cache)
+            if span is not None:
+                span.record()
             host = sampled.reshape(-1).tolist()  # one device->host read per step
             if self.record_timing:
                 self.decode_step_ms.append((time.perf_counter() - t0) * 1e3)
