@@ -173,8 +173,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
     } else if (warp >= 4) {
         // ------------------------------------------------ dequantisers, then epilogue
         const int dt = threadIdx.x - 128;      // 0 .. 255
-        const int row = dt & 127;              // feature row of the tile
-        const int half = dt >> 7;              // which 32 of the stage's 64 reduction elements
+        // adjacent lanes = the two 16-byte halves of ONE weight row: a warp's load touches 16 full 32-byte sectors (the
+        // first version mapped lane <-> row, 32 half-used sectors per load, each fetched again by the warp holding the other half)
+        const int row = dt >> 1;               // feature row of the tile
+        const int half = dt & 1;               // which 32 of the stage's 64 reduction elements
         const int n = min(n_tile * GN + row, K - 1);
         const uint32_t *wrow = b + static_cast<size_t>(n) * (N / 8);
         const T *srow = scales + static_cast<size_t>(n) * G;

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(S6_THREADS, 2) w4a16_stream6_kernel(const __gr
     __syncwarp();
     auto request = [&](int i) {  // unit i of this warp -> slot i % SLOTS   (lane 0 only)
         const int ch = i / P, u = i - ch * P;
-        const int s = i % S6_SLOTS;
+        const int s = (i - begin) % S6_SLOTS;  // the consumer's slot rule
         g_mbar_expect_tx(bar0 + 8 * s, S6_UNIT_BYTES);  // rows past K are zero-filled by the TMA unit and still counted
         g_tma_load_2d(g_smem_u32(ring + s * S6_UNIT_BYTES), &tmap_w, u * (U * 64), r0 + ch * 16, bar0 + 8 * s);
     };
