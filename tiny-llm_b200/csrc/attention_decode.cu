@@ -434,25 +434,28 @@ __global__ void __launch_bounds__(GQA_THREADS) paged_gqa_kernel(
     }
 }
 
-__global__ void __launch_bounds__(GQA_THREADS) paged_gqa_merge_kernel(const float *__restrict__ ws_o,
-                                                                      const float *__restrict__ ws_m,
-                                                                      const float *__restrict__ ws_l,
-                                                                      __nv_bfloat16 *__restrict__ out, int splits) {
+__global__ void __launch_bounds__(GQA_THREADS) paged_gqa_merge_kernel(const float *ws_o, const float *ws_m, const float *ws_l,
+                                                                      __nv_bfloat16 *out, int splits) {
+    // Dependent launch (common.cuh): the partials are the attention kernel's output, in a workspace every layer rewrites
+    // - read them through L2.
+    griddep_launch();
+    griddep_wait();
     const size_t qi = blockIdx.x;
     const int d = threadIdx.x;
     float gm = NEG_BIG;
-    for (int s = 0; s < splits; ++s) gm = fmaxf(gm, ws_m[qi * splits + s]);
+    for (int s = 0; s < splits; ++s) gm = fmaxf(gm, ld_cg(ws_m + qi * splits + s));
     float gl = 0.f, o = 0.f;
     for (int s = 0; s < splits; ++s) {
-        const float f = exp2f(ws_m[qi * splits + s] - gm);
-        gl += ws_l[qi * splits + s] * f;
-        o += ws_o[(qi * splits + s) * GQA_D + d] * f;
+        const float f = exp2f(ld_cg(ws_m + qi * splits + s) - gm);
+        gl += ld_cg(ws_l + qi * splits + s) * f;
+        o += ld_cg(ws_o + (qi * splits + s) * GQA_D + d) * f;
     }
     out[qi * GQA_D + d] = __float2bfloat16_rn(gl == 0.f ? 0.f : o / gl);
 }
 
 int launch_paged_gqa_merge(const float *ws_o, const float *ws_m, const float *ws_l, void *out, int rows_total, int splits, cudaStream_t st) {
-    paged_gqa_merge_kernel<<<static_cast<unsigned>(rows_total), GQA_THREADS, 0, st>>>(ws_o, ws_m, ws_l, static_cast<__nv_bfloat16 *>(out), splits);
+    launch_chained(paged_gqa_merge_kernel, dim3(static_cast<unsigned>(rows_total)), dim3(GQA_THREADS), 0, st, ws_o, ws_m, ws_l,
+                   static_cast<__nv_bfloat16 *>(out), splits);
     TL_LAUNCH_CHECK("paged_gqa_merge");
     return TL_OK;
 }
@@ -524,7 +527,8 @@ int launch_paged_gqa(const void *q, const void *kp, const void *vp, const int32_
 #undef TL_GQA
     TL_LAUNCH_CHECK("paged_gqa");
     if (splits > 1) {
-        paged_gqa_merge_kernel<<<static_cast<unsigned>(rows * L), GQA_THREADS, 0, st>>>(ws_o, ws_m, ws_l, op, splits);
+        launch_chained(paged_gqa_merge_kernel, dim3(static_cast<unsigned>(rows * L)), dim3(GQA_THREADS), 0, st, static_cast<const float *>(ws_o),
+                       static_cast<const float *>(ws_m), static_cast<const float *>(ws_l), op, splits);
         TL_LAUNCH_CHECK("paged_gqa_merge");
     }
     return TL_OK;

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char tsm[];
+    griddep_launch();  // programmatic dependent launch (common.cuh): the successor may set itself up under this grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = static_cast<int>(blockIdx.x) % a.splits;
     const int qb = static_cast<int>(gridDim.x) / a.splits - 1 - static_cast<int>(blockIdx.x) / a.splits;  // long (late) query blocks first
@@ -148,6 +149,9 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     __syncthreads();
     g_tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // q and the newest K/V rows are the predecessor's output, and this grid overwrites buffers (output, split partials)
+    // the predecessor may still read; block tables and context lengths are step inputs uploaded before the chain.
+    griddep_wait();
 
     if (warp == 4) {
         // ------------------------------------------------------------ TMA producer
@@ -475,7 +479,8 @@ int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const
     }
     dim3 grid(q_blocks * a.splits, num_kv_heads, B);
     if (grid.y > 65535 || grid.z > 65535) return fail(TL_EINVAL, "paged_attention: too many heads / requests for one launch");
-    paged_prefill_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mk, mv, a);
+    cudaError_t le = launch_chained(paged_prefill_tc_kernel, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, mq, mk, mv, a);
+    if (le != cudaSuccess) return fail(TL_ECUDA, "paged_attention: launch failed: %s", cudaGetErrorString(le));
     TL_LAUNCH_CHECK("paged_prefill_tc");
     if (a.splits > 1) return launch_paged_gqa_merge(a.ws_o, a.ws_m, a.ws_l, out, rows * L, a.splits, st);
     return TL_OK;

@@ -29,7 +29,6 @@ SOURCES = [
     "c_abi.cu",
     "elementwise.cu",
     "w4a16_matvec.cu",
-    "w4a16_stream6.cu",
     "w4a16_gemm.cu",
     "w4a16_skinny.cu",
     "attention_decode.cu",

@@ -124,6 +124,34 @@ __device__ __forceinline__ __half ld_cg(const __half *p) {
     return __ushort_as_half(r);
 }
 
+// ---- programmatic dependent launch ------------------------------------------
+// A kernel launched through launch_chained() may become resident while its predecessor on the stream is still
+// running (the predecessor lets it in with griddep_launch(), or implicitly by exiting).  It must execute
+// griddep_wait() before it reads anything the predecessor wrote and before it writes anything the predecessor may
+// still read; the wait returns once the predecessor grid has COMPLETED and its writes are visible.  Everything a
+// kernel does before the wait (barrier init, TMEM allocation, tensor-map prefetch, weight prefetch) overlaps the
+// predecessor's tail.  Data written by an earlier kernel of such a chain is read through L2 (ld_cg / TMA), never
+// through a possibly stale L1 line.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool use_pdl();  // kernels.h; TL_PDL=0 turns the attribute off (griddepcontrol.wait then returns at once)
+
+template <typename... P, typename... A>
+static inline cudaError_t launch_chained(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A &&...a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(a)...);
+}
+
 }  // namespace tl
 
 #define TL_LAUNCH_CHECK(name)                    \

@@ -20,9 +20,13 @@ struct Vec {
     static constexpr int N = 16 / sizeof(T);  // elements per 128-bit access
 };
 
-template <typename T>
+template <typename T, bool CG = false>
 __device__ __forceinline__ void load16(const T *p, float (&v)[Vec<T>::N]) {
-    uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    uint4 raw;
+    if constexpr (CG)
+        raw = ld_cg(reinterpret_cast<const uint4 *>(p));  // written by the previous kernel of a dependent-launch chain
+    else
+        raw = *reinterpret_cast<const uint4 *>(p);
     if constexpr (sizeof(T) == 4) {
         v[0] = __uint_as_float(raw.x), v[1] = __uint_as_float(raw.y);
         v[2] = __uint_as_float(raw.z), v[3] = __uint_as_float(raw.w);
@@ -49,8 +53,9 @@ __device__ __forceinline__ void store16(T *p, const float (&v)[Vec<T>::N]) {
 // TPR threads cooperate on one row (32: one warp per row for per-head norms of
 // width 128; 256: one CTA per row for hidden-size rows).
 template <typename T, int TPR, bool VEC>
-__global__ void __launch_bounds__(256) rms_norm_kernel(const T *__restrict__ x, const T *__restrict__ w,
-                                                        T *__restrict__ out, int rows, int dim, float eps) {
+__global__ void __launch_bounds__(256) rms_norm_kernel(const T *x, const T *__restrict__ w, T *out, int rows, int dim, float eps) {
+    griddep_launch();
+    griddep_wait();  // x is the previous kernel's output (common.cuh: programmatic dependent launch)
     constexpr int ROWS = 256 / TPR;
     constexpr int EPV = Vec<T>::N;
     const int sub = threadIdx.x / TPR;
@@ -61,17 +66,26 @@ __global__ void __launch_bounds__(256) rms_norm_kernel(const T *__restrict__ x, 
     T *outr = out + static_cast<size_t>(live ? row : 0) * dim;
 
     float ss = 0.f;
+    constexpr int KEEP = 2;  // chunks per thread that stay in registers between the two passes (dim <= 2 * TPR * EPV: one L2 trip)
+    float keep[KEEP][EPV];
     if (live) {
         if constexpr (VEC) {
-            for (int i = lane * EPV; i < dim; i += TPR * EPV) {
+            int it = 0;
+            for (int i = lane * EPV; i < dim; i += TPR * EPV, ++it) {
                 float v[EPV];
-                load16<T>(xr + i, v);
+                load16<T, true>(xr + i, v);
 #pragma unroll
                 for (int j = 0; j < EPV; ++j) ss += v[j] * v[j];
+#pragma unroll
+                for (int k = 0; k < KEEP; ++k)
+                    if (it == k) {
+#pragma unroll
+                        for (int j = 0; j < EPV; ++j) keep[k][j] = v[j];
+                    }
             }
         } else {
             for (int i = lane; i < dim; i += TPR) {
-                float v = to_f(xr[i]);
+                float v = to_f(ld_cg(xr + i));
                 ss += v * v;
             }
         }
@@ -87,16 +101,23 @@ __global__ void __launch_bounds__(256) rms_norm_kernel(const T *__restrict__ x, 
     if (!live) return;
     const float inv = rsqrtf(ss / static_cast<float>(dim) + eps);
     if constexpr (VEC) {
-        for (int i = lane * EPV; i < dim; i += TPR * EPV) {
+        int it = 0;
+        for (int i = lane * EPV; i < dim; i += TPR * EPV, ++it) {
             float v[EPV], g[EPV];
-            load16<T>(xr + i, v);
+            if (it >= KEEP) load16<T, true>(xr + i, v);
+#pragma unroll
+            for (int k = 0; k < KEEP; ++k)
+                if (it == k) {
+#pragma unroll
+                    for (int j = 0; j < EPV; ++j) v[j] = keep[k][j];
+                }
             load16<T>(w + i, g);
 #pragma unroll
             for (int j = 0; j < EPV; ++j) v[j] = v[j] * inv * g[j];
             store16<T>(outr + i, v);
         }
     } else {
-        for (int i = lane; i < dim; i += TPR) outr[i] = from_f<T>(to_f(xr[i]) * inv * to_f(w[i]));
+        for (int i = lane; i < dim; i += TPR) outr[i] = from_f<T>(to_f(ld_cg(xr + i)) * inv * to_f(w[i]));
     }
 }
 
@@ -110,15 +131,15 @@ static int rms_norm_t(const void *x, const void *w, void *out, int rows, int dim
     if (dim <= 512) {
         dim3 grid(ceil_div(rows, 8));
         if (vec)
-            rms_norm_kernel<T, 32, true><<<grid, 256, 0, st>>>(xp, wp, op, rows, dim, eps);
+            launch_chained(rms_norm_kernel<T, 32, true>, grid, dim3(256), 0, st, xp, wp, op, rows, dim, eps);
         else
-            rms_norm_kernel<T, 32, false><<<grid, 256, 0, st>>>(xp, wp, op, rows, dim, eps);
+            launch_chained(rms_norm_kernel<T, 32, false>, grid, dim3(256), 0, st, xp, wp, op, rows, dim, eps);
     } else {
         dim3 grid(rows);
         if (vec)
-            rms_norm_kernel<T, 256, true><<<grid, 256, 0, st>>>(xp, wp, op, rows, dim, eps);
+            launch_chained(rms_norm_kernel<T, 256, true>, grid, dim3(256), 0, st, xp, wp, op, rows, dim, eps);
         else
-            rms_norm_kernel<T, 256, false><<<grid, 256, 0, st>>>(xp, wp, op, rows, dim, eps);
+            launch_chained(rms_norm_kernel<T, 256, false>, grid, dim3(256), 0, st, xp, wp, op, rows, dim, eps);
     }
     TL_LAUNCH_CHECK("rms_norm");
     return TL_OK;
@@ -613,7 +634,7 @@ int launch_argmax(const void *logits, int32_t *out, int rows, int vocab, int dty
 // Same arithmetic and rounding points as rms_norm -> rope -> paged_cache_update
 // (qwen3_week3.py:69-96), in one launch instead of six.
 template <typename T>
-__global__ void decode_qk_norm_rope_append_kernel(const T *__restrict__ qkv, const T *__restrict__ qw,
+__global__ void decode_qk_norm_rope_append_kernel(const T *qkv, const T *__restrict__ qw,
                                                   const T *__restrict__ kw, const int32_t *__restrict__ offsets,
                                                   const int32_t *__restrict__ bt, const int32_t *__restrict__ cl,
                                                   T *__restrict__ q_out, T *__restrict__ kp, T *__restrict__ vp, int Hq,
@@ -622,6 +643,8 @@ __global__ void decode_qk_norm_rope_append_kernel(const T *__restrict__ qkv, con
     // bt_stride: block-table elements between rows (max_pages: one request per row; 0: every row is a token of ONE
     // request - a prefill chunk).  q_out element (row b, head h) starts at b * q_row_stride + h * q_head_stride.
     __shared__ float warp_part[8];
+    griddep_launch();
+    griddep_wait();  // qkv is the previous kernel's output: read through L2 (common.cuh: programmatic dependent launch)
     const int head = blockIdx.x;  // 0..Hq-1 q | Hq..Hq+Hkv-1 k | rest v
     const int b = blockIdx.y;
     const int half = D / 2;
@@ -632,7 +655,7 @@ __global__ void decode_qk_norm_rope_append_kernel(const T *__restrict__ qkv, con
     const int kvh = is_q ? 0 : (is_k ? head - Hq : head - Hq - Hkv);
 
     float re = 0.f, im = 0.f;
-    if (i < half) re = to_f(src[i]), im = to_f(src[i + half]);
+    if (i < half) re = to_f(ld_cg(src + i)), im = to_f(ld_cg(src + i + half));
     T out_re, out_im;
     if (is_q || is_k) {
         float ss = warp_sum(re * re + im * im);
@@ -688,7 +711,7 @@ int launch_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_w, con
     const int threads = ((D / 2 + 31) / 32) * 32;
     dim3 grid(Hq + 2 * Hkv, batch);
 #define TL_QKN(T)                                                                                                      \
-    decode_qk_norm_rope_append_kernel<T><<<grid, threads, 0, st>>>(                                                    \
+    launch_chained(decode_qk_norm_rope_append_kernel<T>, grid, dim3(threads), 0, st,                                  \
         static_cast<const T *>(qkv), static_cast<const T *>(q_norm_w), static_cast<const T *>(k_norm_w), offsets,     \
         block_table, context_lens, static_cast<T *>(q_out), static_cast<T *>(key_pages), static_cast<T *>(value_pages), \
         Hq, Hkv, D, base, eps, num_pages, page_size, max_pages, bt_stride, q_row_stride, q_head_stride)

@@ -53,10 +53,6 @@ bool use_pdl();
 int launch_w4a16_vanilla(const void *scales, const void *biases, const void *a, const void *b, void *out, int M,
                          int N, int K, int dtype, cudaStream_t st);
 
-// w4a16_stream6.cu (generation 6 of the streaming matvec: TMA -> shared-memory rings, two CTAs per SM; TL_STREAM6=1)
-bool w4a16_stream6_supported(int M, int N, int K, int dtype);
-int launch_w4a16_stream6(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *p1,
-                         const void *residual, int M, int N, int K, int lda, int prologue, int epilogue, float eps, cudaStream_t st);
 
 // w4a16_skinny.cu (swap-AB tcgen05 GEMM with split reduction, 9 <= M <= 128)
 bool w4a16_skinny_supported(int M, int N, int K, int dtype);
@@ -77,7 +73,6 @@ int launch_w4a16_gemm(const void *scales, const void *biases, const void *a, con
 void trace_bind_matvec(unsigned long long *buf, unsigned int *n, unsigned int cap);
 void trace_bind_attention(unsigned long long *buf, unsigned int *n, unsigned int cap);
 void trace_bind_skinny(unsigned long long *buf, unsigned int *n, unsigned int cap);
-void trace_bind_stream6(unsigned long long *buf, unsigned int *n, unsigned int cap);
 #endif
 size_t decode_attention_fused_workspace(int batch, int num_heads, int num_kv_heads);
 int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, const void *k_norm_weight, const int32_t *offsets,

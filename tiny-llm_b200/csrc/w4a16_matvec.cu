@@ -69,7 +69,11 @@ int launch_w4a16_stream(const void *scales, const void *biases, const void *a, c
 //     consumer cannot start before the producer's CTAs exit anyway, the flag traffic only adds);
 //   * forcing the largest shared-memory carveout: the register pipeline keeps up to 128 KiB of weight loads in flight per
 //     SM and those loads are staged in L1 lines even with L1::no_allocate - with ~1 KiB of L1 left every projection was
-//     1.75x slower (lm_head 49 -> 86 us, token 1.42 -> 1.95 ms).  No carveout preference is set here.
+//     1.75x slower (lm_head 49 -> 86 us, token 1.42 -> 1.95 ms).  No carveout preference is set here;
+//   * a sixth generation that moved the weight stream from registers to per-warp TMA rings in shared memory (512-thread
+//     CTAs at 64 registers, two per SM so that two consecutive launches overlap on every SM): parity-green, but the
+//     consume phase pays a shared-memory read per weight word and 296 CTAs hand over more slowly than 140 -
+//     1.43 -> 1.99 ms (profiles/r02_stream6_timeline.txt).
 constexpr int S5_WARPS = 16;
 #ifndef S5_DEPTH_SMALL
 #define S5_DEPTH_SMALL 4
@@ -88,8 +92,6 @@ struct StreamArgs {
     int rows_per_pass;
 };
 
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // MP: activation rows per pass padded to a power of two (template: shared-memory offsets of the
 // B fragments become immediates).  U: 128-column groups per unit (2 when N % 256 == 0).
@@ -368,8 +370,6 @@ int launch_w4a16_fused(const void *scales, const void *biases, const void *b, vo
                        const void *residual, int M, int N, int K, int lda, int prologue, int epilogue, float eps, int dtype,
                        cudaStream_t st) {
     if (M == 0 || K == 0) return TL_OK;
-    if (w4a16_stream6_supported(M, N, K, dtype))
-        return launch_w4a16_stream6(scales, biases, b, out, p0, p1, residual, M, N, K, lda, prologue, epilogue, eps, st);
     StreamArgs args{};
     args.scales = scales, args.biases = biases, args.b = static_cast<const uint32_t *>(b), args.out = out;
     args.p0 = p0, args.p1 = p1, args.residual = residual;

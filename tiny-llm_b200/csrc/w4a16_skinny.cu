@@ -41,14 +41,18 @@ constexpr int SK_DEQ_THREADS = 256;
 constexpr int SK_THREADS = 128 + SK_DEQ_THREADS;
 enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
 
-template <int NT>
+// Two ring geometries.  DEEP = false: 2 packed boxes + 2 dequantised tiles + 4-8 activation tiles = 96 KB (NT <= 64), two
+// CTAs per SM.  DEEP = true: one CTA per SM with 5-6 packed boxes in flight (80-96 KB of weight bytes per SM instead of
+// 2 x 16-32 KB): a box refill is an HBM round trip of 128 scattered 128-byte rows (~2.5 us under load) and a box is
+// consumed in well under 1 us, so the shallow ring leaves the CTA waiting on p_full most of the time.
+template <int NT, bool DEEP>
 struct SkSmem {
-    static constexpr int STAGES = 2;                    // dequantised weight tiles (16 KiB each)
-    static constexpr int PSTAGES = 2;                   // packed boxes: 8 reduction blocks ahead
+    static constexpr int STAGES = DEEP ? 3 : 2;                           // dequantised weight tiles (16 KiB each)
+    static constexpr int PSTAGES = DEEP ? (NT >= 128 ? 5 : 6) : 2;        // packed boxes, four reduction blocks each
     static constexpr int B_BYTES = NT * SK_KB * 2;
     // activation tiles: their own ring, deep enough to cover an L2 round trip (~1 us) at ~0.15 us per block; the first
     // version shared the 2-3 weight-tile slots and paid that latency every other block (0.9 us per block measured)
-    static constexpr int BSTAGES = NT >= 64 ? 4 : 8;  // NT = 64: 96 KB + scales -> two CTAs per SM; NT = 128: 128 KB, one
+    static constexpr int BSTAGES = DEEP ? (NT >= 128 ? 5 : (NT >= 64 ? 6 : 8)) : (NT >= 64 ? 4 : 8);
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = A_OFF + STAGES * SK_A_BYTES;
     static constexpr int P_OFF = B_OFF + BSTAGES * B_BYTES;
@@ -87,10 +91,10 @@ __host__ __device__ constexpr uint32_t sk_instr_desc() {
            (static_cast<uint32_t>(SK_FEAT >> 4) << 24);
 }
 
-template <typename T, int NT>
-__global__ void __launch_bounds__(SK_THREADS, 2)
+template <typename T, int NT, bool DEEP>
+__global__ void __launch_bounds__(SK_THREADS, DEEP ? 1 : 2)
 w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const SkArgs args) {
-    using Smem = SkSmem<NT>;
+    using Smem = SkSmem<NT, DEEP>;
     constexpr int STAGES = Smem::STAGES;
     constexpr int PSTAGES = Smem::PSTAGES;
     constexpr int BSTAGES = Smem::BSTAGES;
@@ -102,6 +106,11 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int n_kb = kb1 - kb0;
     const int G = args.N / 128;
     TL_TRACE_STAMP(30);
+    // Programmatic dependent launch: the next kernel of the stream may become resident now (its own prologue and weight
+    // pipeline do not depend on this grid).  Of THIS kernel only the activation loads and the epilogue depend on the
+    // predecessor: barrier init, TMEM allocation, scale staging, the packed-weight TMA ring and the dequantisers run
+    // ahead of griddep_wait(), i.e. under the predecessor's tail.
+    griddep_launch();
     const int g0 = kb0 >> 1, g_cnt = n_kb > 0 ? ((kb1 - 1) >> 1) - g0 + 1 : 0;
 
     const uint32_t a_base = g_smem_u32(ssm + Smem::A_OFF), b_base = g_smem_u32(ssm + Smem::B_OFF), p_base = g_smem_u32(ssm + Smem::P_OFF);
@@ -163,6 +172,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 3) {
         // ------------------------------------------------ TMA producer: activations
         if (lane == 0) {
+            griddep_wait();  // the activations are the predecessor's output
             for (int i = 0; i < n_kb; ++i) {
                 const int s = i % BSTAGES;
                 g_mbar_wait(b_empty + 8 * s, ((i / BSTAGES) & 1) ^ 1);
@@ -245,6 +255,9 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         // ------------------------------------------------ epilogue: TMEM lane = feature; warps 4-7 take token columns [0, NT/2), 8-11 the rest
         TL_TRACE_STAMP_T(33, 128);  // last weight tile handed to the MMA thread
+        // the epilogue reads the residual and overwrites buffers (output, partial planes) that the predecessor - the
+        // reduction kernel of the previous projection - may still be reading
+        griddep_wait();
         if (n_kb > 0) {
             g_mbar_wait(tmem_full, 0);
             g_tc_fence_after();
@@ -310,7 +323,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                     } else if (live && n < args.K) {
                         T vb = from_f<T>(acc[c]);
-                        if (args.epilogue == SK_EPI_RESIDUAL) vb = from_f<T>(to_f(res[static_cast<size_t>(m) * args.K + n]) + to_f(vb));
+                        if (args.epilogue == SK_EPI_RESIDUAL) vb = from_f<T>(to_f(ld_cg(res + static_cast<size_t>(m) * args.K + n)) + to_f(vb));
                         out[static_cast<size_t>(m) * args.K + n] = vb;
                     }
                 }
@@ -335,30 +348,38 @@ void trace_bind_skinny(unsigned long long *buf, unsigned int *n, unsigned int ca
 // every CTA schedule) and applies the epilogue; one thread per output.  All `splits` loads of a thread are independent
 // and in flight together (the first version let the last CTA of a tile do this with dependent round trips: 40 us).
 template <typename T>
-__global__ void __launch_bounds__(256) w4a16_skinny_reduce_kernel(const float *__restrict__ part, const T *__restrict__ res, T *__restrict__ out,
-                                                                  int M, int K, int splits, int epilogue) {
+__global__ void __launch_bounds__(256) w4a16_skinny_reduce_kernel(const float *part, const T *res, T *out, int M, int K, int splits, int epilogue) {
     const size_t plane = static_cast<size_t>(M) * K;
+    griddep_launch();
+    griddep_wait();  // the planes are the GEMM's output; they are rewritten by every projection, so read them through L2
+    // four planes per round trip, added in split order
+    auto plane_sum = [&](size_t at) {
+        float sum = 0.f;
+        for (int sp0 = 0; sp0 < splits; sp0 += 4) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = sp0 + j < splits ? ld_cg(part + (sp0 + j) * plane + at) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (sp0 + j < splits) sum += v[j];
+        }
+        return sum;
+    };
     if (epilogue == SK_EPI_SWIGLU_PAIRS) {
         const int half = K / 2;
         const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
         if (idx >= static_cast<size_t>(M) * half) return;
         const int m = static_cast<int>(idx / half), feat = static_cast<int>(idx - static_cast<size_t>(m) * half);
         const int n_gate = (feat >> 3) * 16 + (feat & 7);  // rows 16j + r (gate) and 16j + 8 + r (up) -> activation 8j + r
-        float g = 0.f, u = 0.f;
-        for (int sp = 0; sp < splits; ++sp) {
-            g += part[sp * plane + static_cast<size_t>(m) * K + n_gate];
-            u += part[sp * plane + static_cast<size_t>(m) * K + n_gate + 8];
-        }
+        const float g = plane_sum(static_cast<size_t>(m) * K + n_gate), u = plane_sum(static_cast<size_t>(m) * K + n_gate + 8);
         const float gate = to_f(from_f<T>(g)), up = to_f(from_f<T>(u));
         out[idx] = from_f<T>((gate / (1.0f + expf(-gate))) * up);
         return;
     }
     const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= plane) return;
-    float sum = 0.f;
-    for (int sp = 0; sp < splits; ++sp) sum += part[sp * plane + idx];
-    T vb = from_f<T>(sum);
-    if (epilogue == SK_EPI_RESIDUAL) vb = from_f<T>(to_f(res[idx]) + to_f(vb));
+    T vb = from_f<T>(plane_sum(idx));
+    if (epilogue == SK_EPI_RESIDUAL) vb = from_f<T>(to_f(ld_cg(res + idx)) + to_f(vb));
     out[idx] = vb;
 }
 
@@ -374,7 +395,11 @@ bool w4a16_skinny_supported(int M, int N, int K, int dtype) {
 // minimises waves x (reduction blocks per CTA + fixed cost) + reduce launch, with `slots` CTAs resident at once (two per
 // SM up to 64 token columns, one for 128), a fixed cost per CTA worth ~24 blocks (TMEM allocation, first TMA round
 // trips, epilogue: ~3.5 us measured) and ~20 blocks for the extra reduce launch.
-static int skinny_slots(int M) { return (M <= 64 ? 2 : 1) * sm_count(); }
+static bool skinny_deep() {
+    static const bool on = [] { const char *e = getenv("TL_SKINNY_DEEP"); return e == nullptr || e[0] != '0'; }();
+    return on;
+}
+static int skinny_slots(int M) { return (M <= 64 && !skinny_deep() ? 2 : 1) * sm_count(); }
 int w4a16_skinny_splits(int M, int N, int K) {
     const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
     const int num_kb = N / SK_KB;
@@ -441,16 +466,21 @@ static int sk_cached_map(CUtensorMap *out, const void *ptr, int kind, cuuint64_t
     return TL_OK;
 }
 
-template <typename T, int NT>
-static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkArgs &args, int grid, size_t smem, cudaStream_t st) {
+constexpr size_t SK_SMEM_MAX = 227 * 1024;
+
+template <typename T, int NT, bool DEEP>
+static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkArgs &args, int grid, size_t sb_bytes, cudaStream_t st) {
+    const size_t smem = SkSmem<NT, DEEP>::SB_OFF + sb_bytes;
+    if (smem > SK_SMEM_MAX) return fail(TL_EINVAL, "quantized_matmul: scale block does not fit in shared memory (N=%d)", args.N);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SK_SMEM_MAX)) != cudaSuccess ||
+            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, DEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit");
         configured = true;
     }
-    w4a16_skinny_kernel<T, NT><<<grid, SK_THREADS, smem, st>>>(ma, mw, args);
+    cudaError_t e = launch_chained(w4a16_skinny_kernel<T, NT, DEEP>, dim3(grid), dim3(SK_THREADS), smem, st, ma, mw, args);
+    if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_skinny: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("w4a16_skinny");
     return TL_OK;
 }
@@ -477,17 +507,23 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
     const int groups = (args.kb_per_split + 1) / 2 + 1;
     const int grid = tiles * args.splits;
     const size_t sb_bytes = static_cast<size_t>(groups) * SK_FEAT * 4;  // + rings: <= ~120 KB, one or two CTAs per SM
+    // the deep geometry unless its rings plus this split's scale block exceed the shared memory of an SM
+    const bool deep = skinny_deep() && SkSmem<128, true>::SB_OFF + sb_bytes <= SK_SMEM_MAX;
     int rc;
+#define TL_SK(NTV) (deep ? skinny_launch<T, NTV, true>(ma, mw, args, grid, sb_bytes, st) : skinny_launch<T, NTV, false>(ma, mw, args, grid, sb_bytes, st))
     switch (NT) {
-        case 16: rc = skinny_launch<T, 16>(ma, mw, args, grid, SkSmem<16>::SB_OFF + sb_bytes, st); break;
-        case 32: rc = skinny_launch<T, 32>(ma, mw, args, grid, SkSmem<32>::SB_OFF + sb_bytes, st); break;
-        case 64: rc = skinny_launch<T, 64>(ma, mw, args, grid, SkSmem<64>::SB_OFF + sb_bytes, st); break;
-        default: rc = skinny_launch<T, 128>(ma, mw, args, grid, SkSmem<128>::SB_OFF + sb_bytes, st); break;
+        case 16: rc = TL_SK(16); break;
+        case 32: rc = TL_SK(32); break;
+        case 64: rc = TL_SK(64); break;
+        default: rc = TL_SK(128); break;
     }
+#undef TL_SK
     if (rc != TL_OK || args.splits == 1) return rc;
     const size_t outputs = static_cast<size_t>(M) * (epilogue == SK_EPI_SWIGLU_PAIRS ? K / 2 : K);
-    w4a16_skinny_reduce_kernel<T><<<static_cast<unsigned>((outputs + 255) / 256), 256, 0, st>>>(
-        args.partials, static_cast<const T *>(residual), static_cast<T *>(out), M, K, args.splits, epilogue);
+    cudaError_t e = launch_chained(w4a16_skinny_reduce_kernel<T>, dim3(static_cast<unsigned>((outputs + 255) / 256)), dim3(256), 0, st,
+                                   static_cast<const float *>(args.partials), static_cast<const T *>(residual), static_cast<T *>(out), M, K,
+                                   args.splits, epilogue);
+    if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_skinny_reduce: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("w4a16_skinny_reduce");
     return TL_OK;
 }
