@@ -112,8 +112,12 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int last_row = min(q0 + a.RH, a.L) - 1;
     const int key_end = ctx <= 0 ? 0 : (a.is_causal ? min(ctx, max(ctx - a.L + last_row + 1, 0)) : ctx);
     const int all_tiles = (key_end + TC_BN - 1) / TC_BN;
-    const int t0 = min(split * a.tiles_per_split, all_tiles);
-    const int n_tiles = min(a.tiles_per_split, all_tiles - t0);  // this CTA: global tiles t0 .. t0 + n_tiles - 1
+    // Split-KV: the launch fixes the NUMBER of splits from the block table's width (the grid of a captured graph cannot
+    // follow the context), the tiles are dealt out here from the request's real length, so a request far below the
+    // bound still keeps all its splits busy.
+    const int tps = a.splits > 1 ? max((all_tiles + a.splits - 1) / a.splits, 1) : a.tiles_per_split;
+    const int t0 = min(split * tps, all_tiles);
+    const int n_tiles = min(tps, all_tiles - t0);  // this CTA: global tiles t0 .. t0 + n_tiles - 1
 
     const uint32_t q_base = g_smem_u32(tsm + TC_Q_OFF), p_base = g_smem_u32(tsm + TC_P_OFF);
     const uint32_t k_base = g_smem_u32(tsm + TC_K_OFF), v_base = g_smem_u32(tsm + TC_V_OFF);

@@ -38,26 +38,23 @@ constexpr int SK_PK = 4;          // reduction blocks per packed-weight TMA box:
 constexpr int SK_PACKED_BYTES = SK_PK * SK_FEAT * SK_KB / 2;  // 16 KiB per box, 128-byte swizzle
 constexpr int SK_A_BYTES = SK_FEAT * SK_KB * 2;       // 16 KiB dequantised tile
 constexpr int SK_DEQ_THREADS = 256;
+constexpr int SK_GROUP_WARPS = 4;   // dequantiser warps per reduction block (two groups alternate blocks)
 constexpr int SK_THREADS = 128 + SK_DEQ_THREADS;
 enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
 
-// Two ring geometries.  DEEP = false: 2 packed boxes + 2 dequantised tiles + 4-8 activation tiles = 96 KB (NT <= 64), two
-// CTAs per SM.  DEEP = true: one CTA per SM with 5-6 packed boxes in flight (80-96 KB of weight bytes per SM instead of
-// 2 x 16-32 KB): a box refill is an HBM round trip of 128 scattered 128-byte rows (~2.5 us under load) and a box is
-// consumed in well under 1 us, so the shallow ring leaves the CTA waiting on p_full most of the time.
-template <int NT, bool DEEP>
+template <int NT>
 struct SkSmem {
-    static constexpr int STAGES = DEEP ? 3 : 2;                           // dequantised weight tiles (16 KiB each)
-    static constexpr int PSTAGES = DEEP ? (NT >= 128 ? 5 : 6) : 2;        // packed boxes, four reduction blocks each
+    static constexpr int STAGES = 2;                    // dequantised weight tiles (16 KiB each): one per dequantiser group
+    static constexpr int PSTAGES = 2;                   // packed boxes, four reduction blocks each
     static constexpr int B_BYTES = NT * SK_KB * 2;
     // activation tiles: their own ring, deep enough to cover an L2 round trip (~1 us) at ~0.15 us per block; the first
     // version shared the 2-3 weight-tile slots and paid that latency every other block (0.9 us per block measured)
-    static constexpr int BSTAGES = DEEP ? (NT >= 128 ? 5 : (NT >= 64 ? 6 : 8)) : (NT >= 64 ? 4 : 8);
+    static constexpr int BSTAGES = NT >= 64 ? 4 : 8;  // NT <= 64: 96 KB -> two CTAs per SM; NT = 128: 128 KB, one
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = A_OFF + STAGES * SK_A_BYTES;
     static constexpr int P_OFF = B_OFF + BSTAGES * B_BYTES;
     static constexpr int BAR_OFF = P_OFF + PSTAGES * SK_PACKED_BYTES;
-    static constexpr int SB_OFF = BAR_OFF + 512;  // scale|bias pairs [groups][128 rows] u32 follow
+    static constexpr int BYTES = BAR_OFF + 512;
     static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
 };
 
@@ -91,10 +88,10 @@ __host__ __device__ constexpr uint32_t sk_instr_desc() {
            (static_cast<uint32_t>(SK_FEAT >> 4) << 24);
 }
 
-template <typename T, int NT, bool DEEP>
-__global__ void __launch_bounds__(SK_THREADS, DEEP ? 1 : 2)
+template <typename T, int NT>
+__global__ void __launch_bounds__(SK_THREADS, 2)
 w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const SkArgs args) {
-    using Smem = SkSmem<NT, DEEP>;
+    using Smem = SkSmem<NT>;
     constexpr int STAGES = Smem::STAGES;
     constexpr int PSTAGES = Smem::PSTAGES;
     constexpr int BSTAGES = Smem::BSTAGES;
@@ -108,17 +105,15 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     TL_TRACE_STAMP(30);
     // Programmatic dependent launch: the next kernel of the stream may become resident now (its own prologue and weight
     // pipeline do not depend on this grid).  Of THIS kernel only the activation loads and the epilogue depend on the
-    // predecessor: barrier init, TMEM allocation, scale staging, the packed-weight TMA ring and the dequantisers run
-    // ahead of griddep_wait(), i.e. under the predecessor's tail.
+    // predecessor: barrier init, TMEM allocation, the packed-weight TMA ring and the dequantisers run ahead of
+    // griddep_wait(), i.e. under the predecessor's tail.
     griddep_launch();
-    const int g0 = kb0 >> 1, g_cnt = n_kb > 0 ? ((kb1 - 1) >> 1) - g0 + 1 : 0;
 
     const uint32_t a_base = g_smem_u32(ssm + Smem::A_OFF), b_base = g_smem_u32(ssm + Smem::B_OFF), p_base = g_smem_u32(ssm + Smem::P_OFF);
     const uint32_t bar = g_smem_u32(ssm + Smem::BAR_OFF);
     const uint32_t full_a = bar, empty = bar + 8 * STAGES, p_full = bar + 16 * STAGES, p_empty = p_full + 8 * PSTAGES;
     const uint32_t full_b = p_empty + 8 * PSTAGES, b_empty = full_b + 8 * BSTAGES, tmem_full = b_empty + 8 * BSTAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ssm + Smem::BAR_OFF + 16 * STAGES + 16 * PSTAGES + 16 * BSTAGES + 8);
-    uint32_t *sb = reinterpret_cast<uint32_t *>(ssm + Smem::SB_OFF);  // [g_cnt][128]: (scale, bias) of the tile's rows
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -126,7 +121,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            g_mbar_init(full_a + 8 * i, SK_DEQ_THREADS / 32);  // one arrival per dequantiser warp
+            g_mbar_init(full_a + 8 * i, SK_GROUP_WARPS);  // one arrival per warp of the dequantiser group that owns the block
             g_mbar_init(empty + 8 * i, 1);
         }
         for (int i = 0; i < BSTAGES; ++i) {
@@ -143,14 +138,6 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "n"(Smem::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // scale | bias pairs of this tile's rows for the groups of this split (tiny; plain loads)
-    for (int i = threadIdx.x; i < g_cnt * SK_FEAT; i += SK_THREADS) {
-        const int g = i / SK_FEAT, r = i - g * SK_FEAT;
-        const int row = min(tile * SK_FEAT + r, args.K - 1);
-        const size_t at = static_cast<size_t>(row) * G + g0 + g;
-        const uint32_t s = reinterpret_cast<const unsigned short *>(args.scales)[at], bb = reinterpret_cast<const unsigned short *>(args.biases)[at];
-        sb[i] = s | (bb << 16);
     }
     g_tc_fence_before();
     __syncthreads();
@@ -199,33 +186,50 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             g_tc_commit(tmem_full);
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------ dequantisers: thread = (row, 32-element half of the 64-wide block)
-        const int dt = threadIdx.x - 128;
-        const int row = dt >> 1, half = dt & 1;  // the two halves of a row sit in adjacent lanes: one 32-byte shared-memory segment
+        // ------------------------------------------------ dequantisers
+        // Two groups of four warps; group g owns the reduction blocks i = g, g + 2, ... (so the two groups work on
+        // different blocks and meet only in the MMA queue); thread = one feature row of the tile = the TMEM lane it
+        // reads in the epilogue.  Per block a thread turns 32 packed bytes (two 16-byte chunks of its box row) into the
+        // 64 bf16 of its K-major row (8 swizzled 16-byte stores).  One barrier round per 64 weights and thread: the
+        // first version (thread = half a row of EVERY block, 149 instructions per 32 weights, all eight warps in
+        // lockstep on one block) spent 37 % of its time waiting for the stage to come back and 15 % in the store fence.
+        // Scale and bias of the row come straight from global memory (L2), prefetched one own block ahead.
+        const int grp = (warp - 4) >> 2;
+        const int row = ((warp - 4) & 3) * 32 + lane;
         using V2 = typename SkNum<T>::V2;
         const uint32_t magic = SkNum<T>::MAGIC;
         const V2 offset2 = *reinterpret_cast<const V2 *>(&magic);
-        for (int i = 0; i < n_kb; ++i) {
+        const size_t srow = static_cast<size_t>(min(tile * SK_FEAT + row, args.K - 1)) * G;
+        const unsigned short *sc = reinterpret_cast<const unsigned short *>(args.scales) + srow;
+        const unsigned short *bi = reinterpret_cast<const unsigned short *>(args.biases) + srow;
+        const uint32_t swz = static_cast<uint32_t>(row & 7);
+        const unsigned char *p_row = ssm + Smem::P_OFF + row * 128;
+        unsigned char *a_row = ssm + Smem::A_OFF + row * 128;
+        unsigned short s_next = 0, b_next = 0;
+        if (grp < n_kb) s_next = __ldg(sc + ((kb0 + grp) >> 1)), b_next = __ldg(bi + ((kb0 + grp) >> 1));
+        for (int i = grp; i < n_kb; i += 2) {
             const int box = i / SK_PK, sub = i - box * SK_PK;
             const int ps = box % PSTAGES, s = i % STAGES;
-            if (sub == 0) g_mbar_wait(p_full + 8 * ps, (box / PSTAGES) & 1);
+            const unsigned short s16 = s_next, b16 = b_next;
+            if (i + 2 < n_kb) s_next = __ldg(sc + ((kb0 + i + 2) >> 1)), b_next = __ldg(bi + ((kb0 + i + 2) >> 1));
+            if (sub < 2) g_mbar_wait(p_full + 8 * ps, (box / PSTAGES) & 1);  // this group's first block of the box
+            if (i == grp) TL_TRACE_STAMP_T(32, 128);  // first packed box has landed
             // row `row` of the box: 128 bytes = 8 chunks of 16 B, chunk c stored at (c ^ (row & 7)) by the TMA swizzle
-            if (i == 0) TL_TRACE_STAMP_T(32, 128);  // first packed box has landed
-            const int chunk = sub * 2 + half;
-            const uint4 cur = *reinterpret_cast<const uint4 *>(ssm + Smem::P_OFF + ps * SK_PACKED_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4));
-            const uint32_t pair = sb[(((kb0 + i) >> 1) - g0) * SK_FEAT + row];
-            const unsigned short s16 = static_cast<unsigned short>(pair & 0xffffu), b16 = static_cast<unsigned short>(pair >> 16);
+            const unsigned char *src = p_row + ps * SK_PACKED_BYTES;
+            const uint4 lo = *reinterpret_cast<const uint4 *>(src + (((2 * sub) ^ swz) << 4));
+            const uint4 hi = *reinterpret_cast<const uint4 *>(src + (((2 * sub + 1) ^ swz) << 4));
             V2 s2, b2;
             s2.x = s2.y = *reinterpret_cast<const T *>(&s16);
             b2.x = b2.y = *reinterpret_cast<const T *>(&b16);
-            uint32_t outw[16];
-            const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+            uint32_t outw[32];
+            const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 uint32_t p[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    uint32_t bits = ((wv[j] >> (4 * q)) & 0x000F000Fu) | magic;  // (128 + code_q, 128 + code_{q+4})
+                    uint32_t bits;  // (128 + code_q, 128 + code_{q+4}) in one LOP3: ((w >> 4q) & 0x000F000F) | magic
+                    asm("lop3.b32 %0, %1, 0x000F000F, %2, 0xEA;" : "=r"(bits) : "r"(wv[j] >> (4 * q)), "r"(magic));
                     V2 code = __hsub2(*reinterpret_cast<V2 *>(&bits), offset2);
                     V2 v = __hfma2(code, s2, b2);                                   // code * scale + bias, one rounding
                     p[q] = *reinterpret_cast<uint32_t *>(&v);
@@ -236,22 +240,20 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);
             }
             g_mbar_wait(empty + 8 * s, ((i / STAGES) & 1) ^ 1);
-            unsigned char *dst = ssm + Smem::A_OFF + s * SK_A_BYTES + row * 128;
+            unsigned char *dst = a_row + s * SK_A_BYTES;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int chunk = half * 4 + j;
-                *reinterpret_cast<uint4 *>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
-            }
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4 *>(dst + ((static_cast<uint32_t>(j) ^ swz) << 4)) = make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
             g_fence_proxy_async();
-            // one arrival per WARP (256 arrivals on one mbarrier are 256 serialised shared-memory atomics: ~0.4 us per block,
-            // the largest item of the first version's 0.6-1.4 us per block); __syncwarp orders the lanes' stores before it
+            // one arrival per WARP (an arrival per thread is a serialised shared-memory atomic each: ~0.4 us per block in
+            // the first version); __syncwarp orders the lanes' stores before it
             __syncwarp();
             if (lane == 0) g_mbar_arrive(full_a + 8 * s);
-            // Release the packed box only now: the stores above consumed `cur`, so this thread's shared-memory read of the
-            // box has COMPLETED (an arrive issued right behind the load let the TMA refill the box under a load still in
-            // flight - mbarrier ops are not ordered behind the load/store unit - and single feature rows came out wrong in
-            // ~1 of 600 CTA-loops of 40 blocks).
-            if ((sub == SK_PK - 1 || i == n_kb - 1) && lane == 0) g_mbar_arrive(p_empty + 8 * ps);
+            // Release the packed box only now, after this warp's last block in it: the stores above consumed `lo`/`hi`, so
+            // the shared-memory reads of the box have COMPLETED (an arrive issued right behind the load let the TMA refill
+            // the box under a load still in flight - mbarrier ops are not ordered behind the load/store unit - and single
+            // feature rows came out wrong in ~1 of 600 CTA-loops of 40 blocks).
+            if ((sub >= 2 || i + 2 >= n_kb) && lane == 0) g_mbar_arrive(p_empty + 8 * ps);
         }
         // ------------------------------------------------ epilogue: TMEM lane = feature; warps 4-7 take token columns [0, NT/2), 8-11 the rest
         TL_TRACE_STAMP_T(33, 128);  // last weight tile handed to the MMA thread
@@ -395,11 +397,7 @@ bool w4a16_skinny_supported(int M, int N, int K, int dtype) {
 // minimises waves x (reduction blocks per CTA + fixed cost) + reduce launch, with `slots` CTAs resident at once (two per
 // SM up to 64 token columns, one for 128), a fixed cost per CTA worth ~24 blocks (TMEM allocation, first TMA round
 // trips, epilogue: ~3.5 us measured) and ~20 blocks for the extra reduce launch.
-static bool skinny_deep() {
-    static const bool on = [] { const char *e = getenv("TL_SKINNY_DEEP"); return e == nullptr || e[0] != '0'; }();
-    return on;
-}
-static int skinny_slots(int M) { return (M <= 64 && !skinny_deep() ? 2 : 1) * sm_count(); }
+static int skinny_slots(int M) { return (M <= 64 ? 2 : 1) * sm_count(); }
 int w4a16_skinny_splits(int M, int N, int K) {
     const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
     const int num_kb = N / SK_KB;
@@ -466,20 +464,17 @@ static int sk_cached_map(CUtensorMap *out, const void *ptr, int kind, cuuint64_t
     return TL_OK;
 }
 
-constexpr size_t SK_SMEM_MAX = 227 * 1024;
-
-template <typename T, int NT, bool DEEP>
-static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkArgs &args, int grid, size_t sb_bytes, cudaStream_t st) {
-    const size_t smem = SkSmem<NT, DEEP>::SB_OFF + sb_bytes;
-    if (smem > SK_SMEM_MAX) return fail(TL_EINVAL, "quantized_matmul: scale block does not fit in shared memory (N=%d)", args.N);
+template <typename T, int NT>
+static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkArgs &args, int grid, cudaStream_t st) {
+    constexpr size_t smem = SkSmem<NT>::BYTES;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SK_SMEM_MAX)) != cudaSuccess ||
-            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, DEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit");
         configured = true;
     }
-    cudaError_t e = launch_chained(w4a16_skinny_kernel<T, NT, DEEP>, dim3(grid), dim3(SK_THREADS), smem, st, ma, mw, args);
+    cudaError_t e = launch_chained(w4a16_skinny_kernel<T, NT>, dim3(grid), dim3(SK_THREADS), smem, st, ma, mw, args);
     if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_skinny: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("w4a16_skinny");
     return TL_OK;
@@ -504,20 +499,14 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
     const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (int e = sk_cached_map(&ma, a, 0, N, M, SK_KB, NT, dt, 2)) return e;
     if (int e = sk_cached_map(&mw, b, 1, static_cast<cuuint64_t>(N) / 2, K, SK_PK * SK_KB / 2, SK_FEAT, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1)) return e;
-    const int groups = (args.kb_per_split + 1) / 2 + 1;
     const int grid = tiles * args.splits;
-    const size_t sb_bytes = static_cast<size_t>(groups) * SK_FEAT * 4;  // + rings: <= ~120 KB, one or two CTAs per SM
-    // the deep geometry unless its rings plus this split's scale block exceed the shared memory of an SM
-    const bool deep = skinny_deep() && SkSmem<128, true>::SB_OFF + sb_bytes <= SK_SMEM_MAX;
     int rc;
-#define TL_SK(NTV) (deep ? skinny_launch<T, NTV, true>(ma, mw, args, grid, sb_bytes, st) : skinny_launch<T, NTV, false>(ma, mw, args, grid, sb_bytes, st))
     switch (NT) {
-        case 16: rc = TL_SK(16); break;
-        case 32: rc = TL_SK(32); break;
-        case 64: rc = TL_SK(64); break;
-        default: rc = TL_SK(128); break;
+        case 16: rc = skinny_launch<T, 16>(ma, mw, args, grid, st); break;
+        case 32: rc = skinny_launch<T, 32>(ma, mw, args, grid, st); break;
+        case 64: rc = skinny_launch<T, 64>(ma, mw, args, grid, st); break;
+        default: rc = skinny_launch<T, 128>(ma, mw, args, grid, st); break;
     }
-#undef TL_SK
     if (rc != TL_OK || args.splits == 1) return rc;
     const size_t outputs = static_cast<size_t>(M) * (epilogue == SK_EPI_SWIGLU_PAIRS ? K / 2 : K);
     cudaError_t e = launch_chained(w4a16_skinny_reduce_kernel<T>, dim3(static_cast<unsigned>((outputs + 255) / 256)), dim3(256), 0, st,
