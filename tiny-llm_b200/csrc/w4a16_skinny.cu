@@ -42,20 +42,26 @@ constexpr int SK_GROUP_WARPS = 4;   // dequantiser warps per reduction block (tw
 constexpr int SK_THREADS = 128 + SK_DEQ_THREADS;
 enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
 
-template <int NT>
+// TA: the dequantised weight tile goes to TENSOR memory (tcgen05.st, lane = feature row, 32 columns per 64-wide block)
+// and is the MMA's A operand from there: no shared-memory tile, no generic->async proxy fence, and 4-6 stages (192 of
+// the 256 allocated columns) instead of the two 16 KiB tiles that fit in shared memory beside the rings - with two
+// stages each dequantiser group waited ~45 % of its time for the tensor core to hand its only stage back.
+template <int NT, bool TA>
 struct SkSmem {
-    static constexpr int STAGES = 2;                    // dequantised weight tiles (16 KiB each): one per dequantiser group
-    static constexpr int PSTAGES = 2;                   // packed boxes, four reduction blocks each
+    static constexpr int STAGES = TA ? (NT >= 128 ? 4 : 6) : 2;  // dequantised weight tiles: TMEM columns, or 16 KiB of shared memory each
+    static constexpr int PSTAGES = TA ? 4 : 2;                     // packed boxes, four reduction blocks each
     static constexpr int B_BYTES = NT * SK_KB * 2;
     // activation tiles: their own ring, deep enough to cover an L2 round trip (~1 us) at ~0.15 us per block; the first
     // version shared the 2-3 weight-tile slots and paid that latency every other block (0.9 us per block measured)
     static constexpr int BSTAGES = NT >= 64 ? 4 : 8;  // NT <= 64: 96 KB -> two CTAs per SM; NT = 128: 128 KB, one
     static constexpr int A_OFF = 0;
-    static constexpr int B_OFF = A_OFF + STAGES * SK_A_BYTES;
+    static constexpr int B_OFF = A_OFF + (TA ? 0 : STAGES * SK_A_BYTES);
     static constexpr int P_OFF = B_OFF + BSTAGES * B_BYTES;
     static constexpr int BAR_OFF = P_OFF + PSTAGES * SK_PACKED_BYTES;
     static constexpr int BYTES = BAR_OFF + 512;
-    static constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+    static constexpr int D_COLS = NT < 32 ? 32 : NT;               // accumulator columns (fp32, lane = feature)
+    static constexpr int TMEM_COLS = TA ? 256 : D_COLS;            // TA: + STAGES x 32 columns of bf16 pairs
+    static_assert(!TA || D_COLS + STAGES * 32 <= 256, "tensor-memory budget");
 };
 
 struct SkArgs {
@@ -88,10 +94,10 @@ __host__ __device__ constexpr uint32_t sk_instr_desc() {
            (static_cast<uint32_t>(SK_FEAT >> 4) << 24);
 }
 
-template <typename T, int NT>
+template <typename T, int NT, bool TA>
 __global__ void __launch_bounds__(SK_THREADS, 2)
 w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const SkArgs args) {
-    using Smem = SkSmem<NT>;
+    using Smem = SkSmem<NT, TA>;
     constexpr int STAGES = Smem::STAGES;
     constexpr int PSTAGES = Smem::PSTAGES;
     constexpr int BSTAGES = Smem::BSTAGES;
@@ -176,10 +182,16 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 g_mbar_wait(full_a + 8 * s, (i / STAGES) & 1);
                 g_mbar_wait(full_b + 8 * bs, (i / BSTAGES) & 1);
                 g_tc_fence_after();
-                const uint64_t adesc = g_smem_desc_sw128(a_base + s * SK_A_BYTES, 0, 1024);
                 const uint64_t bdesc = g_smem_desc_sw128(b_base + bs * Smem::B_BYTES, 0, 1024);
+                if constexpr (TA) {
+                    const uint32_t a_tmem = tmem_d + Smem::D_COLS + s * 32;  // 16 reduction elements = 8 columns per K step
 #pragma unroll
-                for (int k = 0; k < SK_KB / 16; ++k) g_tc_mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < SK_KB / 16; ++k) g_tc_mma_ts(tmem_d, a_tmem + 8 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                } else {
+                    const uint64_t adesc = g_smem_desc_sw128(a_base + s * SK_A_BYTES, 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < SK_KB / 16; ++k) g_tc_mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
                 g_tc_commit(empty + 8 * s);
                 g_tc_commit(b_empty + 8 * bs);
             }
@@ -240,11 +252,19 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);
             }
             g_mbar_wait(empty + 8 * s, ((i / STAGES) & 1) ^ 1);
-            unsigned char *dst = a_row + s * SK_A_BYTES;
+            if constexpr (TA) {
+                // lane = row, column c = elements (2c, 2c + 1) of the block: outw is already in that order
+                g_tc_fence_after();
+                g_tmem_st32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + Smem::D_COLS + s * 32, outw);
+                g_tmem_st_wait();
+                g_tc_fence_before();
+            } else {
+                unsigned char *dst = a_row + s * SK_A_BYTES;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<uint4 *>(dst + ((static_cast<uint32_t>(j) ^ swz) << 4)) = make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
-            g_fence_proxy_async();
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4 *>(dst + ((static_cast<uint32_t>(j) ^ swz) << 4)) = make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
+                g_fence_proxy_async();
+            }
             // one arrival per WARP (an arrival per thread is a serialised shared-memory atomic each: ~0.4 us per block in
             // the first version); __syncwarp orders the lanes' stores before it
             __syncwarp();
@@ -464,17 +484,17 @@ static int sk_cached_map(CUtensorMap *out, const void *ptr, int kind, cuuint64_t
     return TL_OK;
 }
 
-template <typename T, int NT>
+template <typename T, int NT, bool TA>
 static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkArgs &args, int grid, cudaStream_t st) {
-    constexpr size_t smem = SkSmem<NT>::BYTES;
+    constexpr size_t smem = SkSmem<NT, TA>::BYTES;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
-            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, TA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit");
         configured = true;
     }
-    cudaError_t e = launch_chained(w4a16_skinny_kernel<T, NT>, dim3(grid), dim3(SK_THREADS), smem, st, ma, mw, args);
+    cudaError_t e = launch_chained(w4a16_skinny_kernel<T, NT, TA>, dim3(grid), dim3(SK_THREADS), smem, st, ma, mw, args);
     if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_skinny: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("w4a16_skinny");
     return TL_OK;
@@ -500,13 +520,16 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
     if (int e = sk_cached_map(&ma, a, 0, N, M, SK_KB, NT, dt, 2)) return e;
     if (int e = sk_cached_map(&mw, b, 1, static_cast<cuuint64_t>(N) / 2, K, SK_PK * SK_KB / 2, SK_FEAT, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1)) return e;
     const int grid = tiles * args.splits;
+    static const bool ta = [] { const char *e = getenv("TL_SKINNY_TMEM_A"); return e == nullptr || e[0] != '0'; }();
     int rc;
+#define TL_SK(NTV) (ta ? skinny_launch<T, NTV, true>(ma, mw, args, grid, st) : skinny_launch<T, NTV, false>(ma, mw, args, grid, st))
     switch (NT) {
-        case 16: rc = skinny_launch<T, 16>(ma, mw, args, grid, st); break;
-        case 32: rc = skinny_launch<T, 32>(ma, mw, args, grid, st); break;
-        case 64: rc = skinny_launch<T, 64>(ma, mw, args, grid, st); break;
-        default: rc = skinny_launch<T, 128>(ma, mw, args, grid, st); break;
+        case 16: rc = TL_SK(16); break;
+        case 32: rc = TL_SK(32); break;
+        case 64: rc = TL_SK(64); break;
+        default: rc = TL_SK(128); break;
     }
+#undef TL_SK
     if (rc != TL_OK || args.splits == 1) return rc;
     const size_t outputs = static_cast<size_t>(M) * (epilogue == SK_EPI_SWIGLU_PAIRS ? K / 2 : K);
     cudaError_t e = launch_chained(w4a16_skinny_reduce_kernel<T>, dim3(static_cast<unsigned>((outputs + 255) / 256)), dim3(256), 0, st,
