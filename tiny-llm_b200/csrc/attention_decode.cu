@@ -441,14 +441,31 @@ __global__ void __launch_bounds__(GQA_THREADS) paged_gqa_merge_kernel(const floa
     griddep_launch();
     griddep_wait();
     const size_t qi = blockIdx.x;
-    const int d = threadIdx.x;
+    const int d = threadIdx.x, lane = d & 31;
+    const float *pm = ws_m + qi * splits, *pl = ws_l + qi * splits;
+    // Latency matters here (the whole long-context decode attention of one request is ~17 us): every warp reduces the
+    // split scalars on its own with ONE load round per lane (splits <= 32) and a shuffle tree, then the output column is
+    // gathered eight independent loads at a time.  (The first version walked the splits in two dependent loops: 2 x
+    // splits L2 round trips per thread.)  Fixed order everywhere: same bits on every run.
     float gm = NEG_BIG;
-    for (int s = 0; s < splits; ++s) gm = fmaxf(gm, ld_cg(ws_m + qi * splits + s));
-    float gl = 0.f, o = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        const float f = exp2f(ld_cg(ws_m + qi * splits + s) - gm);
-        gl += ld_cg(ws_l + qi * splits + s) * f;
-        o += ld_cg(ws_o + (qi * splits + s) * GQA_D + d) * f;
+    for (int s = lane; s < splits; s += 32) gm = fmaxf(gm, ld_cg(pm + s));
+    gm = warp_max(gm);
+    float gl = 0.f;
+    for (int s = lane; s < splits; s += 32) gl += ld_cg(pl + s) * exp2f(ld_cg(pm + s) - gm);
+    gl = warp_sum(gl);
+    float o = 0.f;
+    const float *po = ws_o + qi * splits * GQA_D + d;
+    for (int s0 = 0; s0 < splits; s0 += 8) {
+        float v[8], f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool live = s0 + j < splits;
+            v[j] = live ? ld_cg(po + static_cast<size_t>(s0 + j) * GQA_D) : 0.f;
+            f[j] = live ? ld_cg(pm + s0 + j) : gm;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (s0 + j < splits) o += v[j] * exp2f(f[j] - gm);
     }
     out[qi * GQA_D + d] = __float2bfloat16_rn(gl == 0.f ? 0.f : o / gl);
 }

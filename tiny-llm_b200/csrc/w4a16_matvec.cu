@@ -73,7 +73,10 @@ int launch_w4a16_stream(const void *scales, const void *biases, const void *a, c
 //   * a sixth generation that moved the weight stream from registers to per-warp TMA rings in shared memory (512-thread
 //     CTAs at 64 registers, two per SM so that two consecutive launches overlap on every SM): parity-green, but the
 //     consume phase pays a shared-memory read per weight word and 296 CTAs hand over more slowly than 140 -
-//     1.43 -> 1.99 ms (profiles/r02_stream6_timeline.txt).
+//     1.43 -> 1.99 ms (profiles/r02_stream6_timeline.txt);
+//   * asking the CTA's whole weight slice into L2 (cp.async.bulk.prefetch.L2) before griddepcontrol.wait, so that the
+//     consume phase would stream from L2: gate|up consume 4.64 -> 4.48 us, but the prefetch traffic competes with the
+//     activation round trip of the staging step (2.75 -> 3.2 us): 1.426 -> 1.461 ms.
 constexpr int S5_WARPS = 16;
 #ifndef S5_DEPTH_SMALL
 #define S5_DEPTH_SMALL 4
@@ -90,7 +93,6 @@ struct StreamArgs {
     int prologue, epilogue;
     float eps;
     int rows_per_pass;
-    int l2_prefetch;
 };
 
 
@@ -167,18 +169,6 @@ __global__ void __launch_bounds__(S5_WARPS * 32, 1) w4a16_stream5_kernel(const S
     W4Unit<U> buf[DEPTH];
 #pragma unroll
     for (int k = 0; k < DEPTH; ++k) load_next(buf[k]);  // in flight before the activations exist
-    // The register pipeline holds 32 KiB per SM; the rest of this CTA's slice (contiguous rows r0..r1) is asked into L2
-    // now, so that the hand-off and the staging of the activations (~4 us in which HBM would idle) fetch it and the
-    // consume phase streams from L2 instead of HBM.
-    if (args.l2_prefetch && threadIdx.x == NT - 32) {  // the instruction is warp-uniform (UBLKPF): one lane issues it
-        constexpr unsigned PIECE = 16384;
-        const unsigned char *w0 = bbytes + static_cast<size_t>(r0) * row_bytes;
-        const size_t wbytes = static_cast<size_t>(r1 - r0) * row_bytes;
-        for (size_t off = 0; off < wbytes; off += PIECE) {
-            const unsigned n = static_cast<unsigned>(wbytes - off < PIECE ? wbytes - off : PIECE);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(w0 + off), "r"(n) : "memory");
-        }
-    }
     TL_TRACE_STAMP(11);
 
     griddep_wait();  // activations (and the residual) come from the previous kernel
@@ -359,10 +349,6 @@ static int stream5_u(StreamArgs args, cudaStream_t st) {
     const int grid_x = stream5_grid(args.K);
     while (rpp > 1 && stream5_smem_bytes(args.N, args.K, rpp, grid_x) > S5_SMEM_MAX) rpp /= 2;
     args.rows_per_pass = rpp;
-    // L2 prefetch of the CTA slices: only when the whole matrix fits comfortably in L2 beside its neighbours (the tied
-    // head, 206 MB, would evict itself) and a single pass reads it (TL_S5_L2PREFETCH=0 turns it off)
-    static const bool l2_on = [] { const char *e = getenv("TL_S5_L2PREFETCH"); return e == nullptr || e[0] != '0'; }();
-    args.l2_prefetch = l2_on && args.M <= rpp && static_cast<size_t>(args.N) / 2 * args.K <= (48u << 20);
     switch (rpp) {
         case 1: return stream5_launch<T, 1, U>(args, st);
         case 2: return stream5_launch<T, 2, U>(args, st);

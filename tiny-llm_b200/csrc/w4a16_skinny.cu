@@ -38,6 +38,7 @@ constexpr int SK_PK = 4;          // reduction blocks per packed-weight TMA box:
 constexpr int SK_PACKED_BYTES = SK_PK * SK_FEAT * SK_KB / 2;  // 16 KiB per box, 128-byte swizzle
 constexpr int SK_A_BYTES = SK_FEAT * SK_KB * 2;       // 16 KiB dequantised tile
 constexpr int SK_DEQ_THREADS = 256;
+constexpr int SK_TRC_BLOCKS = 40;
 constexpr int SK_GROUP_WARPS = 4;   // dequantiser warps per reduction block (two groups alternate blocks)
 constexpr int SK_THREADS = 128 + SK_DEQ_THREADS;
 enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
@@ -102,6 +103,17 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     constexpr int PSTAGES = Smem::PSTAGES;
     constexpr int BSTAGES = Smem::BSTAGES;
     extern __shared__ __align__(1024) unsigned char ssm[];
+#if TL_TRACE
+    // per-block cycle stamps of CTA 0 (tools/skinny_timeline.py --blocks): role 0 = MMA thread (k: A tile ready, B tile
+    // ready, MMAs issued), roles 1 / 2 = first thread of dequantiser group 0 / 1 (k: box ready, math done, stage free, handed over)
+    __shared__ unsigned long long trc[3][SK_TRC_BLOCKS][4];
+#define SK_TRC(role, i, k)                                                          \
+    do {                                                                            \
+        if (blockIdx.x == 0 && (i) < SK_TRC_BLOCKS) trc[role][i][k] = clock64();    \
+    } while (0)
+#else
+#define SK_TRC(role, i, k) do { } while (0)
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x / args.splits, split = blockIdx.x - tile * args.splits;
     const int num_kb = args.N / SK_KB;
@@ -180,7 +192,9 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int i = 0; i < n_kb; ++i) {
                 const int s = i % STAGES, bs = i % BSTAGES;
                 g_mbar_wait(full_a + 8 * s, (i / STAGES) & 1);
+                SK_TRC(0, i, 0);
                 g_mbar_wait(full_b + 8 * bs, (i / BSTAGES) & 1);
+                SK_TRC(0, i, 1);
                 g_tc_fence_after();
                 const uint64_t bdesc = g_smem_desc_sw128(b_base + bs * Smem::B_BYTES, 0, 1024);
                 if constexpr (TA) {
@@ -194,6 +208,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 g_tc_commit(empty + 8 * s);
                 g_tc_commit(b_empty + 8 * bs);
+                SK_TRC(0, i, 2);
             }
             g_tc_commit(tmem_full);
         }
@@ -226,6 +241,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (i + 2 < n_kb) s_next = __ldg(sc + ((kb0 + i + 2) >> 1)), b_next = __ldg(bi + ((kb0 + i + 2) >> 1));
             if (sub < 2) g_mbar_wait(p_full + 8 * ps, (box / PSTAGES) & 1);  // this group's first block of the box
             if (i == grp) TL_TRACE_STAMP_T(32, 128);  // first packed box has landed
+            if (lane == 0 && (warp & 3) == 0) SK_TRC(1 + grp, i, 0);
             // row `row` of the box: 128 bytes = 8 chunks of 16 B, chunk c stored at (c ^ (row & 7)) by the TMA swizzle
             const unsigned char *src = p_row + ps * SK_PACKED_BYTES;
             const uint4 lo = *reinterpret_cast<const uint4 *>(src + (((2 * sub) ^ swz) << 4));
@@ -251,7 +267,9 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 outw[4 * j + 2] = __byte_perm(p[0], p[1], 0x7632);
                 outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);
             }
+            if (lane == 0 && (warp & 3) == 0) SK_TRC(1 + grp, i, 1);
             g_mbar_wait(empty + 8 * s, ((i / STAGES) & 1) ^ 1);
+            if (lane == 0 && (warp & 3) == 0) SK_TRC(1 + grp, i, 2);
             if constexpr (TA) {
                 // lane = row, column c = elements (2c, 2c + 1) of the block: outw is already in that order
                 g_tc_fence_after();
@@ -269,6 +287,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // the first version); __syncwarp orders the lanes' stores before it
             __syncwarp();
             if (lane == 0) g_mbar_arrive(full_a + 8 * s);
+            if (lane == 0 && (warp & 3) == 0) SK_TRC(1 + grp, i, 3);
             // Release the packed box only now, after this warp's last block in it: the stores above consumed `lo`/`hi`, so
             // the shared-memory reads of the box have COMPLETED (an arrive issued right behind the load let the TMA refill
             // the box under a load still in flight - mbarrier ops are not ordered behind the load/store unit - and single
@@ -360,6 +379,17 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(Smem::TMEM_COLS) : "memory");
     }
     TL_TRACE_STAMP(36);
+#if TL_TRACE
+    if (blockIdx.x == 0 && g_trace_buf != nullptr) {  // dump the per-block stamps: tag = 10000 + role * 1000 + block * 4 + k
+        for (int e = threadIdx.x; e < 3 * SK_TRC_BLOCKS * 4; e += SK_THREADS) {
+            const int role = e / (SK_TRC_BLOCKS * 4), rest = e - role * SK_TRC_BLOCKS * 4;
+            if (rest / 4 < n_kb && (role == 0 || (rest / 4) % 2 == role - 1)) {
+                const unsigned at = atomicAdd(g_trace_n, 1u);
+                if (at < g_trace_cap) g_trace_buf[2 * at] = 10000 + role * 1000 + rest, g_trace_buf[2 * at + 1] = trc[role][rest / 4][rest & 3];
+            }
+        }
+    }
+#endif
 }
 
 #if TL_TRACE
