@@ -159,69 +159,92 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
     if (warp == 4) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0 && n_tiles > 0) {
-            g_mbar_expect_tx(q_full, TC_Q_BYTES);
+        if (n_tiles > 0) {  // whole warp, one elected lane issues (see the MMA warp)
             const int head0 = b * a.Hq + kvh * a.G;
-            g_tma_load_3d(q_base, &tmap_q, 0, q0, head0, q_full);
-            g_tma_load_3d(q_base + TC_Q_BYTES / 2, &tmap_q, 64, q0, head0, q_full);
+            if (g_elect_one()) {
+                g_mbar_expect_tx(q_full, TC_Q_BYTES);
+                g_tma_load_3d(q_base, &tmap_q, 0, q0, head0, q_full);
+                g_tma_load_3d(q_base + TC_Q_BYTES / 2, &tmap_q, 64, q0, head0, q_full);
+            }
+            __syncwarp();
             const int32_t *table = a.block_table + static_cast<size_t>(b) * a.max_pages;
+            int s = 0;
+            uint32_t ph = 1;  // producer side: first pass through the ring does not wait
             for (int j = 0; j < n_tiles; ++j) {
-                const int s = j % TC_STAGES;
-                const uint32_t ph = (j / TC_STAGES) & 1;
                 const int lp = (t0 + j) / a.tiles_per_page;
                 int pid = table[lp];
                 if (pid < 0 || pid >= a.num_pages) pid = a.num_pages;  // outside the tensor: the TMA unit writes zeros
                 const int slot0 = (t0 + j - lp * a.tiles_per_page) * TC_BN;
-                g_mbar_wait(k_empty + 8 * s, ph ^ 1);
-                g_mbar_expect_tx(k_full + 8 * s, TC_KV_TILE);
-                g_tma_load_4d(k_base + s * TC_KV_TILE, &tmap_k, 0, slot0, kvh, pid, k_full + 8 * s);
-                g_tma_load_4d(k_base + s * TC_KV_TILE + TC_KV_TILE / 2, &tmap_k, 64, slot0, kvh, pid, k_full + 8 * s);
-                g_mbar_wait(v_empty + 8 * s, ph ^ 1);
-                g_mbar_expect_tx(v_full + 8 * s, TC_KV_TILE);
-                g_tma_load_4d(v_base + s * TC_KV_TILE, &tmap_v, 0, slot0, kvh, pid, v_full + 8 * s);
-                g_tma_load_4d(v_base + s * TC_KV_TILE + TC_KV_TILE / 2, &tmap_v, 64, slot0, kvh, pid, v_full + 8 * s);
+                g_mbar_wait(k_empty + 8 * s, ph);
+                if (g_elect_one()) {
+                    g_mbar_expect_tx(k_full + 8 * s, TC_KV_TILE);
+                    g_tma_load_4d(k_base + s * TC_KV_TILE, &tmap_k, 0, slot0, kvh, pid, k_full + 8 * s);
+                    g_tma_load_4d(k_base + s * TC_KV_TILE + TC_KV_TILE / 2, &tmap_k, 64, slot0, kvh, pid, k_full + 8 * s);
+                }
+                __syncwarp();
+                g_mbar_wait(v_empty + 8 * s, ph);
+                if (g_elect_one()) {
+                    g_mbar_expect_tx(v_full + 8 * s, TC_KV_TILE);
+                    g_tma_load_4d(v_base + s * TC_KV_TILE, &tmap_v, 0, slot0, kvh, pid, v_full + 8 * s);
+                    g_tma_load_4d(v_base + s * TC_KV_TILE + TC_KV_TILE / 2, &tmap_v, 64, slot0, kvh, pid, v_full + 8 * s);
+                }
+                __syncwarp();
+                if (++s == TC_STAGES) s = 0, ph ^= 1u;
             }
         }
     } else if (warp == 5) {
         // ------------------------------------------------------------ MMA issuer
         // Order: S_0, then per tile j: S_{j+1} (second score buffer) | wait P_j | O += P_j V_j.  The tensor core works
         // on the next tile's scores while the softmax warps are busy with this tile's.
-        if (lane == 0 && n_tiles > 0) {
+        // The whole warp walks the loop (uniform control flow, running stage / phase counters, descriptors derived by
+        // adding to three base descriptors), one elected lane issues (tc05.cuh: g_elect_one - behind `if (lane == 0)`
+        // every tcgen05 instruction sat in an ELECT loop with its operands moved through R2UR, and the issue latency
+        // of a tile was of the order of its 512 cycles of tensor work).
+        if (n_tiles > 0) {
             constexpr uint32_t idesc_s = tc_instr_desc(TC_BN, false);
             constexpr uint32_t idesc_o = tc_instr_desc(TC_D, true);
+            const uint64_t qdesc0 = g_smem_desc_sw128(q_base, 0, 1024), pdesc0 = g_smem_desc_sw128(p_base, 0, 1024);
+            const uint64_t kdesc0 = g_smem_desc_sw128(k_base, 0, 1024);
+            // V: 16 keys = 2 groups of 8 rows (SBO 1024 B); the two 64-wide d blocks are TC_KV_TILE/2 apart (LBO)
+            const uint64_t vdesc0 = g_smem_desc_sw128(v_base, TC_KV_TILE / 2, 1024);
             g_mbar_wait(q_full, 0);
+            int ks = 0, vs = 0;
+            uint32_t kph = 0, vph = 0;
             auto issue_scores = [&](int j) {  // S_j = Q K_j^T: both operands K-major, two 64-wide halves of the head dimension
-                const int s = j % TC_STAGES;
-                g_mbar_wait(k_full + 8 * s, (j / TC_STAGES) & 1);
+                g_mbar_wait(k_full + 8 * ks, kph);
                 g_tc_fence_after();
+                if (g_elect_one()) {
+                    const uint64_t kd = kdesc0 + static_cast<uint64_t>(ks * (TC_KV_TILE >> 4));
 #pragma unroll
-                for (int k = 0; k < TC_D / 16; ++k) {
-                    const uint32_t half = (k >> 2), kk = (k & 3);
-                    const uint64_t adesc = g_smem_desc_sw128(q_base + half * (TC_Q_BYTES / 2), 0, 1024) + 2 * kk;
-                    const uint64_t bdesc = g_smem_desc_sw128(k_base + s * TC_KV_TILE + half * (TC_KV_TILE / 2), 0, 1024) + 2 * kk;
-                    g_tc_mma(tmem + (j & 1) * TC_BN, adesc, bdesc, idesc_s, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < TC_D / 16; ++k) {
+                        const uint32_t half = (k >> 2), kk = (k & 3);
+                        g_tc_mma(tmem + (j & 1) * TC_BN, qdesc0 + half * (TC_Q_BYTES / 2 >> 4) + 2 * kk, kd + half * (TC_KV_TILE / 2 >> 4) + 2 * kk,
+                                 idesc_s, k > 0 ? 1u : 0u);
+                    }
+                    g_tc_commit(k_empty + 8 * ks);       // K stage reusable once these MMAs have read it
+                    g_tc_commit(s_full + 8 * (j & 1));   // ... and the scores of tile j are complete
                 }
-                g_tc_commit(k_empty + 8 * s);        // K stage reusable once these MMAs have read it
-                g_tc_commit(s_full + 8 * (j & 1));   // ... and the scores of tile j are complete
+                __syncwarp();
+                if (++ks == TC_STAGES) ks = 0, kph ^= 1u;
             };
             issue_scores(0);
             for (int j = 0; j < n_tiles; ++j) {
-                const int s = j % TC_STAGES;
                 // score buffer (j+1)&1 was last read for tile j-1, whose P has been waited for below
                 if (j + 1 < n_tiles) issue_scores(j + 1);
                 // ---- O += P V: P K-major [128 x 64 keys], V MN-major [64 keys x 128 d] as loaded from the page
                 g_mbar_wait(p_full, j & 1);
-                g_mbar_wait(v_full + 8 * s, (j / TC_STAGES) & 1);
+                g_mbar_wait(v_full + 8 * vs, vph);
                 g_tc_fence_after();
+                if (g_elect_one()) {
+                    const uint64_t vd = vdesc0 + static_cast<uint64_t>(vs * (TC_KV_TILE >> 4));
 #pragma unroll
-                for (int k = 0; k < TC_BN / 16; ++k) {
-                    const uint64_t adesc = g_smem_desc_sw128(p_base, 0, 1024) + 2 * k;
-                    // 16 keys = 2 groups of 8 rows (SBO 1024 B); the two 64-wide d blocks are TC_KV_TILE/2 apart (LBO)
-                    const uint64_t bdesc = g_smem_desc_sw128(v_base + s * TC_KV_TILE + k * 2048, TC_KV_TILE / 2, 1024);
-                    g_tc_mma(tmem + TC_TMEM_O, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TC_BN / 16; ++k)
+                        g_tc_mma(tmem + TC_TMEM_O, pdesc0 + 2 * k, vd + k * (2048 >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    g_tc_commit(v_empty + 8 * vs);
+                    g_tc_commit(pv_done);  // O holds tiles 0..j and the P buffer is free again
                 }
-                g_tc_commit(v_empty + 8 * s);
-                g_tc_commit(pv_done);  // O holds tiles 0..j and the P buffer is free again
+                __syncwarp();
+                if (++vs == TC_STAGES) vs = 0, vph ^= 1u;
             }
         }
     } else {

@@ -35,6 +35,15 @@ __device__ __forceinline__ void g_tma_load_2d(uint32_t dst, const CUtensorMap *m
         "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// One lane of a converged warp.  The compiler recognises the elect.sync pattern as "exactly one thread" and emits the
+// warp-level tcgen05 / TMA instruction once; behind `if (lane == 0)` it wraps every such instruction in an
+// ELECT ... BRA.U.ANY loop and moves each operand through R2UR (measured: ~1000 cycles of issue latency per reduction
+// block in the MMA thread of the skinny GEMM, for 128 cycles of tensor work).
+__device__ __forceinline__ bool g_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void g_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void g_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void g_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -136,40 +136,50 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------ TMA producer (activations)
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % GSTAGES;
-                const uint32_t ph = (kb / GSTAGES) & 1;
-                g_mbar_wait(empty + 8 * s, ph ^ 1);
+        // ------------------------------------------------ TMA producer (activations): whole warp, one elected lane issues
+        int s = 0;
+        uint32_t ph = 1;  // producer side: the first pass through the ring does not wait
+        for (int kb = 0; kb < num_kb; ++kb) {
+            g_mbar_wait(empty + 8 * s, ph);
+            if (g_elect_one()) {
                 g_mbar_expect_tx(full_a + 8 * s, Smem::A_STAGE);
 #pragma unroll
                 for (int i = 0; i < MT; ++i)  // token rows beyond M are zero-filled by the TMA unit
                     g_tma_load_2d(a_base + s * Smem::A_STAGE + i * G_TILE_BYTES, &tmap_a, kb * GK, (m_tile * MT + i) * GM, full_a + 8 * s);
             }
+            __syncwarp();
+            if (++s == GSTAGES) s = 0, ph ^= 1u;
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = g_instr_desc<T>();
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % GSTAGES;
-                const uint32_t ph = (kb / GSTAGES) & 1;
-                g_mbar_wait(full_a + 8 * s, ph);
-                g_mbar_wait(full_b + 8 * s, ph);
-                g_tc_fence_after();
-                const uint64_t bdesc = g_smem_desc(b_base + s * G_TILE_BYTES);
+        // The whole warp walks the loop (uniform control flow, running stage / phase counters instead of a division per
+        // block), one elected lane issues: behind `if (lane == 0)` the compiler wrapped every tcgen05 instruction in an
+        // ELECT loop and moved its operands through R2UR - ~1000 cycles of issue latency per reduction block, more than
+        // the 512 cycles of tensor work of a two-tile stage (tc05.cuh: g_elect_one).
+        constexpr uint32_t idesc = g_instr_desc<T>();
+        const uint64_t adesc0 = g_smem_desc(a_base), bdesc0 = g_smem_desc(b_base);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            g_mbar_wait(full_a + 8 * s, ph);
+            g_mbar_wait(full_b + 8 * s, ph);
+            g_tc_fence_after();
+            if (g_elect_one()) {
+                const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(s * (G_TILE_BYTES >> 4));
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
-                    const uint64_t adesc = g_smem_desc(a_base + s * Smem::A_STAGE + i * G_TILE_BYTES);
+                    const uint64_t adesc = adesc0 + static_cast<uint64_t>((s * Smem::A_STAGE + i * G_TILE_BYTES) >> 4);
 #pragma unroll
                     for (int k = 0; k < GK / 16; ++k)  // +32 bytes along K per step: +2 in the (addr >> 4) field
                         g_tc_mma(tmem_d + i * G_TMEM_COLS, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 }
                 g_tc_commit(empty + 8 * s);  // stage reusable once these MMAs have read it
             }
-            g_tc_commit(tmem_full);
+            __syncwarp();
+            if (++s == GSTAGES) s = 0, ph ^= 1u;
         }
+        if (g_elect_one()) g_tc_commit(tmem_full);
+        __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------ dequantisers, then epilogue
         const int dt = threadIdx.x - 128;      // 0 .. 255

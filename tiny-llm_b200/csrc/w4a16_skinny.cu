@@ -109,7 +109,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __shared__ unsigned long long trc[3][SK_TRC_BLOCKS][4];
 #define SK_TRC(role, i, k)                                                          \
     do {                                                                            \
-        if (blockIdx.x == 0 && (i) < SK_TRC_BLOCKS) trc[role][i][k] = clock64();    \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (i) < SK_TRC_BLOCKS) trc[role][i][k] = clock64(); \
     } while (0)
 #else
 #define SK_TRC(role, i, k) do { } while (0)
@@ -187,31 +187,40 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer: D[feature, token] += W_tile . A_tile^T
-        if (lane == 0) {
-            constexpr uint32_t idesc = sk_instr_desc<T, NT>();
-            for (int i = 0; i < n_kb; ++i) {
-                const int s = i % STAGES, bs = i % BSTAGES;
-                g_mbar_wait(full_a + 8 * s, (i / STAGES) & 1);
-                SK_TRC(0, i, 0);
-                g_mbar_wait(full_b + 8 * bs, (i / BSTAGES) & 1);
-                SK_TRC(0, i, 1);
-                g_tc_fence_after();
-                const uint64_t bdesc = g_smem_desc_sw128(b_base + bs * Smem::B_BYTES, 0, 1024);
+        // The whole warp walks the loop (uniform control flow: barrier addresses, descriptors and phases stay in
+        // uniform registers, no division per block), one elected lane issues.
+        constexpr uint32_t idesc = sk_instr_desc<T, NT>();
+        const uint64_t bdesc0 = g_smem_desc_sw128(b_base, 0, 1024);
+        const uint64_t adesc0 = g_smem_desc_sw128(a_base, 0, 1024);
+        int s = 0, bs = 0;
+        uint32_t pha = 0, phb = 0;
+        for (int i = 0; i < n_kb; ++i) {
+            g_mbar_wait(full_a + 8 * s, pha);
+            SK_TRC(0, i, 0);
+            g_mbar_wait(full_b + 8 * bs, phb);
+            SK_TRC(0, i, 1);
+            g_tc_fence_after();
+            if (g_elect_one()) {
+                const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(bs * (Smem::B_BYTES >> 4));
                 if constexpr (TA) {
                     const uint32_t a_tmem = tmem_d + Smem::D_COLS + s * 32;  // 16 reduction elements = 8 columns per K step
 #pragma unroll
                     for (int k = 0; k < SK_KB / 16; ++k) g_tc_mma_ts(tmem_d, a_tmem + 8 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 } else {
-                    const uint64_t adesc = g_smem_desc_sw128(a_base + s * SK_A_BYTES, 0, 1024);
+                    const uint64_t adesc = adesc0 + static_cast<uint64_t>(s * (SK_A_BYTES >> 4));
 #pragma unroll
                     for (int k = 0; k < SK_KB / 16; ++k) g_tc_mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 g_tc_commit(empty + 8 * s);
                 g_tc_commit(b_empty + 8 * bs);
-                SK_TRC(0, i, 2);
             }
-            g_tc_commit(tmem_full);
+            __syncwarp();
+            SK_TRC(0, i, 2);
+            if (++s == STAGES) s = 0, pha ^= 1u;
+            if (++bs == BSTAGES) bs = 0, phb ^= 1u;
         }
+        if (g_elect_one()) g_tc_commit(tmem_full);
+        __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------ dequantisers
         // Two groups of four warps; group g owns the reduction blocks i = g, g + 2, ... (so the two groups work on

@@ -36,7 +36,8 @@ tab = {}
 for tag, t in ev:
     if tag >= 10000:
         role, rest = divmod(tag - 10000, 1000)
-        tab[(role, rest // 4, rest % 4)] = t
+        if not (role == 0 and rest % 4 == 3):
+            tab[(role, rest // 4, rest % 4)] = t
 if not tab:
     sys.exit("no per-block stamps (not the trace build?)")
 t0 = min(tab.values())
