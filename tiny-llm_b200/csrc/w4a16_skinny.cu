@@ -14,12 +14,19 @@
 //   * the reduction is split over `splits` CTAs per feature tile so that tiles x splits ~ #SMs; partial
 //     sums go to a workspace in fp32 and a small second launch adds the planes in split order (deterministic)
 //     and runs the epilogue (plain / + residual / SwiGLU of interleaved gate|up rows);
-//   * packed weights arrive by TMA (one 128-row x 128-byte box = four 64-wide reduction blocks per copy, two boxes
-//     in flight: 32 KiB per CTA without a register), 256 dequantiser threads turn them into the K-major
-//     128B-swizzled bf16 tile (LOP3 magic -> exact code -> one HFMA2, the rounding point of the
-//     reference's tiled kernel, quantized_matmul.metal:183-194), activations arrive by TMA (tokens beyond M
-//     zero-filled), one thread issues tcgen05.mma M128 N{16..128} K16.
-// Two CTAs fit per SM (<= 112 KB of shared memory, <= 128 TMEM columns each).
+//   * packed weights arrive by TMA (one 128-row x 128-byte box = two quantisation groups of 128 reduction elements per
+//     copy, three or four boxes in flight); 256 dequantiser threads in two groups of four warps - group g owns the
+//     128-wide reduction blocks g, g + 2, ... - turn them into bf16 (LOP3 magic -> exact code -> one HFMA2, the rounding
+//     point of the reference's tiled kernel, quantized_matmul.metal:183-194) and write them to TENSOR memory
+//     (tcgen05.st, lane = feature row): the MMA reads its A operand from there; activations arrive by TMA (tokens
+//     beyond M zero-filled); the MMA warp issues tcgen05.mma M128 N{16..128} K16 from an elected lane.
+// Two CTAs fit per SM (96 KB of shared memory, 256 TMEM columns each) up to 64 token columns.
+//
+// How it got here (lm_head at 64 rows, 2560 -> 151936, 218 MB: profiles/r02_skinny_history.md): 256 threads on the SAME
+// 64-wide block with the tile in shared memory 156 us -> two alternating groups, thread = row 143 us -> tile in tensor
+// memory (6 stages instead of 2) 136 us -> MMA warp on elect.sync 112 us -> 128-wide blocks (one barrier round trip per
+// quantisation group) RESULT_V3.  The per-block cycle trace (tools/skinny_blocks.py) showed each time which actor the
+// others were waiting for; the arithmetic of the dequantisers (~2.9 instructions per weight) is the floor.
 #include <stdlib.h>
 
 #include <mutex>
@@ -33,36 +40,32 @@
 namespace tl {
 
 constexpr int SK_FEAT = 128;      // features per CTA tile (UMMA M)
-constexpr int SK_KB = 64;         // reduction elements per stage (one 128-byte swizzle atom)
-constexpr int SK_PK = 4;          // reduction blocks per packed-weight TMA box: 128 rows x 128 B (a 32-byte-wide box cost ~3 us per block)
-constexpr int SK_PACKED_BYTES = SK_PK * SK_FEAT * SK_KB / 2;  // 16 KiB per box, 128-byte swizzle
-constexpr int SK_A_BYTES = SK_FEAT * SK_KB * 2;       // 16 KiB dequantised tile
+constexpr int SK_KB = 64;         // reduction elements per activation tile / MMA descriptor (one 128-byte swizzle atom)
+constexpr int SK_GB = 128;        // reduction elements per pipeline step: one quantisation group, two activation tiles, 8 MMAs
+constexpr int SK_PG = 2;          // group blocks per packed-weight TMA box: 128 rows x 128 B (a 32-byte-wide box cost ~3 us per block)
+constexpr int SK_PACKED_BYTES = SK_PG * SK_FEAT * SK_GB / 2;  // 16 KiB per box, 128-byte swizzle
 constexpr int SK_DEQ_THREADS = 256;
 constexpr int SK_TRC_BLOCKS = 40;
-constexpr int SK_GROUP_WARPS = 4;   // dequantiser warps per reduction block (two groups alternate blocks)
+constexpr int SK_GROUP_WARPS = 4;   // dequantiser warps per group block (two groups alternate blocks)
 constexpr int SK_THREADS = 128 + SK_DEQ_THREADS;
 enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
 
-// TA: the dequantised weight tile goes to TENSOR memory (tcgen05.st, lane = feature row, 32 columns per 64-wide block)
-// and is the MMA's A operand from there: no shared-memory tile, no generic->async proxy fence, and 4-6 stages (192 of
-// the 256 allocated columns) instead of the two 16 KiB tiles that fit in shared memory beside the rings - with two
-// stages each dequantiser group waited ~45 % of its time for the tensor core to hand its only stage back.
-template <int NT, bool TA>
+// Shared memory: activation ring (BSTAGES group blocks of two [NT x 64] tiles) + packed-weight ring (PSTAGES boxes) +
+// barriers.  Tensor memory: D[feature, token] in the first D_COLS columns, then ASTAGES dequantised tiles of 64
+// columns (128 reduction elements as bf16 pairs, lane = feature row).
+template <int NT>
 struct SkSmem {
-    static constexpr int STAGES = TA ? (NT >= 128 ? 4 : 6) : 2;  // dequantised weight tiles: TMEM columns, or 16 KiB of shared memory each
-    static constexpr int PSTAGES = TA ? 4 : 2;                     // packed boxes, four reduction blocks each
-    static constexpr int B_BYTES = NT * SK_KB * 2;
-    // activation tiles: their own ring, deep enough to cover an L2 round trip (~1 us) at ~0.15 us per block; the first
-    // version shared the 2-3 weight-tile slots and paid that latency every other block (0.9 us per block measured)
-    static constexpr int BSTAGES = NT >= 64 ? 4 : 8;  // NT <= 64: 96 KB -> two CTAs per SM; NT = 128: 128 KB, one
-    static constexpr int A_OFF = 0;
-    static constexpr int B_OFF = A_OFF + (TA ? 0 : STAGES * SK_A_BYTES);
-    static constexpr int P_OFF = B_OFF + BSTAGES * B_BYTES;
+    static constexpr int B_BYTES = NT * SK_KB * 2;                 // one [NT x 64] activation tile
+    static constexpr int BSTAGES = NT >= 64 ? 3 : 4;               // group blocks in flight: an L2 round trip (~1 us) at ~0.3 us per block
+    static constexpr int PSTAGES = NT >= 128 ? 4 : 3;              // packed boxes in flight (two group blocks each)
+    static constexpr int B_OFF = 0;
+    static constexpr int P_OFF = B_OFF + BSTAGES * 2 * B_BYTES;
     static constexpr int BAR_OFF = P_OFF + PSTAGES * SK_PACKED_BYTES;
     static constexpr int BYTES = BAR_OFF + 512;
-    static constexpr int D_COLS = NT < 32 ? 32 : NT;               // accumulator columns (fp32, lane = feature)
-    static constexpr int TMEM_COLS = TA ? 256 : D_COLS;            // TA: + STAGES x 32 columns of bf16 pairs
-    static_assert(!TA || D_COLS + STAGES * 32 <= 256, "tensor-memory budget");
+    static constexpr int D_COLS = NT < 32 ? 32 : NT;               // accumulator columns (fp32)
+    static constexpr int TMEM_COLS = NT >= 128 ? 512 : 256;        // NT <= 64: two CTAs per SM share the 512 columns
+    static constexpr int ASTAGES = (TMEM_COLS - D_COLS) / 64;      // 3 (NT <= 64) or 6 (NT = 128)
+    static_assert(BYTES <= 227 * 1024 && ASTAGES >= 2, "budget");
 };
 
 struct SkArgs {
@@ -70,7 +73,7 @@ struct SkArgs {
     void *out;
     float *partials;   // [splits][M][K] fp32 (splits > 1)
     int M, N, K;       // tokens, reduction, features
-    int splits, kb_per_split;
+    int splits, gb_per_split;  // reduction split in units of 128-wide group blocks
     int epilogue;
 };
 
@@ -95,31 +98,30 @@ __host__ __device__ constexpr uint32_t sk_instr_desc() {
            (static_cast<uint32_t>(SK_FEAT >> 4) << 24);
 }
 
-template <typename T, int NT, bool TA>
-__global__ void __launch_bounds__(SK_THREADS, 2)
+template <typename T, int NT>
+__global__ void __launch_bounds__(SK_THREADS, NT >= 128 ? 1 : 2)
 w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const SkArgs args) {
-    using Smem = SkSmem<NT, TA>;
-    constexpr int STAGES = Smem::STAGES;
+    using Smem = SkSmem<NT>;
+    constexpr int ASTAGES = Smem::ASTAGES;
     constexpr int PSTAGES = Smem::PSTAGES;
     constexpr int BSTAGES = Smem::BSTAGES;
     extern __shared__ __align__(1024) unsigned char ssm[];
 #if TL_TRACE
-    // per-block cycle stamps of CTA 0 (tools/skinny_timeline.py --blocks): role 0 = MMA thread (k: A tile ready, B tile
-    // ready, MMAs issued), roles 1 / 2 = first thread of dequantiser group 0 / 1 (k: box ready, math done, stage free, handed over)
+    // per-block cycle stamps of CTA 0 (tools/skinny_blocks.py): role 0 = MMA warp (k: A tile ready, B tiles ready, MMAs
+    // issued), roles 1 / 2 = first thread of dequantiser group 0 / 1 (k: box ready, math done, stage free, handed over)
     __shared__ unsigned long long trc[3][SK_TRC_BLOCKS][4];
-#define SK_TRC(role, i, k)                                                          \
-    do {                                                                            \
-        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (i) < SK_TRC_BLOCKS) trc[role][i][k] = clock64(); \
+#define SK_TRC(role, i, k)                                                                                      \
+    do {                                                                                                        \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (i) < SK_TRC_BLOCKS) trc[role][i][k] = clock64();     \
     } while (0)
 #else
 #define SK_TRC(role, i, k) do { } while (0)
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x / args.splits, split = blockIdx.x - tile * args.splits;
-    const int num_kb = args.N / SK_KB;
-    const int kb0 = min(split * args.kb_per_split, num_kb), kb1 = min(kb0 + args.kb_per_split, num_kb);
-    const int n_kb = kb1 - kb0;
-    const int G = args.N / 128;
+    const int G = args.N / SK_GB;  // group blocks of the whole reduction = quantisation groups per row
+    const int gb0 = min(split * args.gb_per_split, G), gb1 = min(gb0 + args.gb_per_split, G);
+    const int n_gb = gb1 - gb0;
     TL_TRACE_STAMP(30);
     // Programmatic dependent launch: the next kernel of the stream may become resident now (its own prologue and weight
     // pipeline do not depend on this grid).  Of THIS kernel only the activation loads and the epilogue depend on the
@@ -127,18 +129,18 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // griddep_wait(), i.e. under the predecessor's tail.
     griddep_launch();
 
-    const uint32_t a_base = g_smem_u32(ssm + Smem::A_OFF), b_base = g_smem_u32(ssm + Smem::B_OFF), p_base = g_smem_u32(ssm + Smem::P_OFF);
+    const uint32_t b_base = g_smem_u32(ssm + Smem::B_OFF), p_base = g_smem_u32(ssm + Smem::P_OFF);
     const uint32_t bar = g_smem_u32(ssm + Smem::BAR_OFF);
-    const uint32_t full_a = bar, empty = bar + 8 * STAGES, p_full = bar + 16 * STAGES, p_empty = p_full + 8 * PSTAGES;
+    const uint32_t full_a = bar, empty = bar + 8 * ASTAGES, p_full = bar + 16 * ASTAGES, p_empty = p_full + 8 * PSTAGES;
     const uint32_t full_b = p_empty + 8 * PSTAGES, b_empty = full_b + 8 * BSTAGES, tmem_full = b_empty + 8 * BSTAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ssm + Smem::BAR_OFF + 16 * STAGES + 16 * PSTAGES + 16 * BSTAGES + 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ssm + Smem::BAR_OFF + 16 * ASTAGES + 16 * PSTAGES + 16 * BSTAGES + 8);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < ASTAGES; ++i) {
             g_mbar_init(full_a + 8 * i, SK_GROUP_WARPS);  // one arrival per warp of the dequantiser group that owns the block
             g_mbar_init(empty + 8 * i, 1);
         }
@@ -164,151 +166,154 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     TL_TRACE_STAMP(31);
 
     if (warp == 0) {
-        // ------------------------------------------------ TMA producer: packed weights, one 128-row x 128-byte box per 4 blocks
-        if (lane == 0) {
-            const int n_box = (n_kb + SK_PK - 1) / SK_PK;
-            for (int i = 0; i < n_box; ++i) {
-                const int ps = i % PSTAGES;
-                g_mbar_wait(p_empty + 8 * ps, ((i / PSTAGES) & 1) ^ 1);
+        // ------------------------------------------------ TMA producer: packed weights, one 128-row x 128-byte box per two group blocks
+        const int n_box = (n_gb + SK_PG - 1) / SK_PG;
+        int ps = 0;
+        uint32_t ph = 1;  // producer side: the first pass through the ring does not wait
+        for (int i = 0; i < n_box; ++i) {
+            g_mbar_wait(p_empty + 8 * ps, ph);
+            if (g_elect_one()) {
                 g_mbar_expect_tx(p_full + 8 * ps, SK_PACKED_BYTES);  // columns past the row end are zero-filled and still counted
-                g_tma_load_2d(p_base + ps * SK_PACKED_BYTES, &tmap_w, (kb0 + i * SK_PK) * (SK_KB / 2), tile * SK_FEAT, p_full + 8 * ps);
+                g_tma_load_2d(p_base + ps * SK_PACKED_BYTES, &tmap_w, (gb0 + i * SK_PG) * (SK_GB / 2), tile * SK_FEAT, p_full + 8 * ps);
             }
+            __syncwarp();
+            if (++ps == PSTAGES) ps = 0, ph ^= 1u;
         }
     } else if (warp == 3) {
-        // ------------------------------------------------ TMA producer: activations
-        if (lane == 0) {
-            griddep_wait();  // the activations are the predecessor's output
-            for (int i = 0; i < n_kb; ++i) {
-                const int s = i % BSTAGES;
-                g_mbar_wait(b_empty + 8 * s, ((i / BSTAGES) & 1) ^ 1);
-                g_mbar_expect_tx(full_b + 8 * s, Smem::B_BYTES);
-                g_tma_load_2d(b_base + s * Smem::B_BYTES, &tmap_a, (kb0 + i) * SK_KB, 0, full_b + 8 * s);
+        // ------------------------------------------------ TMA producer: activations, two [NT x 64] tiles per group block
+        if (lane == 0) griddep_wait();  // the activations are the predecessor's output
+        __syncwarp();
+        int bs = 0;
+        uint32_t ph = 1;
+        for (int i = 0; i < n_gb; ++i) {
+            g_mbar_wait(b_empty + 8 * bs, ph);
+            if (g_elect_one()) {
+                g_mbar_expect_tx(full_b + 8 * bs, 2 * Smem::B_BYTES);
+                g_tma_load_2d(b_base + (2 * bs) * Smem::B_BYTES, &tmap_a, (gb0 + i) * SK_GB, 0, full_b + 8 * bs);
+                g_tma_load_2d(b_base + (2 * bs + 1) * Smem::B_BYTES, &tmap_a, (gb0 + i) * SK_GB + SK_KB, 0, full_b + 8 * bs);
             }
+            __syncwarp();
+            if (++bs == BSTAGES) bs = 0, ph ^= 1u;
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer: D[feature, token] += W_tile . A_tile^T
+        // ------------------------------------------------ MMA issuer: D[feature, token] += W_block . A_block^T, 8 K-steps per group block
         // The whole warp walks the loop (uniform control flow: barrier addresses, descriptors and phases stay in
         // uniform registers, no division per block), one elected lane issues.
         constexpr uint32_t idesc = sk_instr_desc<T, NT>();
         const uint64_t bdesc0 = g_smem_desc_sw128(b_base, 0, 1024);
-        const uint64_t adesc0 = g_smem_desc_sw128(a_base, 0, 1024);
         int s = 0, bs = 0;
         uint32_t pha = 0, phb = 0;
-        for (int i = 0; i < n_kb; ++i) {
+        for (int i = 0; i < n_gb; ++i) {
             g_mbar_wait(full_a + 8 * s, pha);
             SK_TRC(0, i, 0);
             g_mbar_wait(full_b + 8 * bs, phb);
             SK_TRC(0, i, 1);
             g_tc_fence_after();
             if (g_elect_one()) {
-                const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(bs * (Smem::B_BYTES >> 4));
-                if constexpr (TA) {
-                    const uint32_t a_tmem = tmem_d + Smem::D_COLS + s * 32;  // 16 reduction elements = 8 columns per K step
+                const uint32_t a_tmem = tmem_d + Smem::D_COLS + s * 64;  // 16 reduction elements = 8 columns per K step
+                const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(bs * (2 * Smem::B_BYTES >> 4));
 #pragma unroll
-                    for (int k = 0; k < SK_KB / 16; ++k) g_tc_mma_ts(tmem_d, a_tmem + 8 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                } else {
-                    const uint64_t adesc = adesc0 + static_cast<uint64_t>(s * (SK_A_BYTES >> 4));
-#pragma unroll
-                    for (int k = 0; k < SK_KB / 16; ++k) g_tc_mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < SK_GB / 16; ++k)
+                    g_tc_mma_ts(tmem_d, a_tmem + 8 * k, bdesc + (k >> 2) * (Smem::B_BYTES >> 4) + 2 * (k & 3), idesc, (i > 0 || k > 0) ? 1u : 0u);
                 g_tc_commit(empty + 8 * s);
                 g_tc_commit(b_empty + 8 * bs);
             }
             __syncwarp();
             SK_TRC(0, i, 2);
-            if (++s == STAGES) s = 0, pha ^= 1u;
+            if (++s == ASTAGES) s = 0, pha ^= 1u;
             if (++bs == BSTAGES) bs = 0, phb ^= 1u;
         }
         if (g_elect_one()) g_tc_commit(tmem_full);
         __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------ dequantisers
-        // Two groups of four warps; group g owns the reduction blocks i = g, g + 2, ... (so the two groups work on
-        // different blocks and meet only in the MMA queue); thread = one feature row of the tile = the TMEM lane it
-        // reads in the epilogue.  Per block a thread turns 32 packed bytes (two 16-byte chunks of its box row) into the
-        // 64 bf16 of its K-major row (8 swizzled 16-byte stores).  One barrier round per 64 weights and thread: the
-        // first version (thread = half a row of EVERY block, 149 instructions per 32 weights, all eight warps in
-        // lockstep on one block) spent 37 % of its time waiting for the stage to come back and 15 % in the store fence.
-        // Scale and bias of the row come straight from global memory (L2), prefetched one own block ahead.
+        // Two groups of four warps; group g owns the group blocks i = g, g + 2, ... = bytes [64 g, 64 g + 64) of its row
+        // in every packed box, so the two groups work on different blocks and meet only in the MMA queue.  Thread = one
+        // feature row of the tile = the TMEM lane it reads in the epilogue.  Per block: four 16-byte chunks of the box
+        // row -> 128 bf16 (scale and bias of the row's quantisation group: one pair per block, read from global memory
+        // one own block ahead) -> two tcgen05.st of 32 columns -> ONE wait / fence / barrier arrival.
         const int grp = (warp - 4) >> 2;
-        const int row = ((warp - 4) & 3) * 32 + lane;
+        const int row = (warp & 3) * 32 + lane;
         using V2 = typename SkNum<T>::V2;
         const uint32_t magic = SkNum<T>::MAGIC;
         const V2 offset2 = *reinterpret_cast<const V2 *>(&magic);
         const size_t srow = static_cast<size_t>(min(tile * SK_FEAT + row, args.K - 1)) * G;
-        const unsigned short *sc = reinterpret_cast<const unsigned short *>(args.scales) + srow;
-        const unsigned short *bi = reinterpret_cast<const unsigned short *>(args.biases) + srow;
+        const unsigned short *sc = reinterpret_cast<const unsigned short *>(args.scales) + srow + gb0;
+        const unsigned short *bi = reinterpret_cast<const unsigned short *>(args.biases) + srow + gb0;
         const uint32_t swz = static_cast<uint32_t>(row & 7);
         const unsigned char *p_row = ssm + Smem::P_OFF + row * 128;
-        unsigned char *a_row = ssm + Smem::A_OFF + row * 128;
+        const uint32_t lane_base = tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + Smem::D_COLS;
         unsigned short s_next = 0, b_next = 0;
-        if (grp < n_kb) s_next = __ldg(sc + ((kb0 + grp) >> 1)), b_next = __ldg(bi + ((kb0 + grp) >> 1));
-        for (int i = grp; i < n_kb; i += 2) {
-            const int box = i / SK_PK, sub = i - box * SK_PK;
-            const int ps = box % PSTAGES, s = i % STAGES;
+        if (grp < n_gb) s_next = __ldg(sc + grp), b_next = __ldg(bi + grp);
+        int ps = 0, s = grp % ASTAGES;
+        uint32_t php = 0, phe = 1;  // consumer of the packed ring; producer side of the tile ring (first pass does not wait)
+        if (grp >= ASTAGES) phe ^= 1u;
+        for (int i = grp; i < n_gb; i += 2) {
             const unsigned short s16 = s_next, b16 = b_next;
-            if (i + 2 < n_kb) s_next = __ldg(sc + ((kb0 + i + 2) >> 1)), b_next = __ldg(bi + ((kb0 + i + 2) >> 1));
-            if (sub < 2) g_mbar_wait(p_full + 8 * ps, (box / PSTAGES) & 1);  // this group's first block of the box
+            if (i + 2 < n_gb) s_next = __ldg(sc + i + 2), b_next = __ldg(bi + i + 2);
+            g_mbar_wait(p_full + 8 * ps, php);
             if (i == grp) TL_TRACE_STAMP_T(32, 128);  // first packed box has landed
-            if (lane == 0 && (warp & 3) == 0) SK_TRC(1 + grp, i, 0);
-            // row `row` of the box: 128 bytes = 8 chunks of 16 B, chunk c stored at (c ^ (row & 7)) by the TMA swizzle
-            const unsigned char *src = p_row + ps * SK_PACKED_BYTES;
-            const uint4 lo = *reinterpret_cast<const uint4 *>(src + (((2 * sub) ^ swz) << 4));
-            const uint4 hi = *reinterpret_cast<const uint4 *>(src + (((2 * sub + 1) ^ swz) << 4));
+            if ((warp & 3) == 0) SK_TRC(1 + grp, i, 0);
             V2 s2, b2;
             s2.x = s2.y = *reinterpret_cast<const T *>(&s16);
             b2.x = b2.y = *reinterpret_cast<const T *>(&b16);
-            uint32_t outw[32];
-            const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            // row `row` of the box: 128 bytes = 8 chunks of 16 B, chunk c stored at (c ^ (row & 7)) by the TMA swizzle
+            const unsigned char *src = p_row + ps * SK_PACKED_BYTES;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t p[4];
+            for (int h = 0; h < 2; ++h) {  // the two 64-wide halves of the block: 32 tensor-memory columns each
+                const uint4 lo = *reinterpret_cast<const uint4 *>(src + ((static_cast<uint32_t>(4 * grp + 2 * h) ^ swz) << 4));
+                const uint4 hi = *reinterpret_cast<const uint4 *>(src + ((static_cast<uint32_t>(4 * grp + 2 * h + 1) ^ swz) << 4));
+                uint32_t outw[32];
+                const uint32_t wv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t bits;  // (128 + code_q, 128 + code_{q+4}) in one LOP3: ((w >> 4q) & 0x000F000F) | magic
-                    asm("lop3.b32 %0, %1, 0x000F000F, %2, 0xEA;" : "=r"(bits) : "r"(wv[j] >> (4 * q)), "r"(magic));
-                    V2 code = __hsub2(*reinterpret_cast<V2 *>(&bits), offset2);
-                    V2 v = __hfma2(code, s2, b2);                                   // code * scale + bias, one rounding
-                    p[q] = *reinterpret_cast<uint32_t *>(&v);
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t p[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t bits;  // (128 + code_q, 128 + code_{q+4}) in one LOP3: ((w >> 4q) & 0x000F000F) | magic
+                        asm("lop3.b32 %0, %1, 0x000F000F, %2, 0xEA;" : "=r"(bits) : "r"(wv[j] >> (4 * q)), "r"(magic));
+                        V2 code = __hsub2(*reinterpret_cast<V2 *>(&bits), offset2);
+                        V2 v = __hfma2(code, s2, b2);                                   // code * scale + bias, one rounding
+                        p[q] = *reinterpret_cast<uint32_t *>(&v);
+                    }
+                    // column c of the tile = elements (2c, 2c + 1) of the block
+                    outw[4 * j + 0] = __byte_perm(p[0], p[1], 0x5410);
+                    outw[4 * j + 1] = __byte_perm(p[2], p[3], 0x5410);
+                    outw[4 * j + 2] = __byte_perm(p[0], p[1], 0x7632);
+                    outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);
                 }
-                outw[4 * j + 0] = __byte_perm(p[0], p[1], 0x5410);
-                outw[4 * j + 1] = __byte_perm(p[2], p[3], 0x5410);
-                outw[4 * j + 2] = __byte_perm(p[0], p[1], 0x7632);
-                outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);
+                if (h == 0) {
+                    if ((warp & 3) == 0) SK_TRC(1 + grp, i, 1);
+                    g_mbar_wait(empty + 8 * s, phe);
+                    if ((warp & 3) == 0) SK_TRC(1 + grp, i, 2);
+                    g_tc_fence_after();
+                }
+                g_tmem_st32(lane_base + s * 64 + h * 32, outw);
             }
-            if (lane == 0 && (warp & 3) == 0) SK_TRC(1 + grp, i, 1);
-            g_mbar_wait(empty + 8 * s, ((i / STAGES) & 1) ^ 1);
-            if (lane == 0 && (warp & 3) == 0) SK_TRC(1 + grp, i, 2);
-            if constexpr (TA) {
-                // lane = row, column c = elements (2c, 2c + 1) of the block: outw is already in that order
-                g_tc_fence_after();
-                g_tmem_st32(tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + Smem::D_COLS + s * 32, outw);
-                g_tmem_st_wait();
-                g_tc_fence_before();
-            } else {
-                unsigned char *dst = a_row + s * SK_A_BYTES;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4 *>(dst + ((static_cast<uint32_t>(j) ^ swz) << 4)) = make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
-                g_fence_proxy_async();
-            }
+            g_tmem_st_wait();
+            g_tc_fence_before();
             // one arrival per WARP (an arrival per thread is a serialised shared-memory atomic each: ~0.4 us per block in
             // the first version); __syncwarp orders the lanes' stores before it
             __syncwarp();
-            if (lane == 0) g_mbar_arrive(full_a + 8 * s);
-            if (lane == 0 && (warp & 3) == 0) SK_TRC(1 + grp, i, 3);
-            // Release the packed box only now, after this warp's last block in it: the stores above consumed `lo`/`hi`, so
-            // the shared-memory reads of the box have COMPLETED (an arrive issued right behind the load let the TMA refill
-            // the box under a load still in flight - mbarrier ops are not ordered behind the load/store unit - and single
-            // feature rows came out wrong in ~1 of 600 CTA-loops of 40 blocks).
-            if ((sub >= 2 || i + 2 >= n_kb) && lane == 0) g_mbar_arrive(p_empty + 8 * ps);
+            if (lane == 0) {
+                g_mbar_arrive(full_a + 8 * s);
+                // Release the packed box only now: the tensor-memory stores above consumed the loaded words, so this
+                // warp's shared-memory reads of the box have COMPLETED (an arrive issued right behind the load let the TMA
+                // refill the box under a load still in flight - mbarrier ops are not ordered behind the load/store
+                // unit - and single feature rows came out wrong in ~1 of 600 CTA-loops of 40 blocks).
+                g_mbar_arrive(p_empty + 8 * ps);
+            }
+            if ((warp & 3) == 0) SK_TRC(1 + grp, i, 3);
+            if (++ps == PSTAGES) ps = 0, php ^= 1u;
+            s += 2;
+            if (s >= ASTAGES) s -= ASTAGES, phe ^= 1u;
         }
         // ------------------------------------------------ epilogue: TMEM lane = feature; warps 4-7 take token columns [0, NT/2), 8-11 the rest
         TL_TRACE_STAMP_T(33, 128);  // last weight tile handed to the MMA thread
         // the epilogue reads the residual and overwrites buffers (output, partial planes) that the predecessor - the
         // reduction kernel of the previous projection - may still be reading
         griddep_wait();
-        if (n_kb > 0) {
+        if (n_gb > 0) {
             g_mbar_wait(tmem_full, 0);
             g_tc_fence_after();
         }
@@ -328,7 +333,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
                     uint32_t v[32];
-                    if (n_kb > 0) {
+                    if (n_gb > 0) {
                         g_tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + col0 + c0, v);
                     } else {
 #pragma unroll
@@ -350,7 +355,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 float acc[32];
                 {
                     uint32_t v[32];
-                    if (n_kb > 0) {
+                    if (n_gb > 0) {
                         g_tmem_ld32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + col0 + c0, v);
                     } else {
 #pragma unroll
@@ -392,7 +397,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (blockIdx.x == 0 && g_trace_buf != nullptr) {  // dump the per-block stamps: tag = 10000 + role * 1000 + block * 4 + k
         for (int e = threadIdx.x; e < 3 * SK_TRC_BLOCKS * 4; e += SK_THREADS) {
             const int role = e / (SK_TRC_BLOCKS * 4), rest = e - role * SK_TRC_BLOCKS * 4;
-            if (rest / 4 < n_kb && (role == 0 || (rest / 4) % 2 == role - 1)) {
+            if (rest / 4 < n_gb && (role == 0 || (rest / 4) % 2 == role - 1)) {
                 const unsigned at = atomicAdd(g_trace_n, 1u);
                 if (at < g_trace_cap) g_trace_buf[2 * at] = 10000 + role * 1000 + rest, g_trace_buf[2 * at + 1] = trc[role][rest / 4][rest & 3];
             }
@@ -453,21 +458,21 @@ bool w4a16_skinny_supported(int M, int N, int K, int dtype) {
 }
 
 // Split policy (ours; the reference's constants are M4-Pro tuning, quantized_matmul.cpp:138-150): the split count that
-// minimises waves x (reduction blocks per CTA + fixed cost) + reduce launch, with `slots` CTAs resident at once (two per
-// SM up to 64 token columns, one for 128), a fixed cost per CTA worth ~24 blocks (TMEM allocation, first TMA round
-// trips, epilogue: ~3.5 us measured) and ~20 blocks for the extra reduce launch.
+// minimises waves x (group blocks per CTA + fixed cost) + reduce launch, with `slots` CTAs resident at once (two per
+// SM up to 64 token columns, one for 128), a fixed cost per CTA worth ~10 group blocks (TMEM allocation, first TMA
+// round trips, epilogue: ~3 us against ~0.3 us per 128-wide block) and ~8 for the extra reduce launch.
 static int skinny_slots(int M) { return (M <= 64 ? 2 : 1) * sm_count(); }
 int w4a16_skinny_splits(int M, int N, int K) {
     const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
-    const int num_kb = N / SK_KB;
+    const int num_gb = N / SK_GB;
     const int slots = skinny_slots(M);
     int best = 1;
     long long best_cost = -1;
-    for (int s = 1; s <= 16 && s <= num_kb / 4 + (num_kb < 4); ++s) {
-        const int kbps = (num_kb + s - 1) / s;
-        const int real = (num_kb + kbps - 1) / kbps;  // splits that actually get blocks
+    for (int s = 1; s <= 16 && s <= num_gb / 2 + (num_gb < 2); ++s) {
+        const int gbps = (num_gb + s - 1) / s;
+        const int real = (num_gb + gbps - 1) / gbps;  // splits that actually get blocks
         const long long waves = (static_cast<long long>(tiles) * real + slots - 1) / slots;
-        const long long cost = waves * (kbps + 24) + (real > 1 ? 20 : 0);  // in units of one reduction block (~0.15 us)
+        const long long cost = waves * (gbps + 10) + (real > 1 ? 8 : 0);  // in units of one group block
         if (best_cost < 0 || cost < best_cost) best_cost = cost, best = real;
     }
     return best;
@@ -523,17 +528,17 @@ static int sk_cached_map(CUtensorMap *out, const void *ptr, int kind, cuuint64_t
     return TL_OK;
 }
 
-template <typename T, int NT, bool TA>
+template <typename T, int NT>
 static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkArgs &args, int grid, cudaStream_t st) {
-    constexpr size_t smem = SkSmem<NT, TA>::BYTES;
+    constexpr size_t smem = SkSmem<NT>::BYTES;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
-            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, TA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit");
         configured = true;
     }
-    cudaError_t e = launch_chained(w4a16_skinny_kernel<T, NT, TA>, dim3(grid), dim3(SK_THREADS), smem, st, ma, mw, args);
+    cudaError_t e = launch_chained(w4a16_skinny_kernel<T, NT>, dim3(grid), dim3(SK_THREADS), smem, st, ma, mw, args);
     if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_skinny: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("w4a16_skinny");
     return TL_OK;
@@ -545,30 +550,27 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
     if (!aligned16(a) || !aligned16(b)) return fail(TL_EINVAL, "quantized_matmul: a and b must be 16-byte aligned");
     const int NT = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
     const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
-    const int num_kb = N / SK_KB;
+    const int num_gb = N / SK_GB;
     SkArgs args{};
     args.scales = scales, args.biases = biases, args.residual = residual, args.out = out;
     args.M = M, args.N = N, args.K = K, args.epilogue = epilogue;
     args.splits = w4a16_skinny_splits(M, N, K);
-    args.kb_per_split = (num_kb + args.splits - 1) / args.splits;
+    args.gb_per_split = (num_gb + args.splits - 1) / args.splits;
     if (args.splits > 1 && (ws == nullptr || ws_bytes < w4a16_skinny_workspace(M, N, K)))
         return fail(TL_EWORKSPACE, "quantized_matmul: workspace too small (%zu < %zu)", ws_bytes, w4a16_skinny_workspace(M, N, K));
     args.partials = static_cast<float *>(ws);
     CUtensorMap ma, mw;
     const CUtensorMapDataType dt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (int e = sk_cached_map(&ma, a, 0, N, M, SK_KB, NT, dt, 2)) return e;
-    if (int e = sk_cached_map(&mw, b, 1, static_cast<cuuint64_t>(N) / 2, K, SK_PK * SK_KB / 2, SK_FEAT, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1)) return e;
+    if (int e = sk_cached_map(&mw, b, 1, static_cast<cuuint64_t>(N) / 2, K, SK_PG * SK_GB / 2, SK_FEAT, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1)) return e;
     const int grid = tiles * args.splits;
-    static const bool ta = [] { const char *e = getenv("TL_SKINNY_TMEM_A"); return e == nullptr || e[0] != '0'; }();
     int rc;
-#define TL_SK(NTV) (ta ? skinny_launch<T, NTV, true>(ma, mw, args, grid, st) : skinny_launch<T, NTV, false>(ma, mw, args, grid, st))
     switch (NT) {
-        case 16: rc = TL_SK(16); break;
-        case 32: rc = TL_SK(32); break;
-        case 64: rc = TL_SK(64); break;
-        default: rc = TL_SK(128); break;
+        case 16: rc = skinny_launch<T, 16>(ma, mw, args, grid, st); break;
+        case 32: rc = skinny_launch<T, 32>(ma, mw, args, grid, st); break;
+        case 64: rc = skinny_launch<T, 64>(ma, mw, args, grid, st); break;
+        default: rc = skinny_launch<T, 128>(ma, mw, args, grid, st); break;
     }
-#undef TL_SK
     if (rc != TL_OK || args.splits == 1) return rc;
     const size_t outputs = static_cast<size_t>(M) * (epilogue == SK_EPI_SWIGLU_PAIRS ? K / 2 : K);
     cudaError_t e = launch_chained(w4a16_skinny_reduce_kernel<T>, dim3(static_cast<unsigned>((outputs + 255) / 256)), dim3(256), 0, st,
