@@ -33,6 +33,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc05.cuh"
+#include "trace.cuh"
 
 namespace tl {
 
@@ -101,6 +102,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
                                                                   const T *__restrict__ biases, const uint32_t *__restrict__ b,
                                                                   T *__restrict__ out, int M, int N, int K, int vec_store) {
     extern __shared__ __align__(1024) unsigned char gsm[];
+#if TL_TRACE
+    // per-block cycle stamps of CTA (0,0) (tools/gemm_blocks.py): role 0 = MMA warp (k: activation tile ready, weight tile
+    // ready, MMAs issued), role 1 = first dequantiser thread (k: loop top, math done, stage free, handed over)
+    __shared__ unsigned long long trc[2][40][4];
+#define G_TRC(role, i, k)                                                                                                    \
+    do {                                                                                                                     \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (i) < 40) trc[role][i][k] = clock64();         \
+    } while (0)
+#else
+#define G_TRC(role, i, k) do { } while (0)
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x, m_tile = blockIdx.y;
     const int num_kb = N / GK;
@@ -162,7 +174,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
         uint32_t ph = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
             g_mbar_wait(full_a + 8 * s, ph);
+            G_TRC(0, kb, 0);
             g_mbar_wait(full_b + 8 * s, ph);
+            G_TRC(0, kb, 1);
             g_tc_fence_after();
             if (g_elect_one()) {
                 const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(s * (G_TILE_BYTES >> 4));
@@ -176,6 +190,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
                 g_tc_commit(empty + 8 * s);  // stage reusable once these MMAs have read it
             }
             __syncwarp();
+            G_TRC(0, kb, 2);
             if (++s == GSTAGES) s = 0, ph ^= 1u;
         }
         if (g_elect_one()) g_tc_commit(tmem_full);
@@ -198,6 +213,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % GSTAGES;
             const uint32_t ph = (kb / GSTAGES) & 1;
+            if (warp == 4) G_TRC(1, kb, 0);
             const uint4 cur = packed;
             if (kb + 1 < num_kb) packed = *reinterpret_cast<const uint4 *>(wrow + (kb + 1) * 8 + half * 4);
             const T sc = srow[kb >> 1], bi = crow[kb >> 1];
@@ -220,7 +236,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
                 outw[4 * j + 2] = __byte_perm(p[0], p[1], 0x7632);  // (e4, e5)
                 outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);  // (e6, e7)
             }
+            if (warp == 4) G_TRC(1, kb, 1);
             g_mbar_wait(empty + 8 * s, ph ^ 1);
+            if (warp == 4) G_TRC(1, kb, 2);
             unsigned char *tile = gsm + Smem::B_OFF + s * G_TILE_BYTES + row * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -231,6 +249,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
             g_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
             __syncwarp();           // one arrival per warp instead of 256 serialised shared-memory atomics per stage
             if (lane == 0) g_mbar_arrive(full_b + 8 * s);
+            if (warp == 4) G_TRC(1, kb, 3);
         }
         // ---- epilogue: TMEM lane = token row; warps 4-7 take columns 0..63, warps 8-11 columns 64..127
         g_mbar_wait(tmem_full, 0);
@@ -269,6 +288,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
         g_tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
     }
+#if TL_TRACE
+    if (blockIdx.x == 0 && blockIdx.y == 0 && g_trace_buf != nullptr) {  // tag = 20000 + role * 1000 + block * 4 + k
+        for (int e = threadIdx.x; e < 2 * 40 * 4; e += G_THREADS) {
+            const int role = e / 160, rest = e - role * 160;
+            if (rest / 4 < num_kb && !(role == 0 && (rest & 3) == 3)) {
+                const unsigned at = atomicAdd(g_trace_n, 1u);
+                if (at < g_trace_cap) g_trace_buf[2 * at] = 20000 + role * 1000 + rest, g_trace_buf[2 * at + 1] = trc[role][rest / 4][rest & 3];
+            }
+        }
+    }
+#endif
 }
 
 // ---------------------------------------------------------------- host side --
@@ -355,5 +385,9 @@ int launch_w4a16_gemm(const void *scales, const void *biases, const void *a, con
     if (dtype == TL_F16) return gemm_t<__half>(scales, biases, a, b, out, M, N, K, st);
     return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
 }
+
+#if TL_TRACE
+void trace_bind_gemm(unsigned long long *buf, unsigned int *n, unsigned int cap) { trace_bind(buf, n, cap); }
+#endif
 
 }  // namespace tl
