@@ -159,6 +159,14 @@ size_t tl_quantized_matmul_fused_workspace(int M, int N, int K, int lda, int pro
 int tl_quantized_matmul_fused(const void *scales, const void *biases, const void *b, void *out, const void *p0,
                               const void *p1, const void *residual, int M, int N, int K, int lda, int prologue,
                               int epilogue, float eps, int dtype, void *workspace, size_t workspace_bytes, void *stream);
+/* out = residual + projection(p0) and, in the same call, normed_out = rms_norm(out, norm_weight, norm_eps): the
+ * residual-stream projections (o, down) of qwen3_week3.py:204-206 followed by the RMSNorm that opens the next block
+ * (:195-199).  Same rounding points as tl_quantized_matmul_fused(TL_EPI_RESIDUAL) then tl_rms_norm; with a split
+ * reduction (9 <= M <= 128) the normalisation happens inside the kernel that adds the partial planes.  p0 is contiguous
+ * [M, N]; workspace as for tl_quantized_matmul_fused(prologue TL_PRO_NONE). */
+int tl_quantized_matmul_residual_norm(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *residual,
+                                      const void *norm_weight, void *normed_out, int M, int N, int K, float norm_eps, int dtype, void *workspace,
+                                      size_t workspace_bytes, void *stream);
 /* Decode step, L == 1: per-head q/k RMSNorm + RoPE + K/V append in one launch.
  * qkv [B, (Hq + 2*Hkv) * D] (q heads | k heads | v heads); q_out [B, Hq, D];
  * K/V rows land in the page slot of token context_lens[b]-1 (rows with context

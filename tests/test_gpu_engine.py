@@ -54,6 +54,27 @@ def test_fused_projection_equals_the_unfused_operator_sequence(dev, M, N, K):
         torch.testing.assert_close(got.float(), ext.add(res, want).float(), rtol=2**-7, atol=2e-3 * float(want.float().abs().max()) + 2**-7)
 
 
+@pytest.mark.parametrize("M", [3, 16, 64, 128])
+@pytest.mark.parametrize("N,K", [(4096, 2560), (9728, 2560), (256, 96), (2560, 6144)])
+def test_residual_projection_with_the_next_rmsnorm_equals_the_two_operators(dev, M, N, K):
+    """o / down projection + residual, handing back the next block's RMSNorm output too: the residual stream is the
+    two-operator result bit for bit; the normalised row may differ by one bf16 ulp in rare elements (the sum of squares
+    is reduced in another order than the standalone kernel's).  K = 6144 exceeds the in-kernel row limit and K = 96 /
+    M = 3 take the unsplit / streaming paths: the call falls back to rms_norm itself."""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    w, s, b = packed(K, N, g, dev)
+    x = (torch.randn(M, N, generator=g) * 2).to(BF16).to(dev)
+    nw = (1 + 0.1 * torch.randn(K, generator=g)).to(BF16).to(dev)
+    res = torch.randn(M, K, generator=g).to(BF16).to(dev)
+    want_x = ext.quantized_matmul_fused(s, b, w, x, residual=res, epilogue=ext.EPI_RESIDUAL)
+    want_h = ext.rms_norm(want_x, nw, 1e-6)
+    got_x, got_h = ext.quantized_matmul_residual_norm(s, b, w, x, res, nw, 1e-6)
+    assert torch.equal(got_x, want_x)
+    torch.testing.assert_close(got_h.float(), want_h.float(), rtol=2**-7, atol=2**-8 * float(want_h.float().abs().max()))
+    again_x, again_h = ext.quantized_matmul_residual_norm(s, b, w, x, res, nw, 1e-6)
+    assert torch.equal(again_h, got_h) and torch.equal(again_x, got_x)  # same bits on every run
+
+
 @pytest.mark.parametrize("M", [1, 5, 8, 16, 64])
 @pytest.mark.parametrize("N,inter", [(2560, 9728), (256, 384), (1024, 40)])
 def test_swiglu_pairs_epilogue_equals_projection_then_swiglu(dev, M, N, inter):

@@ -281,6 +281,25 @@ int tl_quantized_matmul_fused(const void *scales, const void *biases, const void
                               as_stream(stream));
 }
 
+int tl_quantized_matmul_residual_norm(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *residual,
+                                      const void *norm_weight, void *normed_out, int M, int N, int K, float norm_eps, int dtype, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+    if (!norm_weight || !normed_out) return fail(TL_EINVAL, "quantized_matmul_residual_norm: null pointer");
+    if (dtype != TL_F16 && dtype != TL_BF16) return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
+    if (M < 0 || N <= 0 || K < 0 || N % 128 != 0) return fail(TL_EINVAL, "quantized_matmul_residual_norm: bad shape");
+    if (M == 0 || K == 0) return TL_OK;
+    if (!scales || !biases || !b || !out || !p0 || !residual) return fail(TL_EINVAL, "quantized_matmul_residual_norm: null pointer");
+    bool norm_done = false;
+    int rc;
+    if (use_skinny_kernel(M, N, K, dtype, 1))
+        rc = launch_w4a16_skinny(scales, biases, p0, b, out, residual, M, N, K, TL_EPI_RESIDUAL, dtype, workspace, workspace_bytes, as_stream(stream),
+                                 norm_weight, norm_eps, normed_out, &norm_done);
+    else
+        rc = launch_w4a16_fused(scales, biases, b, out, p0, nullptr, residual, M, N, K, N, TL_PRO_NONE, TL_EPI_RESIDUAL, 0.f, dtype, as_stream(stream));
+    if (rc != TL_OK || norm_done) return rc;
+    return launch_rms_norm(out, norm_weight, normed_out, M, K, norm_eps, dtype, as_stream(stream));
+}
+
 int tl_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, const void *k_norm_weight,
                                   const int32_t *offsets, const int32_t *block_table, const int32_t *context_lens,
                                   void *q_out, void *key_pages, void *value_pages, int batch, int num_heads,

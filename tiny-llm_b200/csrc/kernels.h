@@ -58,8 +58,11 @@ int launch_w4a16_vanilla(const void *scales, const void *biases, const void *a, 
 bool w4a16_skinny_supported(int M, int N, int K, int dtype);
 int w4a16_skinny_splits(int M, int N, int K);
 size_t w4a16_skinny_workspace(int M, int N, int K);
+// norm_w / normed (optional, residual epilogue): also write normed = rms_norm(out, norm_w, norm_eps); *norm_done tells
+// whether the launch did it (split reduction, K <= 4096) or the caller still has to run rms_norm
 int launch_w4a16_skinny(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N,
-                        int K, int epilogue, int dtype, void *ws, size_t ws_bytes, cudaStream_t st);
+                        int K, int epilogue, int dtype, void *ws, size_t ws_bytes, cudaStream_t st, const void *norm_w = nullptr,
+                        float norm_eps = 0.f, void *normed = nullptr, bool *norm_done = nullptr);
 
 // w4a16_gemm.cu (tcgen05 prefill GEMM)
 bool w4a16_gemm_supported(int M, int N, int K, int dtype);

@@ -449,6 +449,52 @@ __global__ void __launch_bounds__(256) w4a16_skinny_reduce_kernel(const float *p
     out[idx] = vb;
 }
 
+// The same reduction for the residual epilogue when the RMSNorm of the NEXT projection follows (o -> post-attention norm,
+// down -> next layer's input norm): one CTA per token row adds the planes, adds the residual, writes the residual
+// stream and - the row being complete in its registers - the normalised row too (week2_kernels.metal:41-47 arithmetic:
+// T(x * rsqrt(mean(x^2) + eps) * w) on the ROUNDED residual sum).  Saves the rms_norm launch and its read of the row.
+constexpr int SK_NORM_PER = 16;  // elements per thread: K <= 4096
+template <typename T>
+__global__ void __launch_bounds__(256) w4a16_skinny_reduce_norm_kernel(const float *part, const T *res, const T *__restrict__ norm_w, T *out, T *normed,
+                                                                       int M, int K, int splits, float eps) {
+    __shared__ float warp_part[8];
+    griddep_launch();
+    griddep_wait();
+    const size_t plane = static_cast<size_t>(M) * K, row = static_cast<size_t>(blockIdx.x) * K;
+    float xs[SK_NORM_PER];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < SK_NORM_PER; ++j) {
+        const int n = threadIdx.x + j * 256;
+        xs[j] = 0.f;
+        if (n < K) {
+            float sum = 0.f;
+            for (int sp0 = 0; sp0 < splits; sp0 += 4) {
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = sp0 + q < splits ? ld_cg(part + (sp0 + q) * plane + row + n) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (sp0 + q < splits) sum += v[q];
+            }
+            const T vb = from_f<T>(to_f(ld_cg(res + row + n)) + to_f(from_f<T>(sum)));
+            out[row + n] = vb;
+            xs[j] = to_f(vb);
+            ss += xs[j] * xs[j];
+        }
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    ss = warp_sum((threadIdx.x & 31) < 8 ? warp_part[threadIdx.x & 31] : 0.f);
+    const float inv = rsqrtf(ss / static_cast<float>(K) + eps);
+#pragma unroll
+    for (int j = 0; j < SK_NORM_PER; ++j) {
+        const int n = threadIdx.x + j * 256;
+        if (n < K) normed[row + n] = from_f<T>(xs[j] * inv * to_f(norm_w[n]));
+    }
+}
+
 // ---------------------------------------------------------------- host side --
 bool w4a16_skinny_supported(int M, int N, int K, int dtype) {
     static const bool off = [] { const char *e = getenv("TL_SKINNY"); return e != nullptr && e[0] == '0'; }();
@@ -546,7 +592,7 @@ static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkA
 
 template <typename T>
 static int skinny_t(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N, int K,
-                    int epilogue, void *ws, size_t ws_bytes, cudaStream_t st) {
+                    int epilogue, void *ws, size_t ws_bytes, const void *norm_w, float norm_eps, void *normed, bool *norm_done, cudaStream_t st) {
     if (!aligned16(a) || !aligned16(b)) return fail(TL_EINVAL, "quantized_matmul: a and b must be 16-byte aligned");
     const int NT = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
     const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
@@ -572,6 +618,15 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
         default: rc = skinny_launch<T, 128>(ma, mw, args, grid, st); break;
     }
     if (rc != TL_OK || args.splits == 1) return rc;
+    if (normed != nullptr && epilogue == SK_EPI_RESIDUAL && K <= 256 * SK_NORM_PER) {
+        cudaError_t e = launch_chained(w4a16_skinny_reduce_norm_kernel<T>, dim3(M), dim3(256), 0, st, static_cast<const float *>(args.partials),
+                                       static_cast<const T *>(residual), static_cast<const T *>(norm_w), static_cast<T *>(out), static_cast<T *>(normed),
+                                       M, K, args.splits, norm_eps);
+        if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_skinny_reduce_norm: launch failed: %s", cudaGetErrorString(e));
+        TL_LAUNCH_CHECK("w4a16_skinny_reduce_norm");
+        *norm_done = true;
+        return TL_OK;
+    }
     const size_t outputs = static_cast<size_t>(M) * (epilogue == SK_EPI_SWIGLU_PAIRS ? K / 2 : K);
     cudaError_t e = launch_chained(w4a16_skinny_reduce_kernel<T>, dim3(static_cast<unsigned>((outputs + 255) / 256)), dim3(256), 0, st,
                                    static_cast<const float *>(args.partials), static_cast<const T *>(residual), static_cast<T *>(out), M, K,
@@ -582,11 +637,16 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
 }
 
 int launch_w4a16_skinny(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N,
-                        int K, int epilogue, int dtype, void *ws, size_t ws_bytes, cudaStream_t st) {
+                        int K, int epilogue, int dtype, void *ws, size_t ws_bytes, cudaStream_t st, const void *norm_w, float norm_eps, void *normed,
+                        bool *norm_done) {
+    bool unused = false;
+    if (norm_done == nullptr) norm_done = &unused;
+    *norm_done = false;
     if (M == 0 || K == 0) return TL_OK;
     if (epilogue == SK_EPI_SWIGLU_PAIRS && K % 16 != 0) return fail(TL_EINVAL, "quantized_matmul: interleaved gate|up rows need K %% 16 == 0");
-    if (dtype == TL_BF16) return skinny_t<__nv_bfloat16>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, st);
-    if (dtype == TL_F16) return skinny_t<__half>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, st);
+    if (dtype == TL_BF16)
+        return skinny_t<__nv_bfloat16>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, norm_w, norm_eps, normed, norm_done, st);
+    if (dtype == TL_F16) return skinny_t<__half>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, norm_w, norm_eps, normed, norm_done, st);
     return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
 }
 

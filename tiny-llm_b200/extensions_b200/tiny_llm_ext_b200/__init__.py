@@ -46,6 +46,7 @@ __all__ = [
     "launch_count",
     "device_info",
     "current_library_path",
+    "quantized_matmul_residual_norm",
 ]
 
 _HERE = Path(__file__).resolve().parent
@@ -81,6 +82,7 @@ _SIGNATURES = {
     "tl_decode_advance": (_I, [_VP] * 6 + [_I, _I, _VP]),
     "tl_quantized_matmul_fused_workspace": (_SZ, [_I] * 6),
     "tl_quantized_matmul_fused": (_I, [_VP] * 7 + [_I] * 6 + [_F, _I, _VP, _SZ, _VP]),
+    "tl_quantized_matmul_residual_norm": (_I, [_VP] * 8 + [_I] * 3 + [_F, _I, _VP, _SZ, _VP]),
     "tl_decode_qk_norm_rope_append": (_I, [_VP] * 9 + [_I] * 4 + [_F, _F] + [_I] * 4 + [_VP]),
     "tl_chunk_qk_norm_rope_append": (_I, [_VP] * 9 + [_I] * 4 + [_F, _F] + [_I] * 4 + [_VP]),
     "tl_decode_attention_fused_workspace": (_SZ, [_I, _I, _I]),
@@ -562,6 +564,37 @@ def quantized_matmul_fused(scales, biases, b, p0, p1=None, residual=None, prolog
         )
     )
     return out
+
+
+def quantized_matmul_residual_norm(scales, biases, b, p0, residual, norm_weight, norm_eps, stream=None):
+    """``x = residual + p0 @ W^T`` and ``h = rms_norm(x, norm_weight, norm_eps)`` in one call (the o / down projection
+    of a block followed by the RMSNorm that opens the next one); returns ``(x, h)``.  Same rounding points as
+    ``quantized_matmul_fused(epilogue=EPI_RESIDUAL)`` followed by ``rms_norm``."""
+    if p0.dim() != 2 or b.dim() != 2 or not p0.is_contiguous():
+        raise RuntimeError("quantized_matmul_residual_norm: p0 must be contiguous [M, N]")
+    M, N = p0.shape
+    K = b.shape[0]
+    if b.shape[1] * 8 != N or tuple(scales.shape) != (K, N // 128) or scales.shape != biases.shape:
+        raise RuntimeError("quantized_matmul_fused: incompatible parameter shapes")
+    if scales.dtype not in _HALF or p0.dtype != scales.dtype or biases.dtype != scales.dtype or norm_weight.dtype != scales.dtype:
+        raise RuntimeError("quantized_matmul: a must be the same dtype as scales")
+    if tuple(residual.shape) != (M, K) or not residual.is_contiguous() or residual.dtype != p0.dtype:
+        raise RuntimeError("quantized_matmul_fused: residual must be contiguous [M, K]")
+    if tuple(norm_weight.shape) != (K,) or not norm_weight.is_contiguous():
+        raise RuntimeError("quantized_matmul_residual_norm: norm weight must be [K]")
+    _gpu("quantized_matmul_residual_norm", scales, biases, b, p0, residual, norm_weight)
+    out = torch.empty((M, K), dtype=p0.dtype, device=p0.device)
+    normed = torch.empty_like(out)
+    code = _DTYPE_CODE[p0.dtype]
+    ws_bytes = _lib.tl_quantized_matmul_fused_workspace(M, N, K, N, int(PRO_NONE), code)
+    ws = _zero_workspace(ws_bytes, p0.device)
+    _check(
+        _lib.tl_quantized_matmul_residual_norm(
+            scales.data_ptr(), biases.data_ptr(), b.data_ptr(), out.data_ptr(), p0.data_ptr(), residual.data_ptr(), norm_weight.data_ptr(),
+            normed.data_ptr(), M, N, K, float(norm_eps), code, None if ws is None else ws.data_ptr(), ws_bytes, _stream_ptr(stream, p0),
+        )
+    )
+    return out, normed
 
 
 def chunk_qk_norm_rope_append(qkv, q_norm_weight, k_norm_weight, offsets, block_table_row, context_lens, key_pages, value_pages,

@@ -237,11 +237,15 @@ class DecodeEngine:
         def normed(h, norm):
             return ext.rms_norm(h, norm._weight_as(h.dtype, h.device), norm.eps)
 
-        for i, block in enumerate(m.layers_inner):
+        layers = list(m.layers_inner)
+        # wide path: the residual projections (o, down) hand the NEXT RMSNorm's output back together with the residual
+        # stream (one launch: the kernel that adds the split-reduction planes has the whole row in registers)
+        h = normed(x, layers[0].input_layernorm) if wide else None
+        for i, block in enumerate(layers):
             at, pk, pool = block.self_attn, self._packed[i], m.page_pools[i]
             ln1, ln2 = block.input_layernorm, block.post_attention_layernorm
             if wide:
-                qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, normed(x, ln1))
+                qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, h)
             else:
                 qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, x, ln1._weight_as(x.dtype, x.device),
                                                  prologue=ext.PRO_RMSNORM, eps=ln1.eps)
@@ -256,18 +260,21 @@ class DecodeEngine:
                                                    Hq, Hkv, at.rope.base, at.q_norm.eps)
                 y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i], self.context_lens,
                                         at.scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
-            x = ext.quantized_matmul_fused(at.wo.scales, at.wo.biases, at.wo.weight, y.view(B, Hq * D), residual=x, epilogue=ext.EPI_RESIDUAL)
-            if wide:
-                act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, normed(x, ln2),
-                                                 epilogue=ext.EPI_SWIGLU_PAIRS)
-            else:
-                act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, x, ln2._weight_as(x.dtype, x.device),
-                                                 prologue=ext.PRO_RMSNORM, eps=ln2.eps, epilogue=ext.EPI_SWIGLU_PAIRS)  # [B, inter]
             wd = block.mlp.w_down
+            if wide:
+                x, h = ext.quantized_matmul_residual_norm(at.wo.scales, at.wo.biases, at.wo.weight, y.view(B, Hq * D), x,
+                                                          ln2._weight_as(x.dtype, x.device), ln2.eps)
+                act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, h, epilogue=ext.EPI_SWIGLU_PAIRS)
+                nxt = layers[i + 1].input_layernorm if i + 1 < len(layers) else m.norm
+                x, h = ext.quantized_matmul_residual_norm(wd.scales, wd.biases, wd.weight, act, x, nxt._weight_as(x.dtype, x.device), nxt.eps)
+                continue
+            x = ext.quantized_matmul_fused(at.wo.scales, at.wo.biases, at.wo.weight, y.view(B, Hq * D), residual=x, epilogue=ext.EPI_RESIDUAL)
+            act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, x, ln2._weight_as(x.dtype, x.device),
+                                             prologue=ext.PRO_RMSNORM, eps=ln2.eps, epilogue=ext.EPI_SWIGLU_PAIRS)  # [B, inter]
             x = ext.quantized_matmul_fused(wd.scales, wd.biases, wd.weight, act, residual=x, epilogue=ext.EPI_RESIDUAL)
         head = m.w_lm_head if m.w_lm_head is not None else m.embedding.weight
         if wide:
-            return ext.quantized_matmul_fused(head.scales, head.biases, head.weight, normed(x, m.norm))
+            return ext.quantized_matmul_fused(head.scales, head.biases, head.weight, h)
         return ext.quantized_matmul_fused(head.scales, head.biases, head.weight, x, m.norm._weight_as(x.dtype, x.device),
                                           prologue=ext.PRO_RMSNORM, eps=m.norm.eps)
 
@@ -585,9 +592,12 @@ class PrefillEngine:
         def proj(h, w):
             return ext.quantized_matmul(w.scales, w.biases, w.group_size, w.bits, h, w.weight, True)
 
-        for i, block in enumerate(m.layers_inner):
+        layers = list(m.layers_inner)
+        h = normed(x, layers[0].input_layernorm) if skinny else None
+        for i, block in enumerate(layers):
             at, pk, pool = block.self_attn, self._packed[i], m.page_pools[i]
-            h = normed(x, block.input_layernorm)
+            if not skinny:
+                h = normed(x, block.input_layernorm)
             qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, h) if skinny else proj(h, pk.qkv)
             q = ext.chunk_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
                                               self.offsets, self.tables[i], self.ctxs, pool._key_pages, pool._value_pages,
@@ -595,17 +605,19 @@ class PrefillEngine:
             y = ext.paged_attention(q, pool._key_pages, pool._value_pages, self.tables[i:i + 1], self.ctx_after, at.scale,
                                     is_causal=True, num_kv_heads=Hkv, num_heads=Hq)  # [Hq, L, D]
             y = y.transpose(0, 1).reshape(L, Hq * D)  # one 2-byte-per-element copy per layer
-            if skinny:
-                x = ext.quantized_matmul_fused(at.wo.scales, at.wo.biases, at.wo.weight, y, residual=x, epilogue=ext.EPI_RESIDUAL)
-                act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, normed(x, block.post_attention_layernorm),
-                                                 epilogue=ext.EPI_SWIGLU_PAIRS)
-                wd = block.mlp.w_down
-                x = ext.quantized_matmul_fused(wd.scales, wd.biases, wd.weight, act, residual=x, epilogue=ext.EPI_RESIDUAL)
+            if skinny:  # the residual projections return the next RMSNorm's output too (DecodeEngine._forward_fused_layers)
+                ln2, wd = block.post_attention_layernorm, block.mlp.w_down
+                x, h = ext.quantized_matmul_residual_norm(at.wo.scales, at.wo.biases, at.wo.weight, y, x, ln2._weight_as(x.dtype, x.device), ln2.eps)
+                act = ext.quantized_matmul_fused(pk.gate_up.scales, pk.gate_up.biases, pk.gate_up.weight, h, epilogue=ext.EPI_SWIGLU_PAIRS)
+                nxt = layers[i + 1].input_layernorm if i + 1 < len(layers) else m.norm
+                x, h = ext.quantized_matmul_residual_norm(wd.scales, wd.biases, wd.weight, act, x, nxt._weight_as(x.dtype, x.device), nxt.eps)
             else:
                 x = ext.add(x, proj(y, at.wo))
                 h = normed(x, block.post_attention_layernorm)
                 x = ext.add(x, proj(ext.swiglu(proj(h, block.mlp.w_gate), proj(h, block.mlp.w_up)), block.mlp.w_down))
-        last = normed(x[L - 1:L], m.norm)  # logits_to_keep = 1: the hidden state is sliced before the final norm (qwen3_week3.py:330-338)
+        # logits_to_keep = 1: the hidden state is sliced before the final norm (qwen3_week3.py:330-338); RMSNorm is row-wise,
+        # so the last row of the already normalised chunk is the same thing
+        last = h[L - 1:L] if skinny else normed(x[L - 1:L], m.norm)
         head = m.w_lm_head if m.w_lm_head is not None else m.embedding.weight
         logits = proj(last, head)
         self.next_token.copy_(ext.argmax(logits))
