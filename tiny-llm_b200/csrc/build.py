@@ -30,6 +30,7 @@ SOURCES = [
     "elementwise.cu",
     "w4a16_matvec.cu",
     "w4a16_gemm.cu",
+    "w4a16_gemm2.cu",
     "w4a16_skinny.cu",
     "attention_decode.cu",
     "attention_prefill.cu",

@@ -54,6 +54,11 @@ int launch_w4a16_vanilla(const void *scales, const void *biases, const void *a, 
                          int N, int K, int dtype, cudaStream_t st);
 
 
+// w4a16_gemm2.cu (CTA pairs, tcgen05 cta_group::2: M > 256)
+bool w4a16_gemm2_supported(int M, int N, int K, int dtype);
+int launch_w4a16_gemm2(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N, int K, int dtype,
+                       cudaStream_t st);
+
 // w4a16_skinny.cu (swap-AB tcgen05 GEMM with split reduction, 9 <= M <= 128)
 bool w4a16_skinny_supported(int M, int N, int K, int dtype);
 int w4a16_skinny_splits(int M, int N, int K);

@@ -381,6 +381,7 @@ static int gemm_t(const void *scales, const void *biases, const void *a, const v
 int launch_w4a16_gemm(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N, int K,
                       int dtype, int /*use_split_k*/, void * /*ws*/, size_t /*ws_bytes*/, cudaStream_t st) {
     if (M == 0 || K == 0) return TL_OK;
+    if (w4a16_gemm2_supported(M, N, K, dtype)) return launch_w4a16_gemm2(scales, biases, a, b, out, M, N, K, dtype, st);  // CTA pairs
     if (dtype == TL_BF16) return gemm_t<__nv_bfloat16>(scales, biases, a, b, out, M, N, K, st);
     if (dtype == TL_F16) return gemm_t<__half>(scales, biases, a, b, out, M, N, K, st);
     return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
