@@ -124,15 +124,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
     const uint32_t a_base = g_smem_u32(gsm + Smem::A_OFF);
     const uint32_t b_base = g_smem_u32(gsm + Smem::B_OFF);
     const uint32_t bar_base = g_smem_u32(gsm + Smem::BAR_OFF);
-    const uint32_t full_a = bar_base, full_b = bar_base + 8 * GSTAGES, empty = bar_base + 16 * GSTAGES;
-    const uint32_t tmem_full = bar_base + 24 * GSTAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gsm + Smem::BAR_OFF + 24 * GSTAGES + 8);
+    // ONE "full" barrier per stage: the TMA's expect_tx arrival + byte count and the eight dequantiser warps arrive on
+    // it, so the MMA warp pays one try_wait (~90 cycles) per block, not two: whatever it executes between the last MMA
+    // of a block and the first of the next is time the tensor core idles (its queue holds one or two MMAs).
+    const uint32_t full = bar_base, empty = bar_base + 8 * GSTAGES;
+    const uint32_t tmem_full = bar_base + 16 * GSTAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gsm + Smem::BAR_OFF + 16 * GSTAGES + 8);
 
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < GSTAGES; ++i) {
-            g_mbar_init(full_a + 8 * i, 1);
-            g_mbar_init(full_b + 8 * i, G_DEQ_WARPS);  // one arrival per dequantiser warp
+            g_mbar_init(full + 8 * i, 1 + G_DEQ_WARPS);  // the producer's expect_tx arrival + one per dequantiser warp
             g_mbar_init(empty + 8 * i, 1);
         }
         g_mbar_init(tmem_full, 1);
@@ -154,10 +156,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
         for (int kb = 0; kb < num_kb; ++kb) {
             g_mbar_wait(empty + 8 * s, ph);
             if (g_elect_one()) {
-                g_mbar_expect_tx(full_a + 8 * s, Smem::A_STAGE);
+                g_mbar_expect_tx(full + 8 * s, Smem::A_STAGE);
 #pragma unroll
                 for (int i = 0; i < MT; ++i)  // token rows beyond M are zero-filled by the TMA unit
-                    g_tma_load_2d(a_base + s * Smem::A_STAGE + i * G_TILE_BYTES, &tmap_a, kb * GK, (m_tile * MT + i) * GM, full_a + 8 * s);
+                    g_tma_load_2d(a_base + s * Smem::A_STAGE + i * G_TILE_BYTES, &tmap_a, kb * GK, (m_tile * MT + i) * GM, full + 8 * s);
             }
             __syncwarp();
             if (++s == GSTAGES) s = 0, ph ^= 1u;
@@ -173,9 +175,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
         int s = 0;
         uint32_t ph = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-            g_mbar_wait(full_a + 8 * s, ph);
+            g_mbar_wait(full + 8 * s, ph);
             G_TRC(0, kb, 0);
-            g_mbar_wait(full_b + 8 * s, ph);
             G_TRC(0, kb, 1);
             g_tc_fence_after();
             if (g_elect_one()) {
@@ -210,13 +211,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
         const uint32_t magic = Deq<T>::MAGIC;
         const V2 offset2 = *reinterpret_cast<const V2 *>(&magic);
         uint4 packed = *reinterpret_cast<const uint4 *>(wrow + half * 4);
+        T sc_next = srow[0], bi_next = crow[0];
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % GSTAGES;
             const uint32_t ph = (kb / GSTAGES) & 1;
             if (warp == 4) G_TRC(1, kb, 0);
             const uint4 cur = packed;
-            if (kb + 1 < num_kb) packed = *reinterpret_cast<const uint4 *>(wrow + (kb + 1) * 8 + half * 4);
-            const T sc = srow[kb >> 1], bi = crow[kb >> 1];
+            const T sc = sc_next, bi = bi_next;
+            if (kb + 1 < num_kb) {  // next block's words and scale pair: one round trip ahead of their use
+                packed = *reinterpret_cast<const uint4 *>(wrow + (kb + 1) * 8 + half * 4);
+                sc_next = srow[(kb + 1) >> 1], bi_next = crow[(kb + 1) >> 1];
+            }
             V2 s2, b2;
             s2.x = sc, s2.y = sc, b2.x = bi, b2.y = bi;
             uint32_t outw[16];
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) w4a16_gemm_kernel(const __grid_c
             }
             g_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
             __syncwarp();           // one arrival per warp instead of 256 serialised shared-memory atomics per stage
-            if (lane == 0) g_mbar_arrive(full_b + 8 * s);
+            if (lane == 0) g_mbar_arrive(full + 8 * s);
             if (warp == 4) G_TRC(1, kb, 3);
         }
         // ---- epilogue: TMEM lane = token row; warps 4-7 take columns 0..63, warps 8-11 columns 64..127

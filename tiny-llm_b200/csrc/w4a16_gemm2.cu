@@ -15,8 +15,8 @@
 // Roles per CTA (384 threads): warp 0 TMA producer (its 128 token rows of each MMA tile), warp 1 MMA issuer in the
 // leader CTA (rank 0) / readiness forwarder in the peer, warp 2 TMEM allocation (cta_group::2, all 512 columns: two
 // accumulators of 256 features), warps 4-11 dequantisers then epilogue (lane = token row).
-// Barriers live at the same offsets in both CTAs: full_a (own TMA), full_b (own dequantisers), peer (leader only: the
-// peer's tiles of the stage are complete), empty and tmem_full (arrived in BOTH CTAs by the leader's multicast commit).
+// Barriers live at the same offsets in both CTAs: full (own TMA + own dequantisers; in the leader also the peer's
+// "my tiles of this stage are complete"), empty and tmem_full (arrived in BOTH CTAs by the leader's multicast commit).
 // Replaces quantized_matmul_simdgroup_w4a16_g128 (/root/reference/src/extensions_ref/src/quantized_matmul.metal:96-249)
 // for M > 256; same rounding points as w4a16_gemm.cu (weights rounded to the activation dtype, fp32 accumulation).
 #include <cuda.h>
@@ -119,16 +119,17 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
 
     const uint32_t smem0 = g_smem_u32(psm);
     const uint32_t bar = smem0 + P_BAR_OFF;
-    const uint32_t full_a = bar, full_b = bar + 8 * P_STAGES, peer = bar + 16 * P_STAGES, empty = bar + 24 * P_STAGES;
-    const uint32_t tmem_full = bar + 32 * P_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(psm + P_BAR_OFF + 32 * P_STAGES + 8);
+    // ONE "full" barrier per stage and CTA: own TMA (expect_tx arrival + bytes) + own eight dequantiser warps; in the
+    // leader one more arrival, sent by the peer when ITS barrier of the stage has completed.  The MMA warp pays a single
+    // try_wait per block: what it executes between two blocks' MMAs is time the tensor cores idle.
+    const uint32_t full = bar, empty = bar + 8 * P_STAGES;
+    const uint32_t tmem_full = bar + 16 * P_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(psm + P_BAR_OFF + 16 * P_STAGES + 8);
 
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < P_STAGES; ++i) {
-            g_mbar_init(full_a + 8 * i, 1);
-            g_mbar_init(full_b + 8 * i, P_DEQ_WARPS);
-            g_mbar_init(peer + 8 * i, 1);
+            g_mbar_init(full + 8 * i, 1 + P_DEQ_WARPS + (rank == 0 ? 1 : 0));
             g_mbar_init(empty + 8 * i, 1);
         }
         g_mbar_init(tmem_full, 1);
@@ -150,11 +151,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
         for (int kb = 0; kb < num_kb; ++kb) {
             g_mbar_wait(empty + 8 * s, ph);
             if (g_elect_one()) {
-                g_mbar_expect_tx(full_a + 8 * s, P_A_STAGE);
+                g_mbar_expect_tx(full + 8 * s, P_A_STAGE);
 #pragma unroll
                 for (int i = 0; i < P_MT; ++i)  // token rows beyond M are zero-filled by the TMA unit
                     g_tma_load_2d(smem0 + s * P_STAGE + i * P_TILE, &tmap_a, kb * P_KB, (m_pair * P_MT + i) * 256 + static_cast<int>(rank) * P_TOK,
-                                  full_a + 8 * s);
+                                  full + 8 * s);
             }
             __syncwarp();
             if (++s == P_STAGES) s = 0, ph ^= 1u;
@@ -167,9 +168,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
             constexpr uint32_t idesc = p_instr_desc<T>();
             const uint64_t adesc0 = g_smem_desc_sw128(smem0, 0, 1024), bdesc0 = g_smem_desc_sw128(smem0 + P_A_STAGE, 0, 1024);
             for (int kb = 0; kb < num_kb; ++kb) {
-                g_mbar_wait(full_a + 8 * s, ph);
-                g_mbar_wait(full_b + 8 * s, ph);
-                p_mbar_wait_cluster(peer + 8 * s, ph);
+                p_mbar_wait_cluster(full + 8 * s, ph);  // cluster-scope acquire: one of the arrivals is the peer's
                 g_tc_fence_after();
                 if (g_elect_one()) {
                     const uint64_t stage = static_cast<uint64_t>(s * (P_STAGE >> 4));
@@ -190,9 +189,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
         } else {
             // ------------------------------------------------ peer: tell the leader when this CTA's tiles of a stage are complete
             for (int kb = 0; kb < num_kb; ++kb) {
-                g_mbar_wait(full_a + 8 * s, ph);
-                g_mbar_wait(full_b + 8 * s, ph);
-                if (lane == 0) p_mbar_arrive_remote(peer + 8 * s, 0);
+                g_mbar_wait(full + 8 * s, ph);
+                if (lane == 0) p_mbar_arrive_remote(full + 8 * s, 0);
                 __syncwarp();
                 if (++s == P_STAGES) s = 0, ph ^= 1u;
             }
@@ -248,7 +246,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
             }
             g_fence_proxy_async();  // generic-proxy stores -> visible to the tensor cores' async proxy (of both SMs)
             __syncwarp();
-            if (lane == 0) g_mbar_arrive(full_b + 8 * s);
+            if (lane == 0) g_mbar_arrive(full + 8 * s);
             if (++s == P_STAGES) s = 0, ph ^= 1u;
         }
         // ---- epilogue: TMEM lane = token row of THIS CTA; warps 4-7 take features 0..127 of the pair, warps 8-11 features 128..255

@@ -461,23 +461,39 @@ __global__ void __launch_bounds__(256) w4a16_skinny_reduce_norm_kernel(const flo
     griddep_launch();
     griddep_wait();
     const size_t plane = static_cast<size_t>(M) * K, row = static_cast<size_t>(blockIdx.x) * K;
+    // all loads of a round (four planes x the thread's elements, then the residual) are issued before the first is used:
+    // ld_cg is a volatile asm, so a load-then-add loop per element would pay one L2 round trip per batch (measured: 14 us
+    // for this kernel against 3 + 2 us for the two it replaces)
     float xs[SK_NORM_PER];
+#pragma unroll
+    for (int j = 0; j < SK_NORM_PER; ++j) xs[j] = 0.f;
+    for (int sp0 = 0; sp0 < splits; sp0 += 4) {
+        float v[SK_NORM_PER][4];
+#pragma unroll
+        for (int j = 0; j < SK_NORM_PER; ++j) {
+            const int n = threadIdx.x + j * 256;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[j][q] = (n < K && sp0 + q < splits) ? ld_cg(part + (sp0 + q) * plane + row + n) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < SK_NORM_PER; ++j) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (sp0 + q < splits) xs[j] += v[j][q];  // split order
+        }
+    }
+    T rs[SK_NORM_PER];
+#pragma unroll
+    for (int j = 0; j < SK_NORM_PER; ++j) {
+        const int n = threadIdx.x + j * 256;
+        rs[j] = n < K ? ld_cg(res + row + n) : from_f<T>(0.f);
+    }
     float ss = 0.f;
 #pragma unroll
     for (int j = 0; j < SK_NORM_PER; ++j) {
         const int n = threadIdx.x + j * 256;
-        xs[j] = 0.f;
         if (n < K) {
-            float sum = 0.f;
-            for (int sp0 = 0; sp0 < splits; sp0 += 4) {
-                float v[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = sp0 + q < splits ? ld_cg(part + (sp0 + q) * plane + row + n) : 0.f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (sp0 + q < splits) sum += v[q];
-            }
-            const T vb = from_f<T>(to_f(ld_cg(res + row + n)) + to_f(from_f<T>(sum)));
+            const T vb = from_f<T>(to_f(rs[j]) + to_f(from_f<T>(xs[j])));
             out[row + n] = vb;
             xs[j] = to_f(vb);
             ss += xs[j] * xs[j];

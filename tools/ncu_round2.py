@@ -1,11 +1,11 @@
 """Driver for the round-2 `ncu --set full` captures (run under gpurun; one launch of each kernel is captured):
 
   ncu --set full --clock-control none --import-source on \
-      -k regex:"paged_prefill_tc|w4a16_skinny|w4a16_stream5" -s <skip> -c <n> -o gpurun_out/r02_kernels python tools/ncu_round2.py
+      -k regex:"paged_prefill_tc|w4a16_skinny_kernel|w4a16_stream5|w4a16_gemm2" -s 21 -c 7 -o gpurun_out/r02_kernels python tools/ncu_round2.py
 
 Order of launches after the warm-up (3 of each): tcgen05 flash prefill (L = S = 4096), the same kernel as split-KV
-decode attention (B = 64, S = 8192), swap-AB GEMM M = 64 at the gate|up and down shapes, streaming matvec M = 1 at the
-gate|up and tied-head shapes."""
+decode attention (B = 64, S = 8192), swap-AB GEMM M = 64 at the gate|up and tied-head shapes, streaming matvec M = 1 at
+the gate|up and tied-head shapes, CTA-pair GEMM at 4096 rows (gate|up)."""
 from __future__ import annotations
 
 import sys
@@ -45,8 +45,8 @@ def matmul(M, N, K):
     return lambda: ext.quantized_matmul(s, b, 128, 4, a, w, True)
 
 
-calls = [attention_inputs(1, 4096, 4096), attention_inputs(64, 1, 8192), matmul(64, 2560, 19456), matmul(64, 9728, 2560),
-         matmul(1, 2560, 19456), matmul(1, 2560, 151936)]
+calls = [attention_inputs(1, 4096, 4096), attention_inputs(64, 1, 8192), matmul(64, 2560, 19456), matmul(64, 2560, 151936),
+         matmul(1, 2560, 19456), matmul(1, 2560, 151936), matmul(4096, 2560, 19456)]
 for rep in range(4):  # three warm-up rounds, the fourth is the one to capture
     for c in calls:
         c()
