@@ -359,6 +359,7 @@ extern "C" int tl_debug_trace(unsigned long long *device_events, unsigned int *d
     trace_bind_attention(device_events, device_count, capacity);
     trace_bind_skinny(device_events, device_count, capacity);
     trace_bind_gemm(device_events, device_count, capacity);
+    trace_bind_gemm2(device_events, device_count, capacity);
     return TL_OK;
 }
 #endif

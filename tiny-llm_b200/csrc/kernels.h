@@ -82,6 +82,7 @@ void trace_bind_matvec(unsigned long long *buf, unsigned int *n, unsigned int ca
 void trace_bind_attention(unsigned long long *buf, unsigned int *n, unsigned int cap);
 void trace_bind_skinny(unsigned long long *buf, unsigned int *n, unsigned int cap);
 void trace_bind_gemm(unsigned long long *buf, unsigned int *n, unsigned int cap);
+void trace_bind_gemm2(unsigned long long *buf, unsigned int *n, unsigned int cap);
 #endif
 size_t decode_attention_fused_workspace(int batch, int num_heads, int num_kv_heads);
 int launch_decode_attention_fused(const void *qkv, const void *q_norm_weight, const void *k_norm_weight, const int32_t *offsets,

@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc05.cuh"
+#include "trace.cuh"
 
 namespace tl {
 
@@ -111,6 +112,17 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
                                                                    const T *__restrict__ biases, const uint32_t *__restrict__ b, T *__restrict__ out,
                                                                    int M, int N, int K, int vec_store) {
     extern __shared__ __align__(1024) unsigned char psm[];
+#if TL_TRACE
+    // per-block cycle stamps of the leader CTA (0,0) (tools/gemm_blocks.py): role 0 = MMA warp (k: stage complete in both
+    // CTAs, -, MMAs issued), role 1 = first dequantiser warp (k: loop top, math done, stage free, handed over)
+    __shared__ unsigned long long trc[2][40][4];
+#define P_TRC(role, i, k)                                                                                                    \
+    do {                                                                                                                     \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (i) < 40) trc[role][i][k] = clock64();         \
+    } while (0)
+#else
+#define P_TRC(role, i, k) do { } while (0)
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = p_cta_rank();                    // 0 = leader (issues the MMAs)
     const int n_pair = blockIdx.x >> 1, m_pair = blockIdx.y;
@@ -169,6 +181,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
             const uint64_t adesc0 = g_smem_desc_sw128(smem0, 0, 1024), bdesc0 = g_smem_desc_sw128(smem0 + P_A_STAGE, 0, 1024);
             for (int kb = 0; kb < num_kb; ++kb) {
                 p_mbar_wait_cluster(full + 8 * s, ph);  // cluster-scope acquire: one of the arrivals is the peer's
+                P_TRC(0, kb, 0);
+                P_TRC(0, kb, 1);
                 g_tc_fence_after();
                 if (g_elect_one()) {
                     const uint64_t stage = static_cast<uint64_t>(s * (P_STAGE >> 4));
@@ -182,6 +196,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
                     p_tc_commit2(empty + 8 * s);  // both CTAs may refill the stage once these MMAs have read it
                 }
                 __syncwarp();
+                P_TRC(0, kb, 2);
                 if (++s == P_STAGES) s = 0, ph ^= 1u;
             }
             if (g_elect_one()) p_tc_commit2(tmem_full);
@@ -211,6 +226,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
         int s = 0;
         uint32_t ph = 1;
         for (int kb = 0; kb < num_kb; ++kb) {
+            if (warp == 4) P_TRC(1, kb, 0);
             const uint4 cur = packed;
             const T sc = sc_next, bi = bi_next;
             if (kb + 1 < num_kb) {  // next block's words and (every other block) the next group's scale pair: one round trip ahead
@@ -237,7 +253,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
                 outw[4 * j + 2] = __byte_perm(p[0], p[1], 0x7632);  // (e4, e5)
                 outw[4 * j + 3] = __byte_perm(p[2], p[3], 0x7632);  // (e6, e7)
             }
+            if (warp == 4) P_TRC(1, kb, 1);
             g_mbar_wait(empty + 8 * s, ph);
+            if (warp == 4) P_TRC(1, kb, 2);
             unsigned char *tile = psm + s * P_STAGE + P_A_STAGE + row * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -247,6 +265,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
             g_fence_proxy_async();  // generic-proxy stores -> visible to the tensor cores' async proxy (of both SMs)
             __syncwarp();
             if (lane == 0) g_mbar_arrive(full + 8 * s);
+            if (warp == 4) P_TRC(1, kb, 3);
             if (++s == P_STAGES) s = 0, ph ^= 1u;
         }
         // ---- epilogue: TMEM lane = token row of THIS CTA; warps 4-7 take features 0..127 of the pair, warps 8-11 features 128..255
@@ -289,7 +308,22 @@ __global__ void __launch_bounds__(P_THREADS, 1) w4a16_gemm2_kernel(const __grid_
         g_tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(P_TMEM_COLS) : "memory");
     }
+#if TL_TRACE
+    if (blockIdx.x == 0 && blockIdx.y == 0 && g_trace_buf != nullptr) {  // tag = 20000 + role * 1000 + block * 4 + k (as w4a16_gemm.cu)
+        for (int e = threadIdx.x; e < 2 * 40 * 4; e += P_THREADS) {
+            const int role = e / 160, rest = e - role * 160;
+            if (rest / 4 < num_kb && !(role == 0 && (rest & 3) == 3)) {
+                const unsigned at = atomicAdd(g_trace_n, 1u);
+                if (at < g_trace_cap) g_trace_buf[2 * at] = 20000 + role * 1000 + rest, g_trace_buf[2 * at + 1] = trc[role][rest / 4][rest & 3];
+            }
+        }
+    }
+#endif
 }
+
+#if TL_TRACE
+void trace_bind_gemm2(unsigned long long *buf, unsigned int *n, unsigned int cap) { trace_bind(buf, n, cap); }
+#endif
 
 // ---------------------------------------------------------------- host side --
 bool w4a16_gemm2_supported(int M, int N, int K, int dtype) {
