@@ -218,6 +218,9 @@ int tl_decode_attention_fused(const void *qkv, const void *q_norm_weight, const 
 /* Programmatic dependent launch for the streaming kernels (on by default; 0 turns it off,
  * TL_PDL=0 in the environment does the same). */
 int tl_set_pdl(int enabled);
+/* Prefill GEMM on CTA pairs (tcgen05 cta_group::2, w4a16_gemm2.cu): 0 never, 1 where the pair grid fills the SMs
+ * (default), 2 for every M > 256.  Same results either way (same rounding points); TL_GEMM2 sets the initial mode. */
+int tl_set_gemm_pairs(int mode);
 /* Device-side bookkeeping between two decode steps of a CUDA-graph loop (the
  * per-request `req.decode_done(token)` + `offset += 1` of batch.py:241-247 done
  * without a host round trip): for every ACTIVE row (context_lens > 0)

@@ -111,21 +111,34 @@ def test_paged_decode_attention_at_serving_sizes_matches_oracle(dev, B, S):
 
 
 # ------------------------------------------------------------------ GEMM at the config-3 shapes --
-@pytest.mark.parametrize("shape", [(4096, 9728, 2560), (4096, 2560, 19456 // 2), (4096, 4096, 2560)], ids=lambda s: "x".join(map(str, s)))
-def test_prefill_gemm_full_size_matches_oracle_on_sampled_rows(dev, shape):
-    """M = 4096 (two / four 128-token tiles per CTA) at the Qwen3-4B down / gate / o shapes: sampled token rows
-    against the tiled kernel's arithmetic restated on the CPU (weights rounded to bf16 before the MMA,
-    quantized_matmul.metal:183-194; fp32 accumulation)."""
+@pytest.mark.parametrize("pairs", [0, 2], ids=["one-cta", "cta-pairs"])
+@pytest.mark.parametrize("shape", [(4096, 9728, 2560), (4096, 2560, 19456 // 2), (4096, 4096, 2560), (1000, 256, 392)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_prefill_gemm_full_size_matches_oracle_on_sampled_rows(dev, shape, pairs):
+    """M = 4096 at the Qwen3-4B down / gate / o shapes (and a ragged one: 1000 rows, 392 features) on BOTH prefill
+    kernels - two / four 128-token tiles per CTA (w4a16_gemm.cu) and the cta_group::2 pair kernel (w4a16_gemm2.cu):
+    sampled token rows against the tiled kernel's arithmetic restated on the CPU (weights rounded to bf16 before the
+    MMA, quantized_matmul.metal:183-194; fp32 accumulation), and the two kernels against each other bit for bit on the
+    whole matrix (same rounding points, same accumulation order along the reduction)."""
     M, N, K = shape
     g = gen(M + N + K)
     words, scales, biases = rand_packed(K, N, g)
     a = torch.randn(M, N, generator=g).to(BF16)
-    got = ext.quantized_matmul(scales.to(dev), biases.to(dev), 128, 4, a.to(dev), words.to(dev), True).cpu()
-    rows = [0, 1, 127, 128, 255, 256, 2047, 2048, 4095]
+    args = (scales.to(dev), biases.to(dev), 128, 4, a.to(dev), words.to(dev), True)
+    try:
+        ext.set_gemm_pairs(pairs)
+        got_dev = ext.quantized_matmul(*args)
+        ext.set_gemm_pairs(0)
+        other = ext.quantized_matmul(*args)
+    finally:
+        ext.set_gemm_pairs(1)
+    got = got_dev.cpu()
+    rows = sorted({0, 1, 127, 128, 255, 256, M // 2 - 1, M // 2, M - 1})
     w = oracle.dequantize_weights(words, scales, biases, 128, 4).float()
     want = (a[rows].float() @ w.T).to(BF16)
     scale_ref = float(want.float().abs().max()) + 1e-6
     torch.testing.assert_close(got[rows].float(), want.float(), rtol=2 * 2.0**-8, atol=2e-3 * scale_ref)
+    assert torch.equal(got_dev, other)
 
 
 def test_reference_acceptance_shape_matvec_1x2560_to_1024(dev):

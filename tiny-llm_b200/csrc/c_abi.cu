@@ -364,6 +364,11 @@ extern "C" int tl_debug_trace(unsigned long long *device_events, unsigned int *d
 }
 #endif
 
+int tl_set_gemm_pairs(int mode) {
+    set_gemm_pairs(mode);
+    return TL_OK;
+}
+
 int tl_set_pdl(int enabled) {
     set_use_pdl(enabled != 0);
     return TL_OK;

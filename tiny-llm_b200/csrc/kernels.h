@@ -56,6 +56,7 @@ int launch_w4a16_vanilla(const void *scales, const void *biases, const void *a, 
 
 // w4a16_gemm2.cu (CTA pairs, tcgen05 cta_group::2: M > 256)
 bool w4a16_gemm2_supported(int M, int N, int K, int dtype);
+void set_gemm_pairs(int mode);  // 0 never, 1 where the pair grid fills the SMs (default), 2 every M > 256
 int launch_w4a16_gemm2(const void *scales, const void *biases, const void *a, const void *b, void *out, int M, int N, int K, int dtype,
                        cudaStream_t st);
 

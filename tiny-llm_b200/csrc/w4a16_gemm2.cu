@@ -326,9 +326,25 @@ void trace_bind_gemm2(unsigned long long *buf, unsigned int *n, unsigned int cap
 #endif
 
 // ---------------------------------------------------------------- host side --
+// Mode: 0 = never, 1 = where the pair grid fills the SMs (default), 2 = every M > 256 (tests, A/B runs).  TL_GEMM2 sets
+// the initial value, tl_set_gemm_pairs() changes it.
+static int pairs_default() {
+    const char *e = getenv("TL_GEMM2");
+    return e == nullptr ? 1 : atoi(e);
+}
+static int g_pairs_mode = pairs_default();
+void set_gemm_pairs(int mode) { g_pairs_mode = mode; }
+
+// Measured at M = 4096 (profiles/r02_gemm_bench.json): the pair kernel and the one-CTA kernel are within 2 % of each
+// other per CTA-second; what decides is the tail - a pair tile is 512 tokens x 256 features, so K = 2560 gives 160 CTAs
+// (1.08 waves of 148: 683 / 743 TF/s on o / down against 766 / 869), while q|k|v (384 CTAs) and gate|up (1216) fill
+// their last wave to > 85 % (896 / 965 TF/s against 891 / 950).
 bool w4a16_gemm2_supported(int M, int N, int K, int dtype) {
-    static const bool off = [] { const char *e = getenv("TL_GEMM2"); return e != nullptr && e[0] == '0'; }();
-    return !off && (dtype == TL_BF16 || dtype == TL_F16) && M > 256 && K > 0 && N % 128 == 0;
+    if (g_pairs_mode <= 0 || !(dtype == TL_BF16 || dtype == TL_F16) || M <= 256 || K <= 0 || N % 128 != 0) return false;
+    if (g_pairs_mode >= 2) return true;
+    const long long ctas = 2LL * ceil_div(K, 256) * ceil_div(M, P_MT * 256);
+    const long long waves = (ctas + sm_count() - 1) / sm_count();
+    return M >= 1024 && ctas * 100 >= waves * sm_count() * 85;
 }
 
 template <typename T>

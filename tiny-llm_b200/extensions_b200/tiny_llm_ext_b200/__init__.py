@@ -43,6 +43,7 @@ __all__ = [
     "decode_qk_norm_rope_append",
     "chunk_qk_norm_rope_append",
     "set_pdl",
+    "set_gemm_pairs",
     "launch_count",
     "device_info",
     "current_library_path",
@@ -89,6 +90,7 @@ _SIGNATURES = {
     "tl_decode_attention_fused": (_I, [_VP] * 11 + [_I] * 4 + [_F, _F] + [_I] * 5 + [_VP]),
     "tl_paged_cache_append_chunk": (_I, [_VP] * 5 + [_I] * 4 + [ctypes.c_longlong, ctypes.c_longlong, _I, _VP]),
     "tl_set_pdl": (_I, [_I]),
+    "tl_set_gemm_pairs": (_I, [_I]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -707,6 +709,11 @@ def decode_attention_fused(qkv, q_norm_weight, k_norm_weight, offsets, block_tab
 def set_pdl(enabled: bool) -> None:
     """Programmatic dependent launch for the weight-streaming kernels."""
     _check(_lib.tl_set_pdl(int(bool(enabled))))
+
+
+def set_gemm_pairs(mode: int) -> None:
+    """Prefill GEMM on CTA pairs: 0 never, 1 where the pair grid fills the SMs (default), 2 every M > 256."""
+    _check(_lib.tl_set_gemm_pairs(int(mode)))
 
 
 def launch_count() -> int:
