@@ -268,7 +268,7 @@ def run_decode(args) -> None:
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = run_cpu_baseline(sample_steps=5)
+        cpu_baseline = run_cpu_baseline(sample_steps=9, warmup_steps=3)
 
     if rank == 0:
         stream_bytes = weight_stream_bytes(margs)
@@ -719,7 +719,26 @@ def run_cpu_baseline(sample_steps: int, warmup_steps: int = 1, mode: str = "deco
     synthetic = _load_standalone("_bench_synthetic", ROOT / "tiny-llm_b200" / "tiny_llm_b200" / "synthetic.py")
     cores = os.cpu_count() or 1
     threads = min(32, cores)
+    # Pin the process to `threads` cores BEFORE the first parallel CPU op creates torch's worker pool (the workers
+    # inherit the mask): on a 128-thread host the unpinned run swung 3x between two launches on the same box (22 vs
+    # 69 ms per step: workers migrating across NUMA nodes away from the first-touched weights).
+    allowed = None
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, set(allowed[:threads]))
+    except (AttributeError, OSError):
+        allowed = None
     torch.set_num_threads(threads)
+    try:
+        return _cpu_baseline_pinned(sample_steps, warmup_steps, mode, synthetic, cores, threads)
+    finally:
+        if allowed is not None:
+            os.sched_setaffinity(0, set(allowed))  # the calling thread only; the CPU workers keep their cores
+
+
+def _cpu_baseline_pinned(sample_steps, warmup_steps, mode, synthetic, cores, threads) -> dict:
+    from oracle.model import ReferenceCpuModel, greedy_decode
+
     full = synthetic.CONFIGS[MODEL]
     ns = synthetic.synthetic_qwen3(MODEL, seed=0, device="cpu", num_hidden_layers=CPU_SAMPLE_LAYERS)
     model = ReferenceCpuModel(ns)
@@ -746,15 +765,16 @@ def run_cpu_baseline(sample_steps: int, warmup_steps: int = 1, mode: str = "deco
     prompt = synthetic_prompt(1000, 8, model.args.vocab_size)
     timings = {}
     greedy_decode(model, prompt, 1 + warmup_steps + sample_steps, timings=timings)
-    per_step = timings["decode_s"][warmup_steps:]
+    per_step = sorted(timings["decode_s"][warmup_steps:])
     scale = (full["num_hidden_layers"] * layer_w + head_w) / (CPU_SAMPLE_LAYERS * layer_w + head_w)
     sample_s = statistics.median(per_step)
-    spread = (max(per_step) - min(per_step)) / sample_s if sample_s else 0.0
+    q1, q3 = per_step[len(per_step) // 4], per_step[(3 * len(per_step)) // 4]
+    spread = (q3 - q1) / sample_s if sample_s else 0.0  # interquartile range over the median
     value = 1.0 / (sample_s * scale)
     return {"value": round(value, 4), "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "port",
             "sample": (f"oracle.model (reference CPU path: dense bf16 weights, readable ops), {CPU_SAMPLE_LAYERS} of "
                        f"{full['num_hidden_layers']} Qwen3-4B blocks + tied head, 8-token prompt, median of {len(per_step)} decode steps "
-                       f"({1e3 * sample_s:.0f} ms each, spread {100 * spread:.0f} %), {threads} threads, scaled x{scale:.2f} by weight bytes to the full depth"),
+                       f"({1e3 * sample_s:.0f} ms each, interquartile spread {100 * spread:.0f} %), {threads} pinned threads, scaled x{scale:.2f} by weight bytes to the full depth"),
             "ms_per_step": round(1e3 * sample_s * scale, 1), "spread": round(spread, 3)}
 
 
@@ -765,8 +785,8 @@ def run_reference(args) -> None:
     steps = args.steps
     workload = args.workload
     mode = "prefill" if workload == "prefill" else "decode"
-    sample = min(max(steps, 1), 6) if mode == "decode" else 2
-    base = run_cpu_baseline(sample_steps=sample, warmup_steps=1, mode=mode)
+    sample = min(max(steps, 9), 16) if mode == "decode" else 2  # a CPU decode step is 20-70 ms: 9-16 samples stay well under a second
+    base = run_cpu_baseline(sample_steps=sample, warmup_steps=3, mode=mode)
     line = {
         "impl": "reference",
         "metric": METRICS[workload],
@@ -774,7 +794,7 @@ def run_reference(args) -> None:
         "unit": UNIT,
         "n_gpus": args.gpus,
         "steps": sample,
-        "warmup": 1,
+        "warmup": 3,
         "ms_per_step": base["ms_per_step"],
         "higher_is_better": True,
         "scaling": "weak",

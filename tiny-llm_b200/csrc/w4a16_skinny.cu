@@ -53,17 +53,21 @@ enum { SK_EPI_NONE = 0, SK_EPI_RESIDUAL = 1, SK_EPI_SWIGLU_PAIRS = 2 };
 // Shared memory: activation ring (BSTAGES group blocks of two [NT x 64] tiles) + packed-weight ring (PSTAGES boxes) +
 // barriers.  Tensor memory: D[feature, token] in the first D_COLS columns, then ASTAGES dequantised tiles of 64
 // columns (128 reduction elements as bf16 pairs, lane = feature row).
-template <int NT>
+// WIDE1 (NT = 128 only): the one-CTA-per-SM geometry of 128 token columns (deeper rings, six tile stages in all 512
+// TMEM columns); the default packs two CTAs per SM there too (two activation stages, two tile stages): the dequantiser
+// throughput of an SM is what bounds this kernel, and one CTA has half the warps.
+template <int NT, bool WIDE1 = false>
 struct SkSmem {
     static constexpr int B_BYTES = NT * SK_KB * 2;                 // one [NT x 64] activation tile
-    static constexpr int BSTAGES = NT >= 64 ? 3 : 4;               // group blocks in flight: an L2 round trip (~1 us) at ~0.3 us per block
-    static constexpr int PSTAGES = NT >= 128 ? 4 : 3;              // packed boxes in flight (two group blocks each)
+    static constexpr int BSTAGES = NT >= 128 ? (WIDE1 ? 3 : 2) : (NT >= 64 ? 3 : 4);  // group blocks in flight (L2 round trip ~1 us)
+    static constexpr int PSTAGES = NT >= 128 && WIDE1 ? 4 : 3;     // packed boxes in flight (two group blocks each)
     static constexpr int B_OFF = 0;
     static constexpr int P_OFF = B_OFF + BSTAGES * 2 * B_BYTES;
     static constexpr int BAR_OFF = P_OFF + PSTAGES * SK_PACKED_BYTES;
     static constexpr int BYTES = BAR_OFF + 512;
     static constexpr int D_COLS = NT < 32 ? 32 : NT;               // accumulator columns (fp32)
-    static constexpr int TMEM_COLS = NT >= 128 ? 512 : 256;        // NT <= 64: two CTAs per SM share the 512 columns
+    static constexpr int TMEM_COLS = NT >= 128 && WIDE1 ? 512 : 256;  // two CTAs per SM share the 512 columns
+    static constexpr int CTAS_PER_SM = NT >= 128 && WIDE1 ? 1 : 2;
     static constexpr int ASTAGES = (TMEM_COLS - D_COLS) / 64;      // 3 (NT <= 64) or 6 (NT = 128)
     static_assert(BYTES <= 227 * 1024 && ASTAGES >= 2, "budget");
 };
@@ -98,10 +102,10 @@ __host__ __device__ constexpr uint32_t sk_instr_desc() {
            (static_cast<uint32_t>(SK_FEAT >> 4) << 24);
 }
 
-template <typename T, int NT>
-__global__ void __launch_bounds__(SK_THREADS, NT >= 128 ? 1 : 2)
+template <typename T, int NT, bool WIDE1>
+__global__ void __launch_bounds__(SK_THREADS, SkSmem<NT, WIDE1>::CTAS_PER_SM)
 w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const SkArgs args) {
-    using Smem = SkSmem<NT>;
+    using Smem = SkSmem<NT, WIDE1>;
     constexpr int ASTAGES = Smem::ASTAGES;
     constexpr int PSTAGES = Smem::PSTAGES;
     constexpr int BSTAGES = Smem::BSTAGES;
@@ -521,9 +525,13 @@ bool w4a16_skinny_supported(int M, int N, int K, int dtype) {
 
 // Split policy (ours; the reference's constants are M4-Pro tuning, quantized_matmul.cpp:138-150): the split count that
 // minimises waves x (group blocks per CTA + fixed cost) + reduce launch, with `slots` CTAs resident at once (two per
-// SM up to 64 token columns, one for 128), a fixed cost per CTA worth ~10 group blocks (TMEM allocation, first TMA
+// SM), a fixed cost per CTA worth ~10 group blocks (TMEM allocation, first TMA
 // round trips, epilogue: ~3 us against ~0.3 us per 128-wide block) and ~8 for the extra reduce launch.
-static int skinny_slots(int M) { return (M <= 64 ? 2 : 1) * sm_count(); }
+static bool skinny_wide1() {  // TL_SKINNY_WIDE1=1: one CTA per SM at 65..128 rows (A/B runs)
+    static const bool on = [] { const char *e = getenv("TL_SKINNY_WIDE1"); return e != nullptr && e[0] == '1'; }();
+    return on;
+}
+static int skinny_slots(int M) { return (M <= 64 || !skinny_wide1() ? 2 : 1) * sm_count(); }
 int w4a16_skinny_splits(int M, int N, int K) {
     const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
     const int num_gb = N / SK_GB;
@@ -590,17 +598,17 @@ static int sk_cached_map(CUtensorMap *out, const void *ptr, int kind, cuuint64_t
     return TL_OK;
 }
 
-template <typename T, int NT>
+template <typename T, int NT, bool WIDE1 = false>
 static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkArgs &args, int grid, cudaStream_t st) {
-    constexpr size_t smem = SkSmem<NT>::BYTES;
+    constexpr size_t smem = SkSmem<NT, WIDE1>::BYTES;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
-            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        if (cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, WIDE1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(w4a16_skinny_kernel<T, NT, WIDE1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             return fail(TL_ECUDA, "quantized_matmul: cannot raise shared memory limit");
         configured = true;
     }
-    cudaError_t e = launch_chained(w4a16_skinny_kernel<T, NT>, dim3(grid), dim3(SK_THREADS), smem, st, ma, mw, args);
+    cudaError_t e = launch_chained(w4a16_skinny_kernel<T, NT, WIDE1>, dim3(grid), dim3(SK_THREADS), smem, st, ma, mw, args);
     if (e != cudaSuccess) return fail(TL_ECUDA, "w4a16_skinny: launch failed: %s", cudaGetErrorString(e));
     TL_LAUNCH_CHECK("w4a16_skinny");
     return TL_OK;
@@ -631,7 +639,7 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
         case 16: rc = skinny_launch<T, 16>(ma, mw, args, grid, st); break;
         case 32: rc = skinny_launch<T, 32>(ma, mw, args, grid, st); break;
         case 64: rc = skinny_launch<T, 64>(ma, mw, args, grid, st); break;
-        default: rc = skinny_launch<T, 128>(ma, mw, args, grid, st); break;
+        default: rc = skinny_wide1() ? skinny_launch<T, 128, true>(ma, mw, args, grid, st) : skinny_launch<T, 128>(ma, mw, args, grid, st); break;
     }
     if (rc != TL_OK || args.splits == 1) return rc;
     if (normed != nullptr && epilogue == SK_EPI_RESIDUAL && K <= 256 * SK_NORM_PER) {
