@@ -767,14 +767,18 @@ def _cpu_baseline_pinned(sample_steps, warmup_steps, mode, synthetic, cores, thr
     greedy_decode(model, prompt, 1 + warmup_steps + sample_steps, timings=timings)
     per_step = sorted(timings["decode_s"][warmup_steps:])
     scale = (full["num_hidden_layers"] * layer_w + head_w) / (CPU_SAMPLE_LAYERS * layer_w + head_w)
-    sample_s = statistics.median(per_step)
+    # Best of N: the GPU boxes' hosts are shared and a CPU decode step (a 2.4 GB GEMV sweep) swings 2-3x from step to
+    # step inside one run (median 20-25 ms, interquartile range > 2x the median on two consecutive runs); the fastest
+    # step is the reproducible one, and it is the most favourable figure for the CPU path.
+    median_s = statistics.median(per_step)
+    sample_s = per_step[0]
     q1, q3 = per_step[len(per_step) // 4], per_step[(3 * len(per_step)) // 4]
-    spread = (q3 - q1) / sample_s if sample_s else 0.0  # interquartile range over the median
+    spread = (q3 - q1) / median_s if median_s else 0.0  # interquartile range over the median
     value = 1.0 / (sample_s * scale)
     return {"value": round(value, 4), "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "port",
             "sample": (f"oracle.model (reference CPU path: dense bf16 weights, readable ops), {CPU_SAMPLE_LAYERS} of "
-                       f"{full['num_hidden_layers']} Qwen3-4B blocks + tied head, 8-token prompt, median of {len(per_step)} decode steps "
-                       f"({1e3 * sample_s:.0f} ms each, interquartile spread {100 * spread:.0f} %), {threads} pinned threads, scaled x{scale:.2f} by weight bytes to the full depth"),
+                       f"{full['num_hidden_layers']} Qwen3-4B blocks + tied head, 8-token prompt, best of {len(per_step)} decode steps "
+                       f"({1e3 * sample_s:.1f} ms; median {1e3 * median_s:.0f} ms, interquartile spread {100 * spread:.0f} %: shared host), {threads} pinned threads, scaled x{scale:.2f} by weight bytes to the full depth"),
             "ms_per_step": round(1e3 * sample_s * scale, 1), "spread": round(spread, 3)}
 
 
