@@ -115,6 +115,12 @@ int tl_paged_attention(const void *q, const void *key_pages, const void *value_p
                        const int32_t *context_lens, void *out, int rows, int L, int D, int num_pages,
                        int page_size, int max_pages, float scale, int is_causal, int num_kv_heads, int num_heads,
                        int dtype, void *workspace, size_t workspace_bytes, void *stream);
+/* The prefill form with the output written token-major: out [B, L, Hq * D] (the layout the o-projection takes; saves
+ * the transpose copy of a chunked-prefill step).  bf16, D == 128, pages a multiple of 64 slots (the tcgen05 kernel);
+ * TL_EINVAL otherwise - callers then use tl_paged_attention and transpose. */
+int tl_paged_attention_token_major(const void *q, const void *key_pages, const void *value_pages, const int32_t *block_table,
+                                   const int32_t *context_lens, void *out, int rows, int L, int num_pages, int page_size, int max_pages,
+                                   float scale, int is_causal, int num_kv_heads, int num_heads, void *stream);
 
 /* ---- B200 extensions behind the same per-op semantics ---------------------
  * Device-driven K/V append for a decode batch (the batched form of

@@ -110,6 +110,23 @@ def test_paged_decode_attention_at_serving_sizes_matches_oracle(dev, B, S):
         torch.testing.assert_close(got[b * Hq : (b + 1) * Hq].float(), want.float(), rtol=2e-2, atol=5e-3, msg=lambda m: f"request {b}: {m}")
 
 
+@pytest.mark.parametrize("B,L,ctx,Hq,Hkv,page", [(1, 128, 640, 32, 8, 128), (2, 100, 300, 16, 8, 64), (1, 40, 40, 8, 8, 128), (1, 4, 200, 32, 8, 128)])
+def test_token_major_prefill_attention_is_the_transposed_head_major_result(dev, B, L, ctx, Hq, Hkv, page):
+    """The chunked-prefill engine asks the tcgen05 kernel for [B * L, Hq * D] directly (the o-projection's layout):
+    bit-identical to paged_attention + transpose; shapes the kernel does not take (here L = 4) fall back to exactly that."""
+    g, D = gen(B * 1000 + L + ctx), 128
+    pages = -(-ctx // page)
+    kp = torch.randn(B * pages, Hkv, page, D, generator=g).to(BF16).to(dev)
+    vp = torch.randn(B * pages, Hkv, page, D, generator=g).to(BF16).to(dev)
+    q = torch.randn(B * Hq, L, D, generator=g).to(BF16).to(dev)
+    bt = torch.randperm(B * pages, generator=g).reshape(B, pages).to(torch.int32).to(dev)
+    cl = torch.tensor([ctx - 7 * b for b in range(B)], dtype=torch.int32).to(dev)
+    want = ext.paged_attention(q, kp, vp, bt, cl, D**-0.5, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
+    got = ext.paged_attention_token_major(q, kp, vp, bt, cl, D**-0.5, True, Hkv, Hq)
+    assert got.shape == (B * L, Hq * D)
+    assert torch.equal(got, want.view(B, Hq, L, D).transpose(1, 2).reshape(B * L, Hq * D))
+
+
 # ------------------------------------------------------------------ GEMM at the config-3 shapes --
 @pytest.mark.parametrize("pairs", [0, 2], ids=["one-cta", "cta-pairs"])
 @pytest.mark.parametrize("shape", [(4096, 9728, 2560), (4096, 2560, 19456 // 2), (4096, 4096, 2560), (1000, 256, 392)],

@@ -94,6 +94,7 @@ struct TcArgs {
     // split-KV (decode, L <= 8): CTA (query block, split) covers key tiles [split * tiles_per_split, ...) and
     // leaves an unnormalised partial (O fp32, running max in log2 units, sum) for paged_gqa_merge_kernel
     int splits, tiles_per_split;
+    int out_token_major;  // unsplit launches only: out[(b, l, head), :] instead of [(b, head, l), :] (the layout the o-projection takes)
     float *ws_o, *ws_m, *ws_l;
 };
 
@@ -361,7 +362,7 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             }
         } else {
         const float inv = (l_sum == 0.f || !row_valid) ? 0.f : 1.0f / l_sum;
-        bf16 *dst = a.out + out_row * TC_D;
+        bf16 *dst = a.out + (a.out_token_major ? (static_cast<size_t>(b) * a.L + l) * a.Hq + (kvh * a.G + g) : out_row) * TC_D;
 #pragma unroll
         for (int cb = 0; cb < TC_D / 32; ++cb) {
             uint32_t ov[32];
@@ -453,7 +454,7 @@ bool paged_prefill_tc_supported(int L, int num_pages, int page_size, int num_kv_
 // partials are combined by paged_gqa_merge_kernel.
 int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out, int rows,
                             int L, int num_pages, int page_size, int max_pages, float scale, int is_causal, int num_kv_heads,
-                            int num_heads, bool allow_split, void *ws, size_t ws_bytes, cudaStream_t st) {
+                            int num_heads, bool allow_split, void *ws, size_t ws_bytes, cudaStream_t st, bool out_token_major) {
     const int G = num_heads / num_kv_heads;
     const int B = rows / num_heads;
     TcArgs a{};
@@ -484,12 +485,13 @@ int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const
     }
     const int q_blocks = (L + a.RH - 1) / a.RH;
     const long long max_tiles = (static_cast<long long>(max_pages) * page_size + TC_BN - 1) / TC_BN;
+    a.out_token_major = out_token_major ? 1 : 0;
     a.splits = 1;
     a.tiles_per_split = static_cast<int>(max_tiles < 1 ? 1 : max_tiles);
-    if (allow_split && ws != nullptr) {
+    if (allow_split && ws != nullptr && !out_token_major) {
         // Split count: the one that minimises waves x (tiles per CTA + fixed cost) + merge launch, in units of one 64-key
-        // tile (~1.45 us of HBM time at a 1/296 share), with 296 CTA slots, ~2 tiles of fixed cost per CTA (set-up, Q load,
-        // epilogue) and ~2 for the merge launch.  (The first policy aimed at 4 x #SMs CTAs: at 64 requests x 1024 tokens
+        // tile (~1.45 us of HBM time at a 1/296 share), with 296 CTA slots, ~3 tiles of fixed cost per CTA (set-up, Q load,
+        // epilogue) and 2 + splits / 4 for the merge launch (it reads one partial per split and row).  (The first policy aimed at 4 x #SMs CTAs: at 64 requests x 1024 tokens
         // that is 1024 CTAs in 3.5 -> 4 waves plus a merge, 60 us, where 512 unsplit CTAs need 2 waves.)
         const long long base = static_cast<long long>(q_blocks) * num_kv_heads * B;
         const long long slots = 2LL * sm_count();
@@ -501,7 +503,7 @@ int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const
             if (real != sp) continue;
             if (sp > 1 && ws_bytes < rows_total * sp * (TC_D + 2) * sizeof(float)) break;
             const long long waves = (base * sp + slots - 1) / slots;
-            const long long cost = waves * (tps + 2) + (sp > 1 ? 2 : 0);
+            const long long cost = 4 * waves * (tps + 3) + (sp > 1 ? 8 + sp : 0);  // x 4: quarter-tile units
             if (best_cost < 0 || cost < best_cost) best_cost = cost, best = sp;
         }
         if (best > 1) {

@@ -245,6 +245,21 @@ int tl_paged_attention(const void *q, const void *key_pages, const void *value_p
                                 page_size, max_pages, scale, is_causal, num_kv_heads, num_heads, dtype, st);
 }
 
+int tl_paged_attention_token_major(const void *q, const void *key_pages, const void *value_pages, const int32_t *block_table,
+                                   const int32_t *context_lens, void *out, int rows, int L, int num_pages, int page_size, int max_pages,
+                                   float scale, int is_causal, int num_kv_heads, int num_heads, void *stream) {
+    if (num_heads <= 0 || num_kv_heads <= 0 || num_heads % num_kv_heads != 0 || rows < 0 || rows % num_heads != 0 || L < 0 || num_pages <= 0 ||
+        page_size <= 0 || max_pages <= 0)
+        return fail(TL_EINVAL, "paged_attention_token_major: bad shape");
+    if (static_cast<long long>(rows) * L == 0) return TL_OK;
+    if (!q || !key_pages || !value_pages || !block_table || !context_lens || !out) return fail(TL_EINVAL, "paged_attention: null pointer");
+    if (!paged_prefill_tc_supported(L, num_pages, page_size, num_kv_heads, num_heads) || !aligned16(q) || !aligned16(out) || !aligned16(key_pages) ||
+        !aligned16(value_pages))
+        return fail(TL_EINVAL, "paged_attention_token_major: needs the tcgen05 kernel (bf16, D = 128, pages a multiple of 64 slots)");
+    return launch_paged_prefill_tc(q, key_pages, value_pages, block_table, context_lens, out, rows, L, num_pages, page_size, max_pages, scale,
+                                   is_causal, num_kv_heads, num_heads, false, nullptr, 0, as_stream(stream), true);
+}
+
 // ------------------------------------------------------------------ misc --
 size_t tl_argmax_workspace(int rows, int vocab) { return argmax_workspace(rows, vocab); }
 

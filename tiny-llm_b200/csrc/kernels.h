@@ -106,7 +106,7 @@ int launch_paged_decode(const void *q, const void *kp, const void *vp, const int
 bool paged_prefill_tc_supported(int L, int num_pages, int page_size, int num_kv_heads, int num_heads);
 int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const int32_t *bt, const int32_t *cl, void *out, int rows,
                             int L, int num_pages, int page_size, int max_pages, float scale, int is_causal, int num_kv_heads,
-                            int num_heads, bool allow_split, void *ws, size_t ws_bytes, cudaStream_t st);
+                            int num_heads, bool allow_split, void *ws, size_t ws_bytes, cudaStream_t st, bool out_token_major = false);
 int launch_paged_gqa_merge(const float *ws_o, const float *ws_m, const float *ws_l, void *out, int rows_total, int splits, cudaStream_t st);
 
 // attention_prefill.cu (mma.sync flash prefill: fallback for page sizes / head ratios the tcgen05 kernel does not take)

@@ -48,6 +48,7 @@ __all__ = [
     "device_info",
     "current_library_path",
     "quantized_matmul_residual_norm",
+    "paged_attention_token_major",
 ]
 
 _HERE = Path(__file__).resolve().parent
@@ -81,6 +82,7 @@ _SIGNATURES = {
     "tl_argmax_workspace": (_SZ, [_I, _I]),
     "tl_argmax": (_I, [_VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "tl_decode_advance": (_I, [_VP] * 6 + [_I, _I, _VP]),
+    "tl_paged_attention_token_major": (_I, [_VP] * 6 + [_I] * 5 + [_F] + [_I] * 3 + [_VP]),
     "tl_quantized_matmul_fused_workspace": (_SZ, [_I] * 6),
     "tl_quantized_matmul_fused": (_I, [_VP] * 7 + [_I] * 6 + [_F, _I, _VP, _SZ, _VP]),
     "tl_quantized_matmul_residual_norm": (_I, [_VP] * 8 + [_I] * 3 + [_F, _I, _VP, _SZ, _VP]),
@@ -566,6 +568,29 @@ def quantized_matmul_fused(scales, biases, b, p0, p1=None, residual=None, prolog
         )
     )
     return out
+
+
+def paged_attention_token_major(query, key_pages, value_pages, block_table, context_lens, scale, is_causal, num_kv_heads, num_heads, stream=None):
+    """Prefill attention (L > 8) with the output already in the o-projection's layout: ``query`` [B * Hq, L, D] ->
+    ``[B * L, Hq * D]``.  Only on the tcgen05 kernel (bf16, D = 128, page size a multiple of 64); otherwise - and for
+    L <= 8 - ``paged_attention`` + a transpose copy."""
+    rows, L, D = query.shape
+    B = rows // num_heads
+    P, Hkv, page_size, _ = key_pages.shape
+    fast = (L > 8 and query.dtype == torch.bfloat16 and D == 128 and page_size % 64 == 0 and 128 % (num_heads // num_kv_heads) == 0
+            and query.is_contiguous() and block_table.shape[0] == B and Hkv == num_kv_heads)
+    if fast:
+        _gpu("paged_attention", query, key_pages, value_pages, block_table, context_lens)
+        out = torch.empty((B * L, num_heads * D), dtype=query.dtype, device=query.device)
+        rc = _lib.tl_paged_attention_token_major(
+            query.data_ptr(), key_pages.data_ptr(), value_pages.data_ptr(), block_table.data_ptr(), context_lens.data_ptr(), out.data_ptr(),
+            rows, L, P, page_size, block_table.shape[1], float(scale), int(bool(is_causal)), int(num_kv_heads), int(num_heads),
+            _stream_ptr(stream, query))
+        if rc == 0:
+            return out
+    y = paged_attention(query, key_pages, value_pages, block_table, context_lens, scale, is_causal=is_causal, num_kv_heads=num_kv_heads,
+                        num_heads=num_heads, stream=stream)
+    return y.view(B, num_heads, L, D).transpose(1, 2).reshape(B * L, num_heads * D)
 
 
 def quantized_matmul_residual_norm(scales, biases, b, p0, residual, norm_weight, norm_eps, stream=None):

@@ -602,9 +602,9 @@ class PrefillEngine:
             q = ext.chunk_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
                                               self.offsets, self.tables[i], self.ctxs, pool._key_pages, pool._value_pages,
                                               Hq, Hkv, at.rope.base, at.q_norm.eps)  # [Hq, L, D]
-            y = ext.paged_attention(q, pool._key_pages, pool._value_pages, self.tables[i:i + 1], self.ctx_after, at.scale,
-                                    is_causal=True, num_kv_heads=Hkv, num_heads=Hq)  # [Hq, L, D]
-            y = y.transpose(0, 1).reshape(L, Hq * D)  # one 2-byte-per-element copy per layer
+            # [L, Hq * D]: the tcgen05 kernel writes the o-projection's layout itself (else: attention + one transpose copy)
+            y = ext.paged_attention_token_major(q, pool._key_pages, pool._value_pages, self.tables[i:i + 1], self.ctx_after, at.scale,
+                                                True, Hkv, Hq)
             if skinny:  # the residual projections return the next RMSNorm's output too (DecodeEngine._forward_fused_layers)
                 ln2, wd = block.post_attention_layernorm, block.mlp.w_down
                 x, h = ext.quantized_matmul_residual_norm(at.wo.scales, at.wo.biases, at.wo.weight, y, x, ln2._weight_as(x.dtype, x.device), ln2.eps)
