@@ -618,8 +618,10 @@ def run_serve(args, long_context: bool) -> None:
     model.decode_graph_max_seq_len = ((max_seq + PAGE_SIZE - 1) // PAGE_SIZE) * PAGE_SIZE
     model.prefill_graph_len = int(os.environ.get("TL_PREFILL_GRAPH", str(prefill_step)))  # captured chunk graph (0: operator path)
 
-    def serve(reqs, timing=True):
-        batcher = ContinuousBatcher(model, None, [p for p, _ in reqs], max_seq_len=max_seq, batch_size=slots, prefill_step=prefill_step,
+    def serve(reqs, timing=True, step=None):
+        step = step or prefill_step
+        model.prefill_graph_len = int(os.environ.get("TL_PREFILL_GRAPH", str(step)))
+        batcher = ContinuousBatcher(model, None, [p for p, _ in reqs], max_seq_len=max_seq, batch_size=slots, prefill_step=step,
                                     verbose=False, device=device, max_new_tokens=[n for _, n in reqs])
         batcher.record_timing = timing
         t0 = time.perf_counter()
@@ -663,6 +665,16 @@ def run_serve(args, long_context: bool) -> None:
         "peak_active_requests": batcher.peak_active_requests, "peak_live_pages": batcher.peak_live_pages,
         "peak_live_kv_gb": round(batcher.peak_live_pages * 2 * margs.num_key_value_heads * PAGE_SIZE * margs.head_dim * 2 / 1e9, 2),
     }
+    # config 4 only: the same queue with larger prefill chunks (the chunk size is the scheduler's knob; 128 is the
+    # reference protocol's default and stays the headline)
+    sweep = []
+    if not long_context and world == 1 and not args.no_extra and not args.prefill_step:
+        for step in (256, 512):
+            serve([(p[: min(len(p), 2 * step)], 4) for p, _ in mine[: min(len(mine), slots + 2)]], timing=False, step=step)
+            b2, w2 = serve(mine, step=step)
+            ms2 = b2.gpu_phase_ms()
+            sweep.append({"prefill_step": step, "output_tok_s": round(sum(b2.generated.values()) / w2, 1), "wall_s": round(w2, 3),
+                          "time_in_prefill_s": round(sum(ms2["prefill"]) / 1e3, 3), "time_in_decode_s": round(sum(ms2["decode"]) / 1e3, 3)})
     if rank == 0:
         peak = measured_peaks()
         # decode-step roofline: weights once + every live request's K/V once per step (median step)
@@ -680,6 +692,7 @@ def run_serve(args, long_context: bool) -> None:
                     "note": "the serving loop IS the public API: tokens go host -> device and sampled ids device -> host every step"},
             "gpu_launches": int(gpu_launches), "clocks": clocks,
             "serving": mine_stats, "prefill_tok_s_all_ranks": round(total_prefill / wall_max, 1),
+            "extra": {"prefill_step_sweep": sweep} if sweep else {},
             "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak["hbm_gbs"], "peak_source": peak["source"], "traffic": None,
                          "kernel": "whole decode step at the median live context (weights + live K/V once)",
                          "achieved": None, "frac": None},
