@@ -662,6 +662,9 @@ def run_serve(args, long_context: bool) -> None:
         "time_in_decode_s": round(decode_ms / 1e3, 3), "time_in_prefill_s": round(prefill_ms / 1e3, 3),
         "timing": "per-phase device time from CUDA events on the scheduler's stream; wall_s is host wall-clock of the whole run",
         "prefill_chunk_ms_p50": round(sorted(gpu_ms["prefill"])[len(gpu_ms["prefill"]) // 2], 3) if gpu_ms["prefill"] else None,
+        "prefill_chunk_ms_max": round(max(gpu_ms["prefill"]), 3) if gpu_ms["prefill"] else None,
+        "prefill_chunks": len(gpu_ms["prefill"]), "prefill_chunks_over_2x_p50": (sum(1 for v in gpu_ms["prefill"] if v > 2 * sorted(gpu_ms["prefill"])[len(gpu_ms["prefill"]) // 2]) if gpu_ms["prefill"] else None),
+        "graph_captures": {"decode": getattr(engine, "captures", None), "prefill": sum(getattr(e, "captures", 0) for e in getattr(model, "_prefill_engines", {}).values())},
         "peak_active_requests": batcher.peak_active_requests, "peak_live_pages": batcher.peak_live_pages,
         "peak_live_kv_gb": round(batcher.peak_live_pages * 2 * margs.num_key_value_heads * PAGE_SIZE * margs.head_dim * 2 / 1e9, 2),
     }

@@ -138,6 +138,7 @@ class DecodeEngine:
         self._slab_ptrs = None
         self._stream = torch.cuda.Stream(device=self.device)
         self.graph_replays = 0
+        self.captures = 0  # graph (re-)captures: 1 + one per move of the page slabs
         self.kernels_per_step = 0
         rope = attn.rope
         self.fused = bool(fused) and not rope.traditional and rope.dims == self.D and self.D % 2 == 0
@@ -279,6 +280,7 @@ class DecodeEngine:
                                           prologue=ext.PRO_RMSNORM, eps=m.norm.eps)
 
     def _capture(self) -> None:
+        self.captures += 1
         self._slab_ptrs = self._slabs()
         forward = self._forward_fused if self.fused else self._forward_unfused
         with torch.cuda.stream(self._stream):
@@ -561,6 +563,7 @@ class PrefillEngine:
         self._upload_event = torch.cuda.Event()
         self._upload_pending = False
         self.replays = 0
+        self.captures = 0
         self.kernels_per_chunk = 0
         self._packed = [
             SimpleNamespace(qkv=_concat_weights([b.self_attn.wq, b.self_attn.wk, b.self_attn.wv]),
@@ -626,6 +629,7 @@ class PrefillEngine:
         self.logits.copy_(logits)
 
     def _capture(self) -> None:
+        self.captures += 1
         self._slab_ptrs = self._slabs()
         with torch.cuda.stream(self._stream):
             self._stream.wait_stream(torch.cuda.current_stream(self.device))

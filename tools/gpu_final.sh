@@ -18,7 +18,7 @@ for w in ["decode", "prefill", "serve", "serve8k", "reference"]:
         print(w, "unreadable", e)
 PY
 # launch lists (per-kernel durations; cold-cache, serialised: shares only)
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/final_launches_decode_b1.csv python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline > gpurun_out/final_ll_b1.log 2>&1; tail -1 gpurun_out/final_ll_b1.log | cut -c1-150
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/final_launches_decode_b1.csv python tools/launch_list.py --mode decode --batch 1 --context 128 > gpurun_out/final_ll_b1.log 2>&1; tail -1 gpurun_out/final_ll_b1.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/final_launches_decode_b64.csv python tools/launch_list.py --mode decode --batch 64 --context 1024 > gpurun_out/final_ll_b64.log 2>&1; tail -1 gpurun_out/final_ll_b64.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/final_launches_chunk128.csv python tools/launch_list.py --mode chunk --chunk 128 --context 512 > gpurun_out/final_ll_chunk.log 2>&1; tail -1 gpurun_out/final_ll_chunk.log
 # full captures of the seven kernels (fourth round of tools/ncu_round2.py)
