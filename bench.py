@@ -481,7 +481,7 @@ def gemm_roofline(model, ext, device, margs, tokens: int) -> dict:
     flops = prefill_flops(margs, tokens)["projections"]
     launches = 7 * len(model.layers_inner)
     achieved = flops / (ms / 1e3) / 1e12
-    return {"kernel": "w4a16_gemm_kernel (tcgen05.mma kind::f16, TMEM accumulators, TMA activations, in-kernel W4 dequant)",
+    return {"kernel": "w4a16_gemm_kernel / w4a16_gemm2_kernel (tcgen05.mma kind::f16, the pair form cta_group::2 for q|k|v and gate|up; TMEM accumulators, TMA activations, in-kernel W4 dequant)",
             "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " (sustained)",
             "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops_sustained"], 4), "traffic": None, "launches": launches,
             "avg_launch_us": round(ms * 1e3 / launches, 2), "algorithmic_flops_per_launch": round(flops / launches),

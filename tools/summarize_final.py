@@ -39,7 +39,7 @@ def launches_md() -> None:
     lines = ["# Launch lists of the final tree (ncu `gpu__time_duration.sum`, `--clock-control none`)\n",
              "Serialised and cold-cache: use the SHARES; the step times quoted in DESIGN.md come from CUDA events.\n"]
     traffic = {}
-    for name, title in [("final_launches_decode_b1.csv", "decode, batch 1 (two steps + one warm-up of `bench.py --steps 2 --warmup 1`)"),
+    for name, title in [("final_launches_decode_b1.csv", "decode, batch 1, context 128 (one step; `tools/launch_list.py --mode decode --batch 1 --context 128`)"),
                         ("final_launches_decode_b64.csv", "decode, 64 slots x 1024-token contexts (one step)"),
                         ("final_launches_chunk128.csv", "one 128-token chunked-prefill step at context 512")]:
         path = OUT / name
