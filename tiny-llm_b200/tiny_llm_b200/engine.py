@@ -118,6 +118,7 @@ class DecodeEngine:
         self.meta_np[: 3 * B] = 0
         self.meta_np[3 * B :] = -1
         self.meta_dev = torch.zeros(self._meta_len, dtype=torch.int32, device=self.device)
+        self._meta_dev_head, self._meta_host_head = self.meta_dev[: 3 * B], self.meta_host[: 3 * B]  # the per-step upload
         self.tokens = self.meta_dev[0:B]
         self.offsets = self.meta_dev[B : 2 * B]
         self.context_lens = self.meta_dev[2 * B : 3 * B]
@@ -175,7 +176,7 @@ class DecodeEngine:
             pool.reserve(pages, self.Hkv, self.D, dtype=torch.bfloat16, device=self.device)
 
     def _slabs(self):
-        return tuple((p._key_pages.data_ptr(), p._value_pages.data_ptr(), p.capacity) for p in self.model.page_pools)
+        return tuple(p.slab_version for p in self.model.page_pools)  # changes whenever a pool's slabs are (re)allocated
 
     # ------------------------------------------------------------ graph body --
     def _forward_unfused(self) -> None:
@@ -455,7 +456,7 @@ class DecodeEngine:
             self.h2d_bytes += self._meta_len * 4
             self._tables_dirty = False
         else:  # tokens | offsets | context_lens only: the block tables on the device are current
-            self.meta_dev[: 3 * B].copy_(self.meta_host[: 3 * B], non_blocking=True)
+            self._meta_dev_head.copy_(self._meta_host_head, non_blocking=True)
             self.h2d_bytes += 3 * B * 4
         self._upload_event.record()
         self._upload_pending = True
@@ -479,14 +480,12 @@ class DecodeEngine:
             self.meta_np[0:B] = tok_host
         self.meta_np[B : 2 * B] = offsets
         self.meta_np[2 * B : 3 * B] = ctx
-        cur = torch.cuda.current_stream(self.device)
-        self._stream.wait_stream(cur)
-        with torch.cuda.stream(self._stream):
-            self._upload()
-            if tok_host is None:
-                self.tokens.copy_(tokens.reshape(-1).to(torch.int32), non_blocking=True)
-            self._graph.replay()
-        cur.wait_stream(self._stream)
+        # upload and replay on the CALLER's stream (the side stream is only needed for capture): two stream waits and a
+        # stream-context switch less per step - host time here is serial with the GPU step when the caller reads every token
+        self._upload()
+        if tok_host is None:
+            self.tokens.copy_(tokens.reshape(-1) if tokens.dtype == torch.int32 else tokens.reshape(-1).to(torch.int32), non_blocking=True)
+        self._graph.replay()
         self.graph_replays += 1
         return self.logits.view(B, 1, self.V), self.next_tokens
 
@@ -580,7 +579,7 @@ class PrefillEngine:
                 and 128 % (attn.num_heads // attn.num_kv_heads) == 0)
 
     def _slabs(self):
-        return tuple((p._key_pages.data_ptr(), p._value_pages.data_ptr(), p.capacity) for p in self.model.page_pools)
+        return tuple(p.slab_version for p in self.model.page_pools)  # changes whenever a pool's slabs are (re)allocated
 
     def _forward(self) -> None:
         m, L = self.model, self.L

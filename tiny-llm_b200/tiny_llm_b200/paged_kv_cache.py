@@ -15,6 +15,7 @@ fill-the-tail-then-allocate appends with snapshot/rollback (:271-312),
 
 from __future__ import annotations
 
+import itertools
 from dataclasses import dataclass
 from typing import Optional
 
@@ -22,6 +23,10 @@ import numpy as np
 import torch
 
 from extensions_b200 import tiny_llm_ext_b200
+
+# Every (re)allocation of a pool's K/V slabs takes a fresh number: the graph engines compare 36 integers per step
+# instead of 72 data_ptr() calls to learn whether the addresses baked into their captured graphs are still valid.
+_SLAB_VERSIONS = itertools.count(1)
 
 from .kv_cache import TinyKvCache
 
@@ -57,6 +62,7 @@ class TinyKvPagedPool:
         self.num_allocated_pages = 0
         self.reused_page_allocations = 0
         self.storage_growths = 0
+        self.slab_version = 0  # no slab yet
         self.copied_pages_on_growth = 0
         self.copied_bytes_on_growth = 0
 
@@ -190,6 +196,7 @@ class TinyKvPagedPool:
             new_k[:carried] = old_k
             new_v[:carried] = old_v
         self._key_pages, self._value_pages = new_k, new_v
+        self.slab_version = next(_SLAB_VERSIONS)
 
     def reserve(self, num_pages: int, heads: int, head_dim: int, dtype=torch.bfloat16, device="cuda") -> None:
         """B200 extension: size the slab once (one counted growth) so that page
@@ -201,6 +208,7 @@ class TinyKvPagedPool:
             self._key_pages = torch.zeros((num_pages, heads, self.page_size, head_dim), dtype=dtype, device=device)
             self._value_pages = torch.zeros_like(self._key_pages)
             self.storage_growths += 1
+            self.slab_version = next(_SLAB_VERSIONS)
             return
         shape = (num_pages, heads, self.page_size, head_dim)
         new_k = torch.zeros(shape, dtype=dtype, device=device)
@@ -212,12 +220,14 @@ class TinyKvPagedPool:
         new_k[:live] = self._key_pages[:live]
         new_v[:live] = self._value_pages[:live]
         self._key_pages, self._value_pages = new_k, new_v
+        self.slab_version = next(_SLAB_VERSIONS)
 
     def reset(self) -> None:
         if self.used_page_ids:
             raise ValueError("Cannot reset a page pool with live requests")
         self._key_pages = None
         self._value_pages = None
+        self.slab_version = next(_SLAB_VERSIONS)
         self.free_page_ids.clear()
         self.num_allocated_pages = 0
         self.reused_page_allocations = 0
