@@ -219,6 +219,44 @@ def test_engine_batch_with_idle_slots_matches_cpu_oracle(dev, B):
     assert all(pool.used_page_ids == set() for pool in model.page_pools)
 
 
+def test_row_variant_graphs_give_the_bits_of_the_full_step(dev, monkeypatch):
+    """A 64-slot engine whose occupied slots are a short prefix replays the 16- or 32-row step graph: the logits of
+    the occupied rows must be bit-identical to what the full 64-row graph produces (same kernels, same split counts),
+    and a later step with a high slot occupied must pick the wide graph again."""
+    ns = to_device(synthetic_qwen3("tiny-d128", seed=5, realistic=True, max_position_embeddings=512), dev)
+    B, g = 64, gen(64)
+
+    def run(variants: str, slots):
+        monkeypatch.setenv("TL_ROW_VARIANTS", variants)
+        model = Qwen3ModelWeek3(ns, page_size=16)
+        engine = DecodeEngine(model, B, 128, dev)
+        engine.reserve_pools()
+        tables = [BatchingKvCache(max_active_requests=B, max_seq_len=128) for _ in range(model.num_hidden_layers)]
+        prompts = {b: [3 + (11 * b + j) % 400 for j in range(4 + b % 7)] for b in slots}
+        for b in slots:
+            cache = model.create_kv_cache()
+            model(torch.tensor([prompts[b]], dtype=torch.int32, device=dev), 0, cache, logits_to_keep=1)
+            for layer_cache, table in zip(cache, tables):
+                table.add_request(layer_cache, b)
+        outs = []
+        for step in range(2):
+            tokens = [7 + b + step if b in prompts else 0 for b in range(B)]
+            offsets = [len(prompts[b]) + step if b in prompts else 0 for b in range(B)]
+            logits, _ = engine.step(tokens, offsets, tables)
+            outs.append(logits.clone())
+        for table in tables:
+            for b in slots:
+                table.remove_request(b)
+        return outs, engine
+
+    for slots, want_rows in (([0, 1, 2, 5, 9], 16), ([0, 3, 17, 30], 32), ([2, 40, 63], 64)):
+        narrow, eng = run("1", slots)
+        full, _ = run("0", slots)
+        assert eng.variant_replays[want_rows] == 2 and sum(eng.variant_replays.values()) == 2
+        for a, b in zip(narrow, full):
+            assert torch.equal(a[slots], b[slots])
+
+
 def test_engine_recapture_after_slab_growth_does_not_touch_released_pages(dev):
     """a second, larger engine moves the page slabs; the first engine then re-captures its graph.
     The warm-up passes of that capture must not append through stale metadata into pages that were released

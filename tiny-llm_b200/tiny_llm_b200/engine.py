@@ -168,6 +168,16 @@ class DecodeEngine:
         if self._attention_fused:
             self._rope_inv_freq = ext.rope_inv_freq_table(self.D, attn0.rope.base, self.device)
             self._attn_ws = torch.empty(ext.decode_attention_fused_workspace(self.B, self.Hq, self.Hkv), dtype=torch.float32, device=self.device)
+        # Row variants: the scheduler fills slots from index 0 (batch.py:220-226), so while few requests are live the
+        # occupied slots are a prefix of the table.  A step graph over the first 16 / 32 rows is captured beside the
+        # full one and step() replays the smallest that covers the highest occupied slot: every kernel of the wide
+        # path costs by rows (swap-AB column count, attention CTAs, reduction planes).  All variants stay on the
+        # >= 9-row kernels and the split counts do not depend on the row count, so a row's result is bit-identical
+        # whichever variant computed it.  (Config 4 runs 64 slots with ~20 live: 3.3 -> RESULT_ROWS ms per step.)
+        rows_env = os.environ.get("TL_ROW_VARIANTS", "1")
+        self._variants = sorted({r for r in (16, 32, 64) if r < self.B} | {self.B}) if (self.fused and self.B > 16 and rows_env != "0") else [self.B]
+        self._graphs: dict = {}
+        self.variant_replays = {r: 0 for r in self._variants}
 
     # ------------------------------------------------------------------ pools --
     def reserve_pools(self, pages_per_layer: int | None = None) -> None:
@@ -216,25 +226,28 @@ class DecodeEngine:
             self.logits = torch.empty_like(logits)
         self.logits.copy_(logits)
 
-    def _forward_fused(self) -> None:
+    def _forward_fused(self, rows: int | None = None) -> None:
         """Same step in ~7 launches per layer: norm / SwiGLU / residual folded into
         the streaming projections, q/k norm + RoPE + K/V append in one kernel.
-        Every rounding point of the operator-by-operator sequence is kept."""
+        Every rounding point of the operator-by-operator sequence is kept.
+        ``rows``: only the first ``rows`` slots (a row variant, see __init__)."""
         m = self.model
+        R = self.B if rows is None else rows
         emb = m.embedding.weight
-        x = ext.quantized_embedding(self.tokens, emb.scales, emb.biases, emb.weight, emb.group_size, emb.bits)
-        logits = self._forward_fused_layers(x)
-        self.next_tokens.copy_(ext.argmax(logits))
+        x = ext.quantized_embedding(self.tokens[:R], emb.scales, emb.biases, emb.weight, emb.group_size, emb.bits)
+        logits = self._forward_fused_layers(x, R)
+        self.next_tokens[:R].copy_(ext.argmax(logits))
         if self.logits is None:
-            self.logits = torch.empty_like(logits)
-        self.logits.copy_(logits)
+            self.logits = torch.zeros((self.B, logits.shape[-1]), dtype=logits.dtype, device=logits.device)
+        self.logits[:R].copy_(logits)
 
-    def _forward_fused_layers(self, x):
+    def _forward_fused_layers(self, x, R: int | None = None):
         m = self.model
-        B, Hq, Hkv, D = self.B, self.Hq, self.Hkv, self.D
+        B, Hq, Hkv, D = (self.B if R is None else R), self.Hq, self.Hkv, self.D
+        offsets, context_lens = self.offsets[:B], self.context_lens[:B]
         # More than 8 rows: the projections run on the swap-AB tcgen05 kernel (w4a16_skinny.cu: weights streamed once
         # for all rows), which has no prologue, so RMSNorm is its own (tiny) launch; the rounding points are the same.
-        wide = B > 8
+        wide = self.B > 8
 
         def normed(h, norm):
             return ext.rms_norm(h, norm._weight_as(h.dtype, h.device), norm.eps)
@@ -253,14 +266,14 @@ class DecodeEngine:
                                                  prologue=ext.PRO_RMSNORM, eps=ln1.eps)
             if self._attention_fused:
                 y = ext.decode_attention_fused(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
-                                               self.offsets, self.tables[i], self.context_lens, self._rope_inv_freq,
+                                               offsets, self.tables[i][:B], context_lens, self._rope_inv_freq,
                                                pool._key_pages, pool._value_pages, Hq, Hkv, at.q_norm.eps, at.scale,
                                                self.max_seq_len, workspace=self._attn_ws)
             else:
                 q = ext.decode_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
-                                                   self.offsets, self.tables[i], self.context_lens, pool._key_pages, pool._value_pages,
+                                                   offsets, self.tables[i][:B], context_lens, pool._key_pages, pool._value_pages,
                                                    Hq, Hkv, at.rope.base, at.q_norm.eps)
-                y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i], self.context_lens,
+                y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i][:B], context_lens,
                                         at.scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
             wd = block.mlp.w_down
             if wide:
@@ -307,6 +320,17 @@ class DecodeEngine:
                 ext.decode_advance(self.tokens, self.next_tokens, self.offsets, self.context_lens, self.out_log, self.step_counter)
             # kernels of libtiny_llm_b200.so recorded into one self-advancing step
             self.kernels_per_step = ext.launch_count() - launched
+            self._graphs = {self.B: self._graph}
+            for rows in self._variants:
+                if rows == self.B:
+                    continue
+                for _ in range(2):  # warm-up (metadata still all-idle): the narrower kernels set their attributes lazily
+                    forward(rows)
+                self._stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._stream, pool=self._graph.pool()):
+                    forward(rows)
+                self._graphs[rows] = g
         torch.cuda.current_stream(self.device).wait_stream(self._stream)
 
     def _ensure_graph(self) -> None:
@@ -485,7 +509,15 @@ class DecodeEngine:
         self._upload()
         if tok_host is None:
             self.tokens.copy_(tokens.reshape(-1) if tokens.dtype == torch.int32 else tokens.reshape(-1).to(torch.int32), non_blocking=True)
-        self._graph.replay()
+        rows = B
+        if len(self._variants) > 1:
+            hi = 0
+            for b, rec in enumerate(self._recs):
+                if rec is not None:
+                    hi = b + 1
+            rows = next(r for r in self._variants if r >= hi)
+            self.variant_replays[rows] += 1
+        self._graphs[rows].replay()
         self.graph_replays += 1
         return self.logits.view(B, 1, self.V), self.next_tokens
 
