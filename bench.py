@@ -664,6 +664,7 @@ def run_serve(args, long_context: bool) -> None:
         "prefill_chunk_ms_p50": round(sorted(gpu_ms["prefill"])[len(gpu_ms["prefill"]) // 2], 3) if gpu_ms["prefill"] else None,
         "prefill_chunk_ms_max": round(max(gpu_ms["prefill"]), 3) if gpu_ms["prefill"] else None,
         "prefill_chunks": len(gpu_ms["prefill"]), "prefill_chunks_over_2x_p50": (sum(1 for v in gpu_ms["prefill"] if v > 2 * sorted(gpu_ms["prefill"])[len(gpu_ms["prefill"]) // 2]) if gpu_ms["prefill"] else None),
+        "row_variant_replays": {str(k): v for k, v in getattr(engine, "variant_replays", {}).items()},
         "graph_captures": {"decode": getattr(engine, "captures", None), "prefill": sum(getattr(e, "captures", 0) for e in getattr(model, "_prefill_engines", {}).values())},
         "peak_active_requests": batcher.peak_active_requests, "peak_live_pages": batcher.peak_live_pages,
         "peak_live_kv_gb": round(batcher.peak_live_pages * 2 * margs.num_key_value_heads * PAGE_SIZE * margs.head_dim * 2 / 1e9, 2),

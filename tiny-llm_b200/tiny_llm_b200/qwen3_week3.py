@@ -236,7 +236,7 @@ class Qwen3ModelWeek3:
         self.decode_graph_max_seq_len = 8192
         self._decode_engines: dict = {}
         self._applies_memo = None
-        # B200 runtime: chunked-prefill steps (B == 1, 8 < L <= prefill_graph_len) of CUDA-resident paged requests
+        # B200 runtime: chunked-prefill steps (B == 1, 1 < L <= prefill_graph_len) of CUDA-resident paged requests
         # replay a captured chunk graph too (engine.PrefillEngine).  0 disables; None = automatic (128, the scheduler's
         # default prefill_step) once a decode engine exists, i.e. once the page slabs have been reserved.
         self.prefill_graph_len: int | None = None
@@ -367,7 +367,10 @@ class Qwen3ModelWeek3:
                 return None
             chunk = 128
         L = inputs.shape[1]
-        if not (8 < L <= chunk) or not PrefillEngine.supported(self, inputs.device):
+        # 2 <= L: tail chunks of a few tokens replay the graph too (right-aligned in its rows).  On the operator path they
+        # are ~700 host-bound launches - 20-30 ms each, 6 % of config 4's requests have such a tail, and their cost
+        # swung the serving number by +-10 % with the load of the (shared) host.
+        if not (1 < L <= chunk) or not PrefillEngine.supported(self, inputs.device):
             return None
         if isinstance(offset, torch.Tensor):
             off = int(offset.reshape(-1)[0])
@@ -384,7 +387,7 @@ class Qwen3ModelWeek3:
     def __call__(self, inputs, offset, cache: list[TinyKvCache], logits_to_keep: int | None = None):
         if self._graph_decode_applies(inputs, cache):
             return self._graph_decode(inputs, offset, cache, logits_to_keep)
-        if inputs.dim() == 2 and inputs.shape[1] > 8 and inputs.is_cuda:
+        if inputs.dim() == 2 and inputs.shape[1] > 1 and inputs.is_cuda:
             out = self._graph_prefill(inputs, offset, cache, logits_to_keep)
             if out is not None:
                 return out
