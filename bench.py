@@ -631,6 +631,12 @@ def run_serve(args, long_context: bool) -> None:
 
     # warm-up: a short queue through the same scheduler (captures the B-slot decode graph, sizes the pools)
     warm = [(p[: min(len(p), 2 * prefill_step)], 4) for p, _ in mine[: min(len(mine), slots + 2)]]
+    # ... plus one prompt with a ONE-token tail chunk: that tail is a B = 1 decode step, whose engine (private packed
+    # weight copies + graph capture, 30-900 ms depending on the host) otherwise gets built inside the timed region by the
+    # first such prompt of the queue
+    long_enough = [p for p, _ in mine if len(p) > prefill_step + 1]
+    if long_enough:
+        warm.append((long_enough[0][: prefill_step + 1], 2))
     serve(warm, timing=False)
     sampler = ClockSampler(device.index or 0)
     if rank == 0:

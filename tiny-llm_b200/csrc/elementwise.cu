@@ -698,24 +698,36 @@ __global__ void decode_qk_norm_rope_append_kernel(const T *qkv, const T *__restr
     dst[i] = out_re, dst[i + half] = out_im;
 }
 
-// The same for D == 128 (every Qwen3): one CTA per ROW (request or chunk token), eight warps, warp w takes heads w, w + 8,
-// ...; lane l owns the RoPE pairs (l, l + 64) and (l + 32, l + 96), so the angle arithmetic (a double-precision exp2 and
-// a sincosf per pair) is done once per lane instead of once per head, and the sum of squares is two warp reductions -
-// no shared memory, no block barrier.  The one-CTA-per-head form cost 5.8 us per layer at 64 rows and 8.7 us at 128
-// (6144 CTAs of 64 threads): 4-5 % of a 64-slot decode step / a 128-token prefill chunk.  Bit-identical to it: the
-// squares are added in the same tree (pairs 0..31 and 32..63 reduced separately, then summed).
+// The same for D == 128 (every Qwen3): one CTA per ROW (request or chunk token), sixteen warps, warp w takes heads w,
+// w + 16, ...; lane l owns the RoPE pairs (l, l + 64) and (l + 32, l + 96), so the angle arithmetic (a double-precision
+// exp2 and a sincosf per pair) is done once per lane instead of once per head, and the sum of squares is two warp
+// reductions - no shared memory, no block barrier.  All of a warp's loads are issued before the first is used (one L2
+// round trip; a first version that walked its heads one after the other was SLOWER than the one-CTA-per-head form:
+// 9.8 vs 5.8 us at 64 rows).  Bit-identical to the per-head kernel: the squares are added in the same tree (pairs
+// 0..31 and 32..63 reduced separately, then summed).
+constexpr int QKN_WARPS = 16, QKN_MAXH = 4;  // up to 64 heads (q + k + v) per row
 template <typename T>
-__global__ void __launch_bounds__(256) decode_qk_norm_rope_append_d128_kernel(const T *qkv, const T *__restrict__ qw, const T *__restrict__ kw,
-                                                                              const int32_t *__restrict__ offsets, const int32_t *__restrict__ bt,
-                                                                              const int32_t *__restrict__ cl, T *q_out, T *kp, T *vp, int Hq, int Hkv,
-                                                                              float base, float eps, int num_pages, int page_size, int max_pages,
-                                                                              int bt_stride, long long q_row_stride, long long q_head_stride) {
+__global__ void __launch_bounds__(QKN_WARPS * 32) decode_qk_norm_rope_append_d128_kernel(
+    const T *qkv, const T *__restrict__ qw, const T *__restrict__ kw, const int32_t *__restrict__ offsets, const int32_t *__restrict__ bt,
+    const int32_t *__restrict__ cl, T *q_out, T *kp, T *vp, int Hq, int Hkv, float base, float eps, int num_pages, int page_size, int max_pages,
+    int bt_stride, long long q_row_stride, long long q_head_stride) {
     constexpr int D = 128, half = 64;
     griddep_launch();
     griddep_wait();  // qkv is the previous kernel's output: read through L2 (common.cuh: programmatic dependent launch)
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int heads = Hq + 2 * Hkv;
+    const T *row = qkv + static_cast<size_t>(b) * heads * D;
+    float re[QKN_MAXH][2], im[QKN_MAXH][2];
+#pragma unroll
+    for (int hh = 0; hh < QKN_MAXH; ++hh) {
+        const int head = warp + QKN_WARPS * hh;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            re[hh][j] = head < heads ? to_f(ld_cg(row + head * D + lane + 32 * j)) : 0.f;
+            im[hh][j] = head < heads ? to_f(ld_cg(row + head * D + lane + 32 * j + half)) : 0.f;
+        }
+    }
     float sn[2], cs[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -737,28 +749,27 @@ __global__ void __launch_bounds__(256) decode_qk_norm_rope_append_d128_kernel(co
             }
         }
     }
-    for (int head = warp; head < heads; head += 8) {
-        const T *src = qkv + (static_cast<size_t>(b) * heads + head) * D;
-        float re[2], im[2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) re[j] = to_f(ld_cg(src + lane + 32 * j)), im[j] = to_f(ld_cg(src + lane + 32 * j + half));
+    for (int hh = 0; hh < QKN_MAXH; ++hh) {
+        const int head = warp + QKN_WARPS * hh;
+        if (head >= heads) break;  // warp-uniform
         const bool is_q = head < Hq, is_k = !is_q && head < Hq + Hkv;
         T o_re[2], o_im[2];
         if (is_q || is_k) {
-            const float tot = warp_sum(re[0] * re[0] + im[0] * im[0]) + warp_sum(re[1] * re[1] + im[1] * im[1]);
+            const float tot = warp_sum(re[hh][0] * re[hh][0] + im[hh][0] * im[hh][0]) + warp_sum(re[hh][1] * re[hh][1] + im[hh][1] * im[hh][1]);
             const float inv = rsqrtf(tot / static_cast<float>(D) + eps);
             const T *w = is_q ? qw : kw;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int i = lane + 32 * j;
-                const float nre = to_f(from_f<T>(re[j] * inv * to_f(w[i])));
-                const float nim = to_f(from_f<T>(im[j] * inv * to_f(w[i + half])));
+                const float nre = to_f(from_f<T>(re[hh][j] * inv * to_f(w[i])));
+                const float nim = to_f(from_f<T>(im[hh][j] * inv * to_f(w[i + half])));
                 o_re[j] = from_f<T>(nre * cs[j] - nim * sn[j]);
                 o_im[j] = from_f<T>(nim * cs[j] + nre * sn[j]);
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) o_re[j] = from_f<T>(re[j]), o_im[j] = from_f<T>(im[j]);
+            for (int j = 0; j < 2; ++j) o_re[j] = from_f<T>(re[hh][j]), o_im[j] = from_f<T>(im[hh][j]);
         }
         T *dst;
         if (is_q) {
@@ -786,9 +797,9 @@ int launch_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_w, con
     const long long q_head_stride = chunk ? static_cast<long long>(batch) * D : D;
     const int threads = ((D / 2 + 31) / 32) * 32;
     dim3 grid(Hq + 2 * Hkv, batch);
-    if (D == 128 && dtype == TL_BF16) {  // one CTA per row (see the kernel's comment)
+    if (D == 128 && dtype == TL_BF16 && Hq + 2 * Hkv <= QKN_WARPS * QKN_MAXH) {  // one CTA per row (see the kernel's comment)
         using T = __nv_bfloat16;
-        launch_chained(decode_qk_norm_rope_append_d128_kernel<T>, dim3(batch), dim3(256), 0, st, static_cast<const T *>(qkv),
+        launch_chained(decode_qk_norm_rope_append_d128_kernel<T>, dim3(batch), dim3(QKN_WARPS * 32), 0, st, static_cast<const T *>(qkv),
                        static_cast<const T *>(q_norm_w), static_cast<const T *>(k_norm_w), offsets, block_table, context_lens, static_cast<T *>(q_out),
                        static_cast<T *>(key_pages), static_cast<T *>(value_pages), Hq, Hkv, base, eps, num_pages, page_size, max_pages, bt_stride,
                        q_row_stride, q_head_stride);
