@@ -701,7 +701,7 @@ __global__ void decode_qk_norm_rope_append_kernel(const T *qkv, const T *__restr
 // The same for D == 128 (every Qwen3): one CTA per ROW (request or chunk token), sixteen warps, warp w takes heads w,
 // w + 16, ...; lane l owns the RoPE pairs (l, l + 64) and (l + 32, l + 96), so the angle arithmetic (a double-precision
 // exp2 and a sincosf per pair) is done once per lane instead of once per head, and the sum of squares is two warp
-// reductions - no shared memory, no block barrier.  All of a warp's loads are issued before the first is used (one L2
+// reductions.  All of a warp's loads are issued before the first is used (one L2
 // round trip; a first version that walked its heads one after the other was SLOWER than the one-CTA-per-head form:
 // 9.8 vs 5.8 us at 64 rows).  Bit-identical to the per-head kernel: the squares are added in the same tree (pairs
 // 0..31 and 32..63 reduced separately, then summed).
@@ -728,14 +728,20 @@ __global__ void __launch_bounds__(QKN_WARPS * 32) decode_qk_norm_rope_append_d12
             im[hh][j] = head < heads ? to_f(ld_cg(row + head * D + lane + 32 * j + half)) : 0.f;
         }
     }
-    float sn[2], cs[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int i = lane + 32 * j;
+    // the 64 (sin, cos) pairs of this row's position: computed ONCE per CTA by its first two warps (one pair index per
+    // thread: a double-precision exp2 and a large-argument sincosf each) and shared; every lane doing its own kept the
+    // FP64 / slow-path trig pipes busy 16x over
+    __shared__ float sn_s[half], cs_s[half];
+    if (threadIdx.x < half) {
+        const int i = threadIdx.x;
         const double inv_freq = exp2(-static_cast<double>(i) / static_cast<double>(half) * log2(static_cast<double>(base)));
         const float angle = static_cast<float>(static_cast<double>(offsets[b]) * inv_freq);
-        sincosf(angle, &sn[j], &cs[j]);
+        sincosf(angle, &sn_s[i], &cs_s[i]);
     }
+    __syncthreads();
+    float sn[2], cs[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) sn[j] = sn_s[lane + 32 * j], cs[j] = cs_s[lane + 32 * j];
     // page slot of this row's token (k / v heads)
     const int ctx = cl[b];
     T *k_dst = nullptr, *v_dst = nullptr;
