@@ -538,13 +538,13 @@ int w4a16_skinny_splits(int M, int N, int K) {
     const int slots = skinny_slots(M);
     int best = 1;
     long long best_cost = -1;
-    static const int cap = [] { const char *e = getenv("TL_SKINNY_MAX_SPLITS"); return e ? atoi(e) : 16; }();  // A/B runs
-    static const int fixed = [] { const char *e = getenv("TL_SKINNY_FIXED_COST"); return e ? atoi(e) : 10; }();
-    for (int s = 1; s <= cap && s <= num_gb / 2 + (num_gb < 2); ++s) {
+    // (a sweep of the cap (4, 8, 16) and of the fixed cost (4, 10, 20) moved single shapes by +-10 % stand-alone and the
+    // 64-slot step by nothing or for the worse: tools/gpu_call27.sh)
+    for (int s = 1; s <= 16 && s <= num_gb / 2 + (num_gb < 2); ++s) {
         const int gbps = (num_gb + s - 1) / s;
         const int real = (num_gb + gbps - 1) / gbps;  // splits that actually get blocks
         const long long waves = (static_cast<long long>(tiles) * real + slots - 1) / slots;
-        const long long cost = waves * (gbps + fixed) + (real > 1 ? 8 : 0);  // in units of one group block
+        const long long cost = waves * (gbps + 10) + (real > 1 ? 8 : 0);  // in units of one group block
         if (best_cost < 0 || cost < best_cost) best_cost = cost, best = real;
     }
     return best;
