@@ -185,8 +185,7 @@ w4a16_skinny_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 3) {
         // ------------------------------------------------ TMA producer: activations, two [NT x 64] tiles per group block
-        if (lane == 0) griddep_wait();  // the activations are the predecessor's output
-        __syncwarp();
+        griddep_wait();  // the activations are the predecessor's output (every lane: whichever one is elected below has waited)
         int bs = 0;
         uint32_t ph = 1;
         for (int i = 0; i < n_gb; ++i) {
