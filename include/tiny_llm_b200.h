@@ -173,6 +173,15 @@ int tl_quantized_matmul_fused(const void *scales, const void *biases, const void
 int tl_quantized_matmul_residual_norm(const void *scales, const void *biases, const void *b, void *out, const void *p0, const void *residual,
                                       const void *norm_weight, void *normed_out, int M, int N, int K, float norm_eps, int dtype, void *workspace,
                                       size_t workspace_bytes, void *stream);
+/* q|k|v projection of `rows` activation rows (p0 [rows, N], packed weight rows = q heads | k heads | v heads) followed by
+ * per-head q/k RMSNorm + RoPE + K/V append (tl_decode_qk_norm_rope_append, or its chunk form when chunk != 0).  With a
+ * split reduction (9..128 rows) the partial planes feed the second kernel directly and q|k|v is never materialised;
+ * otherwise qkv_scratch [rows, (Hq + 2 Hkv) * D] receives it.  Same results as the two calls.  bfloat16; workspace as
+ * for tl_quantized_matmul_fused(prologue TL_PRO_NONE). */
+int tl_qkv_project_rope_append(const void *scales, const void *biases, const void *b, const void *p0, void *qkv_scratch, const void *q_norm_weight,
+                               const void *k_norm_weight, const int32_t *offsets, const int32_t *block_table, const int32_t *context_lens, void *q_out,
+                               void *key_pages, void *value_pages, int rows, int N, int num_heads, int num_kv_heads, int head_dim, float base, float eps,
+                               int num_pages, int page_size, int max_pages, int chunk, int dtype, void *workspace, size_t workspace_bytes, void *stream);
 /* Decode step, L == 1: per-head q/k RMSNorm + RoPE + K/V append in one launch.
  * qkv [B, (Hq + 2*Hkv) * D] (q heads | k heads | v heads); q_out [B, Hq, D];
  * K/V rows land in the page slot of token context_lens[b]-1 (rows with context

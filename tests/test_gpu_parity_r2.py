@@ -127,6 +127,47 @@ def test_token_major_prefill_attention_is_the_transposed_head_major_result(dev, 
     assert torch.equal(got, want.view(B, Hq, L, D).transpose(1, 2).reshape(B * L, Hq * D))
 
 
+@pytest.mark.parametrize("rows,chunk", [(64, False), (16, False), (128, True), (40, True), (4, False)])
+def test_qkv_projection_feeding_rope_append_equals_the_two_calls(dev, rows, chunk):
+    """q|k|v projection whose split-reduction planes go straight into q/k norm + RoPE + append (q|k|v never written):
+    rotated queries and the appended K/V rows bit-identical to projection -> decode / chunk_qk_norm_rope_append
+    (4 rows: the streaming projection, no planes - the call falls back to exactly those two launches)."""
+    Hq, Hkv, D, N, page = 32, 8, 128, 2560, 128
+    g = gen(rows * 3 + int(chunk))
+    K = (Hq + 2 * Hkv) * D
+    words, scales, biases = rand_packed(K, N, g)
+    words, scales, biases = words.to(dev), scales.to(dev), biases.to(dev)
+    h = torch.randn(rows, N, generator=g).to(BF16).to(dev)
+    qw = (1 + 0.1 * torch.randn(D, generator=g)).to(BF16).to(dev)
+    kw = (1 + 0.1 * torch.randn(D, generator=g)).to(BF16).to(dev)
+    if chunk:  # one request, `rows` consecutive tokens starting at position 200
+        pages = 4
+        bt = torch.tensor([3, 1, 0, 2], dtype=torch.int32, device=dev)
+        offsets = torch.arange(200, 200 + rows, dtype=torch.int32, device=dev)
+        ctx = offsets + 1
+    else:  # one request per row, two idle rows
+        pages = 2
+        bt = torch.randperm(rows * pages, generator=g).reshape(rows, pages).to(torch.int32).to(dev)
+        offsets = torch.tensor([(37 * r) % 250 for r in range(rows)], dtype=torch.int32, device=dev)
+        ctx = offsets + 1
+        ctx[1] = 0
+        ctx[rows - 1] = 0
+    P = (pages if chunk else rows * pages)
+    outs = []
+    for fused in (True, False):
+        kp = torch.zeros(P, Hkv, page, D, dtype=BF16, device=dev)
+        vp = torch.zeros_like(kp)
+        if fused:
+            q = ext.qkv_project_rope_append(scales, biases, words, h, qw, kw, offsets, bt, ctx, kp, vp, Hq, Hkv, 1e6, 1e-6, chunk=chunk)
+        else:
+            qkv = ext.quantized_matmul_fused(scales, biases, words, h)
+            fn = ext.chunk_qk_norm_rope_append if chunk else ext.decode_qk_norm_rope_append
+            q = fn(qkv, qw, kw, offsets, bt, ctx, kp, vp, Hq, Hkv, 1e6, 1e-6)
+        outs.append((q, kp, vp))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 # ------------------------------------------------------------------ GEMM at the config-3 shapes --
 @pytest.mark.parametrize("pairs", [0, 2], ids=["one-cta", "cta-pairs"])
 @pytest.mark.parametrize("shape", [(4096, 9728, 2560), (4096, 2560, 19456 // 2), (4096, 4096, 2560), (1000, 256, 392)],

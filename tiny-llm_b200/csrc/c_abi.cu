@@ -315,6 +315,38 @@ int tl_quantized_matmul_residual_norm(const void *scales, const void *biases, co
     return launch_rms_norm(out, norm_weight, normed_out, M, K, norm_eps, dtype, as_stream(stream));
 }
 
+int tl_qkv_project_rope_append(const void *scales, const void *biases, const void *b, const void *p0, void *qkv_scratch, const void *q_norm_weight,
+                               const void *k_norm_weight, const int32_t *offsets, const int32_t *block_table, const int32_t *context_lens, void *q_out,
+                               void *key_pages, void *value_pages, int rows, int N, int num_heads, int num_kv_heads, int head_dim, float base, float eps,
+                               int num_pages, int page_size, int max_pages, int chunk, int dtype, void *workspace, size_t workspace_bytes, void *stream) {
+    if (dtype != TL_BF16) return fail(TL_EDTYPE, "qkv_project_rope_append: bfloat16 required");
+    if (rows < 0 || N <= 0 || N % 128 != 0 || num_heads <= 0 || num_kv_heads <= 0 || head_dim <= 0 || head_dim % 2 != 0 || num_pages <= 0 ||
+        page_size <= 0 || max_pages <= 0)
+        return fail(TL_EINVAL, "qkv_project_rope_append: bad shape");
+    if (rows == 0) return TL_OK;
+    if (!scales || !biases || !b || !p0 || !qkv_scratch || !q_norm_weight || !k_norm_weight || !offsets || !block_table || !context_lens || !q_out ||
+        !key_pages || !value_pages)
+        return fail(TL_EINVAL, "qkv_project_rope_append: null pointer");
+    const int K = (num_heads + 2 * num_kv_heads) * head_dim;
+    cudaStream_t st = as_stream(stream);
+    int planes = 1;
+    int rc;
+    if (use_skinny_kernel(rows, N, K, dtype, 1) && qkv_planes_rope_supported(num_heads, num_kv_heads, head_dim, dtype))
+        rc = launch_w4a16_skinny(scales, biases, p0, b, qkv_scratch, nullptr, rows, N, K, TL_EPI_NONE, dtype, workspace, workspace_bytes, st, nullptr, 0.f,
+                                 nullptr, nullptr, &planes);
+    else
+        rc = tl_quantized_matmul_fused(scales, biases, b, qkv_scratch, p0, nullptr, nullptr, rows, N, K, N, TL_PRO_NONE, TL_EPI_NONE, 0.f, dtype,
+                                       workspace, workspace_bytes, stream);
+    if (rc != TL_OK) return rc;
+    if (planes > 1)  // the split-reduction planes go straight into the norm / RoPE / append kernel: q|k|v is never written
+        return launch_qkv_planes_rope_append(static_cast<const float *>(workspace), planes, q_norm_weight, k_norm_weight, offsets, block_table,
+                                             context_lens, q_out, key_pages, value_pages, rows, num_heads, num_kv_heads, base, eps, num_pages,
+                                             page_size, max_pages, st, chunk != 0);
+    return launch_decode_qk_norm_rope_append(qkv_scratch, q_norm_weight, k_norm_weight, offsets, block_table, context_lens, q_out, key_pages,
+                                             value_pages, rows, num_heads, num_kv_heads, head_dim, base, eps, num_pages, page_size, max_pages, dtype,
+                                             st, chunk != 0);
+}
+
 int tl_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_weight, const void *k_norm_weight,
                                   const int32_t *offsets, const int32_t *block_table, const int32_t *context_lens,
                                   void *q_out, void *key_pages, void *value_pages, int batch, int num_heads,

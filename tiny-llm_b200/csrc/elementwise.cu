@@ -707,9 +707,11 @@ __global__ void decode_qk_norm_rope_append_kernel(const T *qkv, const T *__restr
 // rows - a dependent-latency chain either way (load -> trig -> norm -> store), the gain is the chunk's 6144 tiny CTAs.  Bit-identical to the per-head kernel: the squares are added in the same tree (pairs
 // 0..31 and 32..63 reduced separately, then summed).
 constexpr int QKN_WARPS = 16, QKN_MAXH = 4;  // up to 64 heads (q + k + v) per row
-template <typename T>
+// PLANES: qkv does not exist in memory - its rows are still the fp32 partial planes of the q|k|v projection's split
+// reduction (w4a16_skinny.cu); this kernel adds them (split order, as the reduction launch would) and rounds to T first.
+template <typename T, bool PLANES>
 __global__ void __launch_bounds__(QKN_WARPS * 32) decode_qk_norm_rope_append_d128_kernel(
-    const T *qkv, const T *__restrict__ qw, const T *__restrict__ kw, const int32_t *__restrict__ offsets, const int32_t *__restrict__ bt,
+    const T *qkv, const float *part, int splits, long long plane, const T *__restrict__ qw, const T *__restrict__ kw, const int32_t *__restrict__ offsets, const int32_t *__restrict__ bt,
     const int32_t *__restrict__ cl, T *q_out, T *kp, T *vp, int Hq, int Hkv, float base, float eps, int num_pages, int page_size, int max_pages,
     int bt_stride, long long q_row_stride, long long q_head_stride) {
     constexpr int D = 128, half = 64;
@@ -718,15 +720,46 @@ __global__ void __launch_bounds__(QKN_WARPS * 32) decode_qk_norm_rope_append_d12
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int heads = Hq + 2 * Hkv;
-    const T *row = qkv + static_cast<size_t>(b) * heads * D;
     float re[QKN_MAXH][2], im[QKN_MAXH][2];
+    if constexpr (PLANES) {
+        const float *prow = part + static_cast<size_t>(b) * heads * D;
 #pragma unroll
-    for (int hh = 0; hh < QKN_MAXH; ++hh) {
-        const int head = warp + QKN_WARPS * hh;
+        for (int hh = 0; hh < QKN_MAXH; ++hh)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            re[hh][j] = head < heads ? to_f(ld_cg(row + head * D + lane + 32 * j)) : 0.f;
-            im[hh][j] = head < heads ? to_f(ld_cg(row + head * D + lane + 32 * j + half)) : 0.f;
+            for (int j = 0; j < 2; ++j) re[hh][j] = im[hh][j] = 0.f;
+        for (int sp0 = 0; sp0 < splits; sp0 += 4) {  // four planes per round trip, added in split order
+            float v[QKN_MAXH][4][4];
+#pragma unroll
+            for (int hh = 0; hh < QKN_MAXH; ++hh) {
+                const int head = warp + QKN_WARPS * hh;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool live = head < heads && sp0 + q < splits;
+                    const float *src = prow + (sp0 + q) * plane + head * D + lane;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[hh][q][e] = live ? ld_cg(src + 32 * e) : 0.f;  // e: pairs (l, l+64), (l+32, l+96) -> offsets 0, 32, 64, 96
+                }
+            }
+#pragma unroll
+            for (int hh = 0; hh < QKN_MAXH; ++hh)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (sp0 + q < splits) re[hh][0] += v[hh][q][0], re[hh][1] += v[hh][q][1], im[hh][0] += v[hh][q][2], im[hh][1] += v[hh][q][3];
+        }
+#pragma unroll
+        for (int hh = 0; hh < QKN_MAXH; ++hh)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) re[hh][j] = to_f(from_f<T>(re[hh][j])), im[hh][j] = to_f(from_f<T>(im[hh][j]));  // the projection's rounding
+    } else {
+        const T *row = qkv + static_cast<size_t>(b) * heads * D;
+#pragma unroll
+        for (int hh = 0; hh < QKN_MAXH; ++hh) {
+            const int head = warp + QKN_WARPS * hh;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                re[hh][j] = head < heads ? to_f(ld_cg(row + head * D + lane + 32 * j)) : 0.f;
+                im[hh][j] = head < heads ? to_f(ld_cg(row + head * D + lane + 32 * j + half)) : 0.f;
+            }
         }
     }
     // the 64 (sin, cos) pairs of this row's position: computed ONCE per CTA by its first two warps (one pair index per
@@ -806,8 +839,8 @@ int launch_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_w, con
     dim3 grid(Hq + 2 * Hkv, batch);
     if (D == 128 && dtype == TL_BF16 && Hq + 2 * Hkv <= QKN_WARPS * QKN_MAXH) {  // one CTA per row (see the kernel's comment)
         using T = __nv_bfloat16;
-        launch_chained(decode_qk_norm_rope_append_d128_kernel<T>, dim3(batch), dim3(QKN_WARPS * 32), 0, st, static_cast<const T *>(qkv),
-                       static_cast<const T *>(q_norm_w), static_cast<const T *>(k_norm_w), offsets, block_table, context_lens, static_cast<T *>(q_out),
+        launch_chained(decode_qk_norm_rope_append_d128_kernel<T, false>, dim3(batch), dim3(QKN_WARPS * 32), 0, st, static_cast<const T *>(qkv),
+                       static_cast<const float *>(nullptr), 0, 0LL, static_cast<const T *>(q_norm_w), static_cast<const T *>(k_norm_w), offsets, block_table, context_lens, static_cast<T *>(q_out),
                        static_cast<T *>(key_pages), static_cast<T *>(value_pages), Hq, Hkv, base, eps, num_pages, page_size, max_pages, bt_stride,
                        q_row_stride, q_head_stride);
         TL_LAUNCH_CHECK("decode_qk_norm_rope_append");
@@ -826,6 +859,25 @@ int launch_decode_qk_norm_rope_append(const void *qkv, const void *q_norm_w, con
         return fail(TL_EDTYPE, "decode_qk_norm_rope_append: bfloat16 or float32 required");
 #undef TL_QKN
     TL_LAUNCH_CHECK("decode_qk_norm_rope_append");
+    return TL_OK;
+}
+
+// q/k norm + RoPE + append straight from the split-reduction planes of the q|k|v projection (bf16, D == 128, <= 64 heads)
+bool qkv_planes_rope_supported(int Hq, int Hkv, int D, int dtype) { return D == 128 && dtype == TL_BF16 && Hq + 2 * Hkv <= QKN_WARPS * QKN_MAXH; }
+int launch_qkv_planes_rope_append(const float *part, int splits, const void *q_norm_w, const void *k_norm_w, const int32_t *offsets,
+                                  const int32_t *block_table, const int32_t *context_lens, void *q_out, void *key_pages, void *value_pages, int batch,
+                                  int Hq, int Hkv, float base, float eps, int num_pages, int page_size, int max_pages, cudaStream_t st, bool chunk) {
+    using T = __nv_bfloat16;
+    constexpr int D = 128;
+    const int bt_stride = chunk ? 0 : max_pages;
+    const long long q_row_stride = chunk ? D : static_cast<long long>(Hq) * D;
+    const long long q_head_stride = chunk ? static_cast<long long>(batch) * D : D;
+    const long long plane = static_cast<long long>(batch) * (Hq + 2 * Hkv) * D;
+    launch_chained(decode_qk_norm_rope_append_d128_kernel<T, true>, dim3(batch), dim3(QKN_WARPS * 32), 0, st, static_cast<const T *>(nullptr), part, splits,
+                   plane, static_cast<const T *>(q_norm_w), static_cast<const T *>(k_norm_w), offsets, block_table, context_lens, static_cast<T *>(q_out),
+                   static_cast<T *>(key_pages), static_cast<T *>(value_pages), Hq, Hkv, base, eps, num_pages, page_size, max_pages, bt_stride,
+                   q_row_stride, q_head_stride);
+    TL_LAUNCH_CHECK("qkv_planes_rope_append");
     return TL_OK;
 }
 

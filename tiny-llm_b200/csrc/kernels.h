@@ -68,7 +68,13 @@ size_t w4a16_skinny_workspace(int M, int N, int K);
 // whether the launch did it (split reduction, K <= 4096) or the caller still has to run rms_norm
 int launch_w4a16_skinny(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N,
                         int K, int epilogue, int dtype, void *ws, size_t ws_bytes, cudaStream_t st, const void *norm_w = nullptr,
-                        float norm_eps = 0.f, void *normed = nullptr, bool *norm_done = nullptr);
+                        float norm_eps = 0.f, void *normed = nullptr, bool *norm_done = nullptr, int *planes_out = nullptr);
+// planes_out (optional): with a split reduction the launch stops after the GEMM (partial planes [splits][M][K] fp32 in the
+// workspace, *planes_out = splits) and the caller's fused kernel adds them; *planes_out = 1 means `out` is complete
+bool qkv_planes_rope_supported(int Hq, int Hkv, int D, int dtype);
+int launch_qkv_planes_rope_append(const float *part, int splits, const void *q_norm_w, const void *k_norm_w, const int32_t *offsets,
+                                  const int32_t *block_table, const int32_t *context_lens, void *q_out, void *key_pages, void *value_pages, int batch,
+                                  int Hq, int Hkv, float base, float eps, int num_pages, int page_size, int max_pages, cudaStream_t st, bool chunk);
 
 // w4a16_gemm.cu (tcgen05 prefill GEMM)
 bool w4a16_gemm_supported(int M, int N, int K, int dtype);

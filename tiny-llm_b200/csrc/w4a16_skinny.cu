@@ -617,7 +617,8 @@ static int skinny_launch(const CUtensorMap &ma, const CUtensorMap &mw, const SkA
 
 template <typename T>
 static int skinny_t(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N, int K,
-                    int epilogue, void *ws, size_t ws_bytes, const void *norm_w, float norm_eps, void *normed, bool *norm_done, cudaStream_t st) {
+                    int epilogue, void *ws, size_t ws_bytes, const void *norm_w, float norm_eps, void *normed, bool *norm_done, cudaStream_t st,
+                    int *planes_out) {
     if (!aligned16(a) || !aligned16(b)) return fail(TL_EINVAL, "quantized_matmul: a and b must be 16-byte aligned");
     const int NT = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
     const int tiles = (K + SK_FEAT - 1) / SK_FEAT;
@@ -642,6 +643,10 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
         case 64: rc = skinny_launch<T, 64>(ma, mw, args, grid, st); break;
         default: rc = skinny_wide1() ? skinny_launch<T, 128, true>(ma, mw, args, grid, st) : skinny_launch<T, 128>(ma, mw, args, grid, st); break;
     }
+    if (planes_out != nullptr) {  // the caller adds the planes itself (fused consumer); 1 = `out` holds the finished result
+        *planes_out = args.splits;
+        if (args.splits > 1) return rc;
+    }
     if (rc != TL_OK || args.splits == 1) return rc;
     if (normed != nullptr && epilogue == SK_EPI_RESIDUAL && K <= 256 * SK_NORM_PER) {
         cudaError_t e = launch_chained(w4a16_skinny_reduce_norm_kernel<T>, dim3(M), dim3(256), 0, st, static_cast<const float *>(args.partials),
@@ -663,15 +668,17 @@ static int skinny_t(const void *scales, const void *biases, const void *a, const
 
 int launch_w4a16_skinny(const void *scales, const void *biases, const void *a, const void *b, void *out, const void *residual, int M, int N,
                         int K, int epilogue, int dtype, void *ws, size_t ws_bytes, cudaStream_t st, const void *norm_w, float norm_eps, void *normed,
-                        bool *norm_done) {
+                        bool *norm_done, int *planes_out) {
     bool unused = false;
     if (norm_done == nullptr) norm_done = &unused;
     *norm_done = false;
     if (M == 0 || K == 0) return TL_OK;
     if (epilogue == SK_EPI_SWIGLU_PAIRS && K % 16 != 0) return fail(TL_EINVAL, "quantized_matmul: interleaved gate|up rows need K %% 16 == 0");
     if (dtype == TL_BF16)
-        return skinny_t<__nv_bfloat16>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, norm_w, norm_eps, normed, norm_done, st);
-    if (dtype == TL_F16) return skinny_t<__half>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, norm_w, norm_eps, normed, norm_done, st);
+        return skinny_t<__nv_bfloat16>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, norm_w, norm_eps, normed, norm_done, st,
+                                       planes_out);
+    if (dtype == TL_F16)
+        return skinny_t<__half>(scales, biases, a, b, out, residual, M, N, K, epilogue, ws, ws_bytes, norm_w, norm_eps, normed, norm_done, st, planes_out);
     return fail(TL_EDTYPE, "quantized_matmul: scales must be float16 or bfloat16");
 }
 

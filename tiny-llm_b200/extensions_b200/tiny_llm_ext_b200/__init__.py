@@ -49,6 +49,7 @@ __all__ = [
     "current_library_path",
     "quantized_matmul_residual_norm",
     "paged_attention_token_major",
+    "qkv_project_rope_append",
 ]
 
 _HERE = Path(__file__).resolve().parent
@@ -82,6 +83,7 @@ _SIGNATURES = {
     "tl_argmax_workspace": (_SZ, [_I, _I]),
     "tl_argmax": (_I, [_VP, _VP, _I, _I, _I, _VP, _SZ, _VP]),
     "tl_decode_advance": (_I, [_VP] * 6 + [_I, _I, _VP]),
+    "tl_qkv_project_rope_append": (_I, [_VP] * 13 + [_I] * 5 + [_F, _F] + [_I] * 5 + [_VP, _SZ, _VP]),
     "tl_paged_attention_token_major": (_I, [_VP] * 6 + [_I] * 5 + [_F] + [_I] * 3 + [_VP]),
     "tl_quantized_matmul_fused_workspace": (_SZ, [_I] * 6),
     "tl_quantized_matmul_fused": (_I, [_VP] * 7 + [_I] * 6 + [_F, _I, _VP, _SZ, _VP]),
@@ -680,6 +682,37 @@ def decode_qk_norm_rope_append(qkv, q_norm_weight, k_norm_weight, offsets, block
             context_lens.data_ptr(), q_out.data_ptr(), key_pages.data_ptr(), value_pages.data_ptr(), B, int(num_heads),
             int(num_kv_heads), D, float(base), float(eps), P, page_size, block_table.shape[1], _DTYPE_CODE[qkv.dtype],
             _stream_ptr(stream, qkv),
+        )
+    )
+    return q_out
+
+
+def qkv_project_rope_append(scales, biases, b, p0, q_norm_weight, k_norm_weight, offsets, block_table, context_lens, key_pages, value_pages,
+                            num_heads, num_kv_heads, base, eps, chunk=False, stream=None):
+    """``qkv = p0 @ W_qkv^T`` then per-head q/k RMSNorm + RoPE + K/V append (``decode_qk_norm_rope_append``; ``chunk``: the
+    rows are consecutive tokens of one request and ``block_table`` is its row).  Returns the rotated queries
+    (``[rows, Hq, D]``, or ``[Hq, rows, D]`` for a chunk).  With 9..128 rows the projection's split-reduction planes
+    feed the second kernel directly; results are those of the two separate calls."""
+    rows, N = p0.shape
+    P, Hkv, page_size, D = key_pages.shape
+    K = b.shape[0]
+    if K != (num_heads + 2 * num_kv_heads) * D or Hkv != num_kv_heads or b.shape[1] * 8 != N:
+        raise RuntimeError("qkv_project_rope_append: weight rows must be (Hq + 2*Hkv) * D")
+    if p0.dtype != torch.bfloat16 or key_pages.dtype != p0.dtype or scales.dtype != p0.dtype or not p0.is_contiguous():
+        raise RuntimeError("qkv_project_rope_append: contiguous bfloat16 inputs required")
+    _gpu("qkv_project_rope_append", scales, biases, b, p0, q_norm_weight, k_norm_weight, offsets, block_table, context_lens, key_pages, value_pages)
+    scratch = torch.empty((rows, K), dtype=p0.dtype, device=p0.device)
+    q_out = torch.empty((num_heads, rows, D) if chunk else (rows, num_heads, D), dtype=p0.dtype, device=p0.device)
+    code = _DTYPE_CODE[p0.dtype]
+    ws_bytes = _lib.tl_quantized_matmul_fused_workspace(rows, N, K, N, int(PRO_NONE), code)
+    ws = _zero_workspace(ws_bytes, p0.device)
+    max_pages = block_table.shape[-1]
+    _check(
+        _lib.tl_qkv_project_rope_append(
+            scales.data_ptr(), biases.data_ptr(), b.data_ptr(), p0.data_ptr(), scratch.data_ptr(), q_norm_weight.data_ptr(), k_norm_weight.data_ptr(),
+            offsets.data_ptr(), block_table.data_ptr(), context_lens.data_ptr(), q_out.data_ptr(), key_pages.data_ptr(), value_pages.data_ptr(),
+            rows, N, int(num_heads), int(num_kv_heads), D, float(base), float(eps), P, page_size, max_pages, int(bool(chunk)), code,
+            None if ws is None else ws.data_ptr(), ws_bytes, _stream_ptr(stream, p0),
         )
     )
     return q_out

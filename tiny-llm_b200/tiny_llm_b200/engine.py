@@ -259,9 +259,10 @@ class DecodeEngine:
         for i, block in enumerate(layers):
             at, pk, pool = block.self_attn, self._packed[i], m.page_pools[i]
             ln1, ln2 = block.input_layernorm, block.post_attention_layernorm
-            if wide:
+            qkv = None
+            if wide and self._attention_fused:
                 qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, h)
-            else:
+            elif not wide:
                 qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, x, ln1._weight_as(x.dtype, x.device),
                                                  prologue=ext.PRO_RMSNORM, eps=ln1.eps)
             if self._attention_fused:
@@ -270,9 +271,14 @@ class DecodeEngine:
                                                pool._key_pages, pool._value_pages, Hq, Hkv, at.q_norm.eps, at.scale,
                                                self.max_seq_len, workspace=self._attn_ws)
             else:
-                q = ext.decode_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
-                                                   offsets, self.tables[i][:B], context_lens, pool._key_pages, pool._value_pages,
-                                                   Hq, Hkv, at.rope.base, at.q_norm.eps)
+                if wide:  # projection + q/k norm + RoPE + append: the split-reduction planes feed the second kernel, q|k|v is never written
+                    q = ext.qkv_project_rope_append(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, h, at.q_norm._weight_as(x.dtype, x.device),
+                                                    at.k_norm._weight_as(x.dtype, x.device), offsets, self.tables[i][:B], context_lens,
+                                                    pool._key_pages, pool._value_pages, Hq, Hkv, at.rope.base, at.q_norm.eps)
+                else:
+                    q = ext.decode_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
+                                                       offsets, self.tables[i][:B], context_lens, pool._key_pages, pool._value_pages,
+                                                       Hq, Hkv, at.rope.base, at.q_norm.eps)
                 y = ext.paged_attention(q.view(B * Hq, 1, D), pool._key_pages, pool._value_pages, self.tables[i][:B], context_lens,
                                         at.scale, is_causal=True, num_kv_heads=Hkv, num_heads=Hq)
             wd = block.mlp.w_down
@@ -632,10 +638,14 @@ class PrefillEngine:
             at, pk, pool = block.self_attn, self._packed[i], m.page_pools[i]
             if not skinny:
                 h = normed(x, block.input_layernorm)
-            qkv = ext.quantized_matmul_fused(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, h) if skinny else proj(h, pk.qkv)
-            q = ext.chunk_qk_norm_rope_append(qkv, at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
-                                              self.offsets, self.tables[i], self.ctxs, pool._key_pages, pool._value_pages,
-                                              Hq, Hkv, at.rope.base, at.q_norm.eps)  # [Hq, L, D]
+            if skinny:  # q|k|v projection + q/k norm + RoPE + append: the split-reduction planes feed the second kernel
+                q = ext.qkv_project_rope_append(pk.qkv.scales, pk.qkv.biases, pk.qkv.weight, h, at.q_norm._weight_as(x.dtype, x.device),
+                                                at.k_norm._weight_as(x.dtype, x.device), self.offsets, self.tables[i], self.ctxs,
+                                                pool._key_pages, pool._value_pages, Hq, Hkv, at.rope.base, at.q_norm.eps, chunk=True)  # [Hq, L, D]
+            else:
+                q = ext.chunk_qk_norm_rope_append(proj(h, pk.qkv), at.q_norm._weight_as(x.dtype, x.device), at.k_norm._weight_as(x.dtype, x.device),
+                                                  self.offsets, self.tables[i], self.ctxs, pool._key_pages, pool._value_pages,
+                                                  Hq, Hkv, at.rope.base, at.q_norm.eps)  # [Hq, L, D]
             # [L, Hq * D]: the tcgen05 kernel writes the o-projection's layout itself (else: attention + one transpose copy)
             y = ext.paged_attention_token_major(q, pool._key_pages, pool._value_pages, self.tables[i:i + 1], self.ctx_after, at.scale,
                                                 True, Hkv, Hq)
