@@ -98,6 +98,12 @@ struct TcArgs {
     float *ws_o, *ws_m, *ws_l;
 };
 
+// PT: the probabilities of a tile stay in TENSOR memory - P_j (bf16 pairs, 32 columns) overwrites the first half of the
+// score buffer S_j it was computed from, and P V reads its A operand from there (the TS form of tcgen05.mma).  The
+// shared-memory form kept ONE P tile, so the exponentials of tile j could not start before P V of tile j-1 had finished
+// reading it; now only the (rare) rescale of O waits for that, and the eight 16-byte stores + proxy fence per row become
+// one tcgen05.st.  Buffer reuse needs no barrier: S_{j+2} is issued behind P V_j in the same MMA queue.
+template <bool PT>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const TcArgs a) {
@@ -239,8 +245,12 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 if (g_elect_one()) {
                     const uint64_t vd = vdesc0 + static_cast<uint64_t>(vs * (TC_KV_TILE >> 4));
 #pragma unroll
-                    for (int k = 0; k < TC_BN / 16; ++k)
-                        g_tc_mma(tmem + TC_TMEM_O, pdesc0 + 2 * k, vd + k * (2048 >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TC_BN / 16; ++k) {
+                        if constexpr (PT)  // 16 keys = 8 columns of bf16 pairs per K step
+                            g_tc_mma_ts(tmem + TC_TMEM_O, tmem + (j & 1) * TC_BN + 8 * k, vd + k * (2048 >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                        else
+                            g_tc_mma(tmem + TC_TMEM_O, pdesc0 + 2 * k, vd + k * (2048 >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    }
                     g_tc_commit(v_empty + 8 * vs);
                     g_tc_commit(pv_done);  // O holds tiles 0..j and the P buffer is free again
                 }
@@ -288,10 +298,12 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     }
             }
             const float tile_max = raw_max * a.scale_log2;  // -inf stays -inf
-            if (j > 0) g_mbar_wait(pv_done, (j - 1) & 1);   // P V of tile j-1 complete: O is stable, the P buffer is free
+            if constexpr (!PT)
+                if (j > 0) g_mbar_wait(pv_done, (j - 1) & 1);  // P V of tile j-1 complete: O is stable, the P buffer is free
             // lazy rescale: keep the stale maximum unless this tile exceeds it by more than 2^8
             const bool grow = tile_max > m_used + TC_RESCALE_THRESHOLD || (m_used == -CUDART_INF_F && tile_max != -CUDART_INF_F);
             if (__any_sync(0xffffffffu, grow) && j > 0) {
+                if constexpr (PT) g_mbar_wait(pv_done, (j - 1) & 1);  // O must be stable while it is rescaled
                 g_tc_fence_after();
                 const float m_new = grow ? tile_max : m_used;
                 const float alpha = (grow && m_used != -CUDART_INF_F) ? exp2f(m_used - m_new) : (grow ? 0.f : 1.f);
@@ -322,12 +334,18 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                     pk[h * 16 + c / 2] = pack2<bf16>(p0, p1);
                 }
             l_sum += tile_sum;
-            // P row r: 128 bytes = 8 chunks of 16 B, chunk c at (c ^ (r & 7)) - the 128-byte swizzle of a K-major tile
-            unsigned char *prow = tsm + TC_P_OFF + r * 128;
+            if constexpr (PT) {
+                // lane = row, column c = keys (2c, 2c + 1) of the tile: over the first 32 columns of the score buffer just read
+                g_tmem_st32(tmem + lane_base + (j & 1) * TC_BN, pk);
+                g_tmem_st_wait();
+            } else {
+                // P row r: 128 bytes = 8 chunks of 16 B, chunk c at (c ^ (r & 7)) - the 128-byte swizzle of a K-major tile
+                unsigned char *prow = tsm + TC_P_OFF + r * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<uint4 *>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            g_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4 *>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                g_fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+            }
             g_tc_fence_before();    // orders this thread's tcgen05.ld / st before the MMAs released by the arrive
             __syncwarp();           // one arrival per warp: 128 arrivals on one mbarrier are 128 serialised shared-memory atomics
             if (lane == 0) g_mbar_arrive(p_full);
@@ -478,8 +496,10 @@ int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const
     }
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(paged_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(paged_prefill_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        if (cudaFuncSetAttribute(paged_prefill_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(paged_prefill_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+            cudaFuncSetAttribute(paged_prefill_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(paged_prefill_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             return fail(TL_ECUDA, "paged_attention: cannot raise shared memory limit");
         configured = true;
     }
@@ -515,7 +535,9 @@ int launch_paged_prefill_tc(const void *q, const void *kp, const void *vp, const
     }
     dim3 grid(q_blocks * a.splits, num_kv_heads, B);
     if (grid.y > 65535 || grid.z > 65535) return fail(TL_EINVAL, "paged_attention: too many heads / requests for one launch");
-    cudaError_t le = launch_chained(paged_prefill_tc_kernel, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, mq, mk, mv, a);
+    static const bool p_tmem = [] { const char *e = getenv("TL_FA_P_TMEM"); return e == nullptr || e[0] != '0'; }();  // 0: P through shared memory (control)
+    cudaError_t le = p_tmem ? launch_chained(paged_prefill_tc_kernel<true>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, mq, mk, mv, a)
+                            : launch_chained(paged_prefill_tc_kernel<false>, grid, dim3(TC_THREADS), TC_SMEM_BYTES, st, mq, mk, mv, a);
     if (le != cudaSuccess) return fail(TL_ECUDA, "paged_attention: launch failed: %s", cudaGetErrorString(le));
     TL_LAUNCH_CHECK("paged_prefill_tc");
     if (a.splits > 1) return launch_paged_gqa_merge(a.ws_o, a.ws_m, a.ws_l, out, rows * L, a.splits, st);
