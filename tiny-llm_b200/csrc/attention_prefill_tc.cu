@@ -101,8 +101,8 @@ struct TcArgs {
 // PT: the probabilities of a tile stay in TENSOR memory - P_j (bf16 pairs, 32 columns) overwrites the first half of the
 // score buffer S_j it was computed from, and P V reads its A operand from there (the TS form of tcgen05.mma).  The
 // shared-memory form kept ONE P tile, so the exponentials of tile j could not start before P V of tile j-1 had finished
-// reading it; now only the (rare) rescale of O waits for that, and the eight 16-byte stores + proxy fence per row become
-// one tcgen05.st.  Buffer reuse needs no barrier: S_{j+2} is issued behind P V_j in the same MMA queue.
+// reading it; now the exponentials overlap it (the wait sits just before the barrier arrival, and in the rare rescale
+// of O), and the eight 16-byte stores + proxy fence per row become one tcgen05.st.  Buffer reuse needs no barrier: S_{j+2} is issued behind P V_j in the same MMA queue.
 template <bool PT>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -338,6 +338,11 @@ paged_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 // lane = row, column c = keys (2c, 2c + 1) of the tile: over the first 32 columns of the score buffer just read
                 g_tmem_st32(tmem + lane_base + (j & 1) * TC_BN, pk);
                 g_tmem_st_wait();
+                // Do not ARRIVE for tile j before P V of tile j-1 has completed (its exponentials above did overlap it): p_full
+                // counts four arrivals per phase, and a warp that ran a whole tile ahead would arrive twice in one phase and
+                // complete it without the slowest warp - P V_j then read rows that were not written yet (1907 of 16.7 M
+                // outputs off by up to 3 % in the constant-V test of the first version).
+                if (j > 0) g_mbar_wait(pv_done, (j - 1) & 1);
             } else {
                 // P row r: 128 bytes = 8 chunks of 16 B, chunk c at (c ^ (r & 7)) - the 128-byte swizzle of a K-major tile
                 unsigned char *prow = tsm + TC_P_OFF + r * 128;
