@@ -20,7 +20,7 @@
 //     point of the reference's tiled kernel, quantized_matmul.metal:183-194) and write them to TENSOR memory
 //     (tcgen05.st, lane = feature row): the MMA reads its A operand from there; activations arrive by TMA (tokens
 //     beyond M zero-filled); the MMA warp issues tcgen05.mma M128 N{16..128} K16 from an elected lane.
-// Two CTAs fit per SM (96 KB of shared memory, 256 TMEM columns each) up to 64 token columns.
+// Two CTAs fit per SM (96-113 KB of shared memory, 256 TMEM columns each) at every column count.
 //
 // How it got here (lm_head at 64 rows, 2560 -> 151936, 218 MB: profiles/r02_skinny_history.md): 256 threads on the SAME
 // 64-wide block with the tile in shared memory 156 us -> two alternating groups, thread = row 143 us -> tile in tensor
