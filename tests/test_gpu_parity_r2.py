@@ -260,6 +260,43 @@ def test_engine_batch_with_idle_slots_matches_cpu_oracle(dev, B):
     assert all(pool.used_page_ids == set() for pool in model.page_pools)
 
 
+def test_serving_path_engine_matches_cpu_oracle(dev):
+    """The step as the serving configurations run it - 32 slots behind 1024-token block tables (64-slot pages): more than
+    16 K slot-tokens, so q|k|v projection + RoPE + append as one fused launch pair, attention on the tcgen05 streaming
+    kernel with its split count from the table width, swap-AB projections with the RMSNorm folded into the reduction,
+    and a 16-row step graph (occupied slots 0..12) - against the reference CPU path request by request: teacher-forced
+    log-probabilities of the oracle's top-4 candidates within 0.25 nat over three steps."""
+    kwargs = dict(seed=7, realistic=True, max_position_embeddings=2048)
+    cpu_ns = synthetic_qwen3("tiny-d128", **kwargs)
+    gpu_ns = to_device(synthetic_qwen3("tiny-d128", **kwargs), dev)
+    oracle_model = ReferenceCpuModel(cpu_ns)
+    model = Qwen3ModelWeek3(gpu_ns, page_size=64)
+    B, steps, g = 32, 3, gen(321)
+    active = [b for b in range(13) if b % 4 != 2]
+    prompts = {b: torch.randint(1, 500, (9 + (13 * b) % 90,), generator=g).tolist() for b in active}
+    ref = {b: greedy_decode(oracle_model, prompts[b], steps + 1, return_logprobs=True) for b in active}
+    tables = [BatchingKvCache(max_active_requests=B, max_seq_len=1024) for _ in range(model.num_hidden_layers)]
+    for b in active:
+        cache = model.create_kv_cache()
+        model(torch.tensor([prompts[b]], dtype=torch.int32, device=dev), 0, cache, logits_to_keep=1)
+        for layer_cache, table in zip(cache, tables):
+            table.add_request(layer_cache, b)
+    for step in range(steps):
+        tokens = [ref[b][0][step] if b in prompts else 0 for b in range(B)]
+        offsets = [len(prompts[b]) + step if b in prompts else 0 for b in range(B)]
+        logits = model(torch.tensor(tokens, dtype=torch.int32, device=dev).reshape(B, 1), offsets, tables, logits_to_keep=1)
+        lp = logprobs(logits[:, -1]).cpu()
+        for b in active:
+            top = torch.topk(ref[b][1][step + 1], 4)
+            torch.testing.assert_close(lp[b][top.indices], top.values, rtol=0, atol=0.25, msg=lambda m: f"slot {b} step {step}: {m}")
+    engine = model.decode_engine(B, 1024)
+    assert engine.graph_replays == steps and not engine._attention_fused
+    assert engine.variant_replays[16] == steps, "occupied slots 0..12: the 16-row graph must have been replayed"
+    for table in tables:
+        for b in active:
+            table.remove_request(b)
+
+
 def test_row_variant_graphs_give_the_bits_of_the_full_step(dev, monkeypatch):
     """A 64-slot engine whose occupied slots are a short prefix replays the 16- or 32-row step graph: the logits of
     the occupied rows must be bit-identical to what the full 64-row graph produces (same kernels, same split counts),
